@@ -1,0 +1,143 @@
+/* mucon_b200.h -- C ABI of the B200-native (sm_100a) MuCon hot path.
+ *
+ * The reference (yassersouri/MuCon) is pure Python and has no FFI; the entry points below are
+ * what a ctypes binding placed behind the reference's own call signatures needs (see
+ * INTEGRATION.md for the binding and SURVEY.md section 8b for the boundary):
+ *
+ *   mucon_viterbi_*    replaces core.viterbi.viterbi.Viterbi.decode
+ *                      (reference src/core/viterbi/viterbi.py:49-158), called from
+ *                      MuConEvaluator.batch_eval_calculation (src/mucon/evaluators.py:178-180)
+ *   mucon_masks_*      replaces mucon.masks.create_masks (src/mucon/masks.py:19-74), called from
+ *                      MuCon.mucon_loss (src/mucon/models.py:430-441)
+ *   mucon_backbone_*   replaces WaveNetBlock.forward (src/core/modules/temporal.py:128-147) +
+ *                      MuCon.temporal_modeling_forward tail (src/mucon/models.py:759-768) +
+ *                      frame_classifier_forward / log_softmax (src/mucon/models.py:567-582, :368)
+ *
+ * Conventions: plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its name
+ * ends in _h.  Every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns
+ * 0 or a negative MUCON_E* code, never throws, keeps no global state.  The caller owns all
+ * buffers.  There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MUCON_B200_H_
+#define MUCON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUCON_ABI_VERSION 1
+
+/* call-level errors (return values) */
+#define MUCON_OK 0
+#define MUCON_EINVAL (-1)      /* bad argument (null pointer, non-positive size, ...) */
+#define MUCON_EUNSUPPORTED (-2) /* shape outside what the kernels cover (J > 128, N > 128, ...) */
+#define MUCON_ECUDA (-3)       /* a CUDA runtime call failed; see mucon_last_cuda_error() */
+#define MUCON_EALIGN (-4)      /* pointer not aligned as documented */
+
+/* per-unit status written by mucon_viterbi_decode (int32 each) */
+#define MUCON_UNIT_OK 0
+#define MUCON_UNIT_INFEASIBLE 1 /* T < fs or K > N*J: the reference raises (SURVEY.md V-edge) */
+#define MUCON_UNIT_SHORT 2      /* K < N: score -inf, partial path, same as the reference */
+#define MUCON_UNIT_NONFINITE 3  /* best score is NaN or +inf */
+
+int mucon_abi_version(void);
+const char* mucon_strerror(int code);
+const char* mucon_last_cuda_error(void);
+/* Number of SMs / device name of the current device; 0 / "" without a device. */
+int mucon_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Viterbi, step 1: block scores.
+ * For every video v (rows vid_off[v] .. vid_off[v+1] of logp, row-major [rows, C]):
+ *   F[t,c] = F[t-1,c] + logp[t,c]   sequentially in the input dtype   (viterbi.py:51)
+ *   bs[k,c] = F[fs(k+1)-1,c] - F[fs*k-1,c],  bs[0,c] = F[fs-1,c]      (viterbi.py:68-72)
+ * written to rows blk_off[v] .. blk_off[v+1] of bs ([rows, C], same dtype as logp), with
+ * blk_off[v+1]-blk_off[v] == (vid_off[v+1]-vid_off[v]) / fs.
+ * order: optional [V] permutation (launch order, longest first); NULL = identity.
+ * logp must be 16-byte aligned.
+ */
+int mucon_viterbi_blockscores(const void* logp, int in_is_f64,
+                              const int64_t* vid_off, const int64_t* blk_off, const int32_t* order,
+                              int V, int C, int fs, void* bs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Viterbi, step 2: dynamic program + traceback + label writer, one CTA per unit
+ * (unit = one video x one candidate transcript).
+ */
+typedef struct mucon_viterbi_batch {
+  int32_t U;          /* units */
+  int32_t C;          /* classes (row width of bs) */
+  int32_t fs;         /* frame_sampling (viterbi.py:34; the evaluator uses 30) */
+  int32_t max_len;    /* length_model.max_length() (length_model.py:82; 2000) */
+  int32_t bs_is_f64;  /* dtype of bs */
+  int32_t seg0_f32;   /* 1: segment 0 accumulates in float32 (NumPy>=2 promotion) */
+  int32_t max_N;      /* max transcript length over units (sizes the CTA) */
+  int32_t bp_is_u16;  /* 0: bp is uint8 (requires max_len/fs <= 255), 1: uint16 */
+  const void* bs;            /* [sum K, C] block scores */
+  const int64_t* vid_off;    /* [V+1] frame offsets (T_v = difference) */
+  const int64_t* blk_off;    /* [V+1] block offsets into bs */
+  const int32_t* unit_vid;   /* [U] video of each unit */
+  const int32_t* tr;         /* [sum N] transcripts, concatenated */
+  const int32_t* tr_off;     /* [U+1] */
+  const double* len_rows;    /* [sum N, J] length scores of j=1..J blocks (J = max_len/fs), or NULL */
+  const double* len_params;  /* [sum N, 3] (ln m, m, norms) per transcript position, or NULL */
+  const double* logfact;     /* [J+1] sum_{i<=j*fs} ln i at index j; used with len_params */
+  const int64_t* lab_off;    /* [U] offset of the unit's labels in `labels`, <0 = do not write */
+  const int64_t* bp_off;     /* [U] offset (elements) of the unit's [K,N] back-pointer table */
+  const int32_t* order;      /* [U] launch order or NULL */
+  double* score;             /* [U] */
+  int32_t* labels;           /* frame labels, T_u each */
+  int32_t* seg_blocks;       /* [sum N] segment lengths in blocks (0 = segment not reached) */
+  void* bp;                  /* back-pointers, 0 = no entry */
+  int32_t* final_j;          /* [U] length (blocks) of the last segment */
+  int32_t* status;           /* [U] MUCON_UNIT_* */
+} mucon_viterbi_batch;
+
+int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
+
+/* Arg-max over the candidates of each video: best[v] = unit index with the highest score among
+ * units cand_off[v] .. cand_off[v+1] (lowest index wins ties; units with status INFEASIBLE are
+ * skipped; -1 if none). */
+int mucon_viterbi_select(const double* score, const int32_t* status, const int32_t* cand_off,
+                         int V, int32_t* best, void* stream);
+
+/* Labels for selected units from their seg_blocks: sel[i] is a unit index (or <0 to skip) whose
+ * labels are written at labels + out_off[i]. */
+int mucon_viterbi_labels(const int32_t* sel, int n_sel, const int64_t* out_off,
+                         const int64_t* vid_off, const int32_t* unit_vid, const int32_t* tr,
+                         const int32_t* tr_off, const int32_t* seg_blocks, int fs,
+                         int32_t* labels, void* stream);
+
+/* Host helper: Poisson parameters (ln m, m, norms) for `n` means with libm's log
+ * (length_model.py:54-63).  NumPy callers should build them with numpy instead so that ln()
+ * is the very function the reference used. */
+int mucon_poisson_params_h(const double* means_h, int n, double* out_h);
+/* Host helper: logfact[j] = sum_{i=1..j*fs} ln i for j = 0..J (sequential), J = max_len/fs. */
+int mucon_logfact_h(int fs, int max_len, double* out_h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Masks (src/mucon/masks.py:19-74).  For video v with M_v = n_off[v+1]-n_off[v] lengths and
+ * target size T_v: out rows n_off[v].. are [M_v, T_v] float32 written at out + out_off[v].
+ * L is NOT modified; the scaled lengths L*(1+2*overlap) (the reference's in-place side effect,
+ * masks.py:61) are written to L_scaled when non-NULL.
+ * template_id: 0 box, 1 gaussian(std=20), 2 trapezoid.  align_corners: 0 (torch >= 1.3 default)
+ * or 1 (torch 1.1, the reference's pinned docker).
+ */
+int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
+                    int V, int n_rows /* n_off[V] */, int max_T /* max over T[] */, float overlap,
+                    int template_id, int align_corners, float* L_scaled, float* out, void* stream);
+/* grad_L[i] = d(sum(grad_out * masks))/dL[i], through pi (cumsum) and the scale.
+ * grad_out has the layout of `out`; ws is scratch of 2*n_rows floats. */
+int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
+                    int V, int n_rows, float overlap, int template_id, int align_corners,
+                    const float* grad_out, float* ws, float* grad_L, void* stream);
+/* Host helper: the 100 template taps the kernels use (masks.py:34-54). */
+int mucon_mask_template_h(int template_id, float* out100_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUCON_B200_H_ */

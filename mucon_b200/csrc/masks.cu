@@ -1,0 +1,232 @@
+// masks.cu -- length -> soft mask generation for the mutual-consistency loss (sm_100a).
+//
+// Replaces reference src/mucon/masks.py:19-74 (create_masks): cumsum -> affine map ->
+// affine_grid + bilinear grid_sample (zero padding) of a 100-tap template, fused into one pass
+// that writes each [M, T] mask row with coalesced float4 stores and never materialises the grid.
+//
+// Per row i of a video with target size T (all float32, torch's op order):
+//   pi = cumsum(L)[i] - L[i];  Ls = L[i]*(1+2*ov);  pi -= Ls*(ov/2)              masks.py:58-62
+//   s  = T/Ls;  x = ((pi + Ls/2) - T/2) / (-(Ls/2))                              masks.py:102-120
+//   g_t = (2t+1)/T - 1   (align_corners=0)   |  2t/(T-1) - 1   (align_corners=1) affine_grid
+//   gx = g_t*s + x
+//   u  = ((gx+1)*W - 1)/2 (align_corners=0)  |  (gx+1)/2*(W-1) (align_corners=1) grid_sample
+//   out[i,t] = tmpl[floor u]*(1-frac) + tmpl[floor u + 1]*frac, taps outside [0,W) are 0
+// Backward: d out/d u = tmpl[floor u + 1] - tmpl[floor u]; u depends on L through pi and Ls.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mucon {
+namespace {
+
+constexpr int kW = 100;  // TEMPLATE_WIDTH, masks.py:32
+__constant__ float c_tmpl[3][kW];
+bool g_tmpl_ready[64] = {false};
+
+void fill_templates(float (*t)[kW]) {
+  for (int i = 0; i < kW; ++i) t[0][i] = 1.0f;  // box, masks.py:42-43
+  // gaussian: scipy.signal.gaussian(M=100, std=20) = exp(-0.5*((n-(M-1)/2)/std)^2), masks.py:34-41
+  for (int i = 0; i < kW; ++i) {
+    const double n = i - (kW - 1) / 2.0;
+    t[1][i] = (float)exp(-0.5 * (n / 20.0) * (n / 20.0));
+  }
+  // trapezoid: 25-tap ramps 0.5 -> 1 and 1 -> 0.5 (torch.arange with step 0.02), masks.py:44-54
+  for (int i = 0; i < kW; ++i) t[2][i] = 1.0f;
+  for (int i = 0; i < 25; ++i) {
+    t[2][i] = (float)(0.5 + 0.02 * i);
+    t[2][kW - 25 + i] = (float)(1.0 + (-0.02) * i);
+  }
+}
+
+int ensure_templates() {
+  int dev = 0;
+  MUCON_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 64 && g_tmpl_ready[dev]) return MUCON_OK;
+  float h[3][kW];
+  fill_templates(h);
+  MUCON_CUDA_CHECK(cudaMemcpyToSymbol(c_tmpl, h, sizeof(h)));
+  if (dev < 64) g_tmpl_ready[dev] = true;
+  return MUCON_OK;
+}
+
+struct RowGeom {
+  float s, x, Ls, pi;
+};
+
+__device__ __forceinline__ int find_video(const int32_t* n_off, int V, int row) {
+  int lo = 0, hi = V;  // largest v with n_off[v] <= row
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (n_off[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ RowGeom row_geom(const float* L, int r0, int i, int T, float overlap) {
+  float cum = 0.f;
+  for (int q = 0; q <= i; ++q) cum = cum + L[r0 + q];  // sequential, like torch.cumsum on 1-D
+  const float Li = L[r0 + i];
+  RowGeom g;
+  float pi = cum - Li;
+  g.Ls = Li * (1.0f + 2 * overlap);
+  pi = pi - g.Ls * (overlap / 2);
+  g.pi = pi;
+  const float Tf = static_cast<float>(T);
+  g.s = Tf / g.Ls;
+  g.x = ((pi + g.Ls / 2) - Tf / 2) / (-(g.Ls / 2));
+  return g;
+}
+
+__device__ __forceinline__ float coord_u(const RowGeom& g, int t, int T, int align) {
+  const float Tf = static_cast<float>(T);
+  float gt;
+  if (align) gt = (T > 1) ? (2.0f * t) / (Tf - 1.0f) - 1.0f : -1.0f;
+  else gt = (2.0f * t + 1.0f) / Tf - 1.0f;
+  const float gx = gt * g.s + g.x;
+  return align ? ((gx + 1.f) / 2.f) * (kW - 1) : ((gx + 1.f) * kW - 1.f) / 2.f;
+}
+
+__device__ __forceinline__ float tap(int tid, int i) { return (i >= 0 && i < kW) ? c_tmpl[tid][i] : 0.f; }
+
+__device__ __forceinline__ float sample(int tmpl, float u) {
+  const float fl = floorf(u);
+  // far outside the template: both taps are padding (also keeps the int conversion in range)
+  if (!(fl >= -1.f && fl < (float)kW)) return 0.f;
+  const int i0 = static_cast<int>(fl);
+  const float w1 = u - fl, w0 = 1.f - w1;
+  return tap(tmpl, i0) * w0 + tap(tmpl, i0 + 1) * w1;
+}
+
+__global__ void __launch_bounds__(256) masks_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off,
+                                                        const int32_t* __restrict__ Tv,
+                                                        const int64_t* __restrict__ out_off, int V, float overlap,
+                                                        int tmpl, int align, float* __restrict__ L_scaled,
+                                                        float* __restrict__ out) {
+  const int row = blockIdx.y;
+  const int v = find_video(n_off, V, row);
+  const int T = Tv[v];
+  const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (t0 >= T && !(blockIdx.x == 0 && threadIdx.x == 0)) return;
+  const int r0 = n_off[v], i = row - r0;
+  const RowGeom g = row_geom(L, r0, i, T, overlap);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && L_scaled) L_scaled[row] = g.Ls;
+  if (t0 >= T) return;
+  float* o = out + out_off[v] + static_cast<int64_t>(i) * T;
+  float val[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) val[e] = (t0 + e < T) ? sample(tmpl, coord_u(g, t0 + e, T, align)) : 0.f;
+  if (t0 + 3 < T && ((reinterpret_cast<uintptr_t>(o + t0) & 15) == 0)) {
+    *reinterpret_cast<float4*>(o + t0) = make_float4(val[0], val[1], val[2], val[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (t0 + e < T) o[t0 + e] = val[e];
+  }
+}
+
+// One CTA per mask row: A = dLoss/dpi, B = dLoss/dLs.
+__global__ void __launch_bounds__(256) masks_bwd_rows_kernel(const float* __restrict__ L,
+                                                             const int32_t* __restrict__ n_off,
+                                                             const int32_t* __restrict__ Tv,
+                                                             const int64_t* __restrict__ out_off, int V, float overlap,
+                                                             int tmpl, int align, const float* __restrict__ gout,
+                                                             float* __restrict__ ws) {
+  __shared__ float redA[8], redB[8];
+  const int row = blockIdx.x;
+  const int v = find_video(n_off, V, row);
+  const int T = Tv[v];
+  const int r0 = n_off[v], i = row - r0;
+  const RowGeom g = row_geom(L, r0, i, T, overlap);
+  const float* go = gout + out_off[v] + static_cast<int64_t>(i) * T;
+  // u = a_t * Wn / Ls - c,  a_t = (t + 0.5 - pi) [align 0, Wn = W] or (t*T/(T-1) - pi) [align 1, Wn = W-1]
+  const float Wn = align ? (float)(kW - 1) : (float)kW;
+  const float Tf = (float)T;
+  float A = 0.f, B = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float u = coord_u(g, t, T, align);
+    const float fl = floorf(u);
+    if (!(fl >= -1.f && fl < (float)kW)) continue;
+    const int i0 = static_cast<int>(fl);
+    const float slope = tap(tmpl, i0 + 1) - tap(tmpl, i0);
+    if (slope == 0.f) continue;
+    const float at = align ? ((T > 1) ? (float)t * Tf / (Tf - 1.f) : 0.f) - g.pi : ((float)t + 0.5f) - g.pi;
+    const float w = go[t] * slope;
+    A += w * (-Wn / g.Ls);
+    B += w * (-(at * Wn) / (g.Ls * g.Ls));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    A += __shfl_xor_sync(0xffffffffu, A, off);
+    B += __shfl_xor_sync(0xffffffffu, B, off);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { redA[warp] = A; redB[warp] = B; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += redA[w]; b += redB[w]; }
+    ws[2 * row] = a;
+    ws[2 * row + 1] = b;
+  }
+}
+
+// grad_L[j] = sum_{i>j} A_i - A_j*(1+2ov)*(ov/2) + B_j*(1+2ov)
+__global__ void masks_bwd_combine_kernel(const int32_t* __restrict__ n_off, int V, float overlap,
+                                         const float* __restrict__ ws, float* __restrict__ grad_L) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int r0 = n_off[v], r1 = n_off[v + 1];
+  const float k = 1.0f + 2 * overlap;
+  float suffix = 0.f;
+  for (int r = r1 - 1; r >= r0; --r) {
+    const float A = ws[2 * r], B = ws[2 * r + 1];
+    grad_L[r] = suffix - A * (k * (overlap / 2)) + B * k;
+    suffix += A;
+  }
+}
+
+}  // namespace
+}  // namespace mucon
+
+using namespace mucon;
+
+extern "C" int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off, int V,
+                               int n_rows, int max_T, float overlap, int template_id, int align_corners,
+                               float* L_scaled, float* out, void* stream) {
+  if (!L || !n_off || !T || !out_off || !out || V < 0 || n_rows < 0 || max_T < 0) return MUCON_EINVAL;
+  if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
+  if (V == 0 || n_rows == 0 || max_T == 0) return MUCON_OK;
+  if (n_rows > 65535) return MUCON_EUNSUPPORTED;
+  int rc = ensure_templates();
+  if (rc != MUCON_OK) return rc;
+  dim3 grid((max_T + 1023) / 1024, n_rows);
+  masks_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, n_off, T, out_off, V, overlap, template_id,
+                                                                         align_corners, L_scaled, out);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off, int V,
+                               int n_rows, float overlap, int template_id, int align_corners, const float* grad_out,
+                               float* ws, float* grad_L, void* stream) {
+  if (!L || !n_off || !T || !out_off || !grad_out || !ws || !grad_L || V < 0 || n_rows < 0) return MUCON_EINVAL;
+  if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
+  if (V == 0 || n_rows == 0) return MUCON_OK;
+  int rc = ensure_templates();
+  if (rc != MUCON_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  masks_bwd_rows_kernel<<<n_rows, 256, 0, st>>>(L, n_off, T, out_off, V, overlap, template_id, align_corners, grad_out,
+                                                ws);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  masks_bwd_combine_kernel<<<(V + 127) / 128, 128, 0, st>>>(n_off, V, overlap, ws, grad_L);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_mask_template_h(int template_id, float* out100_h) {
+  if (!out100_h || template_id < 0 || template_id > 2) return MUCON_EINVAL;
+  float h[3][kW];
+  fill_templates(h);
+  for (int i = 0; i < kW; ++i) out100_h[i] = h[template_id][i];
+  return MUCON_OK;
+}

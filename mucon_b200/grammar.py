@@ -1,0 +1,101 @@
+"""Grammars with the reference's interface (reference src/core/viterbi/grammar.py).
+
+The CUDA decoder only needs the list of candidate transcripts a grammar admits; these classes
+keep that list (``candidates``) next to the reference's ``successors`` prefix tree so that code
+written against the reference protocol (n_classes / possible_successors / score) still works.
+"""
+import numpy as np
+
+
+class Grammar(object):
+    def score(self, context, label):
+        return 0.0
+
+    def n_classes(self):
+        return 0
+
+    def start_symbol(self):
+        return -1
+
+    def end_symbol(self):
+        return -2
+
+    def possible_successors(self, context):
+        return set()
+
+    def update_context(self, context, label):
+        return context + (label,)
+
+
+class _TranscriptSetGrammar(Grammar):
+    def _install(self, transcripts, num_classes):
+        self.num_classes = num_classes
+        self.candidates = []
+        seen = set()
+        self.successors = {}
+        for tr in transcripts:
+            tr = [int(x) for x in tr]
+            if tuple(tr) not in seen:
+                seen.add(tuple(tr))
+                self.candidates.append(tr)
+            path = tr + [self.end_symbol()]
+            for i, nxt in enumerate(path):
+                self.successors.setdefault((self.start_symbol(),) + tuple(path[:i]), set()).add(nxt)
+
+    def n_classes(self):
+        return self.num_classes
+
+    def possible_successors(self, context):
+        return self.successors.get(context, set())
+
+    def score(self, context, label):
+        return 0.0 if label in self.possible_successors(context) else -np.inf
+
+
+class SingleTranscriptGrammar(_TranscriptSetGrammar):
+    """grammar.py:196-217 -- exactly one admissible transcript."""
+
+    def __init__(self, transcript, n_classes):
+        self._install([transcript], n_classes)
+
+
+class ModifiedPathGrammar(_TranscriptSetGrammar):
+    """grammar.py:178-191 -- every transcript of a given list."""
+
+    def __init__(self, transcripts, num_classes):
+        self._install(transcripts, num_classes)
+
+
+class PathGrammar(_TranscriptSetGrammar):
+    """grammar.py:143-175 -- transcripts read from a text file, one per line."""
+
+    def __init__(self, transcript_file, label2index_map):
+        with open(transcript_file, "r") as f:
+            lines = f.read().split("\n")[0:-1]
+        self._install([[label2index_map[w] for w in line.split()] for line in lines], len(label2index_map))
+
+
+def lower_grammar(grammar):
+    """Candidate transcripts of any grammar that follows the reference protocol with 0/-inf
+    scores and a finite prefix tree (ours, or the reference's Single/Path grammars)."""
+    cands = getattr(grammar, "candidates", None)
+    if cands is not None:
+        return [list(c) for c in cands]
+    succ = getattr(grammar, "successors", None)
+    if not isinstance(succ, dict):
+        raise TypeError(
+            f"{type(grammar).__name__} cannot be lowered to candidate transcripts; the CUDA decoder "
+            "supports SingleTranscriptGrammar / PathGrammar / ModifiedPathGrammar (there is no CPU fallback)")
+    start, end = grammar.start_symbol(), grammar.end_symbol()
+    out = []
+    stack = [((start,), [])]
+    while stack:
+        ctx, tr = stack.pop()
+        for nxt in sorted(succ.get(ctx, ()), reverse=True):
+            if nxt == end:
+                out.append(tr)
+            else:
+                stack.append((ctx + (nxt,), tr + [int(nxt)]))
+    if not out:
+        raise ValueError("grammar admits no transcript")
+    return out

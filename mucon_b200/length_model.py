@@ -1,0 +1,101 @@
+"""Length models with the reference's interface (reference src/core/viterbi/length_model.py).
+
+``PoissonModel`` keeps the reference constructor and ``score`` / ``max_length`` / ``n_classes``
+but never runs the 2000-iteration Python loop of length_model.py:65-71 (62 ms per video): it
+stores the three per-class numbers the table is made of -- ln m, m, norms -- and the CUDA DP
+kernel rebuilds exactly the rows it needs with IEEE mul/sub in the reference's order.  ln() is
+NumPy's, i.e. the very function the reference calls, so rows are bit-identical to the
+reference's table on the same machine.
+"""
+import numpy as np
+
+_LOGFACT = {}
+_LOGTAIL = np.zeros(2, dtype=np.float64)
+
+
+def log_factorial_prefix(n):
+    """lf[i] = sum_{k=1..i} ln k accumulated sequentially in float64 (length_model.py:67-69)."""
+    lf = _LOGFACT.get(n)
+    if lf is None:
+        lf = np.zeros(n + 1, dtype=np.float64)
+        if n >= 1:
+            lf[1:] = np.cumsum(np.log(np.arange(1, n + 1, dtype=np.float64)))
+        _LOGFACT[n] = lf
+    return lf
+
+
+def _log_tail(top):
+    """tail[i] = sum_{k=2..i} ln k, sequential from k = 2 (length_model.py:59-62)."""
+    global _LOGTAIL
+    if top >= _LOGTAIL.shape[0]:
+        n = max(top + 1, 2 * _LOGTAIL.shape[0])
+        t = np.zeros(n, dtype=np.float64)
+        t[2:] = np.cumsum(np.log(np.arange(2, n, dtype=np.float64)))
+        _LOGTAIL = t
+    return _LOGTAIL
+
+
+def poisson_params(mean_lengths, renormalize=True):
+    """[C, 3] float64: ln m, m, norms (length_model.py:54-63)."""
+    m = np.asarray(mean_lengths, dtype=np.float64)
+    out = np.empty(m.shape + (3,), dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out[..., 0] = np.log(m)
+        out[..., 1] = m
+        if renormalize:
+            r = np.round(m)
+            mi = np.maximum(m.astype(np.int64), 0)
+            tail = _log_tail(int(mi.max(initial=1)))
+            out[..., 2] = (r * np.log(r) - r) - tail[mi]
+        else:
+            out[..., 2] = 0.0
+    return out
+
+
+class LengthModel(object):
+    def n_classes(self):
+        return 0
+
+    def score(self, length, label):
+        return 0.0
+
+    def max_length(self):
+        return np.inf
+
+
+class PoissonModel(LengthModel):
+    """Drop-in for core.viterbi.length_model.PoissonModel (length_model.py:42-83)."""
+
+    def __init__(self, model, max_length=2000, renormalize=True):
+        super().__init__()
+        self.mean_lengths = np.loadtxt(model) if isinstance(model, str) else model
+        self.num_classes = self.mean_lengths.shape[0]
+        self.max_len = max_length
+        self.params = poisson_params(self.mean_lengths, renormalize)
+        self.norms = self.params[:, 2]
+        self._table = None
+
+    @property
+    def poisson(self):
+        """The reference's full [max_len, C] table, built on demand (vectorised)."""
+        if self._table is None:
+            lf = log_factorial_prefix(self.max_len - 1)
+            L = np.arange(self.max_len, dtype=np.float64)[:, None]
+            p = self.params
+            with np.errstate(invalid="ignore"):
+                t = ((L * p[None, :, 0] - p[None, :, 1]) - lf[:, None]) - p[None, :, 2]
+            t[0, :] = -np.inf
+            self._table = t
+        return self._table
+
+    def n_classes(self):
+        return self.num_classes
+
+    def score(self, length, label):
+        if length >= self.max_len or length <= 0:
+            return -np.inf
+        lm, m, nrm = self.params[label]
+        return ((length * lm - m) - log_factorial_prefix(self.max_len - 1)[length]) - nrm
+
+    def max_length(self):
+        return self.max_len

@@ -1,0 +1,331 @@
+"""Transcript-constrained Viterbi alignment on B200 -- host side.
+
+Drop-in surface (reference src/core/viterbi/viterbi.py:34-65, used by
+src/mucon/evaluators.py:80,148,167,178-180):
+
+    dec = Viterbi(grammar, length_model, frame_sampling=30)
+    dec.grammar = ...; dec.length_model = ...          # re-assigned per video by the evaluator
+    score, labels, segments = dec.decode(log_frame_probs)   # np.ndarray [T, C]
+
+plus a batched engine (``AlignPlan`` / ``ViterbiEngine``) that decodes many (video, candidate
+transcript) units in two kernel launches; that is what bench.py and the multi-GPU driver use.
+All compute happens in libmucon_b200.so (CUDA, sm_100a); there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .grammar import lower_grammar
+from .length_model import PoissonModel, log_factorial_prefix, poisson_params
+
+__all__ = ["Viterbi", "ViterbiEngine", "AlignPlan", "Segment", "default_seg0_f32"]
+
+
+def default_seg0_f32(dtype):
+    """The float mix the installed NumPy gives the reference decoder:
+    with float32 log-probs NumPy >= 2 keeps segment 0 in float32, NumPy 1.x promotes to float64."""
+    return np.dtype(dtype) == np.float32 and int(np.__version__.split(".")[0]) >= 2
+
+
+class Segment(object):
+    """Same attributes as the reference's traceback Segment (viterbi.py:141-143)."""
+    __slots__ = ("label", "length")
+
+    def __init__(self, label, length):
+        self.label, self.length = label, length
+
+    def __repr__(self):
+        return f"Segment(label={self.label}, length={self.length})"
+
+
+def _align16(n):
+    return (n + 15) & ~15
+
+
+class _Blob:
+    """Packs several small host arrays into one buffer so they reach the GPU in one copy."""
+
+    def __init__(self):
+        self.parts = []
+        self.size = 0
+
+    def add(self, name, arr):
+        arr = np.ascontiguousarray(arr)
+        off = self.size
+        self.parts.append((name, off, arr))
+        self.size = _align16(off + arr.nbytes)
+        return off
+
+    def upload(self, device, stream=None):
+        host = torch.empty(max(self.size, 16), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        hv = host.numpy()
+        for _, off, arr in self.parts:
+            hv[off:off + arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        dev = host.to(device, non_blocking=True)
+        base = dev.data_ptr()
+        return dev, host, {name: base + off for name, off, _ in self.parts}
+
+
+class AlignPlan:
+    """Shapes, offsets and device metadata of one batch of (video, candidate) units.
+
+    T            frames per video [V]
+    candidates   per video, a list of candidate transcripts (list of int lists)
+    len_params   per video [C, 3] float64 (ln m, m, norms) -- Poisson fast path, or
+    len_rows     per unit [N_u, J] float64 length scores for j = 1..J blocks (any length model)
+    """
+
+    def __init__(self, T, candidates, n_classes, fs=30, max_len=2000, len_params=None, len_rows=None,
+                 device=None, want_bp=True, labels="best"):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.fs, self.max_len, self.C = int(fs), int(max_len), int(n_classes)
+        self.J = self.max_len // self.fs
+        T = np.asarray(T, dtype=np.int64)
+        self.T = T
+        self.V = V = int(T.shape[0])
+        self.K = K = T // self.fs
+        self.vid_off = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+        self.blk_off = np.concatenate([[0], np.cumsum(K)]).astype(np.int64)
+        ncand = np.array([len(c) for c in candidates], dtype=np.int64)
+        if len(candidates) != V or (V and ncand.min() < 1):
+            raise ValueError("need at least one candidate transcript per video")
+        self.cand_off = np.concatenate([[0], np.cumsum(ncand)]).astype(np.int32)
+        self.U = U = int(self.cand_off[-1])
+        self.unit_vid = np.repeat(np.arange(V, dtype=np.int32), ncand)
+        flat = [np.asarray(tr, dtype=np.int32).reshape(-1) for cl in candidates for tr in cl]
+        nlen = np.array([t.shape[0] for t in flat], dtype=np.int64)
+        if U and nlen.min() < 1:
+            raise ValueError("empty transcript")  # the reference crashes at one_hot (SURVEY V-edge)
+        self.N = nlen
+        self.tr_off = np.concatenate([[0], np.cumsum(nlen)]).astype(np.int32)
+        self.tr = np.concatenate(flat).astype(np.int32) if U else np.zeros(0, np.int32)
+        if U and (self.tr.min() < 0 or self.tr.max() >= self.C):
+            raise ValueError("transcript label outside [0, n_classes)")
+        self.max_N = int(nlen.max()) if U else 1
+        self.single = bool(U == V)
+        self.labels_mode = labels
+        uT = T[self.unit_vid]
+        uK = K[self.unit_vid]
+        # labels: per-unit ("all") or per-video, written for the best candidate ("best")
+        if labels == "all":
+            self.lab_off = np.concatenate([[0], np.cumsum(uT)]).astype(np.int64)[:-1]
+            self.n_labels = int(uT.sum())
+        elif self.single:
+            self.lab_off = self.vid_off[:-1].copy()
+            self.n_labels = int(T.sum())
+        else:
+            self.lab_off = np.full(U, -1, dtype=np.int64)
+            self.n_labels = int(T.sum())
+        bp_sz = uK * nlen
+        self.bp_off = np.concatenate([[0], np.cumsum(bp_sz)]).astype(np.int64)
+        self.n_bp = int(self.bp_off[-1])
+        self.total_frames = int(T.sum())
+        self.total_blocks = int(K.sum())
+        self.aligned_frames = int(uT.sum())  # the benchmark's unit of work: T x candidates
+        # launch order: longest first so the tail of the grid is made of short units
+        self.order_v = np.argsort(-T, kind="stable").astype(np.int32)
+        self.order_u = np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32)
+
+        blob = _Blob()
+        blob.add("vid_off", self.vid_off)
+        blob.add("blk_off", self.blk_off)
+        blob.add("unit_vid", self.unit_vid)
+        blob.add("tr", self.tr)
+        blob.add("tr_off", self.tr_off)
+        blob.add("cand_off", self.cand_off)
+        blob.add("lab_off", self.lab_off)
+        blob.add("bp_off", self.bp_off[:-1] if U else self.bp_off)
+        blob.add("order_v", self.order_v)
+        blob.add("order_u", self.order_u)
+        blob.add("vid_lab_off", self.vid_off[:-1])
+        self.use_rows = len_rows is not None
+        if self.use_rows:
+            rows = np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, self.J) for r in len_rows]) \
+                if U else np.zeros((0, self.J))
+            if rows.shape[0] != self.tr.shape[0]:
+                raise ValueError("len_rows must hold one [N_u, J] block per unit")
+            blob.add("len_rows", rows)
+        else:
+            if len_params is None:
+                raise ValueError("need len_params (Poisson) or len_rows")
+            lp = np.asarray(len_params, dtype=np.float64).reshape(V, self.C, 3)
+            pos_vid = np.repeat(self.unit_vid, nlen)
+            blob.add("len_params", lp[pos_vid, self.tr])
+            lf = log_factorial_prefix(self.max_len - 1)
+            idx = np.minimum(np.arange(self.J + 1) * self.fs, self.max_len - 1)
+            blob.add("logfact", lf[idx])
+        self.h2d_meta_bytes = blob.size
+        self._meta_dev, self._meta_host, self.p = blob.upload(self.device)
+
+        dev = self.device
+        self.score = torch.empty(U, dtype=torch.float64, device=dev)
+        self.final_j = torch.empty(U, dtype=torch.int32, device=dev)
+        self.status = torch.empty(U, dtype=torch.int32, device=dev)
+        self.seg_blocks = torch.empty(int(self.tr_off[-1]), dtype=torch.int32, device=dev)
+        self.labels = torch.empty(self.n_labels, dtype=torch.int32, device=dev)
+        self.bp = torch.empty(max(self.n_bp, 1), dtype=torch.uint8, device=dev)
+        self.best = torch.empty(V, dtype=torch.int32, device=dev)
+        self.bs = None  # allocated by the engine once the input dtype is known
+
+
+class ViterbiEngine:
+    """Runs AlignPlans: block-score scan + DP/traceback/labels (+ candidate arg-max)."""
+
+    def __init__(self, device=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.lib = _lib.lib()
+        self.launches = 0  # kernels launched so far (bench.py reports this)
+
+    def run(self, plan, logp, seg0_f32=None, stream=None):
+        """logp: CUDA tensor [sum T, C] float32 or float64, videos concatenated.  Asynchronous."""
+        if not logp.is_cuda:
+            raise _lib.MuconError("ViterbiEngine.run needs a CUDA tensor (no CPU fallback)")
+        if logp.dtype not in (torch.float32, torch.float64) or not logp.is_contiguous():
+            raise TypeError("logp must be contiguous float32/float64")
+        if logp.shape[0] != plan.total_frames or logp.shape[1] != plan.C:
+            raise ValueError(f"logp shape {tuple(logp.shape)} != ({plan.total_frames}, {plan.C})")
+        is64 = logp.dtype == torch.float64
+        if seg0_f32 is None:
+            seg0_f32 = default_seg0_f32(np.float64 if is64 else np.float32)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        sp = C.c_void_p(st.cuda_stream)
+        if plan.bs is None or plan.bs.dtype != logp.dtype:
+            plan.bs = torch.empty((max(plan.total_blocks, 1), plan.C), dtype=logp.dtype, device=self.device)
+        p = plan.p
+        if plan.V == 0:
+            return plan
+        lib = self.lib
+        _lib.check(lib.mucon_viterbi_blockscores(
+            _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["vid_off"]), C.c_void_p(p["blk_off"]),
+            C.c_void_p(p["order_v"]), C.c_int(plan.V), C.c_int(plan.C), C.c_int(plan.fs),
+            _lib.ptr(plan.bs), sp), "mucon_viterbi_blockscores")
+        b = _lib.ViterbiBatch()
+        b.U, b.C, b.fs, b.max_len = plan.U, plan.C, plan.fs, plan.max_len
+        b.bs_is_f64, b.seg0_f32, b.max_N, b.bp_is_u16 = int(is64), int(bool(seg0_f32)), plan.max_N, 0
+        b.bs = plan.bs.data_ptr()
+        b.vid_off, b.blk_off, b.unit_vid = p["vid_off"], p["blk_off"], p["unit_vid"]
+        b.tr, b.tr_off = p["tr"], p["tr_off"]
+        if plan.use_rows:
+            b.len_rows, b.len_params, b.logfact = p["len_rows"], None, None
+        else:
+            b.len_rows, b.len_params, b.logfact = None, p["len_params"], p["logfact"]
+        b.lab_off, b.bp_off, b.order = p["lab_off"], p["bp_off"], p["order_u"]
+        b.score, b.labels = plan.score.data_ptr(), plan.labels.data_ptr()
+        b.seg_blocks, b.bp = plan.seg_blocks.data_ptr(), plan.bp.data_ptr()
+        b.final_j, b.status = plan.final_j.data_ptr(), plan.status.data_ptr()
+        _lib.check(lib.mucon_viterbi_decode(C.byref(b), sp), "mucon_viterbi_decode")
+        self.launches += 2
+        if plan.labels_mode == "best" and not plan.single:
+            _lib.check(lib.mucon_viterbi_select(
+                _lib.ptr(plan.score), _lib.ptr(plan.status), C.c_void_p(p["cand_off"]), C.c_int(plan.V),
+                _lib.ptr(plan.best), sp), "mucon_viterbi_select")
+            _lib.check(lib.mucon_viterbi_labels(
+                _lib.ptr(plan.best), C.c_int(plan.V), C.c_void_p(p["vid_lab_off"]), C.c_void_p(p["vid_off"]),
+                C.c_void_p(p["unit_vid"]), C.c_void_p(p["tr"]), C.c_void_p(p["tr_off"]),
+                _lib.ptr(plan.seg_blocks), C.c_int(plan.fs), _lib.ptr(plan.labels), sp), "mucon_viterbi_labels")
+            self.launches += 2
+        return plan
+
+    # ---- host-side conveniences ------------------------------------------------------------
+    def fetch(self, plan, want_bp=False):
+        """Synchronising device->host read of a finished plan's results (numpy)."""
+        out = dict(score=plan.score.cpu().numpy(), final_j=plan.final_j.cpu().numpy(),
+                   status=plan.status.cpu().numpy(), seg_blocks=plan.seg_blocks.cpu().numpy(),
+                   labels=plan.labels.cpu().numpy())
+        if not plan.single and plan.labels_mode == "best":
+            out["best"] = plan.best.cpu().numpy()
+        if want_bp:
+            out["bp"] = plan.bp.cpu().numpy()[:plan.n_bp]
+            out["bs"] = plan.bs.cpu().numpy()[:plan.total_blocks]
+        return out
+
+
+def _length_rows(length_model, transcript, fs, J):
+    """Generic lowering of any LengthModel: rows[n, j-1] = score(j*fs, label_n)."""
+    tab = getattr(length_model, "poisson", None)
+    max_len = length_model.max_length()
+    rows = np.full((len(transcript), J), -np.inf, dtype=np.float64)
+    for j in range(1, J + 1):
+        l = j * fs
+        if tab is not None and isinstance(tab, np.ndarray):
+            if l < max_len:
+                rows[:, j - 1] = tab[l, transcript]
+        else:
+            rows[:, j - 1] = [length_model.score(l, int(c)) for c in transcript]
+    return rows
+
+
+class Viterbi(object):
+    """Drop-in for core.viterbi.viterbi.Viterbi (viterbi.py:10-65), decoding on the GPU.
+
+    grammar: SingleTranscriptGrammar / PathGrammar / ModifiedPathGrammar (this package's or the
+    reference's).  length_model: PoissonModel (this package's: parameter fast path; the
+    reference's: rows taken from its table) or any LengthModel (rows from score()).
+    ``np_mode``: None = behave like the installed NumPy; "numpy1" / "numpy2" force the float
+    promotion regime of SURVEY.md section 0.4.
+    """
+
+    def __init__(self, grammar, length_model, frame_sampling=1, max_hypotheses=np.inf, device=None, np_mode=None):
+        if max_hypotheses != np.inf:
+            raise NotImplementedError("hypothesis pruning is not implemented (the evaluator never prunes)")
+        self.grammar = grammar
+        self.length_model = length_model
+        self.frame_sampling = frame_sampling
+        self.max_hypotheses = max_hypotheses
+        self.np_mode = np_mode
+        self._engine = None
+        self._device = device
+        self.last = None  # raw outputs of the last decode (back-pointers etc.), for tests
+
+    def set_multi_length(self, mode=True):  # viterbi.py:40-41 -- a no-op there too
+        pass
+
+    def _eng(self):
+        if self._engine is None:
+            self._engine = ViterbiEngine(self._device)
+        return self._engine
+
+    def decode(self, log_frame_probs):
+        logp = np.asarray(log_frame_probs)
+        assert logp.shape[1] == self.grammar.n_classes()  # viterbi.py:50
+        if logp.dtype not in (np.float32, np.float64):
+            logp = logp.astype(np.float64)
+        fs = int(self.frame_sampling)
+        T, Cn = logp.shape
+        if T < fs:
+            raise IndexError(f"sequence of {T} frames is shorter than frame_sampling={fs}")
+        cands = lower_grammar(self.grammar)
+        lm = self.length_model
+        max_len = lm.max_length()
+        if not np.isfinite(max_len):
+            raise TypeError("length model without a finite max_length() is not supported")
+        max_len = int(max_len)
+        J = max_len // fs
+        kw = {}
+        if isinstance(lm, PoissonModel):
+            kw["len_params"] = lm.params[None]
+        else:
+            kw["len_rows"] = [_length_rows(lm, tr, fs, J) for tr in cands]
+        eng = self._eng()
+        plan = AlignPlan([T], [cands], Cn, fs=fs, max_len=max_len, device=eng.device, labels="best", **kw)
+        dev_logp = torch.from_numpy(np.ascontiguousarray(logp)).to(eng.device)
+        if self.np_mode is None:
+            seg0 = default_seg0_f32(logp.dtype)
+        else:
+            seg0 = logp.dtype == np.float32 and self.np_mode == "numpy2"
+        eng.run(plan, dev_logp, seg0_f32=seg0)
+        out = eng.fetch(plan, want_bp=True)
+        self.last = out
+        u = 0 if plan.single else int(out["best"][0])
+        if u < 0 or out["status"][u] == _lib.UNIT_INFEASIBLE:
+            # the reference dies with AttributeError in traceback when every hypothesis has been
+            # dropped (K > N*J); same exception type here
+            raise AttributeError("no hypothesis survives: sequence too long for this transcript and max_length")
+        tr = cands[u]
+        sb = out["seg_blocks"][plan.tr_off[u]:plan.tr_off[u + 1]]
+        K = T // fs
+        segs = [Segment(int(tr[n]), int(fs * sb[n])) for n in range(len(tr)) if sb[n] > 0]
+        segs[-1].length += T - fs * K
+        return np.float64(out["score"][u]), out["labels"][:T].tolist(), segs
