@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- aligned frames/sec of the MuCon Viterbi alignment path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun ... bench.py --gpus N ...           (one rank per GPU, NCCL)
+
+Workload (BASELINE.json configs[1], "c2"): a synthetic Breakfast-shaped split of 1712 videos per
+GPU (T = clip(lognormal(ln 1800, 0.7), 300, 10000), 48 classes, 2..12 transcript segments,
+frame_sampling 30, Poisson length model), float32 log-probabilities.  One step = one pass of the
+alignment path over the whole split: block-score scan kernel + DP/traceback/label kernel
+(mucon_viterbi_blockscores + mucon_viterbi_decode), inputs resident in HBM (`value`), or through
+the host API with pinned host buffers and H2D/D2H copies inside the timed region (`e2e`).
+Weak scaling: every rank aligns its own 1712-video split; for N > 1 the step ends with the NCCL
+all_gather of per-video scores and segment lengths.
+
+--impl reference times the reference's CPU algorithm on the host cores: the reference is pure
+Python and does not travel to the GPU box, so this is the oracle's hypothesis-table port of it
+(oracle/hyp_viterbi.py + the loop-built Poisson table), one process per core.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import synth  # noqa: E402  (synthetic input recipes only; no oracle, no CUDA)
+
+C, FS, MAX_LEN, V_PER_GPU = 48, 30, 2000, 1712
+METRIC, UNIT = "aligned_frames_per_sec", "frames/s"
+WORKLOAD = ("c2: Breakfast-shaped synthetic split, 1712 videos/GPU, T<=10000, 48 classes, N<=12, fs=30, "
+            "1 transcript/video, float32 log-probs -> Viterbi alignment (scan + DP + traceback + labels)")
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_split(seed):
+    T, trs = synth.breakfast_split(seed=seed, V=V_PER_GPU, C=C, fs=FS, J=MAX_LEN // FS)
+    rng = np.random.default_rng(seed + 1000)
+    means = np.stack([synth.class_means(rng.dirichlet(np.ones(len(tr))).astype(np.float32), tr, C, int(t))
+                      for tr, t in zip(trs, T)])
+    return T, trs, means
+
+
+def device_logp(T, trs, seed, device):
+    """log_softmax(N(0,1) + 3*onehot(planted segmentation)), generated on the device."""
+    import torch
+    rng = np.random.default_rng(seed + 2000)
+    planted = np.empty(int(T.sum()), dtype=np.int64)
+    pos = 0
+    for t, tr in zip(T, trs):
+        n = len(tr)
+        cuts = np.sort(rng.choice(np.arange(1, t), size=n - 1, replace=False))
+        planted[pos:pos + t] = np.repeat(tr, np.diff(np.concatenate([[0], cuts, [t]])))
+        pos += t
+    g = torch.Generator(device).manual_seed(seed)
+    x = torch.randn(int(T.sum()), C, device=device, generator=g)
+    x.scatter_add_(1, torch.from_numpy(planted).to(device)[:, None], torch.full((x.shape[0], 1), 3.0, device=device))
+    return torch.log_softmax(x, dim=1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (the oracle port of the reference's CPU path) -- checker code, used only here
+# ------------------------------------------------------------------------------------------------
+_CPU_JOBS = None
+
+
+def _cpu_decode_ref(i):
+    from oracle import hyp_viterbi, poisson
+    logp, tr, means = _CPU_JOBS[i]
+    t0 = time.perf_counter()
+    tab = poisson.poisson_table_loop(means, MAX_LEN)           # PoissonModel(lengths), evaluators.py:167
+    hyp_viterbi.decode(logp, [list(map(int, tr))], tab, MAX_LEN, FS)  # vi_decoder.decode, evaluators.py:178
+    return logp.shape[0], time.perf_counter() - t0
+
+
+def _cpu_decode_c(i):
+    from oracle import coracle, dense_viterbi, poisson
+    logp, tr, means = _CPU_JOBS[i]
+    t0 = time.perf_counter()
+    rows = coracle.poisson_rows(poisson.poisson_params(means)[tr], FS, MAX_LEN)
+    coracle.decode_video(logp, tr, rows, FS, dense_viterbi.numpy_seg0_f32(logp.dtype))
+    return logp.shape[0], time.perf_counter() - t0
+
+
+def cpu_sample_jobs(n_videos, seed=0):
+    """The first n videos of the rank-0 split, with host-generated log-probs of the same recipe."""
+    T, trs, means = make_split(seed)
+    rng = np.random.default_rng(seed + 3000)
+    jobs = []
+    for v in range(min(n_videos, len(T))):
+        lp, _ = synth.planted_logp(rng, int(T[v]), C, trs[v].tolist(), np.float32)
+        jobs.append((lp, trs[v], means[v]))
+    return jobs
+
+
+def run_cpu_pool(fn, n_jobs, cores):
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [fn(i) for i in range(n_jobs)]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(fn, range(n_jobs), chunksize=1)
+    wall = time.perf_counter() - t0
+    frames = sum(r[0] for r in res)
+    return frames / wall, wall, frames, sum(r[1] for r in res)
+
+
+def cpu_baseline(budget_s=12.0):
+    """Times the reference-algorithm port on all host cores over a bounded sample of c2."""
+    global _CPU_JOBS
+    from oracle import build as oracle_build
+    oracle_build.build_oracle()
+    cores = os.cpu_count() or 1
+    _CPU_JOBS = cpu_sample_jobs(2)
+    _, _, f, busy = run_cpu_pool(_cpu_decode_ref, 2, 1)  # calibrate: seconds per frame on one core
+    per_frame = busy / f
+    n = int(max(cores, min(V_PER_GPU, budget_s * cores / (per_frame * 2300))))
+    _CPU_JOBS = cpu_sample_jobs(n)
+    fps, wall, frames, _ = run_cpu_pool(_cpu_decode_ref, n, cores)
+    fps1 = 1.0 / per_frame
+    cfps, cwall, cframes, _ = run_cpu_pool(_cpu_decode_c, n, cores)
+    return {
+        "value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"first {n} videos of the c2 split ({frames} frames), oracle/hyp_viterbi.py + loop-built Poisson "
+                  f"table per video, {cores} processes, {wall:.1f} s",
+        "single_core_value": fps1,
+        "c_port": {"value": cfps, "unit": UNIT, "cores": cores,
+                   "what": f"oracle/oracle.c dense restatement, same sample, {cwall:.2f} s"},
+    }
+
+
+def main_reference(args, rank, world):
+    """The reference arm: the reference's own (CPU, Python) algorithm on the host cores."""
+    if rank != 0:
+        return
+    global _CPU_JOBS
+    from oracle import build as oracle_build
+    oracle_build.build_oracle()
+    cores = os.cpu_count() or 1
+    _CPU_JOBS = cpu_sample_jobs(2)
+    _, _, f, busy = run_cpu_pool(_cpu_decode_ref, 2, 1)
+    per_frame = busy / f
+    # each step: a bounded sample, about 6 s of wall time on all cores
+    n = int(max(cores, min(V_PER_GPU, 6.0 * cores / (per_frame * 2300))))
+    _CPU_JOBS = cpu_sample_jobs(n)
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_pool(_cpu_decode_ref, min(n, cores), cores)
+    walls, frames = [], 0
+    for _ in range(args.steps):
+        fps, wall, frames, _ = run_cpu_pool(_cpu_decode_ref, n, cores)
+        walls.append(wall)
+    value = frames * len(walls) / sum(walls)
+    sample = (f"first {n} videos of the c2 split ({frames} frames) per step, hypothesis-table port of "
+              f"core/viterbi/viterbi.py + loop-built PoissonModel table per video, {cores} processes")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sampled": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from mucon_b200 import dist as mdist
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan, ViterbiEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    T, trs, means = make_split(rank)
+    cands = [[tr.tolist()] for tr in trs]
+    logp = device_logp(T, trs, rank, device)
+    eng = ViterbiEngine(device)
+    params = poisson_params(means)
+    plan = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=params, labels="best")
+    max_pos = V_PER_GPU * 12
+
+    def step(mid=None):
+        eng.run(plan, logp, seg0_f32=True, mid_event=mid)
+        if world > 1:
+            mdist.gather_alignments(plan.score, plan.seg_blocks, plan.tr_off, V_PER_GPU, max_pos)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = eng.launches
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True)
+    t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step(ev[i][1])
+        ev[i][2].record()
+    t_all1.record()
+    barrier()
+    total_ms = t_all0.elapsed_time(t_all1)
+    scan_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    dp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    launches = eng.launches - launches0
+
+    # ---- e2e: host API, pinned host log-probs in, labels + scores + segments out ---------------
+    host_logp = torch.empty(logp.shape, dtype=logp.dtype, pin_memory=True)
+    host_logp.copy_(logp)
+    n_lab = plan.n_labels
+    host_labels = torch.empty(n_lab, dtype=torch.int32, pin_memory=True)
+    host_small = torch.empty(plan.U, dtype=torch.float64, pin_memory=True)
+    host_seg = torch.empty(int(plan.tr_off[-1]), dtype=torch.int32, pin_memory=True)
+    dev_in = torch.empty_like(logp)
+
+    def e2e_step():
+        p = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=poisson_params(means),
+                      labels="best")
+        dev_in.copy_(host_logp, non_blocking=True)
+        eng.run(p, dev_in, seg0_f32=True)
+        host_labels.copy_(p.labels, non_blocking=True)
+        host_small.copy_(p.score, non_blocking=True)
+        host_seg.copy_(p.seg_blocks, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return p
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        p_last = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        p_last = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    h2d = logp.numel() * logp.element_size() + p_last.h2d_meta_bytes
+    d2h = host_labels.numel() * 4 + host_small.numel() * 8 + host_seg.numel() * 4
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, scan_ms, dp_ms, e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, scan_ms, dp_ms, e2e_s = t.tolist()
+        fr = torch.tensor([plan.aligned_frames], dtype=torch.float64, device=device)
+        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+        frames_all = float(fr.item())
+    else:
+        frames_all = float(plan.aligned_frames)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        ms_per_step = total_ms / args.steps
+        # algorithmic bytes: scan reads 4*T*C per video; DP unit writes 4T labels,
+        # 2KN back-pointer bytes, 528N Poisson rows, 8+8N score/segments
+        Tsum, Ksum, Nsum = int(T.sum()), int((T // FS).sum()), int(sum(len(t) for t in trs))
+        KN = int(((T // FS) * np.array([len(t) for t in trs])).sum())
+        scan_bytes = 4 * Tsum * C
+        dp_bytes = 4 * Tsum + 2 * KN + 528 * Nsum + 8 * len(T) + 8 * Nsum
+        scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9
+        path_gbs = (scan_bytes + dp_bytes) / ((scan_ms + dp_ms) * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("scan_kernel_dram_bytes")
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": frames_all / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "videos_per_gpu": V_PER_GPU, "frames_per_gpu": Tsum,
+                       "l2": "inputs (%.0f MB log-probs per GPU) are larger than the 126 MB L2" % (scan_bytes / 1e6),
+                       "collective": "all_gather(scores, segment lengths)" if world > 1 else "none"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": frames_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                    "what": "AlignPlan build + pinned H2D of log-probs + 2 kernels + D2H of labels/scores/segments"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "scan_bulk_kernel (block-score scan)", "achieved": scan_gbs,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": scan_gbs / hbm_peak, "traffic": traffic,
+                         "peak_source": peak_src, "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms},
+            "roofline_path": {"what": "scan + DP kernels, algorithmic bytes 4TC + 4T + 2KN + 528N + 8 + 8N per unit",
+                              "achieved": path_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": path_gbs / hbm_peak,
+                              "bytes_per_step": scan_bytes + dp_bytes, "scan_ms": scan_ms, "dp_ms": dp_ms},
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+    else:
+        main_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -178,7 +178,7 @@ class ViterbiEngine:
         self.lib = _lib.lib()
         self.launches = 0  # kernels launched so far (bench.py reports this)
 
-    def run(self, plan, logp, seg0_f32=None, stream=None):
+    def run(self, plan, logp, seg0_f32=None, stream=None, mid_event=None):
         """logp: CUDA tensor [sum T, C] float32 or float64, videos concatenated.  Asynchronous."""
         if not logp.is_cuda:
             raise _lib.MuconError("ViterbiEngine.run needs a CUDA tensor (no CPU fallback)")
@@ -201,6 +201,8 @@ class ViterbiEngine:
             _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["vid_off"]), C.c_void_p(p["blk_off"]),
             C.c_void_p(p["order_v"]), C.c_int(plan.V), C.c_int(plan.C), C.c_int(plan.fs),
             _lib.ptr(plan.bs), sp), "mucon_viterbi_blockscores")
+        if mid_event is not None:  # lets bench.py time the scan and the DP kernel separately
+            mid_event.record(st)
         b = _lib.ViterbiBatch()
         b.U, b.C, b.fs, b.max_len = plan.U, plan.C, plan.fs, plan.max_len
         b.bs_is_f64, b.seg0_f32, b.max_N, b.bp_is_u16 = int(is64), int(bool(seg0_f32)), plan.max_N, 0

@@ -62,3 +62,23 @@ def class_mean_lengths(rel_lengths, transcript, n_classes, T):
     lengths /= k
     lengths[lengths == 0] = 1
     return lengths
+
+
+def poisson_table_loop(means, max_len=2000):
+    """The table built the way the reference builds it -- a Python loop over all lengths
+    (length_model.py:54-71).  Same values as poisson_table; used where the CPU baseline has to
+    carry the reference's cost profile (bench.py)."""
+    m = np.asarray(means, dtype=np.float64)
+    tab = np.zeros((max_len, m.shape[0]))
+    norms = np.round(m) * np.log(np.round(m)) - np.round(m)
+    for c in range(len(m)):
+        acc = 0
+        for k in range(2, int(m[c]) + 1):
+            acc += np.log(k)
+        norms[c] = norms[c] - acc
+    tab[0, :] = -np.inf
+    acc = 0
+    for l in range(1, max_len):
+        acc += np.log(l)
+        tab[l, :] = l * np.log(m) - m - acc - norms
+    return tab

@@ -16,9 +16,10 @@ def planted_logp(rng, T, C, transcript, dtype=np.float32, boost=3.0):
     return x.astype(dtype), np.diff(bounds)
 
 
-def class_means(rel, transcript, C, T):
+def class_means(rel, transcript, C, T, floor=1.0):
     """Per-class mean absolute lengths the evaluator feeds to PoissonModel
-    (reference src/mucon/evaluators.py:155-165), zeros -> 1."""
+    (reference src/mucon/evaluators.py:155-165), zeros -> 1.  Means are floored at `floor`
+    because the reference's PoissonModel turns any mean < 0.5 into NaN scores (SURVEY.md V-edge)."""
     rel = np.asarray(rel, dtype=np.float32)
     tr = np.asarray(transcript)
     tot = np.zeros(C, dtype=np.float64)
@@ -29,7 +30,7 @@ def class_means(rel, transcript, C, T):
     cnt[cnt == 0] = 1
     tot /= cnt
     tot[tot == 0] = 1
-    return tot
+    return np.maximum(tot, floor)
 
 
 def breakfast_split(seed=0, V=1712, C=48, fs=30, J=66, t_lo=300, t_hi=10000, n_hi=12):

@@ -1,0 +1,252 @@
+"""GPU parity: the CUDA Viterbi path (through the C ABI) against the oracle and the frozen
+reference outputs.  Integer outputs (labels, segments, back-pointers, final j) and block scores
+must be bit-exact; the float64 path score must be equal to the last bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import coracle, dense_viterbi, poisson
+from tests import synth
+from tests.util import golden_names, load_golden, same_score
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(cuda_device):
+    from mucon_b200.viterbi import ViterbiEngine
+    return ViterbiEngine(cuda_device)
+
+
+def run_units(eng, logps, cands, means, fs=30, max_len=2000, seg0=None, labels="all", use_rows=False):
+    """logps: list of [T,C] arrays (one per video); cands: per video list of transcripts; means: per video [C]."""
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan
+    C = logps[0].shape[1]
+    kw = {}
+    if use_rows:
+        J = max_len // fs
+        kw["len_rows"] = [coracle.poisson_rows(poisson.poisson_params(m)[tr], fs, max_len)
+                          for m, cl in zip(means, cands) for tr in cl]
+    else:
+        kw["len_params"] = np.stack([poisson_params(m) for m in means])
+    plan = AlignPlan([l.shape[0] for l in logps], cands, C, fs=fs, max_len=max_len, device=eng.device,
+                     labels=labels, **kw)
+    packed = torch.from_numpy(np.concatenate(logps)).to(eng.device)
+    eng.run(plan, packed, seg0_f32=seg0)
+    torch.cuda.synchronize()
+    return plan, eng.fetch(plan, want_bp=True)
+
+
+def oracle_unit(logp, tr, means, fs, max_len, seg0):
+    rows = coracle.poisson_rows(poisson.poisson_params(means)[tr], fs, max_len)
+    bs = coracle.block_scores(logp, fs)
+    d = coracle.viterbi(bs, tr, rows, seg0)
+    d["labels"] = coracle.decode_video(logp, tr, rows, fs, seg0)["labels"]
+    d["bs"] = bs
+    return d
+
+
+def check_unit(plan, out, u, ref, T):
+    a, b = plan.tr_off[u], plan.tr_off[u + 1]
+    assert out["status"][u] in (0, 2)
+    assert same_score(out["score"][u], ref["score"]), (out["score"][u], ref["score"])
+    assert np.array_equal(out["seg_blocks"][a:b], ref["seg_blocks"])
+    if out["status"][u] == 0:
+        assert out["final_j"][u] == ref["jf"]
+        K, N = ref["bp"].shape
+        bp = out["bp"][plan.bp_off[u]:plan.bp_off[u + 1]].reshape(K, N)
+        assert np.array_equal(bp, ref["bp"].astype(np.uint8))
+    lo = plan.lab_off[u]
+    assert np.array_equal(out["labels"][lo:lo + T], ref["labels"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixture(eng, name):
+    """Frozen outputs of the unmodified reference decoder (tests/golden/make_golden.py)."""
+    g = load_golden(name)
+    T = g["logp"].shape[0]
+    if g["max_len"] // g["fs"] > 128:
+        pytest.skip("J > 128 is outside the register-resident kernel")
+    plan, out = run_units(eng, [g["logp"]], [g["transcripts"]], [g["means"]], g["fs"], g["max_len"],
+                          seg0=g["seg0_f32"], labels="best")
+    if plan.single:
+        u = 0
+    else:
+        u = int(out["best"][0])
+    assert same_score(out["score"][u], g["score"])
+    assert np.array_equal(out["labels"][:T], g["labels"])
+    tr = g["transcripts"][u]
+    sb = out["seg_blocks"][plan.tr_off[u]:plan.tr_off[u + 1]]
+    assert dense_viterbi.segments_from_blocks(sb, tr, g["fs"], T) == g["segments"]
+    if plan.single and np.isfinite(g["score"]):
+        K = T // g["fs"]
+        assert np.array_equal(out["bp"][:K * len(tr)].reshape(K, len(tr)), g["bp"].astype(np.uint8))
+
+
+@pytest.mark.parametrize("dtype,seg0", [(np.float32, True), (np.float32, False), (np.float64, False)])
+def test_random_batch_bit_exact(eng, dtype, seg0):
+    rng = np.random.default_rng(42)
+    logps, cands, means = [], [], []
+    for i in range(24):
+        C = 48
+        N = int(rng.integers(1, 13))
+        K = int(rng.integers(max(N, 1), min(N * 66, 340) + 1))
+        T = K * 30 + int(rng.integers(0, 30))
+        tr = rng.integers(0, C, N).tolist()
+        lp, _ = synth.planted_logp(rng, T, C, tr, dtype)
+        if i % 5 == 0:
+            lp = np.round(lp)  # integer-valued: exercises ties
+        logps.append(lp)
+        cands.append([tr])
+        means.append(synth.class_means(rng.dirichlet(np.ones(N)).astype(np.float32), tr, C, T))
+    plan, out = run_units(eng, logps, cands, means, seg0=seg0)
+    for u in range(plan.U):
+        ref = oracle_unit(logps[u], cands[u][0], means[u], 30, 2000, seg0)
+        bs = out["bs"][plan.blk_off[u]:plan.blk_off[u + 1]]
+        assert np.array_equal(bs, ref["bs"]), f"block scores differ for unit {u}"
+        check_unit(plan, out, u, ref, logps[u].shape[0])
+
+
+@pytest.mark.parametrize("fs,max_len,C", [(7, 91, 12), (1, 20, 5), (13, 200, 7), (30, 2000, 100), (10, 1000, 33)])
+def test_other_sampling_and_class_counts(eng, fs, max_len, C):
+    """C = 5, 7, 33 take the direct scan (row not a multiple of 16 B); max_len % fs == 0 gives -inf rows."""
+    rng = np.random.default_rng(fs * 1000 + C)
+    J = max_len // fs
+    logps, cands, means = [], [], []
+    for i in range(10):
+        N = int(rng.integers(1, 7))
+        K = int(rng.integers(max(N - 1, 1), N * J + 1))
+        T = K * fs + int(rng.integers(0, fs))
+        tr = rng.integers(0, C, N).tolist()
+        logps.append(np.log(rng.dirichlet(np.ones(C), T)).astype([np.float32, np.float64][i % 2]))
+        cands.append([tr])
+        means.append(rng.uniform(0.6, max(T, 2), C))
+    for dt in (np.float32, np.float64):
+        idx = [i for i in range(10) if logps[i].dtype == dt]
+        plan, out = run_units(eng, [logps[i] for i in idx], [cands[i] for i in idx], [means[i] for i in idx],
+                              fs, max_len, seg0=(dt == np.float32))
+        for u, i in enumerate(idx):
+            ref = oracle_unit(logps[i], cands[i][0], means[i], fs, max_len, dt == np.float32)
+            check_unit(plan, out, u, ref, logps[i].shape[0])
+
+
+def test_rows_path_equals_params_path(eng):
+    rng = np.random.default_rng(5)
+    tr = [3, 1, 4, 1, 5]
+    lp, _ = synth.planted_logp(rng, 1700, 9, tr, np.float32)
+    m = rng.uniform(50, 600, 9)
+    _, a = run_units(eng, [lp], [[tr]], [m], use_rows=False)
+    _, b = run_units(eng, [lp], [[tr]], [m], use_rows=True)
+    for k in ("score", "labels", "seg_blocks", "bp", "final_j"):
+        assert np.array_equal(a[k], b[k])
+
+
+def test_edge_cases_status(eng):
+    rng = np.random.default_rng(9)
+    C = 6
+    mk = lambda T: np.log(rng.dirichlet(np.ones(C), T)).astype(np.float32)
+    logps = [mk(3990), mk(100), mk(3960), mk(59)]
+    cands = [[[0, 1]], [[0, 1, 2, 3, 4, 5]], [[1, 2]], [[3]]]
+    means = [np.full(C, 500.0)] * 4
+    plan, out = run_units(eng, logps, cands, means, seg0=True)
+    assert out["status"].tolist() == [1, 2, 0, 0]  # K > N*J infeasible; K < N short; K == N*J ok; K == 1 ok
+    assert np.isnan(out["score"][0]) and out["score"][1] == -np.inf
+    for u in (1, 2, 3):
+        ref = oracle_unit(logps[u], cands[u][0], means[u], 30, 2000, True)
+        check_unit(plan, out, u, ref, logps[u].shape[0])
+    assert out["seg_blocks"][plan.tr_off[2]:plan.tr_off[3]].tolist() == [66, 66]
+
+
+def test_candidates_best_equals_argmax_of_singles(eng):
+    rng = np.random.default_rng(13)
+    logps, cands, means = [], [], []
+    for v in range(6):
+        base = rng.integers(0, 20, int(rng.integers(3, 9))).tolist()
+        T = int(rng.integers(900, 4000))
+        lp, _ = synth.planted_logp(rng, T, 20, base, np.float32)
+        K = T // 30
+        cl = synth.random_edits(rng, base, 20, 16, max(2, -(-K // 66)), min(30, K))
+        logps.append(lp)
+        cands.append(cl)
+        means.append(synth.class_means(rng.dirichlet(np.ones(len(base))).astype(np.float32), base, 20, T))
+    plan, out = run_units(eng, logps, cands, means, seg0=True, labels="best")
+    assert plan.U == 96 and not plan.single
+    for v in range(6):
+        refs = [oracle_unit(logps[v], tr, means[v], 30, 2000, True) for tr in cands[v]]
+        scores = np.array([r["score"] for r in refs])
+        u0 = plan.cand_off[v]
+        assert np.array_equal(out["score"][u0:u0 + 16], scores)
+        b = int(np.argmax(scores))  # first maximum == lowest index wins
+        assert out["best"][v] == u0 + b
+        T = logps[v].shape[0]
+        assert np.array_equal(out["labels"][plan.vid_off[v]:plan.vid_off[v] + T], refs[b]["labels"])
+
+
+def test_long_video_stress_c4(eng):
+    """c4: T=40000, C=100, N=60 (K=1333, 3960 live states), float32 and float64."""
+    rng = np.random.default_rng(4)
+    tr = rng.permutation(100)[:60].tolist()
+    lp, _ = synth.planted_logp(rng, 40000, 100, tr, np.float32)
+    m = synth.class_means(rng.dirichlet(5 * np.ones(60)).astype(np.float32), tr, 100, 40000)
+    for arr, seg0 in ((lp, True), (lp.astype(np.float64), False)):
+        plan, out = run_units(eng, [arr], [[tr]], [m], seg0=seg0)
+        check_unit(plan, out, 0, oracle_unit(arr, tr, m, 30, 2000, seg0), 40000)
+
+
+def test_drop_in_viterbi_class(eng):
+    """Same call sequence as the evaluator (reference src/mucon/evaluators.py:80,148,167,178-180)."""
+    from mucon_b200 import PoissonModel, SingleTranscriptGrammar
+    from mucon_b200.viterbi import Viterbi
+    g = load_golden("c1_f32")
+    dec = Viterbi(None, None, frame_sampling=30, np_mode="numpy2")
+    dec.grammar = SingleTranscriptGrammar(g["transcripts"][0], 48)
+    dec.length_model = PoissonModel(g["means"])
+    dec.set_multi_length(False)
+    score, labels, segs = dec.decode(g["logp"])
+    assert isinstance(labels, list) and len(labels) == 2000
+    assert same_score(score, g["score"])
+    assert labels == g["labels"].tolist()
+    assert [(s.label, s.length) for s in segs] == g["segments"]
+    # infeasible input: the reference raises AttributeError (K > N*J) / IndexError (T < fs)
+    dec.grammar = SingleTranscriptGrammar([0, 1], 48)
+    with pytest.raises(AttributeError):
+        dec.decode(np.zeros((3990, 48), dtype=np.float32))
+    with pytest.raises(IndexError):
+        dec.decode(np.zeros((20, 48), dtype=np.float32))
+
+
+def test_breakfast_split_properties_full_size(eng):
+    """c2 at full size (1712 videos): size-independent properties + oracle spot checks."""
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan
+    T, trs = synth.breakfast_split(seed=0)
+    rng = np.random.default_rng(1)
+    C = 48
+    V = len(T)
+    total = int(T.sum())
+    logp = torch.randn(total, C, device=eng.device, generator=torch.Generator(eng.device).manual_seed(3))
+    logp = torch.log_softmax(logp, dim=1).contiguous()
+    means = np.stack([synth.class_means(rng.dirichlet(np.ones(len(tr))).astype(np.float32), tr, C, int(t))
+                      for tr, t in zip(trs, T)])
+    plan = AlignPlan(T, [[tr.tolist()] for tr in trs], C, device=eng.device, len_params=poisson_params(means))
+    eng.run(plan, logp, seg0_f32=True)
+    torch.cuda.synchronize()
+    out = eng.fetch(plan, want_bp=False)
+    assert (out["status"] == 0).all()
+    K = T // 30
+    sb_sum = np.add.reduceat(out["seg_blocks"], plan.tr_off[:-1])
+    assert np.array_equal(sb_sum, K)  # segment lengths cover every block exactly once
+    assert (out["seg_blocks"] >= 1).all() and (out["seg_blocks"] <= 66).all()
+    # labels are the run-length expansion of (transcript, seg_blocks) with the leftover frames first
+    for v in rng.choice(V, 40, replace=False):
+        a, b = plan.tr_off[v], plan.tr_off[v + 1]
+        rem = int(T[v] - 30 * K[v])
+        exp = np.concatenate([np.full(rem, trs[v][-1])] + [np.full(30 * n, l) for l, n in zip(trs[v], out["seg_blocks"][a:b])])
+        assert np.array_equal(out["labels"][plan.vid_off[v]:plan.vid_off[v + 1]], exp)
+    host = logp.cpu().numpy()
+    for v in rng.choice(V, 25, replace=False):
+        lp = host[plan.vid_off[v]:plan.vid_off[v + 1]]
+        ref = oracle_unit(lp, trs[v].tolist(), means[v], 30, 2000, True)
+        assert same_score(out["score"][v], ref["score"])
+        assert np.array_equal(out["labels"][plan.vid_off[v]:plan.vid_off[v + 1]], ref["labels"])
