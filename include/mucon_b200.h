@@ -71,11 +71,13 @@ typedef struct mucon_viterbi_batch {
   int32_t U;          /* units */
   int32_t C;          /* classes (row width of bs) */
   int32_t fs;         /* frame_sampling (viterbi.py:34; the evaluator uses 30) */
-  int32_t max_len;    /* length_model.max_length() (length_model.py:82; 2000) */
+  int32_t max_len;    /* length_model.max_length() (length_model.py:82; 2000); max_len/fs <= 128 */
   int32_t bs_is_f64;  /* dtype of bs */
   int32_t seg0_f32;   /* 1: segment 0 accumulates in float32 (NumPy>=2 promotion) */
-  int32_t max_N;      /* max transcript length over units (sizes the CTA) */
-  int32_t bp_is_u16;  /* 0: bp is uint8 (requires max_len/fs <= 255), 1: uint16 */
+  int32_t max_N;      /* max transcript length over units (<= 128) */
+  int32_t max_K;      /* max number of blocks over units (sizes the shared back-pointer stage) */
+  int32_t n_cta;      /* number of unit bins, from mucon_viterbi_pack_h */
+  int32_t segs;       /* segments per warp, from mucon_viterbi_pack_h */
   const void* bs;            /* [sum K, C] block scores */
   const int64_t* vid_off;    /* [V+1] frame offsets (T_v = difference) */
   const int64_t* blk_off;    /* [V+1] block offsets into bs */
@@ -86,15 +88,21 @@ typedef struct mucon_viterbi_batch {
   const double* len_params;  /* [sum N, 3] (ln m, m, norms) per transcript position, or NULL */
   const double* logfact;     /* [J+1] sum_{i<=j*fs} ln i at index j; used with len_params */
   const int64_t* lab_off;    /* [U] offset of the unit's labels in `labels`, <0 = do not write */
-  const int64_t* bp_off;     /* [U] offset (elements) of the unit's [K,N] back-pointer table */
-  const int32_t* order;      /* [U] launch order or NULL */
+  const int64_t* bp_off;     /* [U] offset (bytes) of the unit's [K,N] uint8 back-pointer table */
+  const int32_t* warp_unit;  /* [n_cta*16] unit of every warp of every bin (-1 = unused) */
   double* score;             /* [U] */
   int32_t* labels;           /* frame labels, T_u each */
   int32_t* seg_blocks;       /* [sum N] segment lengths in blocks (0 = segment not reached) */
-  void* bp;                  /* back-pointers, 0 = no entry */
+  uint8_t* bp;               /* back-pointers: winning predecessor length, 0 = no entry */
   int32_t* final_j;          /* [U] length (blocks) of the last segment */
   int32_t* status;           /* [U] MUCON_UNIT_* */
 } mucon_viterbi_batch;
+
+/* Host helper: packs units into bins of 16 warps (one CTA each).  A unit needs
+ * ceil(N/segs) consecutive warps; units are taken in order_h (or 0..U-1) -- pass them longest
+ * first.  warp_unit_h needs room for U*16 entries; on return the first *n_cta_out*16 are valid. */
+int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N,
+                         int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* segs_out);
 
 int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 

@@ -14,7 +14,7 @@ UNIT_OK, UNIT_INFEASIBLE, UNIT_SHORT, UNIT_NONFINITE = 0, 1, 2, 3
 # every symbol include/mucon_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
     "mucon_abi_version", "mucon_strerror", "mucon_last_cuda_error", "mucon_device_sm_count",
-    "mucon_viterbi_blockscores", "mucon_viterbi_decode", "mucon_viterbi_select", "mucon_viterbi_labels",
+    "mucon_viterbi_blockscores", "mucon_viterbi_decode", "mucon_viterbi_pack_h", "mucon_viterbi_select", "mucon_viterbi_labels",
     "mucon_poisson_params_h", "mucon_logfact_h",
     "mucon_masks_fwd", "mucon_masks_bwd", "mucon_mask_template_h",
 ]
@@ -28,10 +28,11 @@ class ViterbiBatch(C.Structure):
     """mirror of struct mucon_viterbi_batch"""
     _fields_ = [
         ("U", C.c_int32), ("C", C.c_int32), ("fs", C.c_int32), ("max_len", C.c_int32),
-        ("bs_is_f64", C.c_int32), ("seg0_f32", C.c_int32), ("max_N", C.c_int32), ("bp_is_u16", C.c_int32),
+        ("bs_is_f64", C.c_int32), ("seg0_f32", C.c_int32), ("max_N", C.c_int32), ("max_K", C.c_int32),
+        ("n_cta", C.c_int32), ("segs", C.c_int32),
         ("bs", C.c_void_p), ("vid_off", C.c_void_p), ("blk_off", C.c_void_p), ("unit_vid", C.c_void_p),
         ("tr", C.c_void_p), ("tr_off", C.c_void_p), ("len_rows", C.c_void_p), ("len_params", C.c_void_p),
-        ("logfact", C.c_void_p), ("lab_off", C.c_void_p), ("bp_off", C.c_void_p), ("order", C.c_void_p),
+        ("logfact", C.c_void_p), ("lab_off", C.c_void_p), ("bp_off", C.c_void_p), ("warp_unit", C.c_void_p),
         ("score", C.c_void_p), ("labels", C.c_void_p), ("seg_blocks", C.c_void_p), ("bp", C.c_void_p),
         ("final_j", C.c_void_p), ("status", C.c_void_p),
     ]

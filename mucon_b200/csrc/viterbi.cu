@@ -21,13 +21,10 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "viterbi_dp.cuh"
 
 namespace mucon {
 namespace {
-
-constexpr int kMaxSlots = 4;    // J <= 128
-constexpr int kDpMaxWarps = 16;  // CTA of at most 512 threads
-constexpr int kDpChunk = 32;     // DP steps per block-score staging chunk
 
 __host__ __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
@@ -156,316 +153,6 @@ __global__ void __launch_bounds__(128) scan_direct_kernel(const T* __restrict__ 
 }
 
 // ============================================================================================
-// Dynamic program
-// ============================================================================================
-
-struct Best {
-  double v;
-  int j;  // 0 = no candidate
-};
-
-// max by value, ties -> larger j ("replace iff old <= new" over ascending j, viterbi.py:26-28).
-__device__ __forceinline__ void best_take(Best& a, double v, int j) {
-  const bool take = (j != 0) && ((a.j == 0) || (v > a.v) || (v == a.v && j > a.j));
-  if (take) { a.v = v; a.j = j; }
-}
-
-__device__ __forceinline__ Best warp_best(Best a) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, a.v, off);
-    const int oj = __shfl_xor_sync(0xffffffffu, a.j, off);
-    best_take(a, ov, oj);
-  }
-  return a;
-}
-
-__device__ __forceinline__ int label_of_frame(int64_t t, int64_t rem, const int32_t* trl, const int64_t* segend,
-                                              int last) {
-  if (t < rem) return trl[last];
-  int n = 0;
-  while (n < last && t >= segend[n]) ++n;
-  return trl[n];
-}
-
-// Writes T labels at out.  segend[n] = rem + fs * sum_{m<=n} blocks[m] (frames, exclusive end).
-__device__ void write_labels(int32_t* out, int64_t T, int64_t rem, const int32_t* trl, const int64_t* segend,
-                             int last) {
-  const int tid = threadIdx.x, nth = blockDim.x;
-  const int64_t mis = (reinterpret_cast<uintptr_t>(out) >> 2) & 3;
-  const int64_t head = min64(T, (4 - mis) & 3);
-  for (int64_t t = tid; t < head; t += nth) out[t] = label_of_frame(t, rem, trl, segend, last);
-  const int64_t nvec = (T - head) >> 2;
-  int4* out4 = reinterpret_cast<int4*>(out + head);
-  for (int64_t q = tid; q < nvec; q += nth) {
-    const int64_t t = head + 4 * q;
-    int lab[4];
-    if (t + 3 < rem) {
-      lab[0] = lab[1] = lab[2] = lab[3] = trl[last];
-    } else {
-      int n = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int64_t te = t + e;
-        if (te < rem) {
-          lab[e] = trl[last];
-        } else {
-          while (n < last && te >= segend[n]) ++n;
-          lab[e] = trl[n];
-        }
-      }
-    }
-    out4[q] = make_int4(lab[0], lab[1], lab[2], lab[3]);
-  }
-  for (int64_t t = head + 4 * nvec + tid; t < T; t += nth) out[t] = label_of_frame(t, rem, trl, segend, last);
-}
-
-struct DpSmem {
-  double* rows;     // [N, J]
-  double* E;        // [2, N] entry scores by step parity
-  int64_t* segend;  // [N]
-  int* Ej;          // [2, N] winning predecessor length (0 = no entry)
-  int* trl;         // [N]
-  int* segb;        // [N]
-  void* bsS;        // [2, CH, N] staged block scores of the transcript labels
-};
-
-__host__ __device__ inline size_t dp_smem_bytes(int N, int J, int bs_elem) {
-  size_t b = 0;
-  b += sizeof(double) * (size_t)N * J;
-  b += sizeof(double) * 2 * N;
-  b += sizeof(int64_t) * N;
-  b += sizeof(int) * 2 * N;
-  b += sizeof(int) * N;
-  b += sizeof(int) * N;
-  b = (b + 15) & ~size_t(15);
-  b += (size_t)bs_elem * 2 * kDpChunk * N;
-  return b + 64;
-}
-
-template <typename BST, typename BPT, int SLOTS, int SEGS>
-__global__ void __launch_bounds__(kDpMaxWarps * 32) dp_kernel(const mucon_viterbi_batch b, const int J) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  __shared__ double fin_v;
-  __shared__ int fin_j;
-
-  const int u = b.order ? b.order[blockIdx.x] : blockIdx.x;
-  const int v = b.unit_vid[u];
-  const int64_t T = b.vid_off[v + 1] - b.vid_off[v];
-  const int fs = b.fs;
-  const int64_t K = T / fs;
-  const int tr0 = b.tr_off[u];
-  const int N = b.tr_off[u + 1] - tr0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int C = b.C;
-
-  if (K < 1 || N < 1 || K > static_cast<int64_t>(N) * J) {
-    if (tid == 0) {
-      b.status[u] = MUCON_UNIT_INFEASIBLE;
-      b.score[u] = __longlong_as_double(0x7ff8000000000000ll);
-      b.final_j[u] = 0;
-    }
-    for (int n = tid; n < N; n += blockDim.x) b.seg_blocks[tr0 + n] = 0;
-    return;
-  }
-
-  DpSmem s;
-  {
-    unsigned char* p = sm;
-    s.rows = reinterpret_cast<double*>(p); p += sizeof(double) * (size_t)N * J;
-    s.E = reinterpret_cast<double*>(p); p += sizeof(double) * 2 * N;
-    s.segend = reinterpret_cast<int64_t*>(p); p += sizeof(int64_t) * N;
-    s.Ej = reinterpret_cast<int*>(p); p += sizeof(int) * 2 * N;
-    s.trl = reinterpret_cast<int*>(p); p += sizeof(int) * N;
-    s.segb = reinterpret_cast<int*>(p); p += sizeof(int) * N;
-    p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
-    s.bsS = p;
-  }
-  BST* bsS = reinterpret_cast<BST*>(s.bsS);
-  const BST* bs_g = reinterpret_cast<const BST*>(b.bs) + b.blk_off[v] * C;
-  BPT* bp_g = b.bp ? reinterpret_cast<BPT*>(b.bp) + b.bp_off[u] : nullptr;
-
-  for (int n = tid; n < N; n += blockDim.x) s.trl[n] = b.tr[tr0 + n];
-  // length rows: given, or ((l*ln m - m) - lf_l) - norms   (length_model.py:65-71,76-80)
-  if (b.len_rows) {
-    const double* g = b.len_rows + static_cast<size_t>(tr0) * J;
-    for (int i = tid; i < N * J; i += blockDim.x) s.rows[i] = g[i];
-  } else {
-    const double* g = b.len_params + static_cast<size_t>(tr0) * 3;
-    for (int i = tid; i < N * J; i += blockDim.x) {
-      const int n = i / J, j = i - n * J + 1;
-      const int l = j * fs;
-      double r;
-      if (l >= b.max_len) {
-        r = -INFINITY;
-      } else {
-        r = __dmul_rn(static_cast<double>(l), g[n * 3 + 0]);
-        r = __dsub_rn(r, g[n * 3 + 1]);
-        r = __dsub_rn(r, b.logfact[j]);
-        r = __dsub_rn(r, g[n * 3 + 2]);
-      }
-      s.rows[i] = r;
-    }
-  }
-  if (bp_g) {  // row 0 has no entries
-    for (int n = tid; n < N; n += blockDim.x) bp_g[n] = 0;
-  }
-  __syncthreads();  // trl visible
-
-  const int Wa = (N + SEGS - 1) / SEGS;  // warps that own segments
-  const int nact = Wa * 32;
-  const int64_t rem = T - K * fs;
-  int last = N - 1;
-
-  if (K < N) {
-    // Nothing reaches the last segment: the reference returns -inf and the path with one block
-    // in each of the first K segments (viterbi.py:125-138).
-    last = static_cast<int>(K) - 1;
-    for (int n = tid; n < N; n += blockDim.x) s.segb[n] = (n < K) ? 1 : 0;
-    if (tid == 0) {
-      b.status[u] = MUCON_UNIT_SHORT;
-      b.score[u] = -INFINITY;
-      b.final_j[u] = 1;
-    }
-    if (bp_g) {
-      for (int64_t i = N + tid; i < K * N; i += blockDim.x) bp_g[i] = 0;  // not computed
-    }
-    __syncthreads();
-  } else {
-    if (warp < Wa) {
-      auto stage = [&](int chunk) {
-        const int64_t k0 = static_cast<int64_t>(chunk) * kDpChunk;
-        const int nk = static_cast<int>(min64(kDpChunk, K - k0));
-        BST* dst = bsS + static_cast<size_t>(chunk & 1) * kDpChunk * N;
-        for (int i = tid; i < nk * N; i += nact) {
-          const int kk = i / N, n = i - kk * N;
-          const BST* src = bs_g + (k0 + kk) * C + s.trl[n];
-          if (sizeof(BST) == 4) cp_async4(dst + i, src); else cp_async8(dst + i, src);
-        }
-        cp_async_commit();
-      };
-      const int nchunks = static_cast<int>((K + kDpChunk - 1) / kDpChunk);
-      stage(0);
-      if (nchunks > 1) { stage(1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-      named_bar_sync(1, nact);
-
-      double S[SEGS][SLOTS];
-      int len[SEGS][SLOTS];
-#pragma unroll
-      for (int q = 0; q < SEGS; ++q)
-#pragma unroll
-        for (int i = 0; i < SLOTS; ++i) { S[q][i] = 0.0; len[q][i] = 0; }
-      if (tid == 0) {  // start hypothesis: 0.0 + F[fs-1, tr_0]  (viterbi.py:81-90)
-        S[0][0] = __dadd_rn(0.0, static_cast<double>(bsS[0]));
-        len[0][0] = 1;
-      }
-
-      for (int64_t k = 1; k < K; ++k) {
-        const int chunk = static_cast<int>(k / kDpChunk);
-        const int kk = static_cast<int>(k - static_cast<int64_t>(chunk) * kDpChunk);
-        if (kk == 0) {
-          cp_async_wait<0>();
-          named_bar_sync(1, nact);  // chunk landed for everyone; chunk-1 buffer is free
-          if (chunk + 1 < nchunks) stage(chunk + 1);
-        }
-        const BST* bsk = bsS + (static_cast<size_t>(chunk & 1) * kDpChunk + kk) * N;
-        const int par = static_cast<int>(k & 1);
-#pragma unroll
-        for (int q = 0; q < SEGS; ++q) {
-          const int n = warp * SEGS + q;
-          if (n < N) {
-            const BST bval = bsk[n];
-            const double* row = s.rows + n * J - 1;
-            Best best{0.0, 0};
-#pragma unroll
-            for (int i = 0; i < SLOTS; ++i) {
-              if (len[q][i] > 0) {
-                double a;
-                if (sizeof(BST) == 4 && b.seg0_f32 && n == 0)
-                  a = static_cast<double>(__fadd_rn(static_cast<float>(S[q][i]), static_cast<float>(bval)));
-                else
-                  a = __dadd_rn(S[q][i], static_cast<double>(bval));
-                const double cand = __dadd_rn(__dadd_rn(a, row[len[q][i]]), 0.0);
-                best_take(best, cand, len[q][i]);
-                S[q][i] = a;
-                len[q][i] = (len[q][i] < J) ? len[q][i] + 1 : 0;
-              }
-            }
-            best = warp_best(best);
-            if (lane == 0) {
-              if (n + 1 < N) {
-                s.E[par * N + n + 1] = best.v;
-                s.Ej[par * N + n + 1] = best.j;
-                if (bp_g) bp_g[k * N + n + 1] = static_cast<BPT>(best.j);
-              }
-              if (n == 0 && bp_g) bp_g[k * N] = 0;
-            }
-          }
-        }
-        named_bar_sync(1, nact);
-        const int slot = static_cast<int>(k % J);
-#pragma unroll
-        for (int q = 0; q < SEGS; ++q) {
-          const int n = warp * SEGS + q;
-          if (n > 0 && n < N) {
-            const int ej = s.Ej[par * N + n];
-            if (ej > 0) {
-              const double ev = s.E[par * N + n];
-#pragma unroll
-              for (int i = 0; i < SLOTS; ++i)
-                if (lane + 32 * i == slot) { S[q][i] = ev; len[q][i] = 1; }
-            }
-          }
-        }
-      }
-
-      // end symbol: fold over the last segment (viterbi.py:125-138)
-#pragma unroll
-      for (int q = 0; q < SEGS; ++q) {
-        const int n = warp * SEGS + q;
-        if (n == N - 1) {
-          const double* row = s.rows + n * J - 1;
-          Best best{0.0, 0};
-#pragma unroll
-          for (int i = 0; i < SLOTS; ++i)
-            if (len[q][i] > 0) best_take(best, __dadd_rn(__dadd_rn(S[q][i], row[len[q][i]]), 0.0), len[q][i]);
-          best = warp_best(best);
-          if (lane == 0) { fin_v = best.v; fin_j = best.j; }
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {  // traceback over the back-pointer table (viterbi.py:140-153)
-      const double sc = fin_v;
-      int n = N - 1;
-      int64_t k0 = K - fin_j;
-      s.segb[n] = fin_j;
-      while (n > 0) {
-        const int ln = static_cast<int>(__ldcg(bp_g + k0 * N + n));
-        s.segb[n - 1] = ln;
-        k0 -= ln;
-        --n;
-      }
-      b.score[u] = sc;
-      b.final_j[u] = fin_j;
-      b.status[u] = (isfinite(sc) || sc == -INFINITY) ? MUCON_UNIT_OK : MUCON_UNIT_NONFINITE;
-    }
-    __syncthreads();
-  }
-
-  for (int n = tid; n < N; n += blockDim.x) b.seg_blocks[tr0 + n] = s.segb[n];
-  const int64_t lo = b.lab_off ? b.lab_off[u] : -1;
-  if (lo >= 0) {
-    if (tid == 0) {
-      int64_t pos = rem;
-      for (int n = 0; n < N; ++n) { pos += static_cast<int64_t>(fs) * s.segb[n]; s.segend[n] = pos; }
-    }
-    __syncthreads();
-    write_labels(b.labels + lo, T, rem, s.trl, s.segend, last);
-  }
-}
-
-// ============================================================================================
 // Candidate arg-max and standalone label writer
 // ============================================================================================
 
@@ -521,7 +208,7 @@ __global__ void __launch_bounds__(256) labels_kernel(const int32_t* __restrict__
     last_s = last;
   }
   __syncthreads();
-  write_labels(labels + out_off[blockIdx.x], T, T - K * fs, trl, segend, last_s);
+  write_labels(labels + out_off[blockIdx.x], T, T - K * fs, trl, segend, last_s, threadIdx.x, blockDim.x);
 }
 
 // ============================================================================================
@@ -546,10 +233,10 @@ int launch_scan(const T* logp, const int64_t* vid_off, const int64_t* blk_off, c
     return MUCON_OK;
   }
   const size_t blk_bytes = row_bytes * fs;
-  const int slab_target = env_int("MUCON_SCAN_SLAB_BYTES", 6144);
+  const int slab_target = env_int("MUCON_SCAN_SLAB_BYTES", 23040);
   int bps = (int)(slab_target / blk_bytes);
   if (bps < 1) bps = 1;
-  int stages = env_int("MUCON_SCAN_STAGES", 4);
+  int stages = env_int("MUCON_SCAN_STAGES", 3);
   size_t smem = 128 + (size_t)stages * bps * blk_bytes;
   while (smem > 200 * 1024 && stages > 2) { --stages; smem = 128 + (size_t)stages * bps * blk_bytes; }
   if (smem > 227 * 1024) {  // a single block of frames does not fit: stream from global instead
@@ -567,39 +254,56 @@ int launch_scan(const T* logp, const int64_t* vid_off, const int64_t* blk_off, c
   return MUCON_OK;
 }
 
-template <typename BST, typename BPT, int SLOTS, int SEGS>
+template <typename BST, int SLOTS, int SEGS>
 int launch_dp(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  const int Wa = (b.max_N + SEGS - 1) / SEGS;
-  const size_t smem = dp_smem_bytes(b.max_N, J, sizeof(BST));
-  auto kern = dp_kernel<BST, BPT, SLOTS, SEGS>;
+  constexpr int NS = kDpWarps * SEGS;
+  // keep the back-pointer table in shared memory when it fits next to everything else
+  int bp_rows = b.max_K;
+  size_t smem = dp_layout(NS, J, sizeof(BST), bp_rows).total;
+  const size_t cap = (SEGS <= 2) ? 100 * 1024 : 200 * 1024;
+  if (smem > cap) {
+    bp_rows = 0;
+    smem = dp_layout(NS, J, sizeof(BST), 0).total;
+  }
   if (smem > 227 * 1024) return MUCON_EUNSUPPORTED;
+  auto kern = dp_kernel<BST, SLOTS, SEGS>;
   if (smem > 48 * 1024)
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<b.U, Wa * 32, smem, st>>>(b, J);
+  kern<<<b.n_cta, kDpWarps * 32, smem, st>>>(b, J, b.warp_unit, bp_rows);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
 
-template <typename BST, typename BPT, int SLOTS>
+template <typename BST, int SLOTS>
 int dispatch_segs(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  const int segs = (b.max_N + kDpMaxWarps - 1) / kDpMaxWarps;
-  if (segs <= 1) return launch_dp<BST, BPT, SLOTS, 1>(b, J, st);
-  if (segs <= 2) return launch_dp<BST, BPT, SLOTS, 2>(b, J, st);
-  if (segs <= 4) return launch_dp<BST, BPT, SLOTS, 4>(b, J, st);
-  if (segs <= 8) return launch_dp<BST, BPT, SLOTS, 8>(b, J, st);
-  return MUCON_EUNSUPPORTED;
+  switch (b.segs) {
+    case 1: return launch_dp<BST, SLOTS, 1>(b, J, st);
+    case 2: return launch_dp<BST, SLOTS, 2>(b, J, st);
+    case 4: return launch_dp<BST, SLOTS, 4>(b, J, st);
+    case 8: return launch_dp<BST, SLOTS, 8>(b, J, st);
+    default: return MUCON_EINVAL;
+  }
 }
 
-template <typename BST, typename BPT>
+template <typename BST>
 int dispatch_slots(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
   const int slots = (J + 31) / 32;
   switch (slots) {
-    case 1: return dispatch_segs<BST, BPT, 1>(b, J, st);
-    case 2: return dispatch_segs<BST, BPT, 2>(b, J, st);
-    case 3: return dispatch_segs<BST, BPT, 3>(b, J, st);
-    case 4: return dispatch_segs<BST, BPT, 4>(b, J, st);
+    case 1: return dispatch_segs<BST, 1>(b, J, st);
+    case 2: return dispatch_segs<BST, 2>(b, J, st);
+    case 3: return dispatch_segs<BST, 3>(b, J, st);
+    case 4: return dispatch_segs<BST, 4>(b, J, st);
     default: return MUCON_EUNSUPPORTED;
   }
+}
+
+int segs_for(int max_N) {
+  const int s = (max_N + kDpWarps - 1) / kDpWarps;
+  if (s <= 1) return 1;
+  if (s <= 2) return 2;
+  if (s <= 4) return 4;
+  if (s <= 8) return 8;
+  return 0;
 }
 
 }  // namespace
@@ -623,20 +327,58 @@ extern "C" int mucon_viterbi_blockscores(const void* logp, int in_is_f64, const 
 extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream) {
   if (!bh) return MUCON_EINVAL;
   const mucon_viterbi_batch& b = *bh;
-  if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1) return MUCON_EINVAL;
+  if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1 || b.n_cta < 0 || b.max_K < 0)
+    return MUCON_EINVAL;
   if (!b.bs || !b.vid_off || !b.blk_off || !b.unit_vid || !b.tr || !b.tr_off || !b.score || !b.seg_blocks ||
-      !b.final_j || !b.status || !b.bp || !b.bp_off)
+      !b.final_j || !b.status || !b.bp || !b.bp_off || !b.warp_unit)
     return MUCON_EINVAL;
   if (!b.len_rows && !(b.len_params && b.logfact)) return MUCON_EINVAL;
-  if (b.U == 0) return MUCON_OK;
+  if (b.U == 0 || b.n_cta == 0) return MUCON_OK;
   const int J = b.max_len / b.fs;
-  if (J > 32 * kMaxSlots) return MUCON_EUNSUPPORTED;
-  if (!b.bp_is_u16 && J > 255) return MUCON_EINVAL;
+  if (J > 32 * kDpMaxSlots) return MUCON_EUNSUPPORTED;  // back-pointers are uint8, slots live in registers
+  if (b.segs != segs_for(b.max_N)) return b.segs == 0 || segs_for(b.max_N) == 0 ? MUCON_EUNSUPPORTED : MUCON_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // J <= 128 always fits uint8; the uint16 layout is reserved for the large-J path.
-  if (b.bp_is_u16) return MUCON_EUNSUPPORTED;
-  if (b.bs_is_f64) return dispatch_slots<double, uint8_t>(b, J, st);
-  return dispatch_slots<float, uint8_t>(b, J, st);
+  if (b.bs_is_f64) return dispatch_slots<double>(b, J, st);
+  return dispatch_slots<float>(b, J, st);
+}
+
+extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N,
+                                    int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* segs_out) {
+  if (!N_h || !warp_unit_h || !n_cta_out || !segs_out || U < 0 || max_N < 1) return MUCON_EINVAL;
+  const int segs = segs_for(max_N);
+  if (segs == 0) return MUCON_EUNSUPPORTED;
+  *segs_out = segs;
+  constexpr int kWindow = 8;  // open bins that may still take units (keeps K similar within a bin)
+  int open_bin[kWindow], open_free[kWindow], open_units[kWindow], n_open = 0;
+  int n_cta = 0;
+  for (int i = 0; i < U; ++i) {
+    const int u = order_h ? order_h[i] : i;
+    int need = (N_h[u] + segs - 1) / segs;
+    if (need < 1) need = 1;
+    if (need > kDpWarps) return MUCON_EUNSUPPORTED;
+    int pick = -1;
+    for (int o = 0; o < n_open; ++o)
+      if (open_free[o] >= need && open_units[o] < 15) { pick = o; break; }
+    if (pick < 0) {
+      if (n_open == kWindow) {  // retire the oldest open bin
+        for (int o = 1; o < kWindow; ++o) {
+          open_bin[o - 1] = open_bin[o]; open_free[o - 1] = open_free[o]; open_units[o - 1] = open_units[o];
+        }
+        --n_open;
+      }
+      pick = n_open++;
+      open_bin[pick] = n_cta++;
+      open_free[pick] = kDpWarps;
+      open_units[pick] = 0;
+      for (int w = 0; w < kDpWarps; ++w) warp_unit_h[(size_t)open_bin[pick] * kDpWarps + w] = -1;
+    }
+    const int start = kDpWarps - open_free[pick];
+    for (int w = 0; w < need; ++w) warp_unit_h[(size_t)open_bin[pick] * kDpWarps + start + w] = u;
+    open_free[pick] -= need;
+    open_units[pick] += 1;
+  }
+  *n_cta_out = n_cta;
+  return MUCON_OK;
 }
 
 extern "C" int mucon_viterbi_select(const double* score, const int32_t* status, const int32_t* cand_off, int V,

@@ -127,6 +127,18 @@ class AlignPlan:
         # launch order: longest first so the tail of the grid is made of short units
         self.order_v = np.argsort(-T, kind="stable").astype(np.int32)
         self.order_u = np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32)
+        self.max_K = int(uK.max()) if U else 0
+        # bins of 16 warps: which unit every warp of every CTA works on
+        lib = _lib.lib()
+        wu = np.full(max(U, 1) * 16, -1, dtype=np.int32)
+        n_cta, segs = C.c_int32(0), C.c_int32(0)
+        n32 = np.ascontiguousarray(nlen, dtype=np.int32)
+        _lib.check(lib.mucon_viterbi_pack_h(
+            n32.ctypes.data_as(C.c_void_p), self.order_u.ctypes.data_as(C.c_void_p), C.c_int(U),
+            C.c_int(self.max_N), wu.ctypes.data_as(C.c_void_p), C.byref(n_cta), C.byref(segs)),
+            "mucon_viterbi_pack_h")
+        self.n_cta, self.segs = int(n_cta.value), int(segs.value)
+        self.warp_unit = wu[:max(self.n_cta, 1) * 16]
 
         blob = _Blob()
         blob.add("vid_off", self.vid_off)
@@ -138,7 +150,7 @@ class AlignPlan:
         blob.add("lab_off", self.lab_off)
         blob.add("bp_off", self.bp_off[:-1] if U else self.bp_off)
         blob.add("order_v", self.order_v)
-        blob.add("order_u", self.order_u)
+        blob.add("warp_unit", self.warp_unit)
         blob.add("vid_lab_off", self.vid_off[:-1])
         self.use_rows = len_rows is not None
         if self.use_rows:
@@ -205,7 +217,8 @@ class ViterbiEngine:
             mid_event.record(st)
         b = _lib.ViterbiBatch()
         b.U, b.C, b.fs, b.max_len = plan.U, plan.C, plan.fs, plan.max_len
-        b.bs_is_f64, b.seg0_f32, b.max_N, b.bp_is_u16 = int(is64), int(bool(seg0_f32)), plan.max_N, 0
+        b.bs_is_f64, b.seg0_f32, b.max_N, b.max_K = int(is64), int(bool(seg0_f32)), plan.max_N, plan.max_K
+        b.n_cta, b.segs = plan.n_cta, plan.segs
         b.bs = plan.bs.data_ptr()
         b.vid_off, b.blk_off, b.unit_vid = p["vid_off"], p["blk_off"], p["unit_vid"]
         b.tr, b.tr_off = p["tr"], p["tr_off"]
@@ -213,7 +226,7 @@ class ViterbiEngine:
             b.len_rows, b.len_params, b.logfact = p["len_rows"], None, None
         else:
             b.len_rows, b.len_params, b.logfact = None, p["len_params"], p["logfact"]
-        b.lab_off, b.bp_off, b.order = p["lab_off"], p["bp_off"], p["order_u"]
+        b.lab_off, b.bp_off, b.warp_unit = p["lab_off"], p["bp_off"], p["warp_unit"]
         b.score, b.labels = plan.score.data_ptr(), plan.labels.data_ptr()
         b.seg_blocks, b.bp = plan.seg_blocks.data_ptr(), plan.bp.data_ptr()
         b.final_j, b.status = plan.final_j.data_ptr(), plan.status.data_ptr()
