@@ -33,7 +33,7 @@ extern "C" {
 /* call-level errors (return values) */
 #define MUCON_OK 0
 #define MUCON_EINVAL (-1)      /* bad argument (null pointer, non-positive size, ...) */
-#define MUCON_EUNSUPPORTED (-2) /* shape outside what the kernels cover (J > 128, N > 128, ...) */
+#define MUCON_EUNSUPPORTED (-2) /* shape outside what the kernels cover (J > 128, N > 65, ...) */
 #define MUCON_ECUDA (-3)       /* a CUDA runtime call failed; see mucon_last_cuda_error() */
 #define MUCON_EALIGN (-4)      /* pointer not aligned as documented */
 
@@ -74,10 +74,10 @@ typedef struct mucon_viterbi_batch {
   int32_t max_len;    /* length_model.max_length() (length_model.py:82; 2000); max_len/fs <= 128 */
   int32_t bs_is_f64;  /* dtype of bs */
   int32_t seg0_f32;   /* 1: segment 0 accumulates in float32 (NumPy>=2 promotion) */
-  int32_t max_N;      /* max transcript length over units (<= 128) */
+  int32_t max_N;      /* max transcript length over units (<= 65) */
   int32_t max_K;      /* max number of blocks over units (sizes the shared back-pointer stage) */
   int32_t n_cta;      /* number of unit bins, from mucon_viterbi_pack_h */
-  int32_t segs;       /* segments per warp, from mucon_viterbi_pack_h */
+  int32_t segs;       /* segments per warp (4), from mucon_viterbi_pack_h */
   const void* bs;            /* [sum K, C] block scores */
   const int64_t* vid_off;    /* [V+1] frame offsets (T_v = difference) */
   const int64_t* blk_off;    /* [V+1] block offsets into bs */
@@ -99,7 +99,7 @@ typedef struct mucon_viterbi_batch {
 } mucon_viterbi_batch;
 
 /* Host helper: packs units into bins of 16 warps (one CTA each).  A unit needs
- * ceil(N/segs) consecutive warps; units are taken in order_h (or 0..U-1) -- pass them longest
+ * max(1, ceil((N-1)/4)) consecutive warps; units are taken in order_h (or 0..U-1) -- pass them longest
  * first.  warp_unit_h needs room for U*16 entries; on return the first *n_cta_out*16 are valid. */
 int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N,
                          int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* segs_out);

@@ -254,19 +254,16 @@ int launch_scan(const T* logp, const int64_t* vid_off, const int64_t* blk_off, c
   return MUCON_OK;
 }
 
-template <typename BST, int SLOTS, int SEGS>
+template <typename BST, int SL>
 int launch_dp(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  constexpr int NS = kDpWarps * SEGS;
   // keep the back-pointer table in shared memory when it fits next to everything else
   int bp_rows = b.max_K;
-  size_t smem = dp_layout(NS, J, sizeof(BST), bp_rows).total;
-  const size_t cap = (SEGS <= 2) ? 100 * 1024 : 200 * 1024;
-  if (smem > cap) {
+  size_t smem = dp_layout(J, sizeof(BST), bp_rows).total;
+  if (smem > 200 * 1024) {
     bp_rows = 0;
-    smem = dp_layout(NS, J, sizeof(BST), 0).total;
+    smem = dp_layout(J, sizeof(BST), 0).total;
   }
-  if (smem > 227 * 1024) return MUCON_EUNSUPPORTED;
-  auto kern = dp_kernel<BST, SLOTS, SEGS>;
+  auto kern = dp_kernel<BST, SL>;
   if (smem > 48 * 1024)
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<b.n_cta, kDpWarps * 32, smem, st>>>(b, J, b.warp_unit, bp_rows);
@@ -274,36 +271,22 @@ int launch_dp(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
   return MUCON_OK;
 }
 
-template <typename BST, int SLOTS>
-int dispatch_segs(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  switch (b.segs) {
-    case 1: return launch_dp<BST, SLOTS, 1>(b, J, st);
-    case 2: return launch_dp<BST, SLOTS, 2>(b, J, st);
-    case 4: return launch_dp<BST, SLOTS, 4>(b, J, st);
-    case 8: return launch_dp<BST, SLOTS, 8>(b, J, st);
-    default: return MUCON_EINVAL;
-  }
-}
-
 template <typename BST>
-int dispatch_slots(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  const int slots = (J + 31) / 32;
-  switch (slots) {
-    case 1: return dispatch_segs<BST, 1>(b, J, st);
-    case 2: return dispatch_segs<BST, 2>(b, J, st);
-    case 3: return dispatch_segs<BST, 3>(b, J, st);
-    case 4: return dispatch_segs<BST, 4>(b, J, st);
+int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
+  switch ((J + kDpGroup - 1) / kDpGroup) {
+#define MUCON_SL_CASE(n) case n: return launch_dp<BST, n>(b, J, st);
+    MUCON_SL_CASE(1) MUCON_SL_CASE(2) MUCON_SL_CASE(3) MUCON_SL_CASE(4)
+    MUCON_SL_CASE(5) MUCON_SL_CASE(6) MUCON_SL_CASE(7) MUCON_SL_CASE(8)
+    MUCON_SL_CASE(9) MUCON_SL_CASE(10) MUCON_SL_CASE(11) MUCON_SL_CASE(12)
+    MUCON_SL_CASE(13) MUCON_SL_CASE(14) MUCON_SL_CASE(15) MUCON_SL_CASE(16)
+#undef MUCON_SL_CASE
     default: return MUCON_EUNSUPPORTED;
   }
 }
 
-int segs_for(int max_N) {
-  const int s = (max_N + kDpWarps - 1) / kDpWarps;
-  if (s <= 1) return 1;
-  if (s <= 2) return 2;
-  if (s <= 4) return 4;
-  if (s <= 8) return 8;
-  return 0;
+int warps_for(int N) {
+  const int w = (N - 1 + kDpSegsPerWarp - 1) / kDpSegsPerWarp;
+  return w < 1 ? 1 : w;
 }
 
 }  // namespace
@@ -335,26 +318,25 @@ extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream)
   if (!b.len_rows && !(b.len_params && b.logfact)) return MUCON_EINVAL;
   if (b.U == 0 || b.n_cta == 0) return MUCON_OK;
   const int J = b.max_len / b.fs;
-  if (J > 32 * kDpMaxSlots) return MUCON_EUNSUPPORTED;  // back-pointers are uint8, slots live in registers
-  if (b.segs != segs_for(b.max_N)) return b.segs == 0 || segs_for(b.max_N) == 0 ? MUCON_EUNSUPPORTED : MUCON_EINVAL;
+  if (J > kDpGroup * kDpMaxSL) return MUCON_EUNSUPPORTED;  // ages live in registers, back-pointers are uint8
+  if (b.max_N > kDpMaxN) return MUCON_EUNSUPPORTED;
+  if (b.segs != kDpSegsPerWarp) return MUCON_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (b.bs_is_f64) return dispatch_slots<double>(b, J, st);
-  return dispatch_slots<float>(b, J, st);
+  if (b.bs_is_f64) return dispatch_sl<double>(b, J, st);
+  return dispatch_sl<float>(b, J, st);
 }
 
 extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N,
                                     int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* segs_out) {
   if (!N_h || !warp_unit_h || !n_cta_out || !segs_out || U < 0 || max_N < 1) return MUCON_EINVAL;
-  const int segs = segs_for(max_N);
-  if (segs == 0) return MUCON_EUNSUPPORTED;
-  *segs_out = segs;
+  if (max_N > kDpMaxN) return MUCON_EUNSUPPORTED;
+  *segs_out = kDpSegsPerWarp;
   constexpr int kWindow = 8;  // open bins that may still take units (keeps K similar within a bin)
   int open_bin[kWindow], open_free[kWindow], open_units[kWindow], n_open = 0;
   int n_cta = 0;
   for (int i = 0; i < U; ++i) {
     const int u = order_h ? order_h[i] : i;
-    int need = (N_h[u] + segs - 1) / segs;
-    if (need < 1) need = 1;
+    const int need = warps_for(N_h[u]);
     if (need > kDpWarps) return MUCON_EUNSUPPORTED;
     int pick = -1;
     for (int o = 0; o < n_open; ++o)

@@ -1,26 +1,29 @@
 // viterbi_dp.cuh -- the K x N x J dynamic program, traceback and label writer (sm_100a).
 //
-// Follows reference src/core/viterbi/viterbi.py:81-158 in the dense form of SURVEY.md section 8a.
+// Follows reference src/core/viterbi/viterbi.py:81-158 in the dense form of SURVEY.md section 8a:
+//   step k, segment n, age j (length in blocks before this step):
+//     a = S[n][j] + bs_k[tr_n]                       stay, lands at age j+1   (viterbi.py:97-104)
+//     c = (a + rows[n][j]) + 0.0                     advance candidate        (viterbi.py:106-121)
+//     S'[n+1][1] = fold_j c, ascending j, replace iff old <= new             (viterbi.py:26-28)
+//     bp[k][n+1] = winning j
 //
 // Work decomposition
-//   unit        one (video, candidate transcript); needs ceil(N / SEGS) warps, one warp per SEGS
-//               transcript segments.
-//   CTA         a bin of units packed by the host (mucon_viterbi_pack_h) so that all 16 warps
-//               are busy; every unit synchronises on its own named barrier, units in a bin never
-//               wait for each other.
-//   warp        lane l owns length slots l, l+32, ... of its segment(s).  A slot is a circular
-//               buffer position indexed by (entry step mod J): a hypothesis never moves between
-//               lanes, it just ages (len += 1) until len == J, when the slot is recycled for the
-//               hypothesis entering at that very step.
-//   step k      a   = S + bs_k[tr_n]                            stay        (viterbi.py:97-104)
-//               c   = (a + rows[n][len]) + 0.0                  advance     (viterbi.py:106-121)
-//               S'[n+1][1] = fold over len ascending, replace iff old <= new (viterbi.py:26-28)
-//               The fold is evaluated as: order-preserving 64-bit integer key of c, warp max by
-//               two 32-bit REDUX, then the largest len among the slots holding that maximum --
-//               the same winner as the sequential fold for every non-NaN input.  Because "+ 0.0"
-//               never yields -0.0, equal doubles have equal keys.
-//   back-ptrs   bp[k][n] = winning len, staged in shared memory for the traceback and flushed to
-//               HBM once per unit with coalesced stores.
+//   unit     one (video, candidate transcript).
+//   segment 0 has exactly one hypothesis (entered at step 0), so it is a scalar running sum kept
+//            by lane 0 of the unit's first warp -- in float32 when the reference's NumPy would keep
+//            it in float32, float64 otherwise.
+//   segment n >= 1 is a shift register over ages 1..J held by a group of 8 lanes, SL = ceil(J/8)
+//            consecutive ages per lane, all in registers with static indices: ageing is the
+//            in-place update R[i] = R[i-1] + b, the value leaving a lane moves to the next lane
+//            with one shuffle, and the same shuffle hands the group's winner to the next segment's
+//            group.  Four segments per warp; a unit with N <= 5 is a single warp with no block
+//            barrier at all, larger units use ceil((N-1)/4) warps and one named barrier per step.
+//   dead     hypotheses are -inf: no liveness flags.  The only place liveness is observable is a
+//            fold whose maximum is -inf; there the winner is the oldest live age, which follows
+//            from (k, n, J) alone:  live ages at step k are [max(1, k-n*J), min(J, k-n)].
+//   CTA      a bin of units packed by the host (mucon_viterbi_pack_h); every unit synchronises on
+//            its own named barrier, units in a bin never wait for each other.
+//   bp       staged in shared memory for the traceback, flushed to HBM once per unit.
 #pragma once
 #include <math.h>
 
@@ -28,18 +31,12 @@
 
 namespace mucon {
 
-constexpr int kDpWarps = 16;   // warps per CTA
-constexpr int kDpChunk = 32;   // DP steps per block-score staging chunk
-constexpr int kDpMaxSlots = 4;  // J <= 128
-
-__device__ __forceinline__ unsigned long long dkey(double c) {
-  const long long b = __double_as_longlong(c);
-  return static_cast<unsigned long long>(b) ^ (static_cast<unsigned long long>(b >> 63) | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double dunkey(unsigned long long k) {
-  const unsigned long long b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
-  return __longlong_as_double(static_cast<long long>(b));
-}
+constexpr int kDpWarps = 16;     // warps per CTA
+constexpr int kDpChunk = 32;     // DP steps per block-score staging chunk
+constexpr int kDpGroup = 8;      // lanes per segment
+constexpr int kDpSegsPerWarp = 32 / kDpGroup;
+constexpr int kDpMaxSL = 16;     // J <= 128
+constexpr int kDpMaxN = 1 + kDpWarps * kDpSegsPerWarp;  // 65
 
 __device__ __forceinline__ int label_of_frame(int64_t t, int64_t rem, const int32_t* trl, const int64_t* segend,
                                               int last) {
@@ -82,34 +79,52 @@ __device__ __forceinline__ void write_labels(int32_t* out, int64_t T, int64_t re
   for (int64_t t = head + 4 * nvec + tid; t < T; t += nth) out[t] = label_of_frame(t, rem, trl, segend, last);
 }
 
-// Shared-memory plan of one CTA: NS = kDpWarps * SEGS segment columns.
+// Shared-memory plan of one CTA.  NS = segment columns of a CTA (65 covers 16 warps x 4 + segment 0
+// of a unit that starts at warp 0; units never share a column: column of segment n of the unit
+// that starts at warp w0 is 4*w0 + n... see seg_col()).
+constexpr int kDpNS = kDpWarps * kDpSegsPerWarp + kDpWarps;  // generous: one extra column per unit
+
 struct DpLayout {
-  size_t rows, E, segend, Ej, trl, segb, fin_v, fin_j, bsS, bpS, total;
+  size_t rows0, Ex, segend, trl, segb, fin_v, fin_j, bsS, bpS, total;
 };
-__host__ __device__ inline DpLayout dp_layout(int NS, int J, int bs_elem, int bp_rows) {
+__host__ __device__ inline DpLayout dp_layout(int J, int bs_elem, int bp_rows) {
   DpLayout L;
   size_t o = 0;
-  L.rows = o; o += sizeof(double) * (size_t)NS * J;
-  L.E = o; o += sizeof(double) * 2 * NS;
-  L.segend = o; o += sizeof(int64_t) * NS;
+  L.rows0 = o; o += sizeof(double) * (size_t)kDpWarps * J;  // segment-0 length rows, one per unit slot
+  L.Ex = o; o += sizeof(double) * 2 * kDpWarps;             // cross-warp entry scores by step parity
+  L.segend = o; o += sizeof(int64_t) * kDpNS;
   L.fin_v = o; o += sizeof(double) * kDpWarps;
-  L.Ej = o; o += sizeof(int) * 2 * NS;
-  L.trl = o; o += sizeof(int) * NS;
-  L.segb = o; o += sizeof(int) * NS;
+  L.trl = o; o += sizeof(int) * kDpNS;
+  L.segb = o; o += sizeof(int) * kDpNS;
   L.fin_j = o; o += sizeof(int) * kDpWarps;
   o = (o + 15) & ~size_t(15);
-  L.bsS = o; o += (size_t)bs_elem * 2 * kDpChunk * NS;
+  L.bsS = o; o += (size_t)bs_elem * 2 * kDpChunk * kDpNS;
   o = (o + 15) & ~size_t(15);
-  L.bpS = o; o += (size_t)bp_rows * NS;
+  L.bpS = o; o += (size_t)bp_rows * kDpNS;
   L.total = (o + 15) & ~size_t(15);
   return L;
 }
 
-template <typename BST, int SLOTS, int SEGS>
-__global__ void __launch_bounds__(kDpWarps * 32, (SEGS <= 2) ? 2 : 1)
+// length score of `age` blocks for the label with parameters g[0..2]: ((l*ln m - m) - lf_l) - norms
+// (length_model.py:65-71), -inf when the length is not representable (length_model.py:76-80).
+__device__ __forceinline__ double length_row(const mucon_viterbi_batch& b, int tr0, int n, int age, int J) {
+  if (age < 1 || age > J) return -INFINITY;
+  if (b.len_rows) return b.len_rows[static_cast<size_t>(tr0 + n) * J + age - 1];
+  const int l = age * b.fs;
+  if (l >= b.max_len) return -INFINITY;
+  const double* g = b.len_params + static_cast<size_t>(tr0 + n) * 3;
+  double r = __dmul_rn(static_cast<double>(l), g[0]);
+  r = __dsub_rn(r, g[1]);
+  r = __dsub_rn(r, b.logfact[age]);
+  r = __dsub_rn(r, g[2]);
+  return r;
+}
+
+template <typename BST, int SL>
+__global__ void __launch_bounds__(kDpWarps * 32, 1)
 dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ warp_unit, const int bp_rows) {
   extern __shared__ __align__(16) unsigned char sm[];
-  constexpr int NS = kDpWarps * SEGS;
+  constexpr int G = kDpGroup;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int32_t* wu = warp_unit + static_cast<size_t>(blockIdx.x) * kDpWarps;
   const int u = wu[warp];
@@ -119,7 +134,7 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
   while (w1 < kDpWarps && wu[w1] == u) ++w1;
   const int nw = w1 - w0, wl = warp - w0;
   const int ltid = wl * 32 + lane, nthr = nw * 32;
-  const int s0 = w0 * SEGS;  // first segment column of this unit
+  const int c0 = w0 * (kDpSegsPerWarp + 1);  // first shared-memory column of this unit
   auto ubar = [&]() {
     if (nw == 1) __syncwarp(); else named_bar_sync(1 + w0, nthr);
   };
@@ -142,44 +157,22 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
     return;
   }
 
-  const DpLayout L = dp_layout(NS, J, sizeof(BST), bp_rows);
-  double* rows = reinterpret_cast<double*>(sm + L.rows) + static_cast<size_t>(s0) * J;
-  double* E = reinterpret_cast<double*>(sm + L.E);
-  int64_t* segend = reinterpret_cast<int64_t*>(sm + L.segend) + s0;
-  int* Ej = reinterpret_cast<int*>(sm + L.Ej);
-  int* trl = reinterpret_cast<int*>(sm + L.trl) + s0;
-  int* segb = reinterpret_cast<int*>(sm + L.segb) + s0;
+  const DpLayout L = dp_layout(J, sizeof(BST), bp_rows);
+  double* rows0 = reinterpret_cast<double*>(sm + L.rows0) + static_cast<size_t>(w0) * J;  // [J], ages 1..J
+  double* Ex = reinterpret_cast<double*>(sm + L.Ex);                                       // [2][16] by warp
+  int64_t* segend = reinterpret_cast<int64_t*>(sm + L.segend) + c0;
+  int* trl = reinterpret_cast<int*>(sm + L.trl) + c0;
+  int* segb = reinterpret_cast<int*>(sm + L.segb) + c0;
   double* fin_v = reinterpret_cast<double*>(sm + L.fin_v) + w0;
   int* fin_j = reinterpret_cast<int*>(sm + L.fin_j) + w0;
   BST* bsS = reinterpret_cast<BST*>(sm + L.bsS);
   uint8_t* bpS = sm + L.bpS;
   const BST* bs_g = reinterpret_cast<const BST*>(b.bs) + b.blk_off[v] * C;
-  uint8_t* bp_g = reinterpret_cast<uint8_t*>(b.bp) + b.bp_off[u];
+  uint8_t* bp_g = b.bp + b.bp_off[u];
   const bool bp_in_smem = bp_rows >= K;
 
   for (int n = ltid; n < N; n += nthr) trl[n] = b.tr[tr0 + n];
-  // length rows: given, or ((l*ln m - m) - lf_l) - norms   (length_model.py:65-71,76-80)
-  if (b.len_rows) {
-    const double* g = b.len_rows + static_cast<size_t>(tr0) * J;
-    for (int i = ltid; i < N * J; i += nthr) rows[i] = g[i];
-  } else {
-    const double* g = b.len_params + static_cast<size_t>(tr0) * 3;
-    for (int i = ltid; i < N * J; i += nthr) {
-      const int n = i / J, j = i - n * J + 1;
-      const int l = j * fs;
-      double r;
-      if (l >= b.max_len) {
-        r = -INFINITY;
-      } else {
-        r = __dmul_rn(static_cast<double>(l), g[n * 3 + 0]);
-        r = __dsub_rn(r, g[n * 3 + 1]);
-        r = __dsub_rn(r, b.logfact[j]);
-        r = __dsub_rn(r, g[n * 3 + 2]);
-      }
-      rows[i] = r;
-    }
-  }
-  ubar();  // trl visible
+  for (int j = ltid; j < J; j += nthr) rows0[j] = length_row(b, tr0, 0, j + 1, J);
 
   const int64_t rem = T - static_cast<int64_t>(K) * fs;
   int last = N - 1;
@@ -197,35 +190,42 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
     for (int i = ltid; i < K * N; i += nthr) bp_g[i] = 0;  // not computed
     ubar();
   } else {
+    ubar();  // trl visible
     auto stage = [&](int chunk) {
       const int k0 = chunk * kDpChunk;
       const int nk = min(kDpChunk, K - k0);
-      BST* dst = bsS + static_cast<size_t>(chunk & 1) * kDpChunk * NS + s0;
+      BST* dst = bsS + static_cast<size_t>(chunk & 1) * kDpChunk * kDpNS + c0;
       for (int i = ltid; i < nk * N; i += nthr) {
         const int kk = i / N, n = i - kk * N;
         const BST* src = bs_g + static_cast<int64_t>(k0 + kk) * C + trl[n];
-        if (sizeof(BST) == 4) cp_async4(dst + kk * NS + n, src); else cp_async8(dst + kk * NS + n, src);
+        if (sizeof(BST) == 4) cp_async4(dst + kk * kDpNS + n, src); else cp_async8(dst + kk * kDpNS + n, src);
       }
       cp_async_commit();
     };
     const int nchunks = (K + kDpChunk - 1) / kDpChunk;
     stage(0);
-    if (nchunks > 1) { stage(1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    if (nchunks > 1) stage(1);
+
+    // this lane's segment (n >= 1), its ages a0+1 .. a0+SL and their length scores
+    const int g = lane / G, lig = lane - g * G;
+    const int n = 1 + wl * kDpSegsPerWarp + g;
+    const bool has_seg = n < N;
+    const int a0 = lig * SL;
+    double R[SL], rowr[SL];
+#pragma unroll
+    for (int i = 0; i < SL; ++i) {
+      R[i] = -INFINITY;
+      rowr[i] = has_seg ? length_row(b, tr0, n, a0 + i + 1, J) : -INFINITY;
+    }
+    const int nJ = (n <= 0x7fffffff / J) ? n * J : 0x7fffffff;
+
+    if (nchunks > 1) cp_async_wait<1>(); else cp_async_wait<0>();
     ubar();
 
-    double S[SEGS][SLOTS];
-    int len[SEGS][SLOTS];
-#pragma unroll
-    for (int q = 0; q < SEGS; ++q)
-#pragma unroll
-      for (int i = 0; i < SLOTS; ++i) { S[q][i] = 0.0; len[q][i] = 0; }
-    if (ltid == 0) {  // start hypothesis: 0.0 + F[fs-1, tr_0]  (viterbi.py:81-90)
-      S[0][0] = __dadd_rn(0.0, static_cast<double>(bsS[s0]));
-      len[0][0] = 1;
-    }
+    // segment 0: scalar chain on lane 0 of the first warp; 0.0 + F[fs-1, tr_0]  (viterbi.py:81-90)
     const bool f32seg0 = (sizeof(BST) == 4) && b.seg0_f32;
+    double s0 = __dadd_rn(0.0, static_cast<double>(bsS[c0]));
 
-    int slot = (J > 1) ? 1 : 0;  // k mod J
     int kk = 1, chunk = 0;
     for (int k = 1; k < K; ++k) {
       if (kk == kDpChunk) {
@@ -235,109 +235,107 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
         ubar();  // chunk landed for every thread of the unit; the other buffer is free
         if (chunk + 1 < nchunks) stage(chunk + 1);
       }
-      const BST* bsk = bsS + (static_cast<size_t>(chunk & 1) * kDpChunk + kk) * NS + s0;
+      const BST* bsk = bsS + (static_cast<size_t>(chunk & 1) * kDpChunk + kk) * kDpNS + c0;
       const int par = k & 1;
-#pragma unroll
-      for (int q = 0; q < SEGS; ++q) {
-        const int n = wl * SEGS + q;
-        if (n < N) {  // warp-uniform
-          const BST bval = bsk[n];
-          const double bd = static_cast<double>(bval);
-          const double* row = rows + n * J - 1;
-          unsigned long long key[SLOTS];
-          unsigned long long best = 0;
-#pragma unroll
-          for (int i = 0; i < SLOTS; ++i) {
-            const int ln = len[q][i];
-            double a;
-            if (f32seg0 && n == 0)
-              a = static_cast<double>(__fadd_rn(static_cast<float>(S[q][i]), static_cast<float>(bval)));
-            else
-              a = __dadd_rn(S[q][i], bd);
-            const double c = __dadd_rn(__dadd_rn(a, row[max(ln, 1)]), 0.0);
-            key[i] = (ln > 0) ? dkey(c) : 0ull;
-            best = (key[i] > best) ? key[i] : best;
-            S[q][i] = a;
-          }
-          // warp max of the 64-bit key through two 32-bit REDUX
-          const unsigned hi = static_cast<unsigned>(best >> 32);
-          const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-          const unsigned lo = (hi == mh) ? static_cast<unsigned>(best) : 0u;
-          const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
-          const unsigned long long gk = (static_cast<unsigned long long>(mh) << 32) | ml;
-          unsigned cl = 0;
-#pragma unroll
-          for (int i = 0; i < SLOTS; ++i) {
-            const int ln = len[q][i];
-            const unsigned cand = (key[i] == gk) ? static_cast<unsigned>(ln) : 0u;
-            cl = max(cl, cand);
-            len[q][i] = (ln > 0 && ln < J) ? ln + 1 : 0;
-          }
-          const unsigned jw = __reduce_max_sync(0xffffffffu, cl);  // 0 = no live predecessor
-          if (lane == 0 && n + 1 < N) {
-            E[par * NS + s0 + n + 1] = dunkey(gk);
-            Ej[par * NS + s0 + n + 1] = static_cast<int>(jw);
-            if (bp_in_smem) bpS[static_cast<size_t>(k) * NS + s0 + n + 1] = static_cast<uint8_t>(jw);
-            else bp_g[static_cast<int64_t>(k) * N + n + 1] = static_cast<uint8_t>(jw);
-          }
-        }
+
+      // ---- segment 0 -> entry of segment 1 (uniform work, only lane 0 of warp 0 keeps the result)
+      double e1;
+      {
+        const BST b0 = bsk[0];
+        const double a = f32seg0 ? static_cast<double>(__fadd_rn(static_cast<float>(s0), static_cast<float>(b0)))
+                                 : __dadd_rn(s0, static_cast<double>(b0));
+        s0 = a;
+        // the single hypothesis of segment 0 has age k; it can advance while k <= J
+        e1 = (k <= J) ? __dadd_rn(__dadd_rn(a, rows0[k - 1]), 0.0) : -INFINITY;
       }
-      ubar();
+
+      // ---- segments >= 1: age every hypothesis, build the advance candidates, fold
+      const double bd = static_cast<double>(bsk[has_seg ? n : 0]);
+      const double out = __dadd_rn(R[SL - 1], bd);  // leaves this lane
+      double bv = -INFINITY;
+      int bi = 0;
 #pragma unroll
-      for (int q = 0; q < SEGS; ++q) {
-        const int n = wl * SEGS + q;
-        if (n > 0 && n < N) {
-          const int ej = Ej[par * NS + s0 + n];
-          const double ev = E[par * NS + s0 + n];
+      for (int i = SL - 1; i >= 1; --i) R[i] = __dadd_rn(R[i - 1], bd);
+      // candidates in ascending age: old position i (age a0+i+1) now sits at R[i+1] / out
 #pragma unroll
-          for (int i = 0; i < SLOTS; ++i)
-            if (ej > 0 && lane + 32 * i == slot) { S[q][i] = ev; len[q][i] = 1; }
-        }
+      for (int i = 0; i < SL; ++i) {
+        const double a = (i + 1 < SL) ? R[(i + 1 < SL) ? i + 1 : 0] : out;
+        const double c = __dadd_rn(__dadd_rn(a, rowr[i]), 0.0);
+        if (i == 0 || c >= bv) { bv = c; bi = i; }
       }
+      int bage = a0 + bi + 1;
+#pragma unroll
+      for (int off = 1; off < G; off <<= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oa = __shfl_xor_sync(0xffffffffu, bage, off);
+        if (ov > bv || (ov == bv && oa > bage)) { bv = ov; bage = oa; }
+      }
+      // a fold whose maximum is -inf is decided by liveness alone: oldest live age, or no entry
+      {
+        const int jhi = min(J, k - n), jlo = max(1, k - nJ);
+        if (bv == -INFINITY) bage = (jlo <= jhi) ? jhi : 0;
+      }
+      // shift between lanes; the last lane of a group forwards the group's winner instead
+      const double send = (lig == G - 1) ? bv : out;
+      double inc = __shfl_up_sync(0xffffffffu, send, 1);
+      if (lane == 0) inc = (wl == 0) ? e1 : -INFINITY;  // warp 0: from segment 0; others: patched below
+      if (has_seg && lig == G - 1 && n + 1 < N) {
+        if (bp_in_smem) bpS[static_cast<size_t>(k) * kDpNS + c0 + n + 1] = static_cast<uint8_t>(bage);
+        else bp_g[static_cast<int64_t>(k) * N + n + 1] = static_cast<uint8_t>(bage);
+      }
+      if (ltid == 0 && N > 1) {
+        const uint8_t j1 = (k <= J) ? static_cast<uint8_t>(k) : uint8_t(0);
+        if (bp_in_smem) bpS[static_cast<size_t>(k) * kDpNS + c0 + 1] = j1;
+        else bp_g[static_cast<int64_t>(k) * N + 1] = j1;
+      }
+      if (nw > 1) {
+        if (lane == 31 && wl + 1 < nw) Ex[par * kDpWarps + warp + 1] = bv;
+        named_bar_sync(1 + w0, nthr);
+        if (lane == 0 && wl > 0) inc = Ex[par * kDpWarps + warp];
+      }
+      R[0] = inc;
       ++kk;
-      slot = (slot + 1 == J) ? 0 : slot + 1;
     }
 
     // end symbol: fold over the last segment (viterbi.py:125-138)
-#pragma unroll
-    for (int q = 0; q < SEGS; ++q) {
-      const int n = wl * SEGS + q;
-      if (n == N - 1) {
-        const double* row = rows + n * J - 1;
-        unsigned long long key[SLOTS];
-        unsigned long long best = 0;
-#pragma unroll
-        for (int i = 0; i < SLOTS; ++i) {
-          const int ln = len[q][i];
-          const double c = __dadd_rn(__dadd_rn(S[q][i], row[max(ln, 1)]), 0.0);
-          key[i] = (ln > 0) ? dkey(c) : 0ull;
-          best = (key[i] > best) ? key[i] : best;
-        }
-        const unsigned hi = static_cast<unsigned>(best >> 32);
-        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned lo = (hi == mh) ? static_cast<unsigned>(best) : 0u;
-        const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
-        const unsigned long long gk = (static_cast<unsigned long long>(mh) << 32) | ml;
-        unsigned cl = 0;
-#pragma unroll
-        for (int i = 0; i < SLOTS; ++i) cl = max(cl, (key[i] == gk) ? static_cast<unsigned>(len[q][i]) : 0u);
-        const unsigned jw = __reduce_max_sync(0xffffffffu, cl);
-        if (lane == 0) { *fin_v = dunkey(gk); *fin_j = static_cast<int>(jw); }
+    if (N == 1) {
+      if (ltid == 0) {
+        *fin_v = __dadd_rn(__dadd_rn(s0, rows0[K - 1]), 0.0);  // K <= J is guaranteed by feasibility
+        *fin_j = K;
       }
+    } else if (n == N - 1) {
+      double bv = -INFINITY;
+      int bi = 0;
+#pragma unroll
+      for (int i = 0; i < SL; ++i) {
+        const double c = __dadd_rn(__dadd_rn(R[i], rowr[i]), 0.0);
+        if (i == 0 || c >= bv) { bv = c; bi = i; }
+      }
+      int bage = a0 + bi + 1;
+#pragma unroll
+      for (int off = 1; off < G; off <<= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu >> (32 - G) << (g * G), bv, off);
+        const int oa = __shfl_xor_sync(0xffffffffu >> (32 - G) << (g * G), bage, off);
+        if (ov > bv || (ov == bv && oa > bage)) { bv = ov; bage = oa; }
+      }
+      // after the last step (k = K-1) the live ages of segment n are [max(1, K-n*J), min(J, K-n)]
+      const int jhi = min(J, K - n), jlo = max(1, K - nJ);
+      if (bv == -INFINITY) bage = (jlo <= jhi) ? jhi : 0;
+      if (lig == 0) { *fin_v = bv; *fin_j = bage; }
     }
     ubar();
     if (ltid == 0) {  // traceback over the back-pointer table (viterbi.py:140-153)
       const double sc = *fin_v;
       const int jf = *fin_j;
-      int n = N - 1;
+      int m = N - 1;
       int k0 = K - jf;
-      segb[n] = jf;
-      while (n > 0) {
-        const int ln = bp_in_smem ? static_cast<int>(bpS[static_cast<size_t>(k0) * NS + s0 + n])
-                                  : static_cast<int>(__ldcg(bp_g + static_cast<int64_t>(k0) * N + n));
-        segb[n - 1] = ln;
+      segb[m] = jf;
+      while (m > 0) {
+        const int ln = bp_in_smem ? static_cast<int>(bpS[static_cast<size_t>(k0) * kDpNS + c0 + m])
+                                  : static_cast<int>(__ldcg(bp_g + static_cast<int64_t>(k0) * N + m));
+        segb[m - 1] = ln;
         k0 -= ln;
-        --n;
+        --m;
       }
       b.score[u] = sc;
       b.final_j[u] = jf;
@@ -347,13 +345,13 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
     // back-pointer table -> HBM, [K, N] row-major; row 0 and column 0 hold no entries
     if (bp_in_smem) {
       const int total = K * N;
-      int k = ltid / N, n = ltid - k * N;
+      int k = ltid / N, m = ltid - k * N;
       const int dk = nthr / N, dn = nthr - dk * N;
       for (int i = ltid; i < total; i += nthr) {
-        bp_g[i] = (k > 0 && n > 0) ? bpS[static_cast<size_t>(k) * NS + s0 + n] : uint8_t(0);
+        bp_g[i] = (k > 0 && m > 0) ? bpS[static_cast<size_t>(k) * kDpNS + c0 + m] : uint8_t(0);
         k += dk;
-        n += dn;
-        if (n >= N) { n -= N; ++k; }
+        m += dn;
+        if (m >= N) { m -= N; ++k; }
       }
     } else {
       for (int i = ltid; i < N; i += nthr) bp_g[i] = 0;
@@ -361,12 +359,12 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
     }
   }
 
-  for (int n = ltid; n < N; n += nthr) b.seg_blocks[tr0 + n] = segb[n];
+  for (int m = ltid; m < N; m += nthr) b.seg_blocks[tr0 + m] = segb[m];
   const int64_t lo = b.lab_off ? b.lab_off[u] : -1;
   if (lo >= 0) {
     if (ltid == 0) {
       int64_t pos = rem;
-      for (int n = 0; n < N; ++n) { pos += static_cast<int64_t>(fs) * segb[n]; segend[n] = pos; }
+      for (int m = 0; m < N; ++m) { pos += static_cast<int64_t>(fs) * segb[m]; segend[m] = pos; }
     }
     ubar();
     write_labels(b.labels + lo, T, rem, trl, segend, last, ltid, nthr);
