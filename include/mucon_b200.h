@@ -74,10 +74,10 @@ typedef struct mucon_viterbi_batch {
   int32_t max_len;    /* length_model.max_length() (length_model.py:82; 2000); max_len/fs <= 128 */
   int32_t bs_is_f64;  /* dtype of bs */
   int32_t seg0_f32;   /* 1: segment 0 accumulates in float32 (NumPy>=2 promotion) */
-  int32_t max_N;      /* max transcript length over units (<= 65) */
+  int32_t max_N;      /* max transcript length over units (see mucon_viterbi_pack_h) */
   int32_t max_K;      /* max number of blocks over units (sizes the shared back-pointer stage) */
   int32_t n_cta;      /* number of unit bins, from mucon_viterbi_pack_h */
-  int32_t segs;       /* segments per warp (4), from mucon_viterbi_pack_h */
+  int32_t wpc;        /* warps per CTA (4, 8 or 16), from mucon_viterbi_pack_h */
   const void* bs;            /* [sum K, C] block scores */
   const int64_t* vid_off;    /* [V+1] frame offsets (T_v = difference) */
   const int64_t* blk_off;    /* [V+1] block offsets into bs */
@@ -89,7 +89,7 @@ typedef struct mucon_viterbi_batch {
   const double* logfact;     /* [J+1] sum_{i<=j*fs} ln i at index j; used with len_params */
   const int64_t* lab_off;    /* [U] offset of the unit's labels in `labels`, <0 = do not write */
   const int64_t* bp_off;     /* [U] offset (bytes) of the unit's [K,N] uint8 back-pointer table */
-  const int32_t* warp_unit;  /* [n_cta*16] unit of every warp of every bin (-1 = unused) */
+  const int32_t* warp_unit;  /* [n_cta*wpc] unit of every warp of every bin (-1 = unused) */
   double* score;             /* [U] */
   int32_t* labels;           /* frame labels, T_u each */
   int32_t* seg_blocks;       /* [sum N] segment lengths in blocks (0 = segment not reached) */
@@ -98,11 +98,14 @@ typedef struct mucon_viterbi_batch {
   int32_t* status;           /* [U] MUCON_UNIT_* */
 } mucon_viterbi_batch;
 
-/* Host helper: packs units into bins of 16 warps (one CTA each).  A unit needs
- * max(1, ceil((N-1)/4)) consecutive warps; units are taken in order_h (or 0..U-1) -- pass them longest
- * first.  warp_unit_h needs room for U*16 entries; on return the first *n_cta_out*16 are valid. */
-int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N,
-                         int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* segs_out);
+/* Host helper: packs units into bins of wpc warps (one CTA each; wpc = 4, 8 or 16, the
+ * smallest that holds the largest unit).  With J = max_len/fs, a segment takes G = 4 lanes when
+ * ceil(J/4) <= 17, else 8; a unit needs max(1, ceil((N-1)/(32/G))) consecutive warps, so
+ * N <= 129 (G = 4) or 65 (G = 8).  Units are taken in order_h (or 0..U-1) -- pass them longest
+ * first.  warp_unit_h needs room for U*16 entries; on return the first *n_cta_out * *wpc_out
+ * are valid. */
+int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
+                         int max_len, int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* wpc_out);
 
 int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 

@@ -254,38 +254,48 @@ int launch_scan(const T* logp, const int64_t* vid_off, const int64_t* blk_off, c
   return MUCON_OK;
 }
 
-template <typename BST, int SL>
+template <typename BST, int G, int SL>
 int launch_dp(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
   // keep the back-pointer table in shared memory when it fits next to everything else
   int bp_rows = b.max_K;
-  size_t smem = dp_layout(J, sizeof(BST), bp_rows).total;
-  if (smem > 200 * 1024) {
+  size_t smem = dp_layout(b.wpc, G, J, sizeof(BST), bp_rows).total;
+  if (smem > (size_t)(200 * 1024 / (kDpMaxWarps / b.wpc))) {
     bp_rows = 0;
-    smem = dp_layout(J, sizeof(BST), 0).total;
+    smem = dp_layout(b.wpc, G, J, sizeof(BST), 0).total;
   }
-  auto kern = dp_kernel<BST, SL>;
+  auto kern = dp_kernel<BST, G, SL>;
   if (smem > 48 * 1024)
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<b.n_cta, kDpWarps * 32, smem, st>>>(b, J, b.warp_unit, bp_rows);
+  kern<<<b.n_cta, b.wpc * 32, smem, st>>>(b, J, b.warp_unit, bp_rows);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
 
 template <typename BST>
 int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  switch ((J + kDpGroup - 1) / kDpGroup) {
-#define MUCON_SL_CASE(n) case n: return launch_dp<BST, n>(b, J, st);
-    MUCON_SL_CASE(1) MUCON_SL_CASE(2) MUCON_SL_CASE(3) MUCON_SL_CASE(4)
-    MUCON_SL_CASE(5) MUCON_SL_CASE(6) MUCON_SL_CASE(7) MUCON_SL_CASE(8)
-    MUCON_SL_CASE(9) MUCON_SL_CASE(10) MUCON_SL_CASE(11) MUCON_SL_CASE(12)
-    MUCON_SL_CASE(13) MUCON_SL_CASE(14) MUCON_SL_CASE(15) MUCON_SL_CASE(16)
-#undef MUCON_SL_CASE
+  const int G = dp_group(J);
+  const int SL = (J + G - 1) / G;
+#define MUCON_SL_CASE(g, n) case n: return launch_dp<BST, g, n>(b, J, st);
+  if (G == 4) {
+    switch (SL) {
+      MUCON_SL_CASE(4, 1) MUCON_SL_CASE(4, 2) MUCON_SL_CASE(4, 3) MUCON_SL_CASE(4, 4) MUCON_SL_CASE(4, 5)
+      MUCON_SL_CASE(4, 6) MUCON_SL_CASE(4, 7) MUCON_SL_CASE(4, 8) MUCON_SL_CASE(4, 9) MUCON_SL_CASE(4, 10)
+      MUCON_SL_CASE(4, 11) MUCON_SL_CASE(4, 12) MUCON_SL_CASE(4, 13) MUCON_SL_CASE(4, 14) MUCON_SL_CASE(4, 15)
+      MUCON_SL_CASE(4, 16) MUCON_SL_CASE(4, 17)
+      default: return MUCON_EUNSUPPORTED;
+    }
+  }
+  switch (SL) {
+    MUCON_SL_CASE(8, 9) MUCON_SL_CASE(8, 10) MUCON_SL_CASE(8, 11) MUCON_SL_CASE(8, 12)
+    MUCON_SL_CASE(8, 13) MUCON_SL_CASE(8, 14) MUCON_SL_CASE(8, 15) MUCON_SL_CASE(8, 16)
     default: return MUCON_EUNSUPPORTED;
   }
+#undef MUCON_SL_CASE
 }
 
-int warps_for(int N) {
-  const int w = (N - 1 + kDpSegsPerWarp - 1) / kDpSegsPerWarp;
+int warps_for(int N, int G) {
+  const int spw = 32 / G;
+  const int w = (N - 1 + spw - 1) / spw;
   return w < 1 ? 1 : w;
 }
 
@@ -318,46 +328,49 @@ extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream)
   if (!b.len_rows && !(b.len_params && b.logfact)) return MUCON_EINVAL;
   if (b.U == 0 || b.n_cta == 0) return MUCON_OK;
   const int J = b.max_len / b.fs;
-  if (J > kDpGroup * kDpMaxSL) return MUCON_EUNSUPPORTED;  // ages live in registers, back-pointers are uint8
-  if (b.max_N > kDpMaxN) return MUCON_EUNSUPPORTED;
-  if (b.segs != kDpSegsPerWarp) return MUCON_EINVAL;
+  if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;  // ages live in registers, back-pointers are uint8
+  if (b.max_N > dp_max_n(dp_group(J))) return MUCON_EUNSUPPORTED;
+  if (b.wpc != 4 && b.wpc != 8 && b.wpc != 16) return MUCON_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (b.bs_is_f64) return dispatch_sl<double>(b, J, st);
   return dispatch_sl<float>(b, J, st);
 }
 
-extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N,
-                                    int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* segs_out) {
-  if (!N_h || !warp_unit_h || !n_cta_out || !segs_out || U < 0 || max_N < 1) return MUCON_EINVAL;
-  if (max_N > kDpMaxN) return MUCON_EUNSUPPORTED;
-  *segs_out = kDpSegsPerWarp;
+extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
+                                    int max_len, int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* wpc_out) {
+  if (!N_h || !warp_unit_h || !n_cta_out || !wpc_out || U < 0 || max_N < 1 || fs < 1 || max_len < fs)
+    return MUCON_EINVAL;
+  const int J = max_len / fs;
+  if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;
+  const int G = dp_group(J);
+  if (max_N > dp_max_n(G)) return MUCON_EUNSUPPORTED;
+  // small CTAs keep the grid fine-grained (the block scheduler balances the SMs); a CTA only has
+  // to be as large as the largest unit
+  const int wmax = warps_for(max_N, G);
+  const int wpc = wmax <= 4 ? 4 : (wmax <= 8 ? 8 : 16);
+  *wpc_out = wpc;
   constexpr int kWindow = 8;  // open bins that may still take units (keeps K similar within a bin)
-  int open_bin[kWindow], open_free[kWindow], open_units[kWindow], n_open = 0;
+  int open_bin[kWindow], open_free[kWindow], n_open = 0;
   int n_cta = 0;
   for (int i = 0; i < U; ++i) {
     const int u = order_h ? order_h[i] : i;
-    const int need = warps_for(N_h[u]);
-    if (need > kDpWarps) return MUCON_EUNSUPPORTED;
+    const int need = warps_for(N_h[u], G);
     int pick = -1;
     for (int o = 0; o < n_open; ++o)
-      if (open_free[o] >= need && open_units[o] < 15) { pick = o; break; }
+      if (open_free[o] >= need) { pick = o; break; }
     if (pick < 0) {
       if (n_open == kWindow) {  // retire the oldest open bin
-        for (int o = 1; o < kWindow; ++o) {
-          open_bin[o - 1] = open_bin[o]; open_free[o - 1] = open_free[o]; open_units[o - 1] = open_units[o];
-        }
+        for (int o = 1; o < kWindow; ++o) { open_bin[o - 1] = open_bin[o]; open_free[o - 1] = open_free[o]; }
         --n_open;
       }
       pick = n_open++;
       open_bin[pick] = n_cta++;
-      open_free[pick] = kDpWarps;
-      open_units[pick] = 0;
-      for (int w = 0; w < kDpWarps; ++w) warp_unit_h[(size_t)open_bin[pick] * kDpWarps + w] = -1;
+      open_free[pick] = wpc;
+      for (int w = 0; w < wpc; ++w) warp_unit_h[(size_t)open_bin[pick] * wpc + w] = -1;
     }
-    const int start = kDpWarps - open_free[pick];
-    for (int w = 0; w < need; ++w) warp_unit_h[(size_t)open_bin[pick] * kDpWarps + start + w] = u;
+    const int start = wpc - open_free[pick];
+    for (int w = 0; w < need; ++w) warp_unit_h[(size_t)open_bin[pick] * wpc + start + w] = u;
     open_free[pick] -= need;
-    open_units[pick] += 1;
   }
   *n_cta_out = n_cta;
   return MUCON_OK;

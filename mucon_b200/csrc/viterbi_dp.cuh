@@ -31,12 +31,29 @@
 
 namespace mucon {
 
-constexpr int kDpWarps = 16;     // warps per CTA
+constexpr int kDpMaxWarps = 16;  // warps per CTA: 4, 8 or 16 (chosen by mucon_viterbi_pack_h)
 constexpr int kDpChunk = 32;     // DP steps per block-score staging chunk
-constexpr int kDpGroup = 8;      // lanes per segment
-constexpr int kDpSegsPerWarp = 32 / kDpGroup;
-constexpr int kDpMaxSL = 16;     // J <= 128
-constexpr int kDpMaxN = 1 + kDpWarps * kDpSegsPerWarp;  // 65
+constexpr int kDpMaxJ = 128;     // ages live in registers: 4 lanes x <= 17 or 8 lanes x <= 16
+
+// lanes per segment for a given J: 4 (8 segments per warp) while the per-lane register file
+// holds the ages, else 8
+__host__ __device__ inline int dp_group(int J) { return (J + 3) / 4 <= 17 ? 4 : 8; }
+__host__ __device__ inline int dp_max_n(int G) { return 1 + kDpMaxWarps * (32 / G); }
+
+// Order-preserving map double -> uint64 (and back).  FP64 compares sit on a long-latency pipe and
+// the fold is the loop-carried critical path, so all arg-max work is done on integer keys.  Equal
+// doubles have equal keys except -0.0 / +0.0; candidates are a + row with row != -0.0 (rows are
+// canonicalised when loaded), and such a sum is never -0.0, which also makes the reference's
+// trailing "+ 0.0" (viterbi.py:116) the identity.
+__device__ __forceinline__ unsigned long long dkey(double c) {
+  const long long b = __double_as_longlong(c);
+  return static_cast<unsigned long long>(b) ^ (static_cast<unsigned long long>(b >> 63) | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double(static_cast<long long>(b));
+}
+constexpr unsigned long long kKeyNegInf = 0x000fffffffffffffull;  // dkey(-inf)
 
 __device__ __forceinline__ int label_of_frame(int64_t t, int64_t rem, const int32_t* trl, const int64_t* segend,
                                               int last) {
@@ -79,15 +96,16 @@ __device__ __forceinline__ void write_labels(int32_t* out, int64_t T, int64_t re
   for (int64_t t = head + 4 * nvec + tid; t < T; t += nth) out[t] = label_of_frame(t, rem, trl, segend, last);
 }
 
-// Shared-memory plan of one CTA.  NS = segment columns of a CTA (65 covers 16 warps x 4 + segment 0
-// of a unit that starts at warp 0; units never share a column: column of segment n of the unit
-// that starts at warp w0 is 4*w0 + n... see seg_col()).
-constexpr int kDpNS = kDpWarps * kDpSegsPerWarp + kDpWarps;  // generous: one extra column per unit
+// Shared-memory plan of one CTA of `wpc` warps.  Every warp owns 32/G + 1 segment columns (its
+// segments plus a spare for segment 0 of a unit starting there), so units never share a column:
+// segment n of the unit whose first warp is w0 lives in column (32/G + 1)*w0 + n.
+__host__ __device__ inline int dp_columns(int wpc, int G) { return wpc * (32 / G + 1); }
 
 struct DpLayout {
   size_t rows0, Ex, segend, trl, segb, fin_v, fin_j, bsS, bpS, total;
 };
-__host__ __device__ inline DpLayout dp_layout(int J, int bs_elem, int bp_rows) {
+__host__ __device__ inline DpLayout dp_layout(int wpc, int G, int J, int bs_elem, int bp_rows) {
+  const int kDpNS = dp_columns(wpc, G), kDpWarps = wpc;
   DpLayout L;
   size_t o = 0;
   L.rows0 = o; o += sizeof(double) * (size_t)kDpWarps * J;  // segment-0 length rows, one per unit slot
@@ -109,7 +127,7 @@ __host__ __device__ inline DpLayout dp_layout(int J, int bs_elem, int bp_rows) {
 // (length_model.py:65-71), -inf when the length is not representable (length_model.py:76-80).
 __device__ __forceinline__ double length_row(const mucon_viterbi_batch& b, int tr0, int n, int age, int J) {
   if (age < 1 || age > J) return -INFINITY;
-  if (b.len_rows) return b.len_rows[static_cast<size_t>(tr0 + n) * J + age - 1];
+  if (b.len_rows) return __dadd_rn(b.len_rows[static_cast<size_t>(tr0 + n) * J + age - 1], 0.0);
   const int l = age * b.fs;
   if (l >= b.max_len) return -INFINITY;
   const double* g = b.len_params + static_cast<size_t>(tr0 + n) * 3;
@@ -117,14 +135,15 @@ __device__ __forceinline__ double length_row(const mucon_viterbi_batch& b, int t
   r = __dsub_rn(r, g[1]);
   r = __dsub_rn(r, b.logfact[age]);
   r = __dsub_rn(r, g[2]);
-  return r;
+  return __dadd_rn(r, 0.0);
 }
 
-template <typename BST, int SL>
-__global__ void __launch_bounds__(kDpWarps * 32, 1)
+template <typename BST, int G, int SL>
+__global__ void __launch_bounds__(kDpMaxWarps * 32, 1)
 dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ warp_unit, const int bp_rows) {
   extern __shared__ __align__(16) unsigned char sm[];
-  constexpr int G = kDpGroup;
+  constexpr int kSegsPerWarp = 32 / G;
+  const int kDpWarps = blockDim.x >> 5, kDpNS = dp_columns(kDpWarps, G);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int32_t* wu = warp_unit + static_cast<size_t>(blockIdx.x) * kDpWarps;
   const int u = wu[warp];
@@ -134,7 +153,7 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
   while (w1 < kDpWarps && wu[w1] == u) ++w1;
   const int nw = w1 - w0, wl = warp - w0;
   const int ltid = wl * 32 + lane, nthr = nw * 32;
-  const int c0 = w0 * (kDpSegsPerWarp + 1);  // first shared-memory column of this unit
+  const int c0 = w0 * (kSegsPerWarp + 1);  // first shared-memory column of this unit
   auto ubar = [&]() {
     if (nw == 1) __syncwarp(); else named_bar_sync(1 + w0, nthr);
   };
@@ -157,7 +176,7 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
     return;
   }
 
-  const DpLayout L = dp_layout(J, sizeof(BST), bp_rows);
+  const DpLayout L = dp_layout(kDpWarps, G, J, sizeof(BST), bp_rows);
   double* rows0 = reinterpret_cast<double*>(sm + L.rows0) + static_cast<size_t>(w0) * J;  // [J], ages 1..J
   double* Ex = reinterpret_cast<double*>(sm + L.Ex);                                       // [2][16] by warp
   int64_t* segend = reinterpret_cast<int64_t*>(sm + L.segend) + c0;
@@ -208,7 +227,7 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
 
     // this lane's segment (n >= 1), its ages a0+1 .. a0+SL and their length scores
     const int g = lane / G, lig = lane - g * G;
-    const int n = 1 + wl * kDpSegsPerWarp + g;
+    const int n = 1 + wl * kSegsPerWarp + g;
     const bool has_seg = n < N;
     const int a0 = lig * SL;
     double R[SL], rowr[SL];
@@ -239,41 +258,58 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       const int par = k & 1;
 
       // ---- segment 0 -> entry of segment 1 (uniform work, only lane 0 of warp 0 keeps the result)
-      double e1;
-      {
+      double e1 = -INFINITY;
+      if (wl == 0) {
         const BST b0 = bsk[0];
         const double a = f32seg0 ? static_cast<double>(__fadd_rn(static_cast<float>(s0), static_cast<float>(b0)))
                                  : __dadd_rn(s0, static_cast<double>(b0));
         s0 = a;
         // the single hypothesis of segment 0 has age k; it can advance while k <= J
-        e1 = (k <= J) ? __dadd_rn(__dadd_rn(a, rows0[k - 1]), 0.0) : -INFINITY;
+        e1 = (k <= J) ? __dadd_rn(a, rows0[k - 1]) : -INFINITY;  // rows are never -0.0: no "+ 0.0" needed
       }
 
       // ---- segments >= 1: age every hypothesis, build the advance candidates, fold
       const double bd = static_cast<double>(bsk[has_seg ? n : 0]);
       const double out = __dadd_rn(R[SL - 1], bd);  // leaves this lane
-      double bv = -INFINITY;
-      int bi = 0;
 #pragma unroll
       for (int i = SL - 1; i >= 1; --i) R[i] = __dadd_rn(R[i - 1], bd);
-      // candidates in ascending age: old position i (age a0+i+1) now sits at R[i+1] / out
+      // Candidates: old position i (age a0+i+1) now sits at R[i+1] / out.  The fold is a max by
+      // (value, age) on integer keys.  Positions 1.. do not depend on this step's entry: they are
+      // reduced by a tree (older position wins ties); the youngest candidate -- the only one on
+      // the loop-carried path -- joins last and wins only when strictly greater.
+      unsigned long long key[SL];
+      int idx[SL];
 #pragma unroll
       for (int i = 0; i < SL; ++i) {
         const double a = (i + 1 < SL) ? R[(i + 1 < SL) ? i + 1 : 0] : out;
-        const double c = __dadd_rn(__dadd_rn(a, rowr[i]), 0.0);
-        if (i == 0 || c >= bv) { bv = c; bi = i; }
+        key[i] = dkey(__dadd_rn(a, rowr[i]));
+        idx[i] = i;
       }
+#pragma unroll
+      for (int w = 1; w < SL - 1; w <<= 1) {
+#pragma unroll
+        for (int i = 1; i + w < SL; i += 2 * w) {
+          if (key[i + w] >= key[i]) { key[i] = key[i + w]; idx[i] = idx[i + w]; }
+        }
+      }
+      unsigned long long bk = key[0];
+      int bi = 0;
+      if (SL > 1 && key[1] >= bk) { bk = key[1]; bi = idx[1]; }
       int bage = a0 + bi + 1;
+      // butterfly over the group's lanes: the partner with the higher lane holds older ages, so
+      // it wins ties; the partner with the lower lane must be strictly greater
 #pragma unroll
       for (int off = 1; off < G; off <<= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, off);
         const int oa = __shfl_xor_sync(0xffffffffu, bage, off);
-        if (ov > bv || (ov == bv && oa > bage)) { bv = ov; bage = oa; }
+        const bool take = (lane & off) ? (ok > bk) : (ok >= bk);
+        if (take) { bk = ok; bage = oa; }
       }
+      const double bv = dunkey(bk);
       // a fold whose maximum is -inf is decided by liveness alone: oldest live age, or no entry
       {
         const int jhi = min(J, k - n), jlo = max(1, k - nJ);
-        if (bv == -INFINITY) bage = (jlo <= jhi) ? jhi : 0;
+        if (bk == kKeyNegInf) bage = (jlo <= jhi) ? jhi : 0;
       }
       // shift between lanes; the last lane of a group forwards the group's winner instead
       const double send = (lig == G - 1) ? bv : out;
@@ -308,7 +344,7 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       int bi = 0;
 #pragma unroll
       for (int i = 0; i < SL; ++i) {
-        const double c = __dadd_rn(__dadd_rn(R[i], rowr[i]), 0.0);
+        const double c = __dadd_rn(R[i], rowr[i]);
         if (i == 0 || c >= bv) { bv = c; bi = i; }
       }
       int bage = a0 + bi + 1;
@@ -316,8 +352,10 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       for (int off = 1; off < G; off <<= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu >> (32 - G) << (g * G), bv, off);
         const int oa = __shfl_xor_sync(0xffffffffu >> (32 - G) << (g * G), bage, off);
-        if (ov > bv || (ov == bv && oa > bage)) { bv = ov; bage = oa; }
+        const bool take = (lane & off) ? (ov > bv) : (ov >= bv);
+        if (take) { bv = ov; bage = oa; }
       }
+      bv = __dadd_rn(bv, 0.0);
       // after the last step (k = K-1) the live ages of segment n are [max(1, K-n*J), min(J, K-n)]
       const int jhi = min(J, K - n), jlo = max(1, K - nJ);
       if (bv == -INFINITY) bage = (jlo <= jhi) ? jhi : 0;

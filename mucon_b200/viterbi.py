@@ -135,10 +135,11 @@ class AlignPlan:
         n32 = np.ascontiguousarray(nlen, dtype=np.int32)
         _lib.check(lib.mucon_viterbi_pack_h(
             n32.ctypes.data_as(C.c_void_p), self.order_u.ctypes.data_as(C.c_void_p), C.c_int(U),
-            C.c_int(self.max_N), wu.ctypes.data_as(C.c_void_p), C.byref(n_cta), C.byref(segs)),
+            C.c_int(self.max_N), C.c_int(self.fs), C.c_int(self.max_len), wu.ctypes.data_as(C.c_void_p),
+            C.byref(n_cta), C.byref(segs)),
             "mucon_viterbi_pack_h")
-        self.n_cta, self.segs = int(n_cta.value), int(segs.value)
-        self.warp_unit = wu[:max(self.n_cta, 1) * 16]
+        self.n_cta, self.wpc = int(n_cta.value), int(segs.value)
+        self.warp_unit = wu[:max(self.n_cta, 1) * self.wpc]
 
         blob = _Blob()
         blob.add("vid_off", self.vid_off)
@@ -218,7 +219,7 @@ class ViterbiEngine:
         b = _lib.ViterbiBatch()
         b.U, b.C, b.fs, b.max_len = plan.U, plan.C, plan.fs, plan.max_len
         b.bs_is_f64, b.seg0_f32, b.max_N, b.max_K = int(is64), int(bool(seg0_f32)), plan.max_N, plan.max_K
-        b.n_cta, b.segs = plan.n_cta, plan.segs
+        b.n_cta, b.wpc = plan.n_cta, plan.wpc
         b.bs = plan.bs.data_ptr()
         b.vid_off, b.blk_off, b.unit_vid = p["vid_off"], p["blk_off"], p["unit_vid"]
         b.tr, b.tr_off = p["tr"], p["tr_off"]
