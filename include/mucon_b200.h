@@ -99,9 +99,9 @@ typedef struct mucon_viterbi_batch {
 } mucon_viterbi_batch;
 
 /* Host helper: packs units into bins of wpc warps (one CTA each; wpc = 4, 8 or 16, the
- * smallest that holds the largest unit).  With J = max_len/fs, a segment takes G = 4 lanes when
- * ceil(J/4) <= 17, else 8; a unit needs max(1, ceil((N-1)/(32/G))) consecutive warps, so
- * N <= 129 (G = 4) or 65 (G = 8).  Units are taken in order_h (or 0..U-1) -- pass them longest
+ * smallest that holds the largest unit).  With J = max_len/fs, a segment takes G = 32 lanes
+ * when max_N <= 17, else 4 (J <= 32) or 8; a unit needs max(1, ceil((N-1)/(32/G))) consecutive
+ * warps, so N <= 129 (G = 4) or 65 (G = 8).  Units are taken in order_h (or 0..U-1) -- pass them longest
  * first.  warp_unit_h needs room for U*16 entries; on return the first *n_cta_out * *wpc_out
  * are valid. */
 int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,

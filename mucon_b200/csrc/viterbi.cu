@@ -273,19 +273,24 @@ int launch_dp(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
 
 template <typename BST>
 int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  const int G = dp_group(J);
+  const int G = dp_group(J, b.max_N);
   const int SL = (J + G - 1) / G;
 #define MUCON_SL_CASE(g, n) case n: return launch_dp<BST, g, n>(b, J, st);
+  if (G == 32) {
+    switch (SL) {
+      MUCON_SL_CASE(32, 1) MUCON_SL_CASE(32, 2) MUCON_SL_CASE(32, 3) MUCON_SL_CASE(32, 4)
+      default: return MUCON_EUNSUPPORTED;
+    }
+  }
   if (G == 4) {
     switch (SL) {
-      MUCON_SL_CASE(4, 1) MUCON_SL_CASE(4, 2) MUCON_SL_CASE(4, 3) MUCON_SL_CASE(4, 4) MUCON_SL_CASE(4, 5)
-      MUCON_SL_CASE(4, 6) MUCON_SL_CASE(4, 7) MUCON_SL_CASE(4, 8) MUCON_SL_CASE(4, 9) MUCON_SL_CASE(4, 10)
-      MUCON_SL_CASE(4, 11) MUCON_SL_CASE(4, 12) MUCON_SL_CASE(4, 13) MUCON_SL_CASE(4, 14) MUCON_SL_CASE(4, 15)
-      MUCON_SL_CASE(4, 16) MUCON_SL_CASE(4, 17)
+      MUCON_SL_CASE(4, 1) MUCON_SL_CASE(4, 2) MUCON_SL_CASE(4, 3) MUCON_SL_CASE(4, 4)
+      MUCON_SL_CASE(4, 5) MUCON_SL_CASE(4, 6) MUCON_SL_CASE(4, 7) MUCON_SL_CASE(4, 8)
       default: return MUCON_EUNSUPPORTED;
     }
   }
   switch (SL) {
+    MUCON_SL_CASE(8, 5) MUCON_SL_CASE(8, 6) MUCON_SL_CASE(8, 7) MUCON_SL_CASE(8, 8)
     MUCON_SL_CASE(8, 9) MUCON_SL_CASE(8, 10) MUCON_SL_CASE(8, 11) MUCON_SL_CASE(8, 12)
     MUCON_SL_CASE(8, 13) MUCON_SL_CASE(8, 14) MUCON_SL_CASE(8, 15) MUCON_SL_CASE(8, 16)
     default: return MUCON_EUNSUPPORTED;
@@ -329,7 +334,7 @@ extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream)
   if (b.U == 0 || b.n_cta == 0) return MUCON_OK;
   const int J = b.max_len / b.fs;
   if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;  // ages live in registers, back-pointers are uint8
-  if (b.max_N > dp_max_n(dp_group(J))) return MUCON_EUNSUPPORTED;
+  if (b.max_N > dp_max_n(dp_group(J, b.max_N))) return MUCON_EUNSUPPORTED;
   if (b.wpc != 4 && b.wpc != 8 && b.wpc != 16) return MUCON_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (b.bs_is_f64) return dispatch_sl<double>(b, J, st);
@@ -342,7 +347,7 @@ extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, 
     return MUCON_EINVAL;
   const int J = max_len / fs;
   if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;
-  const int G = dp_group(J);
+  const int G = dp_group(J, max_N);
   if (max_N > dp_max_n(G)) return MUCON_EUNSUPPORTED;
   // small CTAs keep the grid fine-grained (the block scheduler balances the SMs); a CTA only has
   // to be as large as the largest unit

@@ -33,11 +33,19 @@ namespace mucon {
 
 constexpr int kDpMaxWarps = 16;  // warps per CTA: 4, 8 or 16 (chosen by mucon_viterbi_pack_h)
 constexpr int kDpChunk = 32;     // DP steps per block-score staging chunk
-constexpr int kDpMaxJ = 128;     // ages live in registers: 4 lanes x <= 17 or 8 lanes x <= 16
+constexpr int kDpMaxJ = 128;     // ages live in registers: 4 lanes x <= 8 or 8 lanes x <= 16
 
-// lanes per segment for a given J: 4 (8 segments per warp) while the per-lane register file
-// holds the ages, else 8
-__host__ __device__ inline int dp_group(int J) { return (J + 3) / 4 <= 17 ? 4 : 8; }
+// Lanes per segment.  A single warp issues roughly one instruction every 3.5 cycles on this
+// dependent code (measured), so the per-step latency of a unit is set by the instructions per
+// warp-step: 8 lanes x 9 ages for J = 66 keeps a step near 150 instructions while still packing
+// four segments into a warp.
+// Units of up to 17 segments (everything Breakfast-shaped) get a whole warp per segment: the
+// lane butterfly is replaced by three REDUX instructions and a step is ~70 instructions.
+// Longer transcripts share a warp between 4 (or 8) segments.
+__host__ __device__ inline int dp_group(int J, int max_N) {
+  if (max_N <= 1 + kDpMaxWarps) return 32;
+  return J <= 32 ? 4 : 8;
+}
 __host__ __device__ inline int dp_max_n(int G) { return 1 + kDpMaxWarps * (32 / G); }
 
 // Order-preserving map double -> uint64 (and back).  FP64 compares sit on a long-latency pipe and
@@ -245,92 +253,163 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
     const bool f32seg0 = (sizeof(BST) == 4) && b.seg0_f32;
     double s0 = __dadd_rn(0.0, static_cast<double>(bsS[c0]));
 
+    // per-lane pointers so that the step loop does no index arithmetic
+    const BST* bs_lane = bsS + c0 + (has_seg ? n : 0);  // this lane's label column in the stage
+    const BST* bs_seg0 = bsS + c0;
+    const bool bp_writer = has_seg && lig == G - 1 && n + 1 < N;
+    uint8_t* bp_w;       // where this lane records the winner of its group at step k
+    int bp_stride;
+    if (bp_in_smem) { bp_w = bpS + c0 + n + 1; bp_stride = kDpNS; }
+    else { bp_w = bp_g + n + 1; bp_stride = N; }
+    bp_w += bp_stride;   // step 1
+    double* ex_out = Ex + warp + 1;
+    const double* ex_in = Ex + warp;
+    const bool ex_writer = lane == 31 && wl + 1 < nw;
+    const bool ex_reader = lane == 0 && wl > 0;
+    const bool multi = nw > 1;
+    const int bar_id = 1 + w0;
+
+    // The step is software-pipelined.  Only the youngest hypothesis of a segment depends on the
+    // previous step's fold (it IS that fold's winner); everything else is a pure shift-and-add.
+    //   A'(k): out_k, R[i>=2], candidates and tree fold of positions >= 1  -- no dependence on
+    //          the entry produced by step k-1
+    //   C(k):  R[1] = R[0] + b_k, youngest candidate, lane butterfly, hand-over to the next
+    //          segment / warp                                   -- the loop-carried chain
+    // The loop body is C(k); A'(k+1), so the shuffle latencies of C(k) are filled with the
+    // independent arithmetic of A'(k+1).
+    double out = 0.0, tv = -INFINITY, e1 = -INFINITY, bd = 0.0;
+    int ti = 1;
+    // A'(k) for block scores bdn (this lane's label) / b0n (segment 0's label) of step k.
+    // Reads R[1..], writes R[2..] and the pipeline registers (outn, tvn, tin, e1n, s0).
+    auto a_prime = [&](int k, double bdn, BST b0n, double& outn, double& tvn, int& tin, double& e1n) {
+      if (SL > 1) {
+        outn = __dadd_rn(R[SL - 1], bdn);
+#pragma unroll
+        for (int i = SL - 1; i >= 2; --i) R[i] = __dadd_rn(R[i - 1], bdn);
+        double cv[SL];
+        int idx[SL];
+#pragma unroll
+        for (int i = 1; i < SL; ++i) {
+          const double a = (i + 1 < SL) ? R[(i + 1 < SL) ? i + 1 : 0] : outn;
+          cv[i] = __dadd_rn(a, rowr[i]);
+          idx[i] = i;
+        }
+#pragma unroll
+        for (int w = 1; w < SL - 1; w <<= 1) {
+#pragma unroll
+          for (int i = 1; i + w < SL; i += 2 * w) {
+            const bool older = cv[i + w] >= cv[i];  // the older position wins ties
+            cv[i] = older ? cv[i + w] : cv[i];
+            idx[i] = older ? idx[i + w] : idx[i];
+          }
+        }
+        tvn = cv[(SL > 1) ? 1 : 0];
+        tin = idx[(SL > 1) ? 1 : 0];
+      }
+      // segment 0 -> entry of segment 1.  Every warp runs the chain (it is four instructions and
+      // branch-free); only lane 0 of the unit's first warp uses the result.
+      double a;
+      if (f32seg0) a = static_cast<double>(__fadd_rn(static_cast<float>(s0), static_cast<float>(b0n)));
+      else a = __dadd_rn(s0, static_cast<double>(b0n));
+      s0 = a;
+      // the single hypothesis of segment 0 has age k; it can advance while k <= J.
+      // rows are never -0.0, so the reference's trailing "+ 0.0" is the identity here.
+      e1n = (k <= J) ? __dadd_rn(a, rows0[min(k, J) - 1]) : -INFINITY;
+    };
+    // C(k) up to the hand-over value `inc` (before the cross-warp exchange)
+    auto c_step = [&](int k, double& bv, double& inc) {
+      int bi;
+      if (SL > 1) {
+        R[(SL > 1) ? 1 : 0] = __dadd_rn(R[0], bd);
+        const double c0v = __dadd_rn(R[(SL > 1) ? 1 : 0], rowr[0]);
+        const bool young = c0v > tv;  // the youngest wins only when strictly greater
+        bv = young ? c0v : tv;
+        bi = young ? 0 : ti;
+      } else {
+        out = __dadd_rn(R[0], bd);
+        bv = __dadd_rn(out, rowr[0]);
+        bi = 0;
+      }
+      int bage = a0 + bi + 1;
+      if (G == 32) {
+        // whole-warp arg-max on the order-preserving integer key: two REDUX for the 64-bit
+        // maximum, one for the oldest age among the lanes that hold it
+        const unsigned long long key = dkey(bv);
+        const unsigned hi = static_cast<unsigned>(key >> 32);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned lo = (hi == mh) ? static_cast<unsigned>(key) : 0u;
+        const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+        const bool mine = (hi == mh) && (static_cast<unsigned>(key) == ml);
+        bage = static_cast<int>(__reduce_max_sync(0xffffffffu, mine ? static_cast<unsigned>(bage) : 0u));
+        bv = dunkey((static_cast<unsigned long long>(mh) << 32) | ml);
+      } else {
+        // butterfly over the group's lanes: the partner with the higher lane holds older ages,
+        // so it wins ties; the partner with the lower lane must be strictly greater
+#pragma unroll
+        for (int off = 1; off < G; off <<= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+          const int oa = __shfl_xor_sync(0xffffffffu, bage, off);
+          const bool take = (lane & off) ? (ov > bv) : (ov >= bv);
+          bv = take ? ov : bv;
+          bage = take ? oa : bage;
+        }
+      }
+      // shift between lanes; the last lane of a group forwards the group's winner instead
+      const double send = (lig == G - 1) ? bv : out;
+      inc = __shfl_up_sync(0xffffffffu, send, 1);
+      inc = (lane == 0) ? e1 : inc;  // first warp: from segment 0; other warps: patched later
+      // a fold whose maximum is -inf is decided by liveness alone: oldest live age or none
+      const int jhi = min(J, k - n), jlo = max(1, k - nJ);
+      const int dead_age = (jlo <= jhi) ? jhi : 0;
+      bage = (bv == -INFINITY) ? dead_age : bage;
+      if (bp_writer) *bp_w = static_cast<uint8_t>(bage);
+      bp_w += bp_stride;
+    };
+    auto exchange = [&](int k, double bv, double& inc) {
+      if (multi) {
+        const int par = (k & 1) * kDpWarps;
+        if (ex_writer) ex_out[par] = bv;
+        named_bar_sync(bar_id, nthr);
+        if (ex_reader) inc = ex_in[par];
+      }
+    };
+
+    const BST* pb = bs_lane + kDpNS;   // row of step 1 (chunk 0)
+    const BST* p0 = bs_seg0 + kDpNS;
     int kk = 1, chunk = 0;
-    for (int k = 1; k < K; ++k) {
+    if (K > 1) a_prime(1, static_cast<double>(*pb), *p0, out, tv, ti, e1), bd = static_cast<double>(*pb);
+
+    for (int k = 1; k + 1 < K; ++k) {
+      // block scores of step k+1 (handles the staging ring)
+      ++kk;
+      pb += kDpNS;
+      p0 += kDpNS;
       if (kk == kDpChunk) {
         kk = 0;
         ++chunk;
         cp_async_wait<0>();
         ubar();  // chunk landed for every thread of the unit; the other buffer is free
         if (chunk + 1 < nchunks) stage(chunk + 1);
+        const size_t row0 = static_cast<size_t>(chunk & 1) * kDpChunk * kDpNS;
+        pb = bs_lane + row0;
+        p0 = bs_seg0 + row0;
       }
-      const BST* bsk = bsS + (static_cast<size_t>(chunk & 1) * kDpChunk + kk) * kDpNS + c0;
-      const int par = k & 1;
-
-      // ---- segment 0 -> entry of segment 1 (uniform work, only lane 0 of warp 0 keeps the result)
-      double e1 = -INFINITY;
-      if (wl == 0) {
-        const BST b0 = bsk[0];
-        const double a = f32seg0 ? static_cast<double>(__fadd_rn(static_cast<float>(s0), static_cast<float>(b0)))
-                                 : __dadd_rn(s0, static_cast<double>(b0));
-        s0 = a;
-        // the single hypothesis of segment 0 has age k; it can advance while k <= J
-        e1 = (k <= J) ? __dadd_rn(a, rows0[k - 1]) : -INFINITY;  // rows are never -0.0: no "+ 0.0" needed
-      }
-
-      // ---- segments >= 1: age every hypothesis, build the advance candidates, fold
-      const double bd = static_cast<double>(bsk[has_seg ? n : 0]);
-      const double out = __dadd_rn(R[SL - 1], bd);  // leaves this lane
-#pragma unroll
-      for (int i = SL - 1; i >= 1; --i) R[i] = __dadd_rn(R[i - 1], bd);
-      // Candidates: old position i (age a0+i+1) now sits at R[i+1] / out.  The fold is a max by
-      // (value, age) on integer keys.  Positions 1.. do not depend on this step's entry: they are
-      // reduced by a tree (older position wins ties); the youngest candidate -- the only one on
-      // the loop-carried path -- joins last and wins only when strictly greater.
-      unsigned long long key[SL];
-      int idx[SL];
-#pragma unroll
-      for (int i = 0; i < SL; ++i) {
-        const double a = (i + 1 < SL) ? R[(i + 1 < SL) ? i + 1 : 0] : out;
-        key[i] = dkey(__dadd_rn(a, rowr[i]));
-        idx[i] = i;
-      }
-#pragma unroll
-      for (int w = 1; w < SL - 1; w <<= 1) {
-#pragma unroll
-        for (int i = 1; i + w < SL; i += 2 * w) {
-          if (key[i + w] >= key[i]) { key[i] = key[i + w]; idx[i] = idx[i + w]; }
-        }
-      }
-      unsigned long long bk = key[0];
-      int bi = 0;
-      if (SL > 1 && key[1] >= bk) { bk = key[1]; bi = idx[1]; }
-      int bage = a0 + bi + 1;
-      // butterfly over the group's lanes: the partner with the higher lane holds older ages, so
-      // it wins ties; the partner with the lower lane must be strictly greater
-#pragma unroll
-      for (int off = 1; off < G; off <<= 1) {
-        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, off);
-        const int oa = __shfl_xor_sync(0xffffffffu, bage, off);
-        const bool take = (lane & off) ? (ok > bk) : (ok >= bk);
-        if (take) { bk = ok; bage = oa; }
-      }
-      const double bv = dunkey(bk);
-      // a fold whose maximum is -inf is decided by liveness alone: oldest live age, or no entry
-      {
-        const int jhi = min(J, k - n), jlo = max(1, k - nJ);
-        if (bk == kKeyNegInf) bage = (jlo <= jhi) ? jhi : 0;
-      }
-      // shift between lanes; the last lane of a group forwards the group's winner instead
-      const double send = (lig == G - 1) ? bv : out;
-      double inc = __shfl_up_sync(0xffffffffu, send, 1);
-      if (lane == 0) inc = (wl == 0) ? e1 : -INFINITY;  // warp 0: from segment 0; others: patched below
-      if (has_seg && lig == G - 1 && n + 1 < N) {
-        if (bp_in_smem) bpS[static_cast<size_t>(k) * kDpNS + c0 + n + 1] = static_cast<uint8_t>(bage);
-        else bp_g[static_cast<int64_t>(k) * N + n + 1] = static_cast<uint8_t>(bage);
-      }
-      if (ltid == 0 && N > 1) {
-        const uint8_t j1 = (k <= J) ? static_cast<uint8_t>(k) : uint8_t(0);
-        if (bp_in_smem) bpS[static_cast<size_t>(k) * kDpNS + c0 + 1] = j1;
-        else bp_g[static_cast<int64_t>(k) * N + 1] = j1;
-      }
-      if (nw > 1) {
-        if (lane == 31 && wl + 1 < nw) Ex[par * kDpWarps + warp + 1] = bv;
-        named_bar_sync(1 + w0, nthr);
-        if (lane == 0 && wl > 0) inc = Ex[par * kDpWarps + warp];
-      }
+      const double bdn = static_cast<double>(*pb);
+      const BST b0n = *p0;
+      // C(k) and A'(k+1) in one basic block
+      double bv, inc, outn = 0.0, tvn = -INFINITY, e1n;
+      int tin = 1;
+      c_step(k, bv, inc);
+      a_prime(k + 1, bdn, b0n, outn, tvn, tin, e1n);
+      exchange(k, bv, inc);
       R[0] = inc;
-      ++kk;
+      out = outn; tv = tvn; ti = tin; e1 = e1n; bd = bdn;
+    }
+    if (K > 1) {  // last step: C(K-1) only
+      double bv, inc;
+      c_step(K - 1, bv, inc);
+      exchange(K - 1, bv, inc);
+      R[0] = inc;
     }
 
     // end symbol: fold over the last segment (viterbi.py:125-138)
@@ -369,8 +448,10 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       int k0 = K - jf;
       segb[m] = jf;
       while (m > 0) {
-        const int ln = bp_in_smem ? static_cast<int>(bpS[static_cast<size_t>(k0) * kDpNS + c0 + m])
-                                  : static_cast<int>(__ldcg(bp_g + static_cast<int64_t>(k0) * N + m));
+        int ln;  // column 1 (entries from segment 0) is a function of the step alone
+        if (m == 1) ln = (k0 <= J) ? k0 : 0;
+        else ln = bp_in_smem ? static_cast<int>(bpS[static_cast<size_t>(k0) * kDpNS + c0 + m])
+                             : static_cast<int>(__ldcg(bp_g + static_cast<int64_t>(k0) * N + m));
         segb[m - 1] = ln;
         k0 -= ln;
         --m;
@@ -386,14 +467,20 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       int k = ltid / N, m = ltid - k * N;
       const int dk = nthr / N, dn = nthr - dk * N;
       for (int i = ltid; i < total; i += nthr) {
-        bp_g[i] = (k > 0 && m > 0) ? bpS[static_cast<size_t>(k) * kDpNS + c0 + m] : uint8_t(0);
+        uint8_t val = 0;
+        if (k > 0 && m == 1) val = (k <= J) ? static_cast<uint8_t>(k) : uint8_t(0);
+        else if (k > 0 && m > 1) val = bpS[static_cast<size_t>(k) * kDpNS + c0 + m];
+        bp_g[i] = val;
         k += dk;
         m += dn;
         if (m >= N) { m -= N; ++k; }
       }
     } else {
       for (int i = ltid; i < N; i += nthr) bp_g[i] = 0;
-      for (int k = 1 + ltid; k < K; k += nthr) bp_g[static_cast<int64_t>(k) * N] = 0;
+      for (int k = 1 + ltid; k < K; k += nthr) {
+        bp_g[static_cast<int64_t>(k) * N] = 0;
+        if (N > 1) bp_g[static_cast<int64_t>(k) * N + 1] = (k <= J) ? static_cast<uint8_t>(k) : uint8_t(0);
+      }
     }
   }
 

@@ -44,6 +44,12 @@ def time_plan(T, trs, label, reps=20):
 
 rng = np.random.default_rng(0)
 mk = lambda n: rng.integers(0, 48, n)
+if len(sys.argv) > 1 and sys.argv[1] == "persm":
+    time_plan([10000] * 148, [mk(6) for _ in range(148)], "148 units T=10000 N=6", reps=2)
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "perwarp":
+    time_plan([10000] * 592, [mk(6) for _ in range(592)], "592 units T=10000 N=6", reps=2)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "single":
     time_plan([10000], [mk(6)], "1 unit T=10000 N=6 (1 warp)", reps=2)
     sys.exit(0)
