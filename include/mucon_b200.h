@@ -78,6 +78,8 @@ typedef struct mucon_viterbi_batch {
   int32_t max_K;      /* max number of blocks over units (sizes the shared back-pointer stage) */
   int32_t n_cta;      /* number of unit bins, from mucon_viterbi_pack_h */
   int32_t wpc;        /* warps per CTA (4, 8 or 16), from mucon_viterbi_pack_h */
+  int32_t lanes;      /* lanes per segment (4, 8 or 32), from mucon_viterbi_pack_h */
+  int32_t reserved_;
   const void* bs;            /* [sum K, C] block scores */
   const int64_t* vid_off;    /* [V+1] frame offsets (T_v = difference) */
   const int64_t* blk_off;    /* [V+1] block offsets into bs */
@@ -99,13 +101,16 @@ typedef struct mucon_viterbi_batch {
 } mucon_viterbi_batch;
 
 /* Host helper: packs units into bins of wpc warps (one CTA each; wpc = 4, 8 or 16, the
- * smallest that holds the largest unit).  With J = max_len/fs, a segment takes G = 32 lanes
- * when max_N <= 17, else 4 (J <= 32) or 8; a unit needs max(1, ceil((N-1)/(32/G))) consecutive
- * warps, so N <= 129 (G = 4) or 65 (G = 8).  Units are taken in order_h (or 0..U-1) -- pass them longest
- * first.  warp_unit_h needs room for U*16 entries; on return the first *n_cta_out * *wpc_out
- * are valid. */
+ * smallest that holds the largest unit).  `lanes` = lanes per transcript segment: 32 gives every
+ * segment its own warp (lowest latency per DP step; needs max_N <= 17), 0/4/8 lets 8 (J <= 32)
+ * or 4 segments share a warp (fewest instructions; N <= 129 / 65).  The choice made is returned
+ * in *lanes_out and must be passed on in mucon_viterbi_batch.  A unit needs
+ * max(1, ceil((N-1)/(32/lanes))) consecutive warps.  Units are taken in order_h (or 0..U-1) --
+ * pass them longest first.  warp_unit_h needs room for U*16 entries; on return the first
+ * *n_cta_out * *wpc_out are valid. */
 int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
-                         int max_len, int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* wpc_out);
+                         int max_len, int lanes, int32_t* warp_unit_h, int32_t* n_cta_out,
+                         int32_t* wpc_out, int32_t* lanes_out);
 
 int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 

@@ -29,7 +29,7 @@ class ViterbiBatch(C.Structure):
     _fields_ = [
         ("U", C.c_int32), ("C", C.c_int32), ("fs", C.c_int32), ("max_len", C.c_int32),
         ("bs_is_f64", C.c_int32), ("seg0_f32", C.c_int32), ("max_N", C.c_int32), ("max_K", C.c_int32),
-        ("n_cta", C.c_int32), ("wpc", C.c_int32),
+        ("n_cta", C.c_int32), ("wpc", C.c_int32), ("lanes", C.c_int32), ("reserved_", C.c_int32),
         ("bs", C.c_void_p), ("vid_off", C.c_void_p), ("blk_off", C.c_void_p), ("unit_vid", C.c_void_p),
         ("tr", C.c_void_p), ("tr_off", C.c_void_p), ("len_rows", C.c_void_p), ("len_params", C.c_void_p),
         ("logfact", C.c_void_p), ("lab_off", C.c_void_p), ("bp_off", C.c_void_p), ("warp_unit", C.c_void_p),

@@ -273,7 +273,7 @@ int launch_dp(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
 
 template <typename BST>
 int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
-  const int G = dp_group(J, b.max_N);
+  const int G = b.lanes;
   const int SL = (J + G - 1) / G;
 #define MUCON_SL_CASE(g, n) case n: return launch_dp<BST, g, n>(b, J, st);
   if (G == 32) {
@@ -334,7 +334,8 @@ extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream)
   if (b.U == 0 || b.n_cta == 0) return MUCON_OK;
   const int J = b.max_len / b.fs;
   if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;  // ages live in registers, back-pointers are uint8
-  if (b.max_N > dp_max_n(dp_group(J, b.max_N))) return MUCON_EUNSUPPORTED;
+  if (b.lanes != dp_group(J, b.max_N, b.lanes)) return MUCON_EINVAL;
+  if (b.max_N > dp_max_n(b.lanes)) return MUCON_EUNSUPPORTED;
   if (b.wpc != 4 && b.wpc != 8 && b.wpc != 16) return MUCON_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (b.bs_is_f64) return dispatch_sl<double>(b, J, st);
@@ -342,13 +343,16 @@ extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream)
 }
 
 extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
-                                    int max_len, int32_t* warp_unit_h, int32_t* n_cta_out, int32_t* wpc_out) {
-  if (!N_h || !warp_unit_h || !n_cta_out || !wpc_out || U < 0 || max_N < 1 || fs < 1 || max_len < fs)
+                                    int max_len, int lanes, int32_t* warp_unit_h, int32_t* n_cta_out,
+                                    int32_t* wpc_out, int32_t* lanes_out) {
+  if (!N_h || !warp_unit_h || !n_cta_out || !wpc_out || !lanes_out || U < 0 || max_N < 1 || fs < 1 ||
+      max_len < fs)
     return MUCON_EINVAL;
   const int J = max_len / fs;
   if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;
-  const int G = dp_group(J, max_N);
+  const int G = dp_group(J, max_N, lanes);
   if (max_N > dp_max_n(G)) return MUCON_EUNSUPPORTED;
+  *lanes_out = G;
   // small CTAs keep the grid fine-grained (the block scheduler balances the SMs); a CTA only has
   // to be as large as the largest unit
   const int wmax = warps_for(max_N, G);

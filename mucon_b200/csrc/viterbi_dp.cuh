@@ -42,9 +42,13 @@ constexpr int kDpMaxJ = 128;     // ages live in registers: 4 lanes x <= 8 or 8 
 // Units of up to 17 segments (everything Breakfast-shaped) get a whole warp per segment: the
 // lane butterfly is replaced by three REDUX instructions and a step is ~70 instructions.
 // Longer transcripts share a warp between 4 (or 8) segments.
-__host__ __device__ inline int dp_group(int J, int max_N) {
-  if (max_N <= 1 + kDpMaxWarps) return 32;
-  return J <= 32 ? 4 : 8;
+__host__ __device__ inline int dp_group(int J, int max_N, int want) {
+  const int shared = J <= 32 ? 4 : 8;  // segments sharing a warp
+  if (want == 32) return (max_N <= 1 + kDpMaxWarps) ? 32 : shared;
+  if (want == 4 || want == 8) return shared;
+  // auto: a warp per segment costs ~25% more instructions per segment-step but a third less
+  // latency per step; the host asks for it explicitly for its long units
+  return shared;
 }
 __host__ __device__ inline int dp_max_n(int G) { return 1 + kDpMaxWarps * (32 / G); }
 
@@ -146,63 +150,137 @@ __device__ __forceinline__ double length_row(const mucon_viterbi_batch& b, int t
   return __dadd_rn(r, 0.0);
 }
 
-template <typename BST, int G, int SL>
-__global__ void __launch_bounds__(kDpMaxWarps * 32, 1)
-dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ warp_unit, const int bp_rows) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  constexpr int kSegsPerWarp = 32 / G;
-  const int kDpWarps = blockDim.x >> 5, kDpNS = dp_columns(kDpWarps, G);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int32_t* wu = warp_unit + static_cast<size_t>(blockIdx.x) * kDpWarps;
-  const int u = wu[warp];
-  if (u < 0) return;  // unused warp of a partially filled bin
-  int w0 = warp, w1 = warp + 1;
-  while (w0 > 0 && wu[w0 - 1] == u) --w0;
-  while (w1 < kDpWarps && wu[w1] == u) ++w1;
-  const int nw = w1 - w0, wl = warp - w0;
-  const int ltid = wl * 32 + lane, nthr = nw * 32;
-  const int c0 = w0 * (kSegsPerWarp + 1);  // first shared-memory column of this unit
-  auto ubar = [&]() {
-    if (nw == 1) __syncwarp(); else named_bar_sync(1 + w0, nthr);
-  };
+// --------------------------------------------------------------------------------------------
+// One unit's thread team inside a CTA.
+struct DpTeam {
+  int u;          // unit index
+  int lane, wl;   // lane, warp index within the team
+  int nw;         // warps in the team
+  int ltid, nthr; // thread index within the team, team size
+  int bar_id;     // named barrier of the team (used when nw > 1)
+  int slot;       // per-unit slot in the CTA's shared arrays (rows0, fin, Ex base)
+  int c0;         // first segment column of the unit in the CTA's shared arrays
+  int NS;         // segment columns of the CTA (row stride of bsS / bpS)
+  __device__ __forceinline__ void sync() const {
+    if (nw == 1) __syncwarp(); else named_bar_sync(bar_id, nthr);
+  }
+};
 
+struct DpShared {
+  double* rows0;    // [J] length scores of segment 0, ages 1..J
+  double* Ex;       // [2][ex_stride] cross-warp entry scores by step parity, indexed by team warp
+  int ex_stride;
+  int64_t* segend;  // [N]
+  int* trl;         // [N] transcript labels
+  int* segb;        // [N] segment lengths in blocks
+  double* fin_v;
+  int* fin_j;
+  uint8_t* bpS;     // [bp_rows][NS] back-pointer stage (column c0 + n)
+  int bp_rows;
+};
+
+// ---- block-score sources --------------------------------------------------------------------
+// StagedSrc: block scores come from HBM/L2 (written by the scan kernel); the team copies the
+// columns of its transcript labels into a double-buffered shared stage, kDpChunk steps at a time.
+template <typename BST>
+struct StagedSrc {
+  BST* bsS;          // [2][kDpChunk][NS]
+  const BST* bs_g;   // video's [K][C] block scores
+  const int* trl;
+  int C, K, N, NS, c0, nchunks;
+  int kk, chunk;     // position of the row last handed out
+  __device__ __forceinline__ int col(int n, const int*) const { return n; }  // staged by segment
+  __device__ __forceinline__ void stage(const DpTeam& t, int ch) {
+    const int k0 = ch * kDpChunk;
+    const int nk = min(kDpChunk, K - k0);
+    BST* dst = bsS + static_cast<size_t>(ch & 1) * kDpChunk * NS + c0;
+    for (int i = t.ltid; i < nk * N; i += t.nthr) {
+      const int r = i / N, n = i - r * N;
+      const BST* src = bs_g + static_cast<int64_t>(k0 + r) * C + trl[n];
+      if (sizeof(BST) == 4) cp_async4(dst + r * NS + n, src); else cp_async8(dst + r * NS + n, src);
+    }
+    cp_async_commit();
+  }
+  // row 0 (returns after the first chunk has landed for the whole team)
+  __device__ __forceinline__ const BST* begin(const DpTeam& t) {
+    nchunks = (K + kDpChunk - 1) / kDpChunk;
+    stage(t, 0);
+    if (nchunks > 1) { stage(t, 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    t.sync();
+    kk = 0; chunk = 0;
+    return bsS + c0;
+  }
+  // row of the next step
+  __device__ __forceinline__ const BST* next(const DpTeam& t) {
+    if (++kk == kDpChunk) {
+      kk = 0;
+      ++chunk;
+      cp_async_wait<0>();
+      t.sync();  // chunk landed for every thread of the team; the other buffer is free
+      if (chunk + 1 < nchunks) stage(t, chunk + 1);
+    }
+    return bsS + (static_cast<size_t>(chunk & 1) * kDpChunk + kk) * NS + c0;
+  }
+  __device__ __forceinline__ void finish(const DpTeam&) {}
+};
+
+// RingSrc: block scores are produced by the scan warps of the same CTA into a shared ring of
+// slabs ([slab][bps][C], all classes); full/empty mbarriers hand slabs over.
+template <typename BST>
+struct RingSrc {
+  const BST* ring;   // [slabs][bps][C]
+  uint64_t* full;    // [slabs]
+  uint64_t* empty;   // [slabs]
+  int C, bps, slabs;
+  int r, slab;       // row within slab, current slab
+  uint32_t phase;    // parity of `full` for the current pass over the ring
+  __device__ __forceinline__ int col(int n, const int* trl) const { return trl[n]; }  // by label
+  __device__ __forceinline__ const BST* begin(const DpTeam&) {
+    r = 0; slab = 0; phase = 0;
+    mbar_wait(&full[0], 0);
+    return ring;
+  }
+  __device__ __forceinline__ const BST* next(const DpTeam& t) {
+    if (++r == bps) {
+      r = 0;
+      // every thread of the team is past its reads of the old slab (the step ends with a team
+      // barrier / warp sync), so one thread may hand it back
+      t.sync();
+      if (t.ltid == 0) mbar_arrive(&empty[slab]);
+      if (++slab == slabs) { slab = 0; phase ^= 1; }
+      mbar_wait(&full[slab], phase);
+    }
+    return ring + (static_cast<size_t>(slab) * bps + r) * C;
+  }
+  __device__ __forceinline__ void finish(const DpTeam& t) {
+    t.sync();
+    if (t.ltid == 0) mbar_arrive(&empty[slab]);
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+// The dynamic program, traceback and label writer of one unit.
+template <typename BST, int G, int SL, typename Src>
+__device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int J, const DpTeam& t,
+                                        const DpShared& sh, Src& src) {
+  constexpr int kSegsPerWarp = 32 / G;
+  const int u = t.u, lane = t.lane, wl = t.wl, nw = t.nw, ltid = t.ltid, nthr = t.nthr;
   const int v = b.unit_vid[u];
   const int64_t T = b.vid_off[v + 1] - b.vid_off[v];
   const int fs = b.fs;
   const int K = static_cast<int>(T / fs);
   const int tr0 = b.tr_off[u];
   const int N = b.tr_off[u + 1] - tr0;
-  const int C = b.C;
-
-  if (K < 1 || N < 1 || static_cast<int64_t>(K) > static_cast<int64_t>(N) * J) {
-    if (ltid == 0) {
-      b.status[u] = MUCON_UNIT_INFEASIBLE;
-      b.score[u] = __longlong_as_double(0x7ff8000000000000ll);
-      b.final_j[u] = 0;
-    }
-    for (int n = ltid; n < N; n += nthr) b.seg_blocks[tr0 + n] = 0;
-    return;
-  }
-
-  const DpLayout L = dp_layout(kDpWarps, G, J, sizeof(BST), bp_rows);
-  double* rows0 = reinterpret_cast<double*>(sm + L.rows0) + static_cast<size_t>(w0) * J;  // [J], ages 1..J
-  double* Ex = reinterpret_cast<double*>(sm + L.Ex);                                       // [2][16] by warp
-  int64_t* segend = reinterpret_cast<int64_t*>(sm + L.segend) + c0;
-  int* trl = reinterpret_cast<int*>(sm + L.trl) + c0;
-  int* segb = reinterpret_cast<int*>(sm + L.segb) + c0;
-  double* fin_v = reinterpret_cast<double*>(sm + L.fin_v) + w0;
-  int* fin_j = reinterpret_cast<int*>(sm + L.fin_j) + w0;
-  BST* bsS = reinterpret_cast<BST*>(sm + L.bsS);
-  uint8_t* bpS = sm + L.bpS;
-  const BST* bs_g = reinterpret_cast<const BST*>(b.bs) + b.blk_off[v] * C;
+  double* rows0 = sh.rows0;
+  int64_t* segend = sh.segend;
+  int* trl = sh.trl;
+  int* segb = sh.segb;
   uint8_t* bp_g = b.bp + b.bp_off[u];
-  const bool bp_in_smem = bp_rows >= K;
-
-  for (int n = ltid; n < N; n += nthr) trl[n] = b.tr[tr0 + n];
-  for (int j = ltid; j < J; j += nthr) rows0[j] = length_row(b, tr0, 0, j + 1, J);
-
+  const bool bp_in_smem = sh.bp_rows >= K;
   const int64_t rem = T - static_cast<int64_t>(K) * fs;
   int last = N - 1;
+
+  for (int j = ltid; j < J; j += nthr) rows0[j] = length_row(b, tr0, 0, j + 1, J);
 
   if (K < N) {
     // Nothing reaches the last segment: the reference returns -inf and the path with one block
@@ -215,24 +293,13 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       b.final_j[u] = 1;
     }
     for (int i = ltid; i < K * N; i += nthr) bp_g[i] = 0;  // not computed
-    ubar();
+    // drain the source so that a producer never waits for this team
+    const BST* row = src.begin(t);
+    for (int k = 1; k < K; ++k) row = src.next(t);
+    (void)row;
+    src.finish(t);
+    t.sync();
   } else {
-    ubar();  // trl visible
-    auto stage = [&](int chunk) {
-      const int k0 = chunk * kDpChunk;
-      const int nk = min(kDpChunk, K - k0);
-      BST* dst = bsS + static_cast<size_t>(chunk & 1) * kDpChunk * kDpNS + c0;
-      for (int i = ltid; i < nk * N; i += nthr) {
-        const int kk = i / N, n = i - kk * N;
-        const BST* src = bs_g + static_cast<int64_t>(k0 + kk) * C + trl[n];
-        if (sizeof(BST) == 4) cp_async4(dst + kk * kDpNS + n, src); else cp_async8(dst + kk * kDpNS + n, src);
-      }
-      cp_async_commit();
-    };
-    const int nchunks = (K + kDpChunk - 1) / kDpChunk;
-    stage(0);
-    if (nchunks > 1) stage(1);
-
     // this lane's segment (n >= 1), its ages a0+1 .. a0+SL and their length scores
     const int g = lane / G, lig = lane - g * G;
     const int n = 1 + wl * kSegsPerWarp + g;
@@ -245,42 +312,36 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       rowr[i] = has_seg ? length_row(b, tr0, n, a0 + i + 1, J) : -INFINITY;
     }
     const int nJ = (n <= 0x7fffffff / J) ? n * J : 0x7fffffff;
+    const int my_col = src.col(has_seg ? n : 0, trl);
+    const int col0 = src.col(0, trl);
 
-    if (nchunks > 1) cp_async_wait<1>(); else cp_async_wait<0>();
-    ubar();
-
-    // segment 0: scalar chain on lane 0 of the first warp; 0.0 + F[fs-1, tr_0]  (viterbi.py:81-90)
+    const BST* row = src.begin(t);  // block scores of step 0
+    // segment 0: scalar chain; 0.0 + F[fs-1, tr_0]  (viterbi.py:81-90)
     const bool f32seg0 = (sizeof(BST) == 4) && b.seg0_f32;
-    double s0 = __dadd_rn(0.0, static_cast<double>(bsS[c0]));
+    double s0 = __dadd_rn(0.0, static_cast<double>(row[col0]));
 
-    // per-lane pointers so that the step loop does no index arithmetic
-    const BST* bs_lane = bsS + c0 + (has_seg ? n : 0);  // this lane's label column in the stage
-    const BST* bs_seg0 = bsS + c0;
     const bool bp_writer = has_seg && lig == G - 1 && n + 1 < N;
-    uint8_t* bp_w;       // where this lane records the winner of its group at step k
+    uint8_t* bp_w;  // where this lane records the winner of its group at step k
     int bp_stride;
-    if (bp_in_smem) { bp_w = bpS + c0 + n + 1; bp_stride = kDpNS; }
+    if (bp_in_smem) { bp_w = sh.bpS + t.c0 + n + 1; bp_stride = t.NS; }
     else { bp_w = bp_g + n + 1; bp_stride = N; }
-    bp_w += bp_stride;   // step 1
-    double* ex_out = Ex + warp + 1;
-    const double* ex_in = Ex + warp;
+    bp_w += bp_stride;  // step 1
+    double* ex_out = sh.Ex + wl + 1;
+    const double* ex_in = sh.Ex + wl;
     const bool ex_writer = lane == 31 && wl + 1 < nw;
     const bool ex_reader = lane == 0 && wl > 0;
     const bool multi = nw > 1;
-    const int bar_id = 1 + w0;
 
     // The step is software-pipelined.  Only the youngest hypothesis of a segment depends on the
     // previous step's fold (it IS that fold's winner); everything else is a pure shift-and-add.
     //   A'(k): out_k, R[i>=2], candidates and tree fold of positions >= 1  -- no dependence on
     //          the entry produced by step k-1
-    //   C(k):  R[1] = R[0] + b_k, youngest candidate, lane butterfly, hand-over to the next
-    //          segment / warp                                   -- the loop-carried chain
+    //   C(k):  R[1] = R[0] + b_k, youngest candidate, lane butterfly / REDUX, hand-over to the
+    //          next segment / warp                              -- the loop-carried chain
     // The loop body is C(k); A'(k+1), so the shuffle latencies of C(k) are filled with the
     // independent arithmetic of A'(k+1).
     double out = 0.0, tv = -INFINITY, e1 = -INFINITY, bd = 0.0;
     int ti = 1;
-    // A'(k) for block scores bdn (this lane's label) / b0n (segment 0's label) of step k.
-    // Reads R[1..], writes R[2..] and the pipeline registers (outn, tvn, tin, e1n, s0).
     auto a_prime = [&](int k, double bdn, BST b0n, double& outn, double& tvn, int& tin, double& e1n) {
       if (SL > 1) {
         outn = __dadd_rn(R[SL - 1], bdn);
@@ -306,8 +367,8 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
         tvn = cv[(SL > 1) ? 1 : 0];
         tin = idx[(SL > 1) ? 1 : 0];
       }
-      // segment 0 -> entry of segment 1.  Every warp runs the chain (it is four instructions and
-      // branch-free); only lane 0 of the unit's first warp uses the result.
+      // segment 0 -> entry of segment 1.  Every warp runs the chain (four branch-free
+      // instructions); only lane 0 of the team's first warp uses the result.
       double a;
       if (f32seg0) a = static_cast<double>(__fadd_rn(static_cast<float>(s0), static_cast<float>(b0n)));
       else a = __dadd_rn(s0, static_cast<double>(b0n));
@@ -316,7 +377,6 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       // rows are never -0.0, so the reference's trailing "+ 0.0" is the identity here.
       e1n = (k <= J) ? __dadd_rn(a, rows0[min(k, J) - 1]) : -INFINITY;
     };
-    // C(k) up to the hand-over value `inc` (before the cross-warp exchange)
     auto c_step = [&](int k, double& bv, double& inc) {
       int bi;
       if (SL > 1) {
@@ -367,35 +427,22 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
     };
     auto exchange = [&](int k, double bv, double& inc) {
       if (multi) {
-        const int par = (k & 1) * kDpWarps;
+        const int par = (k & 1) * sh.ex_stride;
         if (ex_writer) ex_out[par] = bv;
-        named_bar_sync(bar_id, nthr);
+        named_bar_sync(t.bar_id, nthr);
         if (ex_reader) inc = ex_in[par];
       }
     };
 
-    const BST* pb = bs_lane + kDpNS;   // row of step 1 (chunk 0)
-    const BST* p0 = bs_seg0 + kDpNS;
-    int kk = 1, chunk = 0;
-    if (K > 1) a_prime(1, static_cast<double>(*pb), *p0, out, tv, ti, e1), bd = static_cast<double>(*pb);
-
+    if (K > 1) {
+      row = src.next(t);
+      bd = static_cast<double>(row[my_col]);
+      a_prime(1, bd, row[col0], out, tv, ti, e1);
+    }
     for (int k = 1; k + 1 < K; ++k) {
-      // block scores of step k+1 (handles the staging ring)
-      ++kk;
-      pb += kDpNS;
-      p0 += kDpNS;
-      if (kk == kDpChunk) {
-        kk = 0;
-        ++chunk;
-        cp_async_wait<0>();
-        ubar();  // chunk landed for every thread of the unit; the other buffer is free
-        if (chunk + 1 < nchunks) stage(chunk + 1);
-        const size_t row0 = static_cast<size_t>(chunk & 1) * kDpChunk * kDpNS;
-        pb = bs_lane + row0;
-        p0 = bs_seg0 + row0;
-      }
-      const double bdn = static_cast<double>(*pb);
-      const BST b0n = *p0;
+      row = src.next(t);  // block scores of step k+1
+      const double bdn = static_cast<double>(row[my_col]);
+      const BST b0n = row[col0];
       // C(k) and A'(k+1) in one basic block
       double bv, inc, outn = 0.0, tvn = -INFINITY, e1n;
       int tin = 1;
@@ -411,12 +458,13 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       exchange(K - 1, bv, inc);
       R[0] = inc;
     }
+    src.finish(t);
 
     // end symbol: fold over the last segment (viterbi.py:125-138)
     if (N == 1) {
       if (ltid == 0) {
-        *fin_v = __dadd_rn(__dadd_rn(s0, rows0[K - 1]), 0.0);  // K <= J is guaranteed by feasibility
-        *fin_j = K;
+        *sh.fin_v = __dadd_rn(__dadd_rn(s0, rows0[K - 1]), 0.0);  // K <= J is guaranteed by feasibility
+        *sh.fin_j = K;
       }
     } else if (n == N - 1) {
       double bv = -INFINITY;
@@ -427,10 +475,11 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
         if (i == 0 || c >= bv) { bv = c; bi = i; }
       }
       int bage = a0 + bi + 1;
+      const unsigned gmask = 0xffffffffu >> (32 - G) << (g * G);
 #pragma unroll
       for (int off = 1; off < G; off <<= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu >> (32 - G) << (g * G), bv, off);
-        const int oa = __shfl_xor_sync(0xffffffffu >> (32 - G) << (g * G), bage, off);
+        const double ov = __shfl_xor_sync(gmask, bv, off);
+        const int oa = __shfl_xor_sync(gmask, bage, off);
         const bool take = (lane & off) ? (ov > bv) : (ov >= bv);
         if (take) { bv = ov; bage = oa; }
       }
@@ -438,19 +487,19 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       // after the last step (k = K-1) the live ages of segment n are [max(1, K-n*J), min(J, K-n)]
       const int jhi = min(J, K - n), jlo = max(1, K - nJ);
       if (bv == -INFINITY) bage = (jlo <= jhi) ? jhi : 0;
-      if (lig == 0) { *fin_v = bv; *fin_j = bage; }
+      if (lig == 0) { *sh.fin_v = bv; *sh.fin_j = bage; }
     }
-    ubar();
+    t.sync();
     if (ltid == 0) {  // traceback over the back-pointer table (viterbi.py:140-153)
-      const double sc = *fin_v;
-      const int jf = *fin_j;
+      const double sc = *sh.fin_v;
+      const int jf = *sh.fin_j;
       int m = N - 1;
       int k0 = K - jf;
       segb[m] = jf;
       while (m > 0) {
         int ln;  // column 1 (entries from segment 0) is a function of the step alone
         if (m == 1) ln = (k0 <= J) ? k0 : 0;
-        else ln = bp_in_smem ? static_cast<int>(bpS[static_cast<size_t>(k0) * kDpNS + c0 + m])
+        else ln = bp_in_smem ? static_cast<int>(sh.bpS[static_cast<size_t>(k0) * t.NS + t.c0 + m])
                              : static_cast<int>(__ldcg(bp_g + static_cast<int64_t>(k0) * N + m));
         segb[m - 1] = ln;
         k0 -= ln;
@@ -460,7 +509,7 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       b.final_j[u] = jf;
       b.status[u] = (isfinite(sc) || sc == -INFINITY) ? MUCON_UNIT_OK : MUCON_UNIT_NONFINITE;
     }
-    ubar();
+    t.sync();
     // back-pointer table -> HBM, [K, N] row-major; row 0 and column 0 hold no entries
     if (bp_in_smem) {
       const int total = K * N;
@@ -469,7 +518,7 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       for (int i = ltid; i < total; i += nthr) {
         uint8_t val = 0;
         if (k > 0 && m == 1) val = (k <= J) ? static_cast<uint8_t>(k) : uint8_t(0);
-        else if (k > 0 && m > 1) val = bpS[static_cast<size_t>(k) * kDpNS + c0 + m];
+        else if (k > 0 && m > 1) val = sh.bpS[static_cast<size_t>(k) * t.NS + t.c0 + m];
         bp_g[i] = val;
         k += dk;
         m += dn;
@@ -491,9 +540,77 @@ dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ 
       int64_t pos = rem;
       for (int m = 0; m < N; ++m) { pos += static_cast<int64_t>(fs) * segb[m]; segend[m] = pos; }
     }
-    ubar();
+    t.sync();
     write_labels(b.labels + lo, T, rem, trl, segend, last, ltid, nthr);
   }
+}
+
+// Unit-level feasibility (uniform over the team).  Returns false after writing the status.
+__device__ __forceinline__ bool dp_feasible(const mucon_viterbi_batch& b, int J, const DpTeam& t) {
+  const int u = t.u;
+  const int v = b.unit_vid[u];
+  const int64_t T = b.vid_off[v + 1] - b.vid_off[v];
+  const int64_t K = T / b.fs;
+  const int tr0 = b.tr_off[u];
+  const int N = b.tr_off[u + 1] - tr0;
+  if (K >= 1 && N >= 1 && K <= static_cast<int64_t>(N) * J) return true;
+  if (t.ltid == 0) {
+    b.status[u] = MUCON_UNIT_INFEASIBLE;
+    b.score[u] = __longlong_as_double(0x7ff8000000000000ll);
+    b.final_j[u] = 0;
+  }
+  for (int n = t.ltid; n < N; n += t.nthr) b.seg_blocks[tr0 + n] = 0;
+  return false;
+}
+
+// --------------------------------------------------------------------------------------------
+// Kernel 1: DP over block scores already in HBM (any number of candidates per video).
+template <typename BST, int G, int SL>
+__global__ void __launch_bounds__(kDpMaxWarps * 32, 1)
+dp_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ warp_unit, const int bp_rows) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  constexpr int kSegsPerWarp = 32 / G;
+  const int wpc = blockDim.x >> 5, NS = dp_columns(wpc, G);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t* wu = warp_unit + static_cast<size_t>(blockIdx.x) * wpc;
+  const int u = wu[warp];
+  if (u < 0) return;  // unused warp of a partially filled bin
+  int w0 = warp, w1 = warp + 1;
+  while (w0 > 0 && wu[w0 - 1] == u) --w0;
+  while (w1 < wpc && wu[w1] == u) ++w1;
+  DpTeam t;
+  t.u = u; t.lane = lane; t.wl = warp - w0; t.nw = w1 - w0;
+  t.ltid = t.wl * 32 + lane; t.nthr = t.nw * 32;
+  t.bar_id = 1 + w0; t.slot = w0; t.c0 = w0 * (kSegsPerWarp + 1); t.NS = NS;
+  if (!dp_feasible(b, J, t)) return;
+
+  const DpLayout L = dp_layout(wpc, G, J, sizeof(BST), bp_rows);
+  DpShared sh;
+  sh.rows0 = reinterpret_cast<double*>(sm + L.rows0) + static_cast<size_t>(w0) * J;
+  sh.Ex = reinterpret_cast<double*>(sm + L.Ex) + w0;
+  sh.ex_stride = wpc;
+  sh.segend = reinterpret_cast<int64_t*>(sm + L.segend) + t.c0;
+  sh.trl = reinterpret_cast<int*>(sm + L.trl) + t.c0;
+  sh.segb = reinterpret_cast<int*>(sm + L.segb) + t.c0;
+  sh.fin_v = reinterpret_cast<double*>(sm + L.fin_v) + w0;
+  sh.fin_j = reinterpret_cast<int*>(sm + L.fin_j) + w0;
+  sh.bpS = sm + L.bpS;
+  sh.bp_rows = bp_rows;
+
+  const int v = b.unit_vid[u];
+  const int tr0 = b.tr_off[u];
+  const int N = b.tr_off[u + 1] - tr0;
+  for (int n = t.ltid; n < N; n += t.nthr) sh.trl[n] = b.tr[tr0 + n];
+  t.sync();  // trl visible
+
+  StagedSrc<BST> src;
+  src.bsS = reinterpret_cast<BST*>(sm + L.bsS);
+  src.bs_g = reinterpret_cast<const BST*>(b.bs) + b.blk_off[v] * b.C;
+  src.trl = sh.trl;
+  src.C = b.C;
+  src.K = static_cast<int>((b.vid_off[v + 1] - b.vid_off[v]) / b.fs);
+  src.N = N; src.NS = NS; src.c0 = t.c0;
+  dp_unit<BST, G, SL>(b, J, t, sh, src);
 }
 
 }  // namespace mucon

@@ -78,7 +78,7 @@ class AlignPlan:
     """
 
     def __init__(self, T, candidates, n_classes, fs=30, max_len=2000, len_params=None, len_rows=None,
-                 device=None, want_bp=True, labels="best"):
+                 device=None, want_bp=True, labels="best", groups=None, long_K=150):
         self.device = torch.device(device if device is not None else "cuda")
         self.fs, self.max_len, self.C = int(fs), int(max_len), int(n_classes)
         self.J = self.max_len // self.fs
@@ -124,22 +124,48 @@ class AlignPlan:
         self.total_frames = int(T.sum())
         self.total_blocks = int(K.sum())
         self.aligned_frames = int(uT.sum())  # the benchmark's unit of work: T x candidates
-        # launch order: longest first so the tail of the grid is made of short units
+        # Launch plan.  Videos are sorted longest first and cut into groups; group g's DP runs on
+        # a second stream while group g+1 is still being scanned (the scan is HBM-bound, the DP is
+        # issue-bound, so they overlap well).  Group 0 holds the longest videos: their DP is a long
+        # serial chain, so it starts first and gives every transcript segment its own warp.
         self.order_v = np.argsort(-T, kind="stable").astype(np.int32)
-        self.order_u = np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32)
         self.max_K = int(uK.max()) if U else 0
-        # bins of 16 warps: which unit every warp of every CTA works on
+        if groups is None:
+            groups = 1  # measured: cutting the scan into groups serialises its long videos
+        cumT = np.cumsum(T[self.order_v]) / max(1, T.sum())
+        cuts = [0.12, 0.40, 0.72, 1.0] if groups == 4 else list(np.linspace(0, 1, groups + 1)[1:])
+        bounds = [0] + [int(np.searchsorted(cumT, c, side="left")) + 1 for c in cuts[:-1]] + [V]
+        bounds = sorted(set(min(max(x, 0), V) for x in bounds))
         lib = _lib.lib()
-        wu = np.full(max(U, 1) * 16, -1, dtype=np.int32)
-        n_cta, segs = C.c_int32(0), C.c_int32(0)
         n32 = np.ascontiguousarray(nlen, dtype=np.int32)
-        _lib.check(lib.mucon_viterbi_pack_h(
-            n32.ctypes.data_as(C.c_void_p), self.order_u.ctypes.data_as(C.c_void_p), C.c_int(U),
-            C.c_int(self.max_N), C.c_int(self.fs), C.c_int(self.max_len), wu.ctypes.data_as(C.c_void_p),
-            C.byref(n_cta), C.byref(segs)),
-            "mucon_viterbi_pack_h")
-        self.n_cta, self.wpc = int(n_cta.value), int(segs.value)
-        self.warp_unit = wu[:max(self.n_cta, 1) * self.wpc]
+        group_of_video = np.zeros(V, dtype=np.int64)
+        for gi in range(len(bounds) - 1):
+            group_of_video[self.order_v[bounds[gi]:bounds[gi + 1]]] = gi
+        unit_group = group_of_video[self.unit_vid]
+        self.groups = []
+        wu_all = []
+        for gi in range(len(bounds) - 1):
+            v0, v1 = bounds[gi], bounds[gi + 1]
+            units = np.nonzero(unit_group == gi)[0]
+            if v1 <= v0:
+                continue
+            order_u = units[np.argsort(-(uK[units] * 1024 + nlen[units]), kind="stable")].astype(np.int32)
+            gmaxN = int(nlen[units].max()) if units.size else 1
+            gmaxK = int(uK[units].max()) if units.size else 0
+            want = 32 if (gi == 0 and len(bounds) > 2 and gmaxK >= long_K) else 0
+            wu = np.full(max(units.size, 1) * 16, -1, dtype=np.int32)
+            n_cta, wpc, lanes = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+            _lib.check(lib.mucon_viterbi_pack_h(
+                n32.ctypes.data_as(C.c_void_p), order_u.ctypes.data_as(C.c_void_p), C.c_int(int(units.size)),
+                C.c_int(gmaxN), C.c_int(self.fs), C.c_int(self.max_len), C.c_int(want),
+                wu.ctypes.data_as(C.c_void_p), C.byref(n_cta), C.byref(wpc), C.byref(lanes)),
+                "mucon_viterbi_pack_h")
+            self.groups.append(dict(v0=v0, v1=v1, n_cta=int(n_cta.value), wpc=int(wpc.value), lanes=int(lanes.value),
+                                    max_N=gmaxN, max_K=gmaxK, wu_off=sum(len(x) for x in wu_all)))
+            wu_all.append(wu[:int(n_cta.value) * int(wpc.value)])
+        self.warp_unit = np.concatenate(wu_all) if wu_all else np.full(16, -1, np.int32)
+        self.n_cta = sum(g["n_cta"] for g in self.groups)
+        self.wpc = self.groups[0]["wpc"] if self.groups else 4
 
         blob = _Blob()
         blob.add("vid_off", self.vid_off)
@@ -190,6 +216,19 @@ class ViterbiEngine:
         self.device = torch.device(device if device is not None else "cuda")
         self.lib = _lib.lib()
         self.launches = 0  # kernels launched so far (bench.py reports this)
+        self._side = None
+        self._events = {}
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
+    def _event(self, i):
+        ev = self._events.get(i)
+        if ev is None:
+            ev = self._events[i] = torch.cuda.Event()
+        return ev
 
     def run(self, plan, logp, seg0_f32=None, stream=None, mid_event=None):
         """logp: CUDA tensor [sum T, C] float32 or float64, videos concatenated.  Asynchronous."""
@@ -210,16 +249,9 @@ class ViterbiEngine:
         if plan.V == 0:
             return plan
         lib = self.lib
-        _lib.check(lib.mucon_viterbi_blockscores(
-            _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["vid_off"]), C.c_void_p(p["blk_off"]),
-            C.c_void_p(p["order_v"]), C.c_int(plan.V), C.c_int(plan.C), C.c_int(plan.fs),
-            _lib.ptr(plan.bs), sp), "mucon_viterbi_blockscores")
-        if mid_event is not None:  # lets bench.py time the scan and the DP kernel separately
-            mid_event.record(st)
         b = _lib.ViterbiBatch()
         b.U, b.C, b.fs, b.max_len = plan.U, plan.C, plan.fs, plan.max_len
-        b.bs_is_f64, b.seg0_f32, b.max_N, b.max_K = int(is64), int(bool(seg0_f32)), plan.max_N, plan.max_K
-        b.n_cta, b.wpc = plan.n_cta, plan.wpc
+        b.bs_is_f64, b.seg0_f32 = int(is64), int(bool(seg0_f32))
         b.bs = plan.bs.data_ptr()
         b.vid_off, b.blk_off, b.unit_vid = p["vid_off"], p["blk_off"], p["unit_vid"]
         b.tr, b.tr_off = p["tr"], p["tr_off"]
@@ -227,12 +259,35 @@ class ViterbiEngine:
             b.len_rows, b.len_params, b.logfact = p["len_rows"], None, None
         else:
             b.len_rows, b.len_params, b.logfact = None, p["len_params"], p["logfact"]
-        b.lab_off, b.bp_off, b.warp_unit = p["lab_off"], p["bp_off"], p["warp_unit"]
+        b.lab_off, b.bp_off = p["lab_off"], p["bp_off"]
         b.score, b.labels = plan.score.data_ptr(), plan.labels.data_ptr()
         b.seg_blocks, b.bp = plan.seg_blocks.data_ptr(), plan.bp.data_ptr()
         b.final_j, b.status = plan.final_j.data_ptr(), plan.status.data_ptr()
-        _lib.check(lib.mucon_viterbi_decode(C.byref(b), sp), "mucon_viterbi_decode")
-        self.launches += 2
+        overlap = len(plan.groups) > 1
+        if overlap:
+            side = self._side_stream()
+            ssp = C.c_void_p(side.cuda_stream)
+        for gi, g in enumerate(plan.groups):
+            _lib.check(lib.mucon_viterbi_blockscores(
+                _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["vid_off"]), C.c_void_p(p["blk_off"]),
+                C.c_void_p(p["order_v"] + 4 * g["v0"]), C.c_int(g["v1"] - g["v0"]), C.c_int(plan.C), C.c_int(plan.fs),
+                _lib.ptr(plan.bs), sp), "mucon_viterbi_blockscores")
+            if mid_event is not None and gi == len(plan.groups) - 1:
+                mid_event.record(st)  # end of the last scan: lets bench.py split scan and DP tail
+            b.max_N, b.max_K, b.n_cta, b.wpc, b.lanes = g["max_N"], g["max_K"], g["n_cta"], g["wpc"], g["lanes"]
+            b.warp_unit = p["warp_unit"] + 4 * g["wu_off"]
+            if overlap:
+                ev = self._event(gi)
+                ev.record(st)
+                side.wait_event(ev)
+                _lib.check(lib.mucon_viterbi_decode(C.byref(b), ssp), "mucon_viterbi_decode")
+            else:
+                _lib.check(lib.mucon_viterbi_decode(C.byref(b), sp), "mucon_viterbi_decode")
+            self.launches += 2
+        if overlap:
+            done = self._event(len(plan.groups))
+            done.record(side)
+            st.wait_event(done)
         if plan.labels_mode == "best" and not plan.single:
             _lib.check(lib.mucon_viterbi_select(
                 _lib.ptr(plan.score), _lib.ptr(plan.status), C.c_void_p(p["cand_off"]), C.c_int(plan.V),

@@ -37,8 +37,8 @@ def test_loader_symbol_list_matches_header(built_lib):
 
 def test_struct_layout_matches_header():
     from mucon_b200 import _lib
-    # 10 int32 + 18 pointers
-    assert ctypes.sizeof(_lib.ViterbiBatch) == 10 * 4 + 18 * 8
+    # 12 int32 + 18 pointers
+    assert ctypes.sizeof(_lib.ViterbiBatch) == 12 * 4 + 18 * 8
 
 
 def test_argument_validation_without_gpu(built_lib):
