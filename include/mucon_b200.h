@@ -114,6 +114,18 @@ int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int 
 
 int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 
+/* One-launch alignment: block-score scan and DP of a unit fused in one CTA (scan warps feed the
+ * DP warps through shared memory; block scores do not travel through HBM).  Same inputs and
+ * outputs as mucon_viterbi_blockscores + mucon_viterbi_decode; warp_unit / n_cta / wpc / lanes of
+ * the batch are ignored.  Meant for one transcript per video (a unit re-scans its video).
+ * logp: [sum T, C] log-probabilities, 16-byte aligned, dtype given by in_is_f64 (must match
+ * batch.bs_is_f64).  order: optional [U] launch order (longest first).  write_bs != 0 also stores
+ * the block scores to batch.bs.  Returns MUCON_EUNSUPPORTED when the shape does not fit
+ * (C*sizeof(dtype) % 16 != 0, C > 128, more than 6 DP warps per unit, ...): call the two-step
+ * path instead. */
+int mucon_viterbi_align_fused(const mucon_viterbi_batch* batch_h, const void* logp, int in_is_f64,
+                              const int32_t* order, int write_bs, void* stream);
+
 /* Arg-max over the candidates of each video: best[v] = unit index with the highest score among
  * units cand_off[v] .. cand_off[v+1] (lowest index wins ties; units with status INFEASIBLE are
  * skipped; -1 if none). */

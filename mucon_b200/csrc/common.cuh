@@ -74,6 +74,14 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// -0 is the exact additive identity of IEEE addition (x + -0 == x for every x, including -0)
+template <typename T>
+__device__ __forceinline__ T neg_zero();
+template <>
+__device__ __forceinline__ float neg_zero<float>() { return -0.0f; }
+template <>
+__device__ __forceinline__ double neg_zero<double>() { return -0.0; }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "viterbi_dp.cuh"
+#include "viterbi_fused.cuh"
 
 namespace mucon {
 namespace {
@@ -31,13 +32,6 @@ __host__ __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return
 // ============================================================================================
 // Block-score scan
 // ============================================================================================
-
-template <typename T>
-__device__ __forceinline__ T neg_zero();
-template <>
-__device__ __forceinline__ float neg_zero<float>() { return -0.0f; }
-template <>
-__device__ __forceinline__ double neg_zero<double>() { return -0.0; }
 
 // TMA-staged variant.  Requires C*sizeof(T) % 16 == 0 and logp 16-byte aligned.
 // smem: [stages] mbarriers, then stages x slab (slab = bps blocks of fs rows of C values).
@@ -298,6 +292,59 @@ int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
 #undef MUCON_SL_CASE
 }
 
+template <typename BST, int G, int SL>
+int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int32_t* order, int write_bs,
+                 cudaStream_t st) {
+  FusedCfg cfg;
+  cfg.scan_threads = b.C <= 32 ? 32 : (b.C <= 64 ? 64 : 128);
+  const int spw = 32 / G;
+  cfg.dp_warps = (b.max_N - 1 + spw - 1) / spw;
+  if (cfg.dp_warps < 1) cfg.dp_warps = 1;
+  if (cfg.scan_threads + 32 * cfg.dp_warps > kFusedMaxThreads) return MUCON_EUNSUPPORTED;
+  const size_t blk_bytes = (size_t)b.C * sizeof(BST) * b.fs;
+  cfg.bps = (int)(env_int("MUCON_FUSED_SLAB_BYTES", 17280) / blk_bytes);
+  if (cfg.bps < 1) cfg.bps = 1;
+  cfg.stages = env_int("MUCON_FUSED_STAGES", 3);
+  cfg.ring_slabs = env_int("MUCON_FUSED_RING", 4);
+  if (cfg.stages < 2 || cfg.stages > 8 || cfg.ring_slabs < 2 || cfg.ring_slabs > 8) return MUCON_EINVAL;
+  cfg.write_bs = write_bs && b.bs;
+  cfg.bp_rows = b.max_K;
+  size_t smem = fused_smem_bytes(cfg, G, J, b.C, b.fs, sizeof(BST));
+  if (smem > 100 * 1024) {  // a long back-pointer table would cost residency: trace from HBM instead
+    cfg.bp_rows = 0;
+    smem = fused_smem_bytes(cfg, G, J, b.C, b.fs, sizeof(BST));
+  }
+  if (smem > 227 * 1024) return MUCON_EUNSUPPORTED;
+  auto kern = (b.fs == 30) ? align_fused_kernel<BST, G, SL, 30> : align_fused_kernel<BST, G, SL, 0>;
+  if (smem > 48 * 1024)
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<b.U, cfg.scan_threads + 32 * cfg.dp_warps, smem, st>>>(b, J, logp, order, cfg);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+template <typename BST>
+int dispatch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int32_t* order, int write_bs,
+                   cudaStream_t st) {
+  const int G = J <= 32 ? 4 : 8;
+  const int SL = (J + G - 1) / G;
+#define MUCON_SL_CASE(g, n) case n: return launch_fused<BST, g, n>(b, J, logp, order, write_bs, st);
+  if (G == 4) {
+    switch (SL) {
+      MUCON_SL_CASE(4, 1) MUCON_SL_CASE(4, 2) MUCON_SL_CASE(4, 3) MUCON_SL_CASE(4, 4)
+      MUCON_SL_CASE(4, 5) MUCON_SL_CASE(4, 6) MUCON_SL_CASE(4, 7) MUCON_SL_CASE(4, 8)
+      default: return MUCON_EUNSUPPORTED;
+    }
+  }
+  switch (SL) {
+    MUCON_SL_CASE(8, 5) MUCON_SL_CASE(8, 6) MUCON_SL_CASE(8, 7) MUCON_SL_CASE(8, 8)
+    MUCON_SL_CASE(8, 9) MUCON_SL_CASE(8, 10) MUCON_SL_CASE(8, 11) MUCON_SL_CASE(8, 12)
+    MUCON_SL_CASE(8, 13) MUCON_SL_CASE(8, 14) MUCON_SL_CASE(8, 15) MUCON_SL_CASE(8, 16)
+    default: return MUCON_EUNSUPPORTED;
+  }
+#undef MUCON_SL_CASE
+}
+
 int warps_for(int N, int G) {
   const int spw = 32 / G;
   const int w = (N - 1 + spw - 1) / spw;
@@ -340,6 +387,26 @@ extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (b.bs_is_f64) return dispatch_sl<double>(b, J, st);
   return dispatch_sl<float>(b, J, st);
+}
+
+extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
+                                         const int32_t* order, int write_bs, void* stream) {
+  if (!bh || !logp) return MUCON_EINVAL;
+  const mucon_viterbi_batch& b = *bh;
+  if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1 || b.max_K < 0) return MUCON_EINVAL;
+  if (!b.vid_off || !b.blk_off || !b.unit_vid || !b.tr || !b.tr_off || !b.score || !b.seg_blocks || !b.final_j ||
+      !b.status || !b.bp || !b.bp_off)
+    return MUCON_EINVAL;
+  if (!b.len_rows && !(b.len_params && b.logfact)) return MUCON_EINVAL;
+  if ((in_is_f64 != 0) != (b.bs_is_f64 != 0)) return MUCON_EINVAL;
+  if (b.U == 0) return MUCON_OK;
+  const int J = b.max_len / b.fs;
+  if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;
+  const size_t row_bytes = (size_t)b.C * (in_is_f64 ? 8 : 4);
+  if (row_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(logp) & 15) != 0 || b.C > 128) return MUCON_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_is_f64) return dispatch_fused<double>(b, J, static_cast<const double*>(logp), order, write_bs, st);
+  return dispatch_fused<float>(b, J, static_cast<const float*>(logp), order, write_bs, st);
 }
 
 extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,

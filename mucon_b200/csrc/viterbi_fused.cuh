@@ -1,0 +1,175 @@
+// viterbi_fused.cuh -- block-score scan and dynamic program of one video in ONE CTA (sm_100a).
+//
+// For batches with a single transcript per video (the evaluator's case, reference
+// src/mucon/evaluators.py:147-180) the scan and the DP are warp-specialised roles of the same
+// CTA: the scan warps stream the video's log-probabilities through a TMA ring (UBLKCP +
+// mbarrier), keep the sequential per-class running sum (np.cumsum, viterbi.py:51) and publish
+// the block scores (viterbi.py:68-72) of every class into a small shared ring; the DP warps
+// (dp_unit, viterbi_dp.cuh) consume that ring step by step.  Block scores never travel through
+// HBM, the two roles overlap (the scan is HBM-latency-bound, the DP is issue-bound), and the
+// whole alignment of a batch is a single launch.
+#pragma once
+#include "viterbi_dp.cuh"
+
+namespace mucon {
+
+struct FusedCfg {
+  int scan_threads;  // 32 / 64 / 128, >= C
+  int dp_warps;      // DP warps per CTA (>= warps of the largest unit)
+  int bps;           // blocks per slab (TMA slab == ring slab)
+  int stages;        // TMA ring depth
+  int ring_slabs;    // block-score ring depth
+  int bp_rows;       // rows of the shared back-pointer stage (0: trace from HBM)
+  int write_bs;      // also store the block scores to b.bs
+};
+
+constexpr int kFusedMaxThreads = 256;
+constexpr int kFusedBarBytes = 256;  // mbarriers: tma_full[<=8], ring_full[<=8], ring_empty[<=8]
+
+__host__ __device__ inline size_t fused_smem_bytes(const FusedCfg& c, int G, int J, int C, int fs, int elem) {
+  size_t o = kFusedBarBytes;
+  o += (size_t)c.stages * c.bps * fs * C * elem;
+  o += (size_t)c.ring_slabs * c.bps * C * elem;
+  o = (o + 15) & ~size_t(15);
+  o += dp_layout(c.dp_warps, G, J, 0, c.bp_rows).total;
+  return o;
+}
+
+template <typename BST, int G, int SL, int FS>
+__global__ void __launch_bounds__(kFusedMaxThreads, 1)
+align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restrict__ logp,
+                   const int32_t* __restrict__ order, const FusedCfg cfg) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int fs = FS ? FS : b.fs;
+  const int C = b.C;
+  const int u = order ? order[blockIdx.x] : blockIdx.x;
+  const int v = b.unit_vid[u];
+  const int64_t r0 = b.vid_off[v];
+  const int64_t T = b.vid_off[v + 1] - r0;
+  const int K = static_cast<int>(T / fs);
+  const int tr0 = b.tr_off[u];
+  const int N = b.tr_off[u + 1] - tr0;
+  const bool feasible = K >= 1 && N >= 1 && static_cast<int64_t>(K) <= static_cast<int64_t>(N) * J;
+
+  uint64_t* tma_full = reinterpret_cast<uint64_t*>(sm);
+  uint64_t* ring_full = tma_full + 8;
+  uint64_t* ring_empty = tma_full + 16;
+  BST* slabs = reinterpret_cast<BST*>(sm + kFusedBarBytes);
+  const uint32_t slab_elems = static_cast<uint32_t>(cfg.bps) * fs * C;
+  BST* ring = slabs + static_cast<size_t>(cfg.stages) * slab_elems;
+  size_t dp_off = kFusedBarBytes + (static_cast<size_t>(cfg.stages) * slab_elems +
+                                    static_cast<size_t>(cfg.ring_slabs) * cfg.bps * C) * sizeof(BST);
+  dp_off = (dp_off + 15) & ~size_t(15);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < cfg.stages; ++s) mbar_init(&tma_full[s], 1);
+    for (int s = 0; s < cfg.ring_slabs; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (static_cast<int>(threadIdx.x) < cfg.scan_threads) {
+    // ===================================== scan role =====================================
+    if (K < 1) return;
+    const int bps = cfg.bps, stages = cfg.stages;
+    const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(BST);
+    const int nslabs = (K + bps - 1) / bps;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(logp) + r0 * row_bytes;
+    auto issue = [&](int slab, int st) {
+      const int b0 = slab * bps;
+      const int nb = min(bps, K - b0);
+      const uint32_t bytes = static_cast<uint32_t>(nb) * fs * row_bytes;
+      mbar_arrive_expect_tx(&tma_full[st], bytes);
+      bulk_g2s(slabs + static_cast<size_t>(st) * slab_elems, src + static_cast<int64_t>(b0) * fs * row_bytes, bytes,
+               &tma_full[st]);
+    };
+    if (threadIdx.x == 0) {
+      const int pre = min(stages, nslabs);
+      for (int s = 0; s < pre; ++s) issue(s, s);
+    }
+    const int c = threadIdx.x;
+    const bool active = c < C;
+    BST run = neg_zero<BST>();  // -0 is the exact additive identity (F[0] = logp[0])
+    BST prev = 0;
+    BST* out_g = (cfg.write_bs && b.bs) ? const_cast<BST*>(reinterpret_cast<const BST*>(b.bs)) + b.blk_off[v] * C + c
+                                        : nullptr;
+    int st = 0, rs = 0;
+    uint32_t parity = 0, rpass = 0;
+    for (int i = 0; i < nslabs; ++i) {
+      mbar_wait(&tma_full[st], parity);
+      if (feasible && rpass > 0) mbar_wait(&ring_empty[rs], (rpass & 1) ^ 1);  // DP is done with this ring slab
+      if (active) {
+        const int b0 = i * bps;
+        const int nb = min(bps, K - b0);
+        const BST* s = slabs + static_cast<size_t>(st) * slab_elems + c;
+        BST* rp = ring + static_cast<size_t>(rs) * bps * C + c;
+        for (int bb = 0; bb < nb; ++bb) {
+          if (FS) {
+#pragma unroll
+            for (int r = 0; r < (FS ? FS : 1); ++r) run = run + s[r * C];
+          } else {
+#pragma unroll 4
+            for (int r = 0; r < fs; ++r) run = run + s[r * C];
+          }
+          s += fs * C;
+          const BST o = (b0 + bb == 0) ? run : run - prev;
+          prev = run;
+          rp[bb * C] = o;
+          if (out_g) out_g[static_cast<int64_t>(b0 + bb) * C] = o;
+        }
+      }
+      named_bar_sync(15, cfg.scan_threads);  // stage st consumed, ring slab rs written
+      if (threadIdx.x == 0) {
+        if (feasible) mbar_arrive(&ring_full[rs]);
+        if (i + stages < nslabs) issue(i + stages, st);
+      }
+      if (++st == stages) { st = 0; parity ^= 1; }
+      if (++rs == cfg.ring_slabs) { rs = 0; ++rpass; }
+    }
+    return;
+  }
+
+  // ======================================= DP role =======================================
+  constexpr int kSegsPerWarp = 32 / G;
+  const int dpt = threadIdx.x - cfg.scan_threads;
+  DpTeam t;
+  t.u = u;
+  t.lane = dpt & 31;
+  t.wl = dpt >> 5;
+  t.nw = max(1, (N - 1 + kSegsPerWarp - 1) / kSegsPerWarp);
+  if (t.wl >= t.nw) return;  // this unit needs fewer warps than the CTA has
+  t.ltid = dpt;
+  t.nthr = t.nw * 32;
+  t.bar_id = 1;
+  t.slot = 0;
+  t.c0 = 0;
+  t.NS = dp_columns(cfg.dp_warps, G);
+  if (!dp_feasible(b, J, t)) return;
+
+  const DpLayout L = dp_layout(cfg.dp_warps, G, J, 0, cfg.bp_rows);
+  unsigned char* dsm = sm + dp_off;
+  DpShared sh;
+  sh.rows0 = reinterpret_cast<double*>(dsm + L.rows0);
+  sh.Ex = reinterpret_cast<double*>(dsm + L.Ex);
+  sh.ex_stride = cfg.dp_warps;
+  sh.segend = reinterpret_cast<int64_t*>(dsm + L.segend);
+  sh.trl = reinterpret_cast<int*>(dsm + L.trl);
+  sh.segb = reinterpret_cast<int*>(dsm + L.segb);
+  sh.fin_v = reinterpret_cast<double*>(dsm + L.fin_v);
+  sh.fin_j = reinterpret_cast<int*>(dsm + L.fin_j);
+  sh.bpS = dsm + L.bpS;
+  sh.bp_rows = cfg.bp_rows;
+  for (int n = t.ltid; n < N; n += t.nthr) sh.trl[n] = b.tr[tr0 + n];
+  t.sync();  // trl visible
+
+  RingSrc<BST> src;
+  src.ring = ring;
+  src.full = ring_full;
+  src.empty = ring_empty;
+  src.C = C;
+  src.bps = cfg.bps;
+  src.slabs = cfg.ring_slabs;
+  dp_unit<BST, G, SL>(b, J, t, sh, src);
+}
+
+}  // namespace mucon

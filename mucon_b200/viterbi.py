@@ -178,6 +178,7 @@ class AlignPlan:
         blob.add("bp_off", self.bp_off[:-1] if U else self.bp_off)
         blob.add("order_v", self.order_v)
         blob.add("warp_unit", self.warp_unit)
+        blob.add("order_u", np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32))
         blob.add("vid_lab_off", self.vid_off[:-1])
         self.use_rows = len_rows is not None
         if self.use_rows:
@@ -230,8 +231,13 @@ class ViterbiEngine:
             ev = self._events[i] = torch.cuda.Event()
         return ev
 
-    def run(self, plan, logp, seg0_f32=None, stream=None, mid_event=None):
-        """logp: CUDA tensor [sum T, C] float32 or float64, videos concatenated.  Asynchronous."""
+    def run(self, plan, logp, seg0_f32=None, stream=None, mid_event=None, mode="auto", write_bs=True):
+        """logp: CUDA tensor [sum T, C] float32 or float64, videos concatenated.  Asynchronous.
+
+        mode: "fused"  one launch, scan and DP of a video in the same CTA (one transcript per video)
+              "split"  block-score scan kernel + DP kernel (any number of candidates per video)
+              "auto"   fused when every video has a single candidate and the shape fits
+        write_bs: fused mode only -- also store the block scores to plan.bs."""
         if not logp.is_cuda:
             raise _lib.MuconError("ViterbiEngine.run needs a CUDA tensor (no CPU fallback)")
         if logp.dtype not in (torch.float32, torch.float64) or not logp.is_contiguous():
@@ -263,6 +269,22 @@ class ViterbiEngine:
         b.score, b.labels = plan.score.data_ptr(), plan.labels.data_ptr()
         b.seg_blocks, b.bp = plan.seg_blocks.data_ptr(), plan.bp.data_ptr()
         b.final_j, b.status = plan.final_j.data_ptr(), plan.status.data_ptr()
+        self.last_mode = "split"
+        if mode not in ("auto", "fused", "split"):
+            raise ValueError(mode)
+        if mode == "fused" or (mode == "auto" and plan.single):
+            b.max_N, b.max_K = plan.max_N, plan.max_K
+            b.n_cta, b.wpc, b.lanes, b.warp_unit = 0, 4, 0, None
+            rc = lib.mucon_viterbi_align_fused(C.byref(b), _lib.ptr(logp), C.c_int(int(is64)),
+                                               C.c_void_p(p["order_u"]), C.c_int(int(bool(write_bs))), sp)
+            if rc == 0:
+                self.launches += 1
+                self.last_mode = "fused"
+                if mid_event is not None:
+                    mid_event.record(st)
+                return self._finish(plan, sp)
+            if rc != -2 or mode == "fused":
+                _lib.check(rc, "mucon_viterbi_align_fused")
         overlap = len(plan.groups) > 1
         if overlap:
             side = self._side_stream()
@@ -288,6 +310,10 @@ class ViterbiEngine:
             done = self._event(len(plan.groups))
             done.record(side)
             st.wait_event(done)
+        return self._finish(plan, sp)
+
+    def _finish(self, plan, sp):
+        lib, p = self.lib, plan.p
         if plan.labels_mode == "best" and not plan.single:
             _lib.check(lib.mucon_viterbi_select(
                 _lib.ptr(plan.score), _lib.ptr(plan.status), C.c_void_p(p["cand_off"]), C.c_int(plan.V),

@@ -18,7 +18,13 @@ def eng(cuda_device):
     return ViterbiEngine(cuda_device)
 
 
-def run_units(eng, logps, cands, means, fs=30, max_len=2000, seg0=None, labels="all", use_rows=False):
+@pytest.fixture(params=["auto", "split"])
+def mode(request):
+    """auto = fused single-launch kernel where it applies (falls back to split); split = scan + DP kernels."""
+    return request.param
+
+
+def run_units(eng, logps, cands, means, fs=30, max_len=2000, seg0=None, labels="all", use_rows=False, mode="auto"):
     """logps: list of [T,C] arrays (one per video); cands: per video list of transcripts; means: per video [C]."""
     from mucon_b200.length_model import poisson_params
     from mucon_b200.viterbi import AlignPlan
@@ -33,7 +39,7 @@ def run_units(eng, logps, cands, means, fs=30, max_len=2000, seg0=None, labels="
     plan = AlignPlan([l.shape[0] for l in logps], cands, C, fs=fs, max_len=max_len, device=eng.device,
                      labels=labels, **kw)
     packed = torch.from_numpy(np.concatenate(logps)).to(eng.device)
-    eng.run(plan, packed, seg0_f32=seg0)
+    eng.run(plan, packed, seg0_f32=seg0, mode=mode)
     torch.cuda.synchronize()
     return plan, eng.fetch(plan, want_bp=True)
 
@@ -62,14 +68,14 @@ def check_unit(plan, out, u, ref, T):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_golden_fixture(eng, name):
+def test_golden_fixture(eng, name, mode):
     """Frozen outputs of the unmodified reference decoder (tests/golden/make_golden.py)."""
     g = load_golden(name)
     T = g["logp"].shape[0]
     if g["max_len"] // g["fs"] > 128:
         pytest.skip("J > 128 is outside the register-resident kernel")
     plan, out = run_units(eng, [g["logp"]], [g["transcripts"]], [g["means"]], g["fs"], g["max_len"],
-                          seg0=g["seg0_f32"], labels="best")
+                          seg0=g["seg0_f32"], labels="best", mode=mode)
     if plan.single:
         u = 0
     else:
@@ -85,7 +91,7 @@ def test_golden_fixture(eng, name):
 
 
 @pytest.mark.parametrize("dtype,seg0", [(np.float32, True), (np.float32, False), (np.float64, False)])
-def test_random_batch_bit_exact(eng, dtype, seg0):
+def test_random_batch_bit_exact(eng, dtype, seg0, mode):
     rng = np.random.default_rng(42)
     logps, cands, means = [], [], []
     for i in range(24):
@@ -100,7 +106,8 @@ def test_random_batch_bit_exact(eng, dtype, seg0):
         logps.append(lp)
         cands.append([tr])
         means.append(synth.class_means(rng.dirichlet(np.ones(N)).astype(np.float32), tr, C, T))
-    plan, out = run_units(eng, logps, cands, means, seg0=seg0)
+    plan, out = run_units(eng, logps, cands, means, seg0=seg0, mode=mode)
+    assert eng.last_mode == ("fused" if mode == "auto" else "split")
     for u in range(plan.U):
         ref = oracle_unit(logps[u], cands[u][0], means[u], 30, 2000, seg0)
         bs = out["bs"][plan.blk_off[u]:plan.blk_off[u + 1]]
@@ -109,7 +116,7 @@ def test_random_batch_bit_exact(eng, dtype, seg0):
 
 
 @pytest.mark.parametrize("fs,max_len,C", [(7, 91, 12), (1, 20, 5), (13, 200, 7), (30, 2000, 100), (10, 1000, 33)])
-def test_other_sampling_and_class_counts(eng, fs, max_len, C):
+def test_other_sampling_and_class_counts(eng, fs, max_len, C, mode):
     """C = 5, 7, 33 take the direct scan (row not a multiple of 16 B); max_len % fs == 0 gives -inf rows."""
     rng = np.random.default_rng(fs * 1000 + C)
     J = max_len // fs
@@ -125,7 +132,7 @@ def test_other_sampling_and_class_counts(eng, fs, max_len, C):
     for dt in (np.float32, np.float64):
         idx = [i for i in range(10) if logps[i].dtype == dt]
         plan, out = run_units(eng, [logps[i] for i in idx], [cands[i] for i in idx], [means[i] for i in idx],
-                              fs, max_len, seg0=(dt == np.float32))
+                              fs, max_len, seg0=(dt == np.float32), mode=mode)
         for u, i in enumerate(idx):
             ref = oracle_unit(logps[i], cands[i][0], means[i], fs, max_len, dt == np.float32)
             check_unit(plan, out, u, ref, logps[i].shape[0])
@@ -142,14 +149,14 @@ def test_rows_path_equals_params_path(eng):
         assert np.array_equal(a[k], b[k])
 
 
-def test_edge_cases_status(eng):
+def test_edge_cases_status(eng, mode):
     rng = np.random.default_rng(9)
     C = 6
     mk = lambda T: np.log(rng.dirichlet(np.ones(C), T)).astype(np.float32)
     logps = [mk(3990), mk(100), mk(3960), mk(59)]
     cands = [[[0, 1]], [[0, 1, 2, 3, 4, 5]], [[1, 2]], [[3]]]
     means = [np.full(C, 500.0)] * 4
-    plan, out = run_units(eng, logps, cands, means, seg0=True)
+    plan, out = run_units(eng, logps, cands, means, seg0=True, mode=mode)
     assert out["status"].tolist() == [1, 2, 0, 0]  # K > N*J infeasible; K < N short; K == N*J ok; K == 1 ok
     assert np.isnan(out["score"][0]) and out["score"][1] == -np.inf
     for u in (1, 2, 3):
@@ -183,14 +190,14 @@ def test_candidates_best_equals_argmax_of_singles(eng):
         assert np.array_equal(out["labels"][plan.vid_off[v]:plan.vid_off[v] + T], refs[b]["labels"])
 
 
-def test_long_video_stress_c4(eng):
+def test_long_video_stress_c4(eng, mode):
     """c4: T=40000, C=100, N=60 (K=1333, 3960 live states), float32 and float64."""
     rng = np.random.default_rng(4)
     tr = rng.permutation(100)[:60].tolist()
     lp, _ = synth.planted_logp(rng, 40000, 100, tr, np.float32)
     m = synth.class_means(rng.dirichlet(5 * np.ones(60)).astype(np.float32), tr, 100, 40000)
     for arr, seg0 in ((lp, True), (lp.astype(np.float64), False)):
-        plan, out = run_units(eng, [arr], [[tr]], [m], seg0=seg0)
+        plan, out = run_units(eng, [arr], [[tr]], [m], seg0=seg0, mode=mode)
         check_unit(plan, out, 0, oracle_unit(arr, tr, m, 30, 2000, seg0), 40000)
 
 
@@ -216,7 +223,7 @@ def test_drop_in_viterbi_class(eng):
         dec.decode(np.zeros((20, 48), dtype=np.float32))
 
 
-def test_breakfast_split_properties_full_size(eng):
+def test_breakfast_split_properties_full_size(eng, mode):
     """c2 at full size (1712 videos): size-independent properties + oracle spot checks."""
     from mucon_b200.length_model import poisson_params
     from mucon_b200.viterbi import AlignPlan
@@ -230,8 +237,9 @@ def test_breakfast_split_properties_full_size(eng):
     means = np.stack([synth.class_means(rng.dirichlet(np.ones(len(tr))).astype(np.float32), tr, C, int(t))
                       for tr, t in zip(trs, T)])
     plan = AlignPlan(T, [[tr.tolist()] for tr in trs], C, device=eng.device, len_params=poisson_params(means))
-    eng.run(plan, logp, seg0_f32=True)
+    eng.run(plan, logp, seg0_f32=True, mode=mode)
     torch.cuda.synchronize()
+    assert eng.last_mode == ("fused" if mode == "auto" else "split")
     out = eng.fetch(plan, want_bp=False)
     assert (out["status"] == 0).all()
     K = T // 30
