@@ -7,8 +7,8 @@
 Workload (BASELINE.json configs[1], "c2"): a synthetic Breakfast-shaped split of 1712 videos per
 GPU (T = clip(lognormal(ln 1800, 0.7), 300, 10000), 48 classes, 2..12 transcript segments,
 frame_sampling 30, Poisson length model), float32 log-probabilities.  One step = one pass of the
-alignment path over the whole split: block-score scan kernel + DP/traceback/label kernel
-(mucon_viterbi_blockscores + mucon_viterbi_decode), inputs resident in HBM (`value`), or through
+alignment path over the whole split: the fused scan + DP + traceback + label kernel
+(mucon_viterbi_align_fused, one launch), inputs resident in HBM (`value`), or through
 the host API with pinned host buffers and H2D/D2H copies inside the timed region (`e2e`).
 Weak scaling: every rank aligns its own 1712-video split; for N > 1 the step ends with the NCCL
 all_gather of per-video scores and segment lengths.
@@ -242,8 +242,8 @@ def main_ours(args, rank, world, local_rank):
     plan = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=params, labels="best")
     max_pos = V_PER_GPU * 12
 
-    def step(mid=None):
-        eng.run(plan, logp, seg0_f32=True, mid_event=mid)
+    def step(mode="auto"):
+        eng.run(plan, logp, seg0_f32=True, mode=mode, write_bs=False)
         if world > 1:
             mdist.gather_alignments(plan.score, plan.seg_blocks, plan.tr_off, V_PER_GPU, max_pos)
 
@@ -256,9 +256,10 @@ def main_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    assert eng.last_mode == "fused", "the fused kernel did not run"
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     launches0 = eng.launches
     barrier()
     t_all0 = torch.cuda.Event(enable_timing=True)
@@ -266,14 +267,26 @@ def main_ours(args, rank, world, local_rank):
     t_all0.record()
     for i in range(args.steps):
         ev[i][0].record()
-        step(ev[i][1])
-        ev[i][2].record()
+        step()
+        ev[i][1].record()
     t_all1.record()
     barrier()
     total_ms = t_all0.elapsed_time(t_all1)
-    scan_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    dp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    fused_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     launches = eng.launches - launches0
+
+    # the two-kernel path (what candidate sets use): scan kernel and DP kernel timed separately
+    for _ in range(3):
+        step("split")
+    barrier()
+    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(5)]
+    for e in sev:
+        e[0].record()
+        eng.run(plan, logp, seg0_f32=True, mode="split", mid_event=e[1])
+        e[2].record()
+    barrier()
+    scan_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in sev]))
+    dp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in sev]))
 
     # ---- e2e: host API, pinned host log-probs in, labels + scores + segments out ---------------
     host_logp = torch.empty(logp.shape, dtype=logp.dtype, pin_memory=True)
@@ -288,7 +301,7 @@ def main_ours(args, rank, world, local_rank):
         p = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=poisson_params(means),
                       labels="best")
         dev_in.copy_(host_logp, non_blocking=True)
-        eng.run(p, dev_in, seg0_f32=True)
+        eng.run(p, dev_in, seg0_f32=True, write_bs=False)
         host_labels.copy_(p.labels, non_blocking=True)
         host_small.copy_(p.score, non_blocking=True)
         host_seg.copy_(p.seg_blocks, non_blocking=True)
@@ -311,9 +324,9 @@ def main_ours(args, rank, world, local_rank):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, scan_ms, dp_ms, e2e_s], dtype=torch.float64, device=device)
+        t = torch.tensor([total_ms, scan_ms, dp_ms, e2e_s, fused_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, scan_ms, dp_ms, e2e_s = t.tolist()
+        total_ms, scan_ms, dp_ms, e2e_s, fused_ms = t.tolist()
         fr = torch.tensor([plan.aligned_frames], dtype=torch.float64, device=device)
         dist.all_reduce(fr, op=dist.ReduceOp.SUM)
         frames_all = float(fr.item())
@@ -335,11 +348,12 @@ def main_ours(args, rank, world, local_rank):
         KN = int(((T // FS) * np.array([len(t) for t in trs])).sum())
         scan_bytes = 4 * Tsum * C
         dp_bytes = 4 * Tsum + 2 * KN + 528 * Nsum + 8 * len(T) + 8 * Nsum
+        path_bytes = scan_bytes + dp_bytes
+        fused_gbs = path_bytes / (fused_ms * 1e-3) / 1e9
         scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9
-        path_gbs = (scan_bytes + dp_bytes) / ((scan_ms + dp_ms) * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("scan_kernel_dram_bytes")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("align_fused_kernel_dram_bytes")
         except Exception:
             pass
         out = {
@@ -353,14 +367,19 @@ def main_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": frames_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                    "what": "AlignPlan build + pinned H2D of log-probs + 2 kernels + D2H of labels/scores/segments"},
+                    "what": "AlignPlan build + pinned H2D of log-probs + fused kernel + D2H of labels/scores/segments"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "scan_bulk_kernel (block-score scan)", "achieved": scan_gbs,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": scan_gbs / hbm_peak, "traffic": traffic,
-                         "peak_source": peak_src, "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms},
-            "roofline_path": {"what": "scan + DP kernels, algorithmic bytes 4TC + 4T + 2KN + 528N + 8 + 8N per unit",
-                              "achieved": path_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": path_gbs / hbm_peak,
-                              "bytes_per_step": scan_bytes + dp_bytes, "scan_ms": scan_ms, "dp_ms": dp_ms},
+            "roofline": {"bound": "hbm", "kernel": "align_fused_kernel (scan + DP + traceback + labels, one launch)",
+                         "achieved": fused_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fused_gbs / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": path_bytes,
+                         "ms_per_launch": fused_ms,
+                         "algorithmic_bytes": "4TC + 4T + 2KN + 528N + 8 + 8N per unit (SURVEY.md 8d)"},
+            "two_kernel_path": {"what": "same batch through mucon_viterbi_blockscores + mucon_viterbi_decode "
+                                        "(the path candidate sets use)",
+                                "scan_kernel": {"achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                                "frac": scan_gbs / hbm_peak, "bytes_per_launch": scan_bytes,
+                                                "ms_per_launch": scan_ms},
+                                "dp_kernel_ms": dp_ms},
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()

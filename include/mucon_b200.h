@@ -116,8 +116,10 @@ int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 
 /* One-launch alignment: block-score scan and DP of a unit fused in one CTA (scan warps feed the
  * DP warps through shared memory; block scores do not travel through HBM).  Same inputs and
- * outputs as mucon_viterbi_blockscores + mucon_viterbi_decode; warp_unit / n_cta / wpc / lanes of
- * the batch are ignored.  Meant for one transcript per video (a unit re-scans its video).
+ * outputs as mucon_viterbi_blockscores + mucon_viterbi_decode; warp_unit / n_cta / wpc of the
+ * batch are ignored; batch.U CTAs are launched for the units order[0..U) (so a subset can be
+ * aligned); batch.lanes == 32 gives every transcript segment its own warp (lower latency per DP
+ * step, for long videos; needs max_N <= 15), anything else shares a warp between 4 or 8 segments.  Meant for one transcript per video (a unit re-scans its video).
  * logp: [sum T, C] log-probabilities, 16-byte aligned, dtype given by in_is_f64 (must match
  * batch.bs_is_f64).  order: optional [U] launch order (longest first).  write_bs != 0 also stores
  * the block scores to batch.bs.  Returns MUCON_EUNSUPPORTED when the shape does not fit

@@ -300,7 +300,8 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
   const int spw = 32 / G;
   cfg.dp_warps = (b.max_N - 1 + spw - 1) / spw;
   if (cfg.dp_warps < 1) cfg.dp_warps = 1;
-  if (cfg.scan_threads + 32 * cfg.dp_warps > kFusedMaxThreads) return MUCON_EUNSUPPORTED;
+  if (cfg.scan_threads + 32 * cfg.dp_warps > (G == 32 ? kFusedMaxThreadsWide : kFusedMaxThreads))
+    return MUCON_EUNSUPPORTED;
   const size_t blk_bytes = (size_t)b.C * sizeof(BST) * b.fs;
   cfg.bps = (int)(env_int("MUCON_FUSED_SLAB_BYTES", 17280) / blk_bytes);
   if (cfg.bps < 1) cfg.bps = 1;
@@ -326,9 +327,15 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
 template <typename BST>
 int dispatch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int32_t* order, int write_bs,
                    cudaStream_t st) {
-  const int G = J <= 32 ? 4 : 8;
+  const int G = b.lanes == 32 ? 32 : (J <= 32 ? 4 : 8);
   const int SL = (J + G - 1) / G;
 #define MUCON_SL_CASE(g, n) case n: return launch_fused<BST, g, n>(b, J, logp, order, write_bs, st);
+  if (G == 32) {
+    switch (SL) {
+      MUCON_SL_CASE(32, 1) MUCON_SL_CASE(32, 2) MUCON_SL_CASE(32, 3) MUCON_SL_CASE(32, 4)
+      default: return MUCON_EUNSUPPORTED;
+    }
+  }
   if (G == 4) {
     switch (SL) {
       MUCON_SL_CASE(4, 1) MUCON_SL_CASE(4, 2) MUCON_SL_CASE(4, 3) MUCON_SL_CASE(4, 4)

@@ -320,6 +320,10 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
     const bool f32seg0 = (sizeof(BST) == 4) && b.seg0_f32;
     double s0 = __dadd_rn(0.0, static_cast<double>(row[col0]));
 
+    const unsigned gmask = (G == 32) ? 0xffffffffu : ((0xffffffffu >> (32 - G)) << (g * G));
+    bool tie_ok[5];  // butterfly level lv: the partner is the higher lane (older ages), ties go to it
+#pragma unroll
+    for (int lv = 0; lv < 5; ++lv) tie_ok[lv] = (lane & (1 << lv)) == 0;
     const bool bp_writer = has_seg && lig == G - 1 && n + 1 < N;
     uint8_t* bp_w;  // where this lane records the winner of its group at step k
     int bp_stride;
@@ -393,7 +397,8 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
       int bage = a0 + bi + 1;
       if (G == 32) {
         // whole-warp arg-max on the order-preserving integer key: two REDUX for the 64-bit
-        // maximum, one for the oldest age among the lanes that hold it
+        // maximum, one for the oldest age among the lanes that hold it.  (REDUX with per-group
+        // member masks is serialised by the compiler, so smaller groups use the butterfly.)
         const unsigned long long key = dkey(bv);
         const unsigned hi = static_cast<unsigned>(key >> 32);
         const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
@@ -406,10 +411,10 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
         // butterfly over the group's lanes: the partner with the higher lane holds older ages,
         // so it wins ties; the partner with the lower lane must be strictly greater
 #pragma unroll
-        for (int off = 1; off < G; off <<= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-          const int oa = __shfl_xor_sync(0xffffffffu, bage, off);
-          const bool take = (lane & off) ? (ov > bv) : (ov >= bv);
+        for (int lv = 0; (1 << lv) < G; ++lv) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, 1 << lv);
+          const int oa = __shfl_xor_sync(0xffffffffu, bage, 1 << lv);
+          const bool take = (ov > bv) || (tie_ok[lv] && ov == bv);
           bv = take ? ov : bv;
           bage = take ? oa : bage;
         }
@@ -475,7 +480,6 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
         if (i == 0 || c >= bv) { bv = c; bi = i; }
       }
       int bage = a0 + bi + 1;
-      const unsigned gmask = 0xffffffffu >> (32 - G) << (g * G);
 #pragma unroll
       for (int off = 1; off < G; off <<= 1) {
         const double ov = __shfl_xor_sync(gmask, bv, off);

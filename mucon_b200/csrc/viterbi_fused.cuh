@@ -23,7 +23,8 @@ struct FusedCfg {
   int write_bs;      // also store the block scores to b.bs
 };
 
-constexpr int kFusedMaxThreads = 256;
+constexpr int kFusedMaxThreads = 256;      // segments sharing a warp (G = 4 / 8)
+constexpr int kFusedMaxThreadsWide = 512;  // a warp per segment (G = 32)
 constexpr int kFusedBarBytes = 256;  // mbarriers: tma_full[<=8], ring_full[<=8], ring_empty[<=8]
 
 __host__ __device__ inline size_t fused_smem_bytes(const FusedCfg& c, int G, int J, int C, int fs, int elem) {
@@ -36,7 +37,7 @@ __host__ __device__ inline size_t fused_smem_bytes(const FusedCfg& c, int G, int
 }
 
 template <typename BST, int G, int SL, int FS>
-__global__ void __launch_bounds__(kFusedMaxThreads, 1)
+__global__ void __launch_bounds__(G == 32 ? kFusedMaxThreadsWide : kFusedMaxThreads, 1)
 align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restrict__ logp,
                    const int32_t* __restrict__ order, const FusedCfg cfg) {
   extern __shared__ __align__(128) unsigned char sm[];

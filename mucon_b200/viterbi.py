@@ -78,7 +78,7 @@ class AlignPlan:
     """
 
     def __init__(self, T, candidates, n_classes, fs=30, max_len=2000, len_params=None, len_rows=None,
-                 device=None, want_bp=True, labels="best", groups=None, long_K=150):
+                 device=None, want_bp=True, labels="best", groups=None, long_K=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.fs, self.max_len, self.C = int(fs), int(max_len), int(n_classes)
         self.J = self.max_len // self.fs
@@ -152,7 +152,7 @@ class AlignPlan:
             order_u = units[np.argsort(-(uK[units] * 1024 + nlen[units]), kind="stable")].astype(np.int32)
             gmaxN = int(nlen[units].max()) if units.size else 1
             gmaxK = int(uK[units].max()) if units.size else 0
-            want = 32 if (gi == 0 and len(bounds) > 2 and gmaxK >= long_K) else 0
+            want = 32 if (gi == 0 and len(bounds) > 2 and long_K and gmaxK >= long_K) else 0
             wu = np.full(max(units.size, 1) * 16, -1, dtype=np.int32)
             n_cta, wpc, lanes = C.c_int32(0), C.c_int32(0), C.c_int32(0)
             _lib.check(lib.mucon_viterbi_pack_h(
@@ -179,6 +179,9 @@ class AlignPlan:
         blob.add("order_v", self.order_v)
         blob.add("warp_unit", self.warp_unit)
         blob.add("order_u", np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32))
+        # optional: videos of >= long_K blocks get a launch of their own with a warp per segment
+        # (measured slower than one uniform launch on Breakfast-shaped batches, so off by default)
+        self.n_long = int((uK >= long_K).sum()) if long_K else 0
         blob.add("vid_lab_off", self.vid_off[:-1])
         self.use_rows = len_rows is not None
         if self.use_rows:
@@ -273,17 +276,40 @@ class ViterbiEngine:
         if mode not in ("auto", "fused", "split"):
             raise ValueError(mode)
         if mode == "fused" or (mode == "auto" and plan.single):
-            b.max_N, b.max_K = plan.max_N, plan.max_K
-            b.n_cta, b.wpc, b.lanes, b.warp_unit = 0, 4, 0, None
-            rc = lib.mucon_viterbi_align_fused(C.byref(b), _lib.ptr(logp), C.c_int(int(is64)),
-                                               C.c_void_p(p["order_u"]), C.c_int(int(bool(write_bs))), sp)
+            # Long videos are a long serial chain of DP steps: they get their own launch with a
+            # warp per transcript segment (fewer instructions per step), on a second stream so
+            # that both launches share the GPU.  order_u is sorted longest first.
+            b.n_cta, b.wpc, b.warp_unit = 0, 4, None
+            n_long = plan.n_long if (plan.max_N <= 15 and plan.U >= 64) else 0
+            rc = 0
+            if n_long:
+                side = self._side_stream()
+                ev = self._event(0)
+                ev.record(st)
+                side.wait_event(ev)
+                b.U, b.lanes, b.max_N, b.max_K = n_long, 32, plan.max_N, plan.max_K
+                rc = lib.mucon_viterbi_align_fused(C.byref(b), _lib.ptr(logp), C.c_int(int(is64)),
+                                                   C.c_void_p(p["order_u"]), C.c_int(int(bool(write_bs))),
+                                                   C.c_void_p(side.cuda_stream))
+                if rc == -2:
+                    n_long, rc = 0, 0
             if rc == 0:
-                self.launches += 1
+                b.U, b.lanes, b.max_N, b.max_K = plan.U - n_long, 0, plan.max_N, plan.max_K
+                rc = lib.mucon_viterbi_align_fused(C.byref(b), _lib.ptr(logp), C.c_int(int(is64)),
+                                                   C.c_void_p(p["order_u"] + 4 * n_long),
+                                                   C.c_int(int(bool(write_bs))), sp)
+            if n_long:
+                done = self._event(1)
+                done.record(side)
+                st.wait_event(done)
+            b.U = plan.U
+            if rc == 0:
+                self.launches += 2 if n_long else 1
                 self.last_mode = "fused"
                 if mid_event is not None:
                     mid_event.record(st)
                 return self._finish(plan, sp)
-            if rc != -2 or mode == "fused":
+            if rc != -2 or mode == "fused" or n_long:
                 _lib.check(rc, "mucon_viterbi_align_fused")
         overlap = len(plan.groups) > 1
         if overlap:

@@ -1,0 +1,14 @@
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from mucon_b200.length_model import poisson_params
+from mucon_b200.viterbi import AlignPlan, ViterbiEngine
+dev = torch.device("cuda:0")
+T, trs, means = bench.make_split(0)
+logp = bench.device_logp(T, trs, 0, dev)
+eng = ViterbiEngine(dev)
+plan = AlignPlan(T, [[t.tolist()] for t in trs], 48, device=dev, len_params=poisson_params(means), long_K=10**6)
+for _ in range(4):
+    eng.run(plan, logp, seg0_f32=True, mode="fused", write_bs=False)
+torch.cuda.synchronize()
