@@ -25,3 +25,9 @@ def load_golden(name):
 def same_score(a, b):
     a, b = np.float64(a), np.float64(b)
     return (a == b) or (np.isnan(a) and np.isnan(b))
+
+
+def mask_atol(T, L):
+    """Absolute tolerance for float32 masks: the template coordinate is evaluated in float32 from
+    values as large as T/L, so its rounding error -- and a ramp value -- scales with T / min(L)."""
+    return 1.5e-5 * max(1.0, float(T) / float(np.min(L)))
