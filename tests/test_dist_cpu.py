@@ -1,0 +1,65 @@
+"""CPU: the multi-GPU plumbing on gloo with world_size 2 (sharding + the single gather)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mucon_b200 import dist as mdist
+
+
+def test_shard_videos_balances_and_partitions():
+    rng = np.random.default_rng(0)
+    T = rng.integers(300, 10000, 500)
+    nc = rng.integers(1, 5, 500)
+    for world in (1, 2, 4, 8):
+        parts = mdist.shard_videos(T, nc, world)
+        allv = np.sort(np.concatenate(parts))
+        assert np.array_equal(allv, np.arange(500))  # every video on exactly one rank
+        load = np.array([(T[p] * nc[p]).sum() for p in parts])
+        assert load.max() <= 1.02 * load.mean() + (T * nc).max()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    U = 5 + 3 * rank
+    N = rng.integers(1, 7, U)
+    tr_off = np.concatenate([[0], np.cumsum(N)]).astype(np.int32)
+    score = torch.from_numpy(rng.standard_normal(U))
+    seg = torch.from_numpy(rng.integers(1, 66, int(tr_off[-1])).astype(np.int32))
+    all_sc, all_int = mdist.gather_alignments(score, seg, tr_off, max_units=16, max_positions=128)
+    got = mdist.unpack_gathered(all_sc, all_int, 128)
+    ok = True
+    for r in range(world):
+        rr = np.random.default_rng(100 + r)
+        Ur = 5 + 3 * r
+        Nr = rr.integers(1, 7, Ur)
+        offr = np.concatenate([[0], np.cumsum(Nr)]).astype(np.int32)
+        scr = rr.standard_normal(Ur)
+        segr = rr.integers(1, 66, int(offr[-1])).astype(np.int32)
+        ok &= np.array_equal(got[r]["score"], scr) and np.array_equal(got[r]["seg_blocks"], segr)
+        ok &= np.array_equal(got[r]["tr_off"], offr)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_gather_alignments_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
