@@ -167,6 +167,38 @@ int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, cons
 /* Host helper: the 100 template taps the kernels use (masks.py:34-54). */
 int mucon_mask_template_h(int template_id, float* out100_h);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backbone forward (inference).  Activations are time-major with channels contiguous: a video
+ * is a [T, C] block of rows and videos are concatenated; row_off[V+1] are the row offsets at the
+ * resolution of the call.  The host mirror (mucon_b200/temporal.py, model.py) strings these ops
+ * together exactly like WaveNetBlock.forward (src/core/modules/temporal.py:128-147),
+ * temporal_modeling_forward (src/mucon/models.py:746-773), frame_classifier_forward (:567-582)
+ * and predict's log_softmax (:368).
+ */
+/* out[m, n] = act(sum_k A[m,k]*W[n,k] + bias[n]), A [M,K] fp32 row-major, W [N,K] fp32 (a Conv1d
+ * weight [out, in, 1]), N must be 128, K a multiple of 32.  tcgen05.mma.kind::tf32 (operands are
+ * read as TF32: 10-bit mantissa, fp32 accumulate).  Replaces first_conv + ReLU (temporal.py:133). */
+int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const float* W, int N, const float* bias,
+                             float* out, int relu, void* stream);
+/* k = 1 or k = 3 dilated Conv1d with padding = dilation (temporal.py:21-31,48-52), fp32:
+ *   out[t, co] = bias[co] + sum_tap sum_ci W_tco[tap][ci][co] * f(in[t + (tap - taps/2)*dilation, ci])
+ * f = ReLU when relu_in; ReLU on the result when relu_out; `residual` ([rows, Cout] or NULL) is
+ * added last (y += x, temporal.py:52).  W_tco is the Conv1d weight permuted to [tap][Cin][Cout]. */
+int mucon_conv1d(const float* in, float* out, const float* W_tco, const float* bias, const float* residual,
+                 const int64_t* row_off, int V, int max_T, int Cin, int Cout, int taps, int dilation,
+                 int relu_in, int relu_out, void* stream);
+/* max_pool1d(kernel_size=2) per video (temporal.py:139): off_out rows = floor(off_in rows / 2). */
+int mucon_maxpool2(const float* in, float* out, const int64_t* off_in, const int64_t* off_out, int V,
+                   int max_T_out, int C, void* stream);
+/* GroupNorm(groups, C) over each video's (T x C/groups) elements + optional ReLU (models.py:759-764). */
+int mucon_groupnorm_relu(const float* in, float* out, const float* gamma, const float* beta,
+                         const int64_t* row_off, int V, int C, int groups, float eps, int relu, void* stream);
+/* log_softmax over C classes of the pooled-resolution logits, expanded to every frame with the
+ * nearest-neighbour index of F.interpolate: out[t,:] = lsm(logits[min(floor(t*(float)Tz/T), Tz-1), :])
+ * (models.py:574-580 with the 1x1 classifier applied before the upsample, and :368). */
+int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z, const int64_t* off_t, int V, int max_T,
+                            int C, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,302 @@
+// backbone.cu -- forward pass of the dilated temporal-conv backbone (sm_100a).
+//
+// Replaces, for inference, reference src/core/modules/temporal.py:43-53,128-147 (WaveNetLayer /
+// WaveNetBlock.forward), src/mucon/models.py:759-768 (GroupNorm + ReLU tail), :567-582 (nearest
+// upsample + 1x1 classifier) and :368 (log_softmax).  Activations are time-major, channels
+// contiguous: a video is a [T, C] block of rows, videos are concatenated (row offsets per
+// resolution), so a 1x1 conv is a GEMM over rows and the classifier can run at the pooled
+// resolution before the nearest-neighbour expansion (a 1x1 conv commutes with it).
+//
+//   mucon_gemm_tf32_bias_act      2048 -> 128 input projection on tcgen05 (backbone_gemm.cuh)
+//   mucon_conv1d                  k = 1 / k = 3 dilated conv, fused bias / ReLU / residual (fp32 FFMA)
+//   mucon_maxpool2                max_pool1d(2), floor
+//   mucon_groupnorm_relu          GroupNorm over (channels of the group x time) per video, + ReLU
+//   mucon_logsoftmax_expand       log_softmax over classes at pooled resolution, expanded to T frames
+#include <cuda.h>
+#include <math.h>
+
+#include "backbone_gemm.cuh"
+#include "common.cuh"
+
+namespace mucon {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, cols] fp32 row-major, box [box_rows, 32 cols] with 128-byte swizzle
+int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MUCON_ECUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MUCON_OK : MUCON_ECUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k = 1 / k = 3 dilated conv on CUDA cores: out[t, co] = b[co] + sum_tap sum_ci W[tap][ci][co] * x[t + (tap-c)*dil, ci]
+// with zero padding at the video's ends (Conv1d(padding = dilation), temporal.py:21-27).
+// CTA: 64 rows x 64 output channels, 256 threads, 4 x 4 outputs per thread.
+template <int TAPS>
+__global__ void __launch_bounds__(256) conv1d_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                     const float* __restrict__ W, const float* __restrict__ bias,
+                                                     const float* __restrict__ residual,
+                                                     const int64_t* __restrict__ off, int Cin, int Cout, int dil,
+                                                     int relu_in, int relu_out) {
+  __shared__ float Xs[64][33];
+  __shared__ float Ws[32][64];
+  const int v = blockIdx.y;
+  const int64_t r0 = off[v];
+  const int T = static_cast<int>(off[v + 1] - r0);
+  const int t0 = blockIdx.x * 64;
+  if (t0 >= T) return;
+  const int co0 = blockIdx.z * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int tap = 0; tap < TAPS; ++tap) {
+    const int shift = (tap - TAPS / 2) * dil;
+    // a tap that only ever sees padding contributes nothing (dilation >= T: temporal.py layers 8-10)
+    if (shift >= T || -shift >= T) continue;
+    for (int ci0 = 0; ci0 < Cin; ci0 += 32) {
+      for (int i = tid; i < 64 * 32; i += 256) {
+        const int r = i >> 5, c = i & 31;
+        const int t = t0 + r + shift;
+        float x = 0.f;
+        if (t >= 0 && t < T && ci0 + c < Cin) {
+          x = in[(r0 + t) * Cin + ci0 + c];
+          if (relu_in) x = fmaxf(x, 0.f);
+        }
+        Xs[r][c] = x;
+      }
+      for (int i = tid; i < 32 * 64; i += 256) {
+        const int c = i >> 6, o = i & 63;
+        Ws[c][o] = (ci0 + c < Cin && co0 + o < Cout) ? W[(static_cast<size_t>(tap) * Cin + ci0 + c) * Cout + co0 + o] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        float xv[4], wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = Xs[ty * 4 + i][c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[j] = Ws[c][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty * 4 + i;
+    if (t >= T) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co >= Cout) continue;
+      float y = acc[i][j] + bias[co];
+      if (relu_out) y = fmaxf(y, 0.f);
+      if (residual) y += residual[(r0 + t) * Cout + co];
+      out[(r0 + t) * Cout + co] = y;
+    }
+  }
+}
+
+__global__ void maxpool2_kernel(const float* __restrict__ in, float* __restrict__ out, const int64_t* __restrict__ off_in,
+                                const int64_t* __restrict__ off_out, int C) {
+  const int v = blockIdx.y;
+  const int64_t i0 = off_in[v], o0 = off_out[v];
+  const int To = static_cast<int>(off_out[v + 1] - o0);
+  const int64_t n = static_cast<int64_t>(To) * C;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / C;
+    const int c = static_cast<int>(i - t * C);
+    out[o0 * C + i] = fmaxf(in[(i0 + 2 * t) * C + c], in[(i0 + 2 * t + 1) * C + c]);
+  }
+}
+
+// GroupNorm(groups, C) over one video's [T, C] block (statistics over T x C/groups), optional ReLU.
+__global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const int64_t* __restrict__ off, int C, int groups, float eps,
+                                                        int relu) {
+  extern __shared__ double red[];  // [2][C]
+  const int v = blockIdx.x;
+  const int64_t r0 = off[v];
+  const int T = static_cast<int>(off[v + 1] - r0);
+  double* s1 = red;
+  double* s2 = red + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const double x = in[(r0 + t) * C + c];
+      a += x;
+      b += x * x;
+    }
+    s1[c] = a;
+    s2[c] = b;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < cpg; ++k) { a += s1[g * cpg + k]; b += s2[g * cpg + k]; }
+    const double n = static_cast<double>(T) * cpg;
+    const double mean = a / n;
+    double var = b / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float mu = static_cast<float>(mean);
+    const float ga = gamma[c], be = beta[c];
+    for (int t = 0; t < T; ++t) {
+      float y = (in[(r0 + t) * C + c] - mu) * rstd * ga + be;
+      if (relu) y = fmaxf(y, 0.f);
+      out[(r0 + t) * C + c] = y;
+    }
+  }
+}
+
+// log_softmax over C classes of the pooled-resolution logits row idx(t), written for every frame t:
+// idx(t) = min(floor(t * (float)Tz / T), Tz - 1) -- F.interpolate(mode="nearest") (models.py:574-576).
+// One warp per output frame.
+__global__ void __launch_bounds__(256) logsoftmax_expand_kernel(const float* __restrict__ logits,
+                                                                const int64_t* __restrict__ off_z,
+                                                                const int64_t* __restrict__ off_t, int C,
+                                                                float* __restrict__ out) {
+  const int v = blockIdx.y;
+  const int64_t z0 = off_z[v], t0 = off_t[v];
+  const int Tz = static_cast<int>(off_z[v + 1] - z0);
+  const int T = static_cast<int>(off_t[v + 1] - t0);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float scale = static_cast<float>(Tz) / static_cast<float>(T);
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
+    int iz = static_cast<int>(floorf(static_cast<float>(t) * scale));
+    if (iz > Tz - 1) iz = Tz - 1;
+    const float* row = logits + (z0 + iz) * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = m + logf(s);
+    float* orow = out + (t0 + t) * C;
+    for (int c = lane; c < C; c += 32) orow[c] = row[c] - lse;
+  }
+}
+
+}  // namespace
+}  // namespace mucon
+
+using namespace mucon;
+
+extern "C" int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const float* W, int N, const float* bias,
+                                        float* out, int relu, void* stream) {
+  if (!A || !W || !bias || !out || M < 0 || K < 1) return MUCON_EINVAL;
+  if (N != gemm::BN || K % gemm::BK != 0) return MUCON_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15))
+    return MUCON_EALIGN;
+  if (M == 0) return MUCON_OK;
+  if (M > 0x7fffffff) return MUCON_EUNSUPPORTED;
+  CUtensorMap ta, tb;
+  int rc = make_map_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), gemm::BM);
+  if (rc != MUCON_OK) return rc;
+  rc = make_map_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), gemm::BN);
+  if (rc != MUCON_OK) return rc;
+  static int sms = 0;
+  if (!sms) sms = mucon_device_sm_count();
+  const int tiles = static_cast<int>((M + gemm::BM - 1) / gemm::BM);
+  const int grid = tiles < sms ? tiles : sms;
+  MUCON_CUDA_CHECK(cudaFuncSetAttribute(gemm::proj_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        gemm::SMEM_BYTES));
+  gemm::proj_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+      ta, tb, bias, out, static_cast<int>(M), K, relu);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_conv1d(const float* in, float* out, const float* W_tco, const float* bias, const float* residual,
+                            const int64_t* row_off, int V, int max_T, int Cin, int Cout, int taps, int dilation,
+                            int relu_in, int relu_out, void* stream) {
+  if (!in || !out || !W_tco || !bias || !row_off || V < 0 || max_T < 0 || Cin < 1 || Cout < 1 || dilation < 1)
+    return MUCON_EINVAL;
+  if (taps != 1 && taps != 3) return MUCON_EUNSUPPORTED;
+  if (V == 0 || max_T == 0) return MUCON_OK;
+  if (V > 65535) return MUCON_EUNSUPPORTED;
+  dim3 grid((max_T + 63) / 64, V, (Cout + 63) / 64);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (taps == 1)
+    conv1d_kernel<1><<<grid, 256, 0, st>>>(in, out, W_tco, bias, residual, row_off, Cin, Cout, dilation, relu_in, relu_out);
+  else
+    conv1d_kernel<3><<<grid, 256, 0, st>>>(in, out, W_tco, bias, residual, row_off, Cin, Cout, dilation, relu_in, relu_out);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_maxpool2(const float* in, float* out, const int64_t* off_in, const int64_t* off_out, int V,
+                              int max_T_out, int C, void* stream) {
+  if (!in || !out || !off_in || !off_out || V < 0 || C < 1 || max_T_out < 0) return MUCON_EINVAL;
+  if (V == 0 || max_T_out == 0) return MUCON_OK;
+  if (V > 65535) return MUCON_EUNSUPPORTED;
+  int bx = static_cast<int>((static_cast<int64_t>(max_T_out) * C + 255) / 256);
+  if (bx > 64) bx = 64;
+  maxpool2_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, off_in, off_out, C);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_groupnorm_relu(const float* in, float* out, const float* gamma, const float* beta,
+                                    const int64_t* row_off, int V, int C, int groups, float eps, int relu,
+                                    void* stream) {
+  if (!in || !out || !gamma || !beta || !row_off || V < 0 || C < 1 || groups < 1 || C % groups) return MUCON_EINVAL;
+  if (V == 0) return MUCON_OK;
+  groupnorm_kernel<<<V, 128, 2 * C * sizeof(double), static_cast<cudaStream_t>(stream)>>>(in, out, gamma, beta, row_off,
+                                                                                         C, groups, eps, relu);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z, const int64_t* off_t, int V, int max_T,
+                                       int C, float* out, void* stream) {
+  if (!logits || !off_z || !off_t || !out || V < 0 || C < 1 || max_T < 0) return MUCON_EINVAL;
+  if (V == 0 || max_T == 0) return MUCON_OK;
+  if (V > 65535) return MUCON_EUNSUPPORTED;
+  int bx = (max_T + 7) / 8;
+  if (bx > 128) bx = 128;
+  logsoftmax_expand_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, off_z, off_t, C, out);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}

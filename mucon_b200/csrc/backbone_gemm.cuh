@@ -1,0 +1,208 @@
+// backbone_gemm.cuh -- tcgen05 (5th-gen tensor core) GEMM for the backbone's dense contractions.
+//
+//   out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] )        A: [M, K] fp32, W: [N = 128, K] fp32
+//
+// used for the 2048 -> 128 input projection of reference src/core/modules/temporal.py:133
+// (`first_conv`, a 1x1 Conv1d == a GEMM over frames).  The fp32 operands are consumed as TF32 by
+// `tcgen05.mma.kind::tf32` straight from shared memory: no conversion pass over the 8 KB/frame
+// feature stream, which is what bounds this op (HBM).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: 2-D tiled `cp.async.bulk.tensor` loads of a [128 x 32] fp32 A tile and
+//               a [128 x 32] W tile (128-byte rows, SWIZZLE_128B) per stage, completion on mbarriers
+//   warp 1      allocates TMEM (2 x 128 columns: double-buffered 128x128 fp32 accumulators) and
+//               issues the MMAs (one elected lane): 4 x (M128 N128 K8) per stage, `tcgen05.commit`
+//               releases the stage / publishes the accumulator
+//   warps 2-5   epilogue: `tcgen05.ld` 32 lanes x 32 columns, + bias, ReLU, 16-byte stores
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mucon {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 32;    // BK fp32 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;                     // tf32: 32 bytes of K per instruction
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp layout):
+// start address >> 4 in [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major), SBO >> 4 in
+// [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major,
+// N >> 3 in [17,23), M >> 4 in [24,29)
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const float* __restrict__ bias, float* __restrict__ out, int M, int K, int relu) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_mem = base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;       // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (M + BM - 1) / BM;
+  const int num_kb = K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // TMEM: 256 columns = two 128x128 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          unsigned char* a = stage_mem + s * STAGE_BYTES;
+          tma_load_2d(a, &tmA, kb * BK, m0, &full[s]);
+          tma_load_2d(a + A_BYTES, &tmB, kb * BK, 0, &full[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(stage_mem + s * STAGE_BYTES);
+          const uint64_t adesc = smem_desc(a_addr), bdesc = smem_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes of K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          mma_commit(&empty[s]);                       // frees the stage when these MMAs retire
+          if (kb == num_kb - 1) mma_commit(&tfull[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const int row = tile * BM + q * 32 + lane;
+      float* orow = out + static_cast<int64_t>(row) * BN;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = __uint_as_float(r[j + 0]) + __ldg(bias + c * 32 + j + 0);
+            v.y = __uint_as_float(r[j + 1]) + __ldg(bias + c * 32 + j + 1);
+            v.z = __uint_as_float(r[j + 2]) + __ldg(bias + c * 32 + j + 2);
+            v.w = __uint_as_float(r[j + 3]) + __ldg(bias + c * 32 + j + 3);
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(orow + c * 32 + j) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+}  // namespace gemm
+}  // namespace mucon

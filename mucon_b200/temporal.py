@@ -1,0 +1,235 @@
+"""Dilated temporal-conv backbone on the GPU -- host side (inference).
+
+Drop-in surface: `WaveNetBlock` with the constructor, parameter names and forward signature of
+reference src/core/modules/temporal.py:77-147 (`first_conv`, `l_{i}.dilated_conv`, `l_{i}.conv_1x1`,
+`last_conv`), so a reference state_dict loads unchanged, and `MuConBackbone` with the attribute
+names the reference model uses around it (`ft`, `ft_last_gn`, `conv_classifier`,
+src/mucon/models.py:160-191,276-278) and its three forward helpers (models.py:360-374,567-582,746-773).
+
+Internally activations are time-major ([rows, channels], videos concatenated) and every op is a
+call into libmucon_b200.so (include/mucon_b200.h); `BackbonePlan` holds the per-resolution row
+offsets of a batch of variable-length videos.  Forward only: training-mode dropout and autograd are
+not implemented here (the reference trains with its own PyTorch layers).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class BackbonePlan:
+    """Row offsets of a batch of videos at every pooling level (floor halving per max-pool)."""
+
+    def __init__(self, T, n_pools, device):
+        self.device = torch.device(device)
+        T = np.asarray(T, dtype=np.int64)
+        self.V = int(T.shape[0])
+        self.T = [T]
+        for _ in range(n_pools):
+            self.T.append(self.T[-1] // 2)
+        offs = [np.concatenate([[0], np.cumsum(t)]).astype(np.int64) for t in self.T]
+        self.rows = [int(o[-1]) for o in offs]
+        self.max_T = [int(t.max(initial=0)) for t in self.T]
+        self.off_host = offs
+        flat = torch.from_numpy(np.concatenate(offs)).to(self.device)
+        n = self.V + 1
+        self.off = [flat[i * n:(i + 1) * n] for i in range(len(offs))]
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def gemm_tf32_bias_act(A, W, bias, relu):
+    """act(A @ W.T + bias) on tcgen05 (TF32 operands, fp32 accumulate).  A [M,K], W [128,K]."""
+    out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.float32, device=A.device)
+    _lib.check(_lib.lib().mucon_gemm_tf32_bias_act(
+        _lib.ptr(A), C.c_int64(A.shape[0]), C.c_int(A.shape[1]), _lib.ptr(W), C.c_int(W.shape[0]), _lib.ptr(bias),
+        _lib.ptr(out), C.c_int(int(relu)), _stream(A.device)), "mucon_gemm_tf32_bias_act")
+    return out
+
+
+def conv1d_rows(x, W_tco, bias, off, V, max_T, dilation=1, relu_in=False, relu_out=False, residual=None):
+    """k=1/k=3 dilated conv over time-major rows.  W_tco: [taps, Cin, Cout]."""
+    taps, Cin, Cout = W_tco.shape
+    out = torch.empty((x.shape[0], Cout), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().mucon_conv1d(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(W_tco), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(off), C.c_int(V),
+        C.c_int(max_T), C.c_int(Cin), C.c_int(Cout), C.c_int(taps), C.c_int(dilation), C.c_int(int(relu_in)),
+        C.c_int(int(relu_out)), _stream(x.device)), "mucon_conv1d")
+    return out
+
+
+def maxpool2_rows(x, plan, level):
+    Cc = x.shape[1]
+    out = torch.empty((plan.rows[level + 1], Cc), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().mucon_maxpool2(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(plan.off[level]), _lib.ptr(plan.off[level + 1]), C.c_int(plan.V),
+        C.c_int(plan.max_T[level + 1]), C.c_int(Cc), _stream(x.device)), "mucon_maxpool2")
+    return out
+
+
+def groupnorm_relu_rows(x, gamma, beta, off, V, groups, eps, relu):
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mucon_groupnorm_relu(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(off), C.c_int(V), C.c_int(x.shape[1]),
+        C.c_int(groups), C.c_float(eps), C.c_int(int(relu)), _stream(x.device)), "mucon_groupnorm_relu")
+    return out
+
+
+def logsoftmax_expand_rows(logits, plan, z_level):
+    Cc = logits.shape[1]
+    out = torch.empty((plan.rows[0], Cc), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.lib().mucon_logsoftmax_expand(
+        _lib.ptr(logits), _lib.ptr(plan.off[z_level]), _lib.ptr(plan.off[0]), C.c_int(plan.V), C.c_int(plan.max_T[0]),
+        C.c_int(Cc), _lib.ptr(out), _stream(logits.device)), "mucon_logsoftmax_expand")
+    return out
+
+
+def _tco(conv):
+    """Conv1d weight [Cout, Cin, k] -> contiguous [k, Cin, Cout]."""
+    return conv.weight.detach().permute(2, 1, 0).contiguous().float()
+
+
+class WaveNetLayer(nn.Module):
+    """Parameter container with the reference's names (temporal.py:9-53)."""
+
+    def __init__(self, num_channels, kernel_size, dilation, drop=0.25, leaky=False):
+        super().__init__()
+        self.num_channels, self.kernel_size, self.dilation, self.leaky = num_channels, kernel_size, dilation, leaky
+        self.dilated_conv = nn.Conv1d(num_channels, num_channels, kernel_size, dilation=dilation, padding=dilation)
+        self.conv_1x1 = nn.Conv1d(num_channels, num_channels, kernel_size=1)
+        self.drop = nn.Dropout(drop)
+
+
+class WaveNetBlock(nn.Module):
+    """Drop-in for core.modules.temporal.WaveNetBlock (temporal.py:77-147), forward on the GPU."""
+
+    def __init__(self, in_channels, stages=(1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024), out_dims=64, kernel_size=3,
+                 pooling=True, pooling_layers=(1, 2, 4, 8), pooling_type="max", dropout_rate=0.25, leaky=False):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError("kernel_size != 3")
+        if leaky:
+            raise NotImplementedError("leaky ReLU variant (model.ft.leaky_relu) is not implemented")
+        if pooling and pooling_type != "max":
+            raise NotImplementedError("only max pooling is implemented")
+        self.in_channels, self.stages, self.out_dims = in_channels, list(stages), out_dims
+        self.num_stages = len(self.stages)
+        self.kernel_size, self.pooling, self.pooling_type = kernel_size, pooling, pooling_type
+        self.pooling_layers, self.dropout_rate, self.leaky = list(pooling_layers), dropout_rate, leaky
+        self.first_conv = nn.Conv1d(in_channels, out_dims, kernel_size=1)
+        self.last_conv = nn.Conv1d(out_dims, out_dims, kernel_size=1)
+        self.layers = []
+        for i, d in enumerate(self.stages):
+            layer = WaveNetLayer(out_dims, kernel_size, d, drop=dropout_rate, leaky=leaky)
+            self.layers.append(layer)
+            self.add_module("l_{}".format(i), layer)
+        self._cache = None
+
+    def n_pools(self):
+        return sum(1 for i in range(self.num_stages) if self.pooling and i in self.pooling_layers)
+
+    def _weights(self):
+        key = tuple(p._version for p in self.parameters()) + (str(self.first_conv.weight.device),)
+        if self._cache is None or self._cache[0] != key:
+            w = dict(first_w=self.first_conv.weight.detach()[:, :, 0].contiguous().float(),
+                     first_b=self.first_conv.bias.detach().contiguous().float(),
+                     last_w=_tco(self.last_conv), last_b=self.last_conv.bias.detach().contiguous().float(),
+                     layers=[(_tco(l.dilated_conv), l.dilated_conv.bias.detach().contiguous().float(),
+                              _tco(l.conv_1x1), l.conv_1x1.bias.detach().contiguous().float()) for l in self.layers])
+            self._cache = (key, w)
+        return self._cache[1]
+
+    def forward_packed(self, feats, plan):
+        """feats [sum T, in_channels] float32 rows (time-major, videos concatenated) -> [sum T', out_dims]."""
+        if self.training and self.dropout_rate > 0:
+            raise NotImplementedError("training-mode dropout is not implemented; call .eval()")
+        if not feats.is_cuda:
+            raise _lib.MuconError("the backbone needs CUDA tensors (there is no CPU fallback)")
+        w = self._weights()
+        V = plan.V
+        if self.out_dims == 128 and self.in_channels % 32 == 0:
+            x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True)       # temporal.py:133
+        else:
+            x = conv1d_rows(feats, w["first_w"].t().contiguous()[None], w["first_b"], plan.off[0], V, plan.max_T[0],
+                            relu_out=True)
+        level = 0
+        for i, (wd, bd, w1, b1) in enumerate(w["layers"]):
+            off, mt = plan.off[level], plan.max_T[level]
+            y = conv1d_rows(x, wd, bd, off, V, mt, dilation=self.stages[i], relu_out=True)   # temporal.py:48-49
+            x = conv1d_rows(y, w1, b1, off, V, mt, residual=x)                                # temporal.py:50-52
+            if self.pooling and i in self.pooling_layers:
+                x = maxpool2_rows(x, plan, level)                                              # temporal.py:139
+                level += 1
+        return conv1d_rows(x, w["last_w"], w["last_b"], plan.off[level], V, plan.max_T[level], relu_in=True)  # :144-145
+
+    def forward(self, x):
+        """x [B, in_channels, T] -> [B, out_dims, T']  (temporal.py:128-147)."""
+        B, _, T = x.shape
+        plan = BackbonePlan([T] * B, self.n_pools(), x.device)
+        rows = x.detach().permute(0, 2, 1).reshape(B * T, self.in_channels).contiguous().float()
+        z = self.forward_packed(rows, plan)
+        Tz = plan.T[-1][0]
+        return z.view(B, Tz, self.out_dims).permute(0, 2, 1).contiguous()
+
+
+class MuConBackbone(nn.Module):
+    """The backbone-side members of the reference model, under the reference's attribute names:
+    `ft` (models.py:162-171), `ft_last_gn` (:188-191), `conv_classifier` (:276-278)."""
+
+    def __init__(self, input_feature_size=2048, num_classes=48, hidden_size=128,
+                 stages=(1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024), pooling=True, pooling_layers=(1, 2, 4, 8),
+                 last_gn=True, last_gn_num_groups=32, last_relu=True):
+        super().__init__()
+        self.num_classes, self.hidden_size = num_classes, hidden_size
+        self.last_gn, self.last_relu = last_gn, last_relu
+        self.ft = WaveNetBlock(input_feature_size, stages=stages, out_dims=hidden_size, pooling=pooling,
+                               pooling_layers=pooling_layers)
+        self.ft_last_gn = nn.GroupNorm(num_groups=last_gn_num_groups, num_channels=hidden_size)
+        self.conv_classifier = nn.Conv1d(hidden_size, num_classes, kernel_size=1)
+
+    def plan(self, T, device=None):
+        return BackbonePlan(T, self.ft.n_pools(), device or self.conv_classifier.weight.device)
+
+    # ---- packed (variable-length batch) API ----------------------------------------------------
+    def encode_packed(self, feats, plan):
+        """temporal_modeling_forward for a packed batch: [sum T, D] -> [sum Tz, hidden]."""
+        z = self.ft.forward_packed(feats, plan)
+        lvl = len(plan.off) - 1
+        if self.last_gn:
+            z = groupnorm_relu_rows(z, self.ft_last_gn.weight.detach().float(), self.ft_last_gn.bias.detach().float(),
+                                    plan.off[lvl], plan.V, self.ft_last_gn.num_groups, self.ft_last_gn.eps,
+                                    relu=self.last_relu)
+        elif self.last_relu:
+            z = torch.relu(z)
+        return z
+
+    def logprobs_packed(self, z, plan):
+        """frame_classifier_forward + predict's log_softmax: [sum Tz, hidden] -> [sum T, classes]."""
+        lvl = len(plan.off) - 1
+        w = self.conv_classifier.weight.detach().permute(2, 1, 0).contiguous().float()
+        logits = conv1d_rows(z, w, self.conv_classifier.bias.detach().float(), plan.off[lvl], plan.V, plan.max_T[lvl])
+        return logsoftmax_expand_rows(logits, plan, lvl)
+
+    # ---- the reference's signatures (batch size 1) -----------------------------------------------
+    def temporal_modeling_forward(self, input):
+        """[B, T, D] -> [B, T', D']  (models.py:746-773), eval mode."""
+        B, T, D = input.shape
+        plan = self.plan([T] * B, input.device)
+        z = self.encode_packed(input.detach().reshape(B * T, D).contiguous().float(), plan)
+        return z.view(B, -1, self.hidden_size)
+
+    def frame_classifier_forward(self, temporal_encoded, target_length):
+        """[1, Ds, Tz] -> [1, num_classes, Tf] logits (models.py:567-582)."""
+        z = temporal_encoded.detach()[0].t().contiguous().float()  # [Tz, Ds]
+        Tz = z.shape[0]
+        off = torch.tensor([0, Tz], dtype=torch.int64, device=z.device)
+        w = self.conv_classifier.weight.detach().permute(2, 1, 0).contiguous().float()
+        logits = conv1d_rows(z, w, self.conv_classifier.bias.detach().float(), off, 1, Tz)
+        idx = torch.clamp(torch.floor(torch.arange(target_length, device=z.device, dtype=torch.float32)
+                                      * (float(np.float32(Tz) / np.float32(target_length)))).long(), max=Tz - 1)
+        return logits[idx].t().unsqueeze(0).contiguous()

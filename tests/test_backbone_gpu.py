@@ -1,0 +1,107 @@
+"""GPU parity of the backbone forward against the reference's frozen outputs and the torch oracle.
+
+Tolerances: everything after the input projection is fp32 FFMA: rtol 1e-4 / atol 1e-4 against the
+oracle given the same projection output.  The projection runs on tcgen05 with TF32 operands (10-bit
+mantissa, fp32 accumulate), so end-to-end activations are compared with atol = 1e-2 * RMS of the
+reference tensor; the GEMM alone is checked against an fp64 matmul of the
+TF32-truncated operands with rtol 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backbone as ob
+from tests.backbone_util import CASES, G, POOL, STAGES, case_inputs, state_dict_of
+
+pytestmark = pytest.mark.gpu
+
+
+def rms(x):
+    return float(np.sqrt(np.mean(np.square(x))))
+
+
+def tf32_trunc(x):
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,K", [(128, 32), (300, 2048), (5000, 2048), (77, 256), (148 * 128 * 2 + 5, 64)])
+def test_tcgen05_gemm_against_truncated_operands(cuda_device, M, K):
+    from mucon_b200.temporal import gemm_tf32_bias_act
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(128, K, generator=g) / K ** 0.5
+    b = torch.randn(128, generator=g)
+    out = gemm_tf32_bias_act(A.to(cuda_device), W.to(cuda_device), b.to(cuda_device), relu=False).cpu()
+    ref = (tf32_trunc(A).double() @ tf32_trunc(W).double().t() + b.double()).float()
+    full = (A.double() @ W.double().t() + b.double()).float()
+    err_t, err_f = (out - ref).abs().max().item(), (out - full).abs().max().item()
+    assert err_t <= 2e-4 * max(1.0, ref.abs().max().item()), (err_t, err_f)
+    assert err_f <= 1e-2 * rms(full.numpy()) * 3
+    out_r = gemm_tf32_bias_act(A.to(cuda_device), W.to(cuda_device), b.to(cuda_device), relu=True).cpu()
+    assert torch.equal(out_r, torch.relu(out))
+
+
+def test_fp32_layers_against_oracle_given_same_projection(cuda_device):
+    """Dilated layers, pools, last conv, GroupNorm, classifier, log-softmax: fp32 parity (in_channels = 64
+    takes the fp32 conv kernel for the projection too, so the whole path is fp32)."""
+    from mucon_b200.temporal import MuConBackbone
+    torch.manual_seed(3)
+    m = MuConBackbone(input_feature_size=48, num_classes=20).eval()  # 48 % 32 != 0 -> fp32 projection
+    with torch.no_grad():
+        m.ft_last_gn.weight.uniform_(0.5, 1.5)
+        m.ft_last_gn.bias.uniform_(-0.5, 0.5)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    Ts = [700, 333, 64, 1999, 16]
+    feats = [torch.randn(1, t, 48).abs() for t in Ts]
+    mc = m.to(cuda_device)
+    plan = mc.plan(Ts)
+    packed = torch.cat([f[0] for f in feats]).to(cuda_device)
+    z = mc.encode_packed(packed, plan)
+    logp = mc.logprobs_packed(z, plan)
+    zo, lo = plan.off_host[-1], plan.off_host[0]
+    for v, t in enumerate(Ts):
+        with torch.no_grad():
+            rz = ob.encode(sd, feats[v], STAGES, POOL)
+            rl = ob.logprobs(sd, rz, t)
+        gz = z[zo[v]:zo[v + 1]].cpu()
+        assert torch.allclose(gz, rz[0], rtol=1e-4, atol=1e-4), (v, (gz - rz[0]).abs().max())
+        gl = logp[lo[v]:lo[v + 1]].cpu()
+        assert torch.allclose(gl, rl, rtol=1e-4, atol=1e-4), (v, (gl - rl).abs().max())
+
+
+@pytest.mark.parametrize("i", range(len(CASES)))
+def test_reference_golden_end_to_end(cuda_device, i):
+    from mucon_b200.temporal import MuConBackbone
+    (T, D, H, C), (ft, gn, cls), feats, fresh = case_inputs(i)
+    if not fresh:
+        pytest.skip("torch RNG stream differs from the one the fixture was minted with")
+    m = MuConBackbone(input_feature_size=D, num_classes=C, hidden_size=H).eval()
+    m.load_state_dict(state_dict_of(ft, gn, cls))
+    m = m.to(cuda_device)
+    enc = m.temporal_modeling_forward(feats.to(cuda_device))  # reference signature: [1, T, D] -> [1, Tz, H]
+    want_z = G[f"c{i}_z"]
+    assert tuple(enc.shape) == (1,) + want_z.shape
+    assert np.abs(enc[0].cpu().numpy() - want_z).max() <= 1e-2 * rms(want_z) * 4
+    seg = m.frame_classifier_forward(enc.permute(0, 2, 1), T)  # [1, C, T] logits
+    logp = torch.log_softmax(seg[0].t(), dim=1).cpu().numpy()
+    plan = m.plan([T])
+    logp2 = m.logprobs_packed(enc[0].contiguous(), plan).cpu().numpy()
+    assert np.abs(logp - logp2).max() <= 1e-5
+    want = G[f"c{i}_logp"]
+    got = logp2 if T <= 800 else logp2[::7]
+    assert np.abs(got - want).max() <= 1e-2 * rms(want) * 4
+    assert np.mean(np.argmax(got, 1) == np.argmax(want, 1)) >= 0.98
+
+
+def test_wavenet_block_reference_signature(cuda_device):
+    from mucon_b200.temporal import WaveNetBlock
+    torch.manual_seed(9)
+    blk = WaveNetBlock(64, stages=STAGES, out_dims=128, pooling_layers=POOL).eval()
+    sd = {"ft." + k: v.clone() for k, v in blk.state_dict().items()}
+    x = torch.randn(2, 64, 500)
+    out = blk.to(cuda_device)(x.to(cuda_device)).cpu()
+    with torch.no_grad():
+        ref = ob.wavenet_block(sd, x, STAGES, POOL)
+    assert out.shape == ref.shape == (2, 128, 31)
+    assert (out - ref).abs().max().item() <= 1e-2 * rms(ref.numpy()) * 4
+    with pytest.raises(NotImplementedError):
+        blk.train()(x.to(cuda_device))
