@@ -239,13 +239,15 @@ def main_ours(args, rank, world, local_rank):
     logp = device_logp(T, trs, rank, device)
     eng = ViterbiEngine(device)
     params = poisson_params(means)
-    plan = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=params, labels="best")
-    max_pos = V_PER_GPU * 12
+    payload_cap = 8 * V_PER_GPU + 4 * V_PER_GPU * 12  # same on every rank: [scores | segment lengths | pad]
+    plan = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=params, labels="best",
+                     payload_capacity=payload_cap)
+    recv = torch.empty(world * plan.payload.numel(), dtype=torch.uint8, device=device) if world > 1 else None
 
     def step(mode="auto"):
         eng.run(plan, logp, seg0_f32=True, mode=mode, write_bs=False)
         if world > 1:
-            mdist.gather_alignments(plan.score, plan.seg_blocks, plan.tr_off, V_PER_GPU, max_pos)
+            mdist.gather_payload(plan, recv)
 
     def barrier():
         torch.cuda.synchronize()
@@ -298,9 +300,9 @@ def main_ours(args, rank, world, local_rank):
     dev_in = torch.empty_like(logp)
 
     def e2e_step():
+        dev_in.copy_(host_logp, non_blocking=True)   # the 740 MB copy runs while the host builds the plan
         p = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=poisson_params(means),
                       labels="best")
-        dev_in.copy_(host_logp, non_blocking=True)
         eng.run(p, dev_in, seg0_f32=True, write_bs=False)
         host_labels.copy_(p.labels, non_blocking=True)
         host_small.copy_(p.score, non_blocking=True)

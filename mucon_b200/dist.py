@@ -28,6 +28,23 @@ def shard_videos(T, n_cands, world_size):
     return [np.array(sorted(b), dtype=np.int64) for b in bins]
 
 
+def gather_payload(plan, recv=None, group=None):
+    """The one collective of the data path: all_gather of every rank's AlignPlan.payload
+    ([score f64 x U | seg_blocks i32 x sum N | padding], written in place by the kernels; all ranks
+    must have built their plans with the same payload_capacity).  Returns [world, capacity] uint8."""
+    world = dist.get_world_size(group)
+    n = plan.payload.numel()
+    if recv is None:
+        recv = torch.empty(world * n, dtype=torch.uint8, device=plan.payload.device)
+    dist.all_gather_into_tensor(recv, plan.payload, group=group)
+    return recv.view(world, n)
+
+
+def unpack_payload(row, U, n_pos):
+    """(scores [U] float64, seg_blocks [n_pos] int32) views of one rank's gathered payload row."""
+    return row[:8 * U].view(torch.float64), row[8 * U:8 * U + 4 * n_pos].view(torch.int32)
+
+
 def gather_alignments(score, seg_blocks, tr_off, max_units, max_positions, group=None):
     """all_gather of per-unit scores [U] (float64) and segment lengths [sum N] (int32) plus the
     transcript offsets, padded to the given maxima.  Returns lists indexed by rank of

@@ -78,7 +78,7 @@ class AlignPlan:
     """
 
     def __init__(self, T, candidates, n_classes, fs=30, max_len=2000, len_params=None, len_rows=None,
-                 device=None, want_bp=True, labels="best", groups=None, long_K=None):
+                 device=None, want_bp=True, labels="best", groups=None, long_K=None, payload_capacity=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.fs, self.max_len, self.C = int(fs), int(max_len), int(n_classes)
         self.J = self.max_len // self.fs
@@ -203,10 +203,16 @@ class AlignPlan:
         self._meta_dev, self._meta_host, self.p = blob.upload(self.device)
 
         dev = self.device
-        self.score = torch.empty(U, dtype=torch.float64, device=dev)
+        # scores and segment lengths -- what the multi-GPU gather moves -- share one buffer so that
+        # the collective needs no packing step: [score f64 x U | seg_blocks i32 x sum N | padding]
+        n_pos = int(self.tr_off[-1])
+        need = 8 * U + 4 * n_pos
+        cap = max(need, int(payload_capacity or 0), 16)
+        self.payload = torch.zeros((cap + 7) // 8 * 8, dtype=torch.uint8, device=dev)
+        self.score = self.payload[:8 * U].view(torch.float64)
         self.final_j = torch.empty(U, dtype=torch.int32, device=dev)
         self.status = torch.empty(U, dtype=torch.int32, device=dev)
-        self.seg_blocks = torch.empty(int(self.tr_off[-1]), dtype=torch.int32, device=dev)
+        self.seg_blocks = self.payload[8 * U:8 * U + 4 * n_pos].view(torch.int32)
         self.labels = torch.empty(self.n_labels, dtype=torch.int32, device=dev)
         self.bp = torch.empty(max(self.n_bp, 1), dtype=torch.uint8, device=dev)
         self.best = torch.empty(V, dtype=torch.int32, device=dev)

@@ -52,6 +52,24 @@ def _worker(rank, world, port, ret):
         segr = rr.integers(1, 66, int(offr[-1])).astype(np.int32)
         ok &= np.array_equal(got[r]["score"], scr) and np.array_equal(got[r]["seg_blocks"], segr)
         ok &= np.array_equal(got[r]["tr_off"], offr)
+    # the zero-copy variant: every rank's plan payload gathered as bytes
+    class P:
+        pass
+    plan = P()
+    cap = 8 * 16 + 4 * 128
+    plan.payload = torch.zeros(cap, dtype=torch.uint8)
+    plan.payload[:8 * U].view(torch.float64).copy_(score)
+    plan.payload[8 * U:8 * U + 4 * int(tr_off[-1])].view(torch.int32).copy_(seg)
+    rows = mdist.gather_payload(plan)
+    for r in range(world):
+        rr = np.random.default_rng(100 + r)
+        Ur = 5 + 3 * r
+        Nr = rr.integers(1, 7, Ur)
+        npos = int(Nr.sum())
+        scr = rr.standard_normal(Ur)
+        segr = rr.integers(1, 66, npos).astype(np.int32)
+        sc_v, sg_v = mdist.unpack_payload(rows[r], Ur, npos)
+        ok &= np.array_equal(sc_v.numpy(), scr) and np.array_equal(sg_v.numpy(), segr)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
