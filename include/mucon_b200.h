@@ -180,6 +180,16 @@ int mucon_mask_template_h(int template_id, float* out100_h);
  * read as TF32: 10-bit mantissa, fp32 accumulate).  Replaces first_conv + ReLU (temporal.py:133). */
 int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const float* W, int N, const float* bias,
                              float* out, int relu, void* stream);
+/* The same convolution for 128 -> 128 channels on tcgen05 (TF32 operands, fp32 accumulate): every
+ * tap is four k-blocks of one TMEM accumulator, A tiles are TMA loads of the time-major activations
+ * at a shifted row, rows outside the video are zeroed in shared memory (Conv1d zero padding).
+ *   out[t,:] = relu_final( relu_mid( sum_tap in[t + (tap - taps/2)*dilation, :] . W[tap]^T + bias ) + residual[t,:] )
+ * W_kco: Conv1d weight [Cout, Cin, k] permuted to [k][Cout][Cin].  tiles: device array of
+ * {int64 row0; int32 t0; int32 T} (16 bytes each): one entry per 128-row tile of a video (row0 =
+ * first row of the video at this resolution, t0 = tile start within it, T = its length). */
+int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const float* bias,
+                         const float* residual, const void* tiles, int num_tiles, int64_t rows, int taps,
+                         int dilation, int relu_mid, int relu_final, void* stream);
 /* k = 1 or k = 3 dilated Conv1d with padding = dilation (temporal.py:21-31,48-52), fp32:
  *   out[t, co] = bias[co] + sum_tap sum_ci W_tco[tap][ci][co] * f(in[t + (tap - taps/2)*dilation, ci])
  * f = ReLU when relu_in; ReLU on the result when relu_out; `residual` ([rows, Cout] or NULL) is

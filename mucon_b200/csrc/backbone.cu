@@ -248,6 +248,33 @@ extern "C" int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const 
   return MUCON_OK;
 }
 
+extern "C" int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const float* bias,
+                                    const float* residual, const void* tiles, int num_tiles, int64_t rows, int taps,
+                                    int dilation, int relu_mid, int relu_final, void* stream) {
+  if (!in || !out || !W_kco || !bias || !tiles || num_tiles < 0 || rows < 0 || dilation < 1) return MUCON_EINVAL;
+  if (taps != 1 && taps != 3) return MUCON_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(W_kco) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (residual && (reinterpret_cast<uintptr_t>(residual) & 15)))
+    return MUCON_EALIGN;
+  if (num_tiles == 0 || rows == 0) return MUCON_OK;
+  if (rows > 0x7fffffff - 4096) return MUCON_EUNSUPPORTED;
+  CUtensorMap tx, tw;
+  int rc = make_map_2d(&tx, in, static_cast<uint64_t>(rows), convgemm::C, gemm::BM);
+  if (rc != MUCON_OK) return rc;
+  rc = make_map_2d(&tw, W_kco, static_cast<uint64_t>(taps) * convgemm::C, convgemm::C, gemm::BN);
+  if (rc != MUCON_OK) return rc;
+  static int sms = 0;
+  if (!sms) sms = mucon_device_sm_count();
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  MUCON_CUDA_CHECK(cudaFuncSetAttribute(convgemm::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        convgemm::CSMEM_BYTES));
+  convgemm::conv_gemm_kernel<<<grid, convgemm::CTHREADS, convgemm::CSMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+      tx, tw, static_cast<const convgemm::Tile*>(tiles), num_tiles, taps, dilation, bias, residual, out, relu_mid,
+      relu_final);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 extern "C" int mucon_conv1d(const float* in, float* out, const float* W_tco, const float* bias, const float* residual,
                             const int64_t* row_off, int V, int max_T, int Cin, int Cout, int taps, int dilation,
                             int relu_in, int relu_out, void* stream) {

@@ -205,4 +205,209 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 }  // namespace gemm
+
+// =============================================================================================
+// Temporal convolution as a tcgen05 GEMM (k = 1 or k = 3 dilated, 128 -> 128 channels).
+//
+//   out[t, :] = act( sum_tap X[t + (tap - taps/2)*dil, :] . W[tap]^T + bias ) (+ residual) (ReLU)
+//
+// For a fixed tap the rows of a [128 time steps x 128 channels] activation tile shifted by
+// (tap-1)*dil are again consecutive rows of the time-major activation tensor, so each tap is four
+// more k-blocks of the same accumulator: A tiles are TMA loads at a shifted row coordinate, B tiles
+// are the tap's [Cout x Cin] weight slice.  Zero padding at a video's ends (Conv1d(padding=dil),
+// reference src/core/modules/temporal.py:21-27): taps that only see padding are skipped, rows of a
+// tile that fall outside the video are zeroed in shared memory by a fix-up warp that sits between
+// the TMA producer and the MMA issuer (generic-proxy writes are made visible to the tensor core's
+// async proxy with fence.proxy.async before the stage is handed on).
+// 224 threads: warp 0 producer, warp 1 MMA + TMEM, warp 2 fix-up, warps 3-6 epilogue.
+namespace convgemm {
+
+using namespace gemm;
+constexpr int CTHREADS = 224;
+constexpr int C = 128;          // channels in = channels out
+constexpr int KB_PER_TAP = C / BK;
+constexpr int CSMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512;
+
+struct Tile {
+  long long row0;  // global row of the video's first time step at this resolution
+  int t0;          // first time step of the tile within the video
+  int T;           // video length at this resolution
+};
+
+__device__ __forceinline__ bool tap_live(int shift, int T) { return shift < T && -shift < T; }
+
+__global__ void __launch_bounds__(CTHREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 const Tile* __restrict__ tiles, int num_tiles, int taps, int dil, const float* __restrict__ bias,
+                 const float* __restrict__ residual, float* __restrict__ out, int relu_mid, int relu_final) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_mem = base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* ready = full + STAGES;
+  uint64_t* empty = ready + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int center = taps / 2;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
+        const Tile tl = tiles[ti];
+        for (int tap = 0; tap < taps; ++tap) {
+          const int shift = (tap - center) * dil;
+          if (!tap_live(shift, tl.T)) continue;
+          const int row = static_cast<int>(tl.row0) + tl.t0 + shift;  // may be negative: TMA zero-fills
+          for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+            unsigned char* a = stage_mem + s * STAGE_BYTES;
+            tma_load_2d(a, &tmX, kc * BK, row, &full[s]);
+            tma_load_2d(a + A_BYTES, &tmW, kc * BK, tap * C, &full[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ fix-up warp =================================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
+      const Tile tl = tiles[ti];
+      for (int tap = 0; tap < taps; ++tap) {
+        const int shift = (tap - center) * dil;
+        if (!tap_live(shift, tl.T)) continue;
+        const int lo = -(tl.t0 + shift);          // rows r < lo are before the video
+        const int hi = tl.T - (tl.t0 + shift);    // rows r >= hi are after it
+        const bool fix = lo > 0 || hi < BM;
+        for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+          mbar_wait(&full[s], ph);
+          if (fix) {
+            // a tile row is one 128-byte line (the swizzle permutes 16-byte chunks inside it)
+            float4* a4 = reinterpret_cast<float4*>(stage_mem + s * STAGE_BYTES);
+            for (int r = lane; r < BM; r += 32) {
+              if (r < lo || r >= hi) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a4[r * 8 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x, ++it) {
+      const Tile tl = tiles[ti];
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      int issued = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int shift = (tap - center) * dil;
+        if (!tap_live(shift, tl.T)) continue;
+        for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+          mbar_wait(&ready[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(stage_mem + s * STAGE_BYTES);
+            const uint64_t adesc = smem_desc(a_addr), bdesc = smem_desc(a_addr + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (issued | k) != 0);
+            mma_commit(&empty[s]);
+          }
+          __syncwarp();
+          ++issued;
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+      if (lane == 0) mma_commit(&tfull[acc]);  // the centre tap is always live, so issued > 0
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;
+    int it = 0;
+    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x, ++it) {
+      const Tile tl = tiles[ti];
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const int t = tl.t0 + q * 32 + lane;
+      const long long row = tl.row0 + t;
+      float* orow = out + row * C;
+      const float* rrow = residual ? residual + row * C : nullptr;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+        if (t < tl.T) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[e] = __uint_as_float(r[j + e]) + __ldg(bias + c * 32 + j + e);
+              if (relu_mid) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (rrow) {
+              const float4 rv = *reinterpret_cast<const float4*>(rrow + c * 32 + j);
+              v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+            }
+            if (relu_final) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+}  // namespace convgemm
 }  // namespace mucon

@@ -316,7 +316,15 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
     smem = fused_smem_bytes(cfg, G, J, b.C, b.fs, sizeof(BST));
   }
   if (smem > 227 * 1024) return MUCON_EUNSUPPORTED;
-  auto kern = (b.fs == 30) ? align_fused_kernel<BST, G, SL, 30> : align_fused_kernel<BST, G, SL, 0>;
+  void (*kern)(const mucon_viterbi_batch, const int, const BST*, const int32_t*, const FusedCfg) =
+      (b.fs == 30) ? align_fused_kernel<BST, G, SL, 30> : align_fused_kernel<BST, G, SL, 0>;
+  if constexpr (sizeof(BST) == 4 && G == 8 && SL == 9) {
+    const int minb = env_int("MUCON_FUSED_MINB", 0);
+    if (b.fs == 30 && cfg.scan_threads + 32 * cfg.dp_warps <= 160 && minb == 4)
+      kern = align_fused_kernel<BST, G, SL, 30, 160, 4>;
+    if (b.fs == 30 && cfg.scan_threads + 32 * cfg.dp_warps <= 160 && minb == 3)
+      kern = align_fused_kernel<BST, G, SL, 30, 160, 3>;
+  }
   if (smem > 48 * 1024)
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<b.U, cfg.scan_threads + 32 * cfg.dp_warps, smem, st>>>(b, J, logp, order, cfg);

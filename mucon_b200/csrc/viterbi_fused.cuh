@@ -36,8 +36,11 @@ __host__ __device__ inline size_t fused_smem_bytes(const FusedCfg& c, int G, int
   return o;
 }
 
-template <typename BST, int G, int SL, int FS>
-__global__ void __launch_bounds__(G == 32 ? kFusedMaxThreadsWide : kFusedMaxThreads, 1)
+// MAXT / MINB: launch bounds.  The generic instantiations allow 256 (512 for G = 32) threads and
+// one CTA per SM; the Breakfast shape (float32, J = 66, fs = 30, <= 13 segments: 160 threads) has a
+// dedicated instantiation whose bounds let the compiler target more resident CTAs.
+template <typename BST, int G, int SL, int FS, int MAXT = (G == 32 ? kFusedMaxThreadsWide : kFusedMaxThreads), int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
 align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restrict__ logp,
                    const int32_t* __restrict__ order, const FusedCfg cfg) {
   extern __shared__ __align__(128) unsigned char sm[];

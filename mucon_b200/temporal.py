@@ -37,6 +37,19 @@ class BackbonePlan:
         flat = torch.from_numpy(np.concatenate(offs)).to(self.device)
         n = self.V + 1
         self.off = [flat[i * n:(i + 1) * n] for i in range(len(offs))]
+        # 128-row tiles of every video at every level, for the tcgen05 conv kernel:
+        # {int64 row0, int32 t0, int32 T} per tile, longest videos first
+        self.tiles, self.n_tiles = [], []
+        for lvl, t in enumerate(self.T):
+            nt = (t + 127) // 128
+            vid = np.repeat(np.arange(self.V), nt)
+            first = np.concatenate([[0], np.cumsum(nt)])[:-1]
+            t0 = (np.arange(int(nt.sum())) - np.repeat(first, nt)) * 128
+            rec = np.zeros(int(nt.sum()), dtype=[("row0", "<i8"), ("t0", "<i4"), ("T", "<i4")])
+            rec["row0"], rec["t0"], rec["T"] = offs[lvl][:-1][vid], t0, t[vid]
+            self.n_tiles.append(int(rec.shape[0]))
+            self.tiles.append(torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(self.device)
+                              if rec.shape[0] else torch.zeros(16, dtype=torch.uint8, device=self.device))
 
 
 def _stream(dev):
@@ -60,6 +73,17 @@ def conv1d_rows(x, W_tco, bias, off, V, max_T, dilation=1, relu_in=False, relu_o
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(W_tco), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(off), C.c_int(V),
         C.c_int(max_T), C.c_int(Cin), C.c_int(Cout), C.c_int(taps), C.c_int(dilation), C.c_int(int(relu_in)),
         C.c_int(int(relu_out)), _stream(x.device)), "mucon_conv1d")
+    return out
+
+
+def conv_gemm_rows(x, W_kco, bias, plan, level, dilation=1, relu_mid=False, relu_final=False, residual=None):
+    """128 -> 128 channel conv (k = 1 / 3) on tcgen05.  W_kco: [taps*128, 128] = weight [k][Cout][Cin]."""
+    out = torch.empty_like(x)
+    taps = W_kco.shape[0] // 128
+    _lib.check(_lib.lib().mucon_conv_gemm_tf32(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(W_kco), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(plan.tiles[level]),
+        C.c_int(plan.n_tiles[level]), C.c_int64(x.shape[0]), C.c_int(taps), C.c_int(dilation), C.c_int(int(relu_mid)),
+        C.c_int(int(relu_final)), _stream(x.device)), "mucon_conv_gemm_tf32")
     return out
 
 
@@ -92,6 +116,12 @@ def logsoftmax_expand_rows(logits, plan, z_level):
 def _tco(conv):
     """Conv1d weight [Cout, Cin, k] -> contiguous [k, Cin, Cout]."""
     return conv.weight.detach().permute(2, 1, 0).contiguous().float()
+
+
+def _kco(conv):
+    """Conv1d weight [Cout, Cin, k] -> contiguous [k*Cout, Cin] (tcgen05 B operand, K-major)."""
+    w = conv.weight.detach().permute(2, 0, 1).contiguous().float()
+    return w.view(w.shape[0] * w.shape[1], w.shape[2])
 
 
 class WaveNetLayer(nn.Module):
@@ -141,11 +171,15 @@ class WaveNetBlock(nn.Module):
                      last_w=_tco(self.last_conv), last_b=self.last_conv.bias.detach().contiguous().float(),
                      layers=[(_tco(l.dilated_conv), l.dilated_conv.bias.detach().contiguous().float(),
                               _tco(l.conv_1x1), l.conv_1x1.bias.detach().contiguous().float()) for l in self.layers])
+            if self.out_dims == 128:  # tensor-core layouts
+                w["last_k"] = _kco(self.last_conv)
+                w["layers_k"] = [(_kco(l.dilated_conv), _kco(l.conv_1x1)) for l in self.layers]
             self._cache = (key, w)
         return self._cache[1]
 
-    def forward_packed(self, feats, plan):
-        """feats [sum T, in_channels] float32 rows (time-major, videos concatenated) -> [sum T', out_dims]."""
+    def forward_packed(self, feats, plan, tensor_cores=True):
+        """feats [sum T, in_channels] float32 rows (time-major, videos concatenated) -> [sum T', out_dims].
+        tensor_cores=False keeps the 128->128 convolutions on the fp32 FFMA kernels (exact fp32)."""
         if self.training and self.dropout_rate > 0:
             raise NotImplementedError("training-mode dropout is not implemented; call .eval()")
         if not feats.is_cuda:
@@ -158,14 +192,28 @@ class WaveNetBlock(nn.Module):
             x = conv1d_rows(feats, w["first_w"].t().contiguous()[None], w["first_b"], plan.off[0], V, plan.max_T[0],
                             relu_out=True)
         level = 0
+        tc = tensor_cores and self.out_dims == 128
+        last = self.num_stages - 1
         for i, (wd, bd, w1, b1) in enumerate(w["layers"]):
             off, mt = plan.off[level], plan.max_T[level]
-            y = conv1d_rows(x, wd, bd, off, V, mt, dilation=self.stages[i], relu_out=True)   # temporal.py:48-49
-            x = conv1d_rows(y, w1, b1, off, V, mt, residual=x)                                # temporal.py:50-52
-            if self.pooling and i in self.pooling_layers:
-                x = maxpool2_rows(x, plan, level)                                              # temporal.py:139
+            pooled = self.pooling and i in self.pooling_layers
+            if tc:
+                wdk, w1k = w["layers_k"][i]
+                y = conv_gemm_rows(x, wdk, bd, plan, level, dilation=self.stages[i], relu_mid=True)      # temporal.py:48-49
+                # the ReLU in front of last_conv (temporal.py:144) is folded into the last layer's store
+                x = conv_gemm_rows(y, w1k, b1, plan, level, residual=x, relu_final=(i == last and not pooled))
+            else:
+                y = conv1d_rows(x, wd, bd, off, V, mt, dilation=self.stages[i], relu_out=True)           # temporal.py:48-49
+                x = conv1d_rows(y, w1, b1, off, V, mt, residual=x)                                        # temporal.py:50-52
+            if pooled:
+                x = maxpool2_rows(x, plan, level)                                                          # temporal.py:139
                 level += 1
-        return conv1d_rows(x, w["last_w"], w["last_b"], plan.off[level], V, plan.max_T[level], relu_in=True)  # :144-145
+        if tc:
+            folded = not (self.pooling and last in self.pooling_layers)
+            if not folded:
+                x = torch.relu(x)
+            return conv_gemm_rows(x, w["last_k"], w["last_b"], plan, level)                               # temporal.py:144-145
+        return conv1d_rows(x, w["last_w"], w["last_b"], plan.off[level], V, plan.max_T[level], relu_in=True)
 
     def forward(self, x):
         """x [B, in_channels, T] -> [B, out_dims, T']  (temporal.py:128-147)."""
@@ -196,9 +244,9 @@ class MuConBackbone(nn.Module):
         return BackbonePlan(T, self.ft.n_pools(), device or self.conv_classifier.weight.device)
 
     # ---- packed (variable-length batch) API ----------------------------------------------------
-    def encode_packed(self, feats, plan):
+    def encode_packed(self, feats, plan, tensor_cores=True):
         """temporal_modeling_forward for a packed batch: [sum T, D] -> [sum Tz, hidden]."""
-        z = self.ft.forward_packed(feats, plan)
+        z = self.ft.forward_packed(feats, plan, tensor_cores=tensor_cores)
         lvl = len(plan.off) - 1
         if self.last_gn:
             z = groupnorm_relu_rows(z, self.ft_last_gn.weight.detach().float(), self.ft_last_gn.bias.detach().float(),
