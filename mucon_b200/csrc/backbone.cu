@@ -135,6 +135,18 @@ __global__ void maxpool2_kernel(const float* __restrict__ in, float* __restrict_
   const int64_t i0 = off_in[v], o0 = off_out[v];
   const int To = static_cast<int>(off_out[v + 1] - o0);
   const int64_t n = static_cast<int64_t>(To) * C;
+  if ((C & 3) == 0) {  // 16-byte path: rows are multiples of 16 bytes
+    const int c4 = C >> 2;
+    const int n4 = static_cast<int>(n >> 2);
+    const float4* in4 = reinterpret_cast<const float4*>(in + i0 * C);
+    float4* out4 = reinterpret_cast<float4*>(out + o0 * C);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const int t = i / c4, q = i - t * c4;
+      const float4 a = in4[(2 * t) * c4 + q], b = in4[(2 * t + 1) * c4 + q];
+      out4[i] = make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t t = i / C;
@@ -187,33 +199,79 @@ __global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict_
 
 // log_softmax over C classes of the pooled-resolution logits row idx(t), written for every frame t:
 // idx(t) = min(floor(t * (float)Tz / T), Tz - 1) -- F.interpolate(mode="nearest") (models.py:574-576).
-// One warp per output frame.
+// A CTA owns kLseFrames consecutive frames: its warps first turn the few source rows those frames
+// map to into log-probabilities in shared memory, then all threads stream them out with coalesced
+// 16-byte stores (the output, 4*C bytes per frame, is the only large traffic of this kernel).
+constexpr int kLseFrames = 256;
+constexpr int kLseMaxRows = 64;
 __global__ void __launch_bounds__(256) logsoftmax_expand_kernel(const float* __restrict__ logits,
                                                                 const int64_t* __restrict__ off_z,
                                                                 const int64_t* __restrict__ off_t, int C,
                                                                 float* __restrict__ out) {
+  extern __shared__ float lrows[];  // [kLseMaxRows][C]
   const int v = blockIdx.y;
-  const int64_t z0 = off_z[v], t0 = off_t[v];
+  const int64_t z0 = off_z[v], t0v = off_t[v];
   const int Tz = static_cast<int>(off_z[v + 1] - z0);
-  const int T = static_cast<int>(off_t[v + 1] - t0);
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  const int T = static_cast<int>(off_t[v + 1] - t0v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const float scale = static_cast<float>(Tz) / static_cast<float>(T);
-  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
+  auto src_row = [&](int t) {
     int iz = static_cast<int>(floorf(static_cast<float>(t) * scale));
-    if (iz > Tz - 1) iz = Tz - 1;
-    const float* row = logits + (z0 + iz) * C;
-    float m = -INFINITY;
-    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+    return iz > Tz - 1 ? Tz - 1 : iz;
+  };
+  for (int t0 = blockIdx.x * kLseFrames; t0 < T; t0 += gridDim.x * kLseFrames) {
+    const int t1 = min(T, t0 + kLseFrames);
+    const int iz0 = src_row(t0), iz1 = src_row(t1 - 1);
+    const int nrows = iz1 - iz0 + 1;
+    if (nrows <= kLseMaxRows) {
+      for (int r = warp; r < nrows; r += nwarp) {
+        const float* row = logits + (z0 + iz0 + r) * C;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float lse = m + logf(s);
-    float* orow = out + (t0 + t) * C;
-    for (int c = lane; c < C; c += 32) orow[c] = row[c] - lse;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float lse = m + logf(s);
+        for (int c = lane; c < C; c += 32) lrows[r * C + c] = row[c] - lse;
+      }
+      __syncthreads();
+      float* obase = out + (t0v + t0) * C;
+      if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
+        const int c4 = C >> 2;
+        const int n = (t1 - t0) * c4;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const int t = i / c4, q = i - t * c4;
+          const int r = src_row(t0 + t) - iz0;
+          reinterpret_cast<float4*>(obase)[i] = *reinterpret_cast<const float4*>(lrows + r * C + 4 * q);
+        }
+      } else {
+        const int n = (t1 - t0) * C;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const int t = i / C, c = i - t * C;
+          obase[i] = lrows[(src_row(t0 + t) - iz0) * C + c];
+        }
+      }
+      __syncthreads();
+    } else {
+      // down-sampling or nearly 1:1 mapping: one warp per frame
+      for (int t = t0 + warp; t < t1; t += nwarp) {
+        const float* row = logits + (z0 + src_row(t)) * C;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float lse = m + logf(s);
+        float* orow = out + (t0v + t) * C;
+        for (int c = lane; c < C; c += 32) orow[c] = row[c] - lse;
+      }
+    }
   }
 }
 
@@ -321,9 +379,11 @@ extern "C" int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z
   if (!logits || !off_z || !off_t || !out || V < 0 || C < 1 || max_T < 0) return MUCON_EINVAL;
   if (V == 0 || max_T == 0) return MUCON_OK;
   if (V > 65535) return MUCON_EUNSUPPORTED;
-  int bx = (max_T + 7) / 8;
-  if (bx > 128) bx = 128;
-  logsoftmax_expand_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, off_z, off_t, C, out);
+  int bx = (max_T + kLseFrames - 1) / kLseFrames;
+  if (bx > 64) bx = 64;
+  const size_t smem = sizeof(float) * kLseMaxRows * C;
+  if (smem > 48 * 1024) return MUCON_EUNSUPPORTED;
+  logsoftmax_expand_kernel<<<dim3(bx, V), 256, smem, static_cast<cudaStream_t>(stream)>>>(logits, off_z, off_t, C, out);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

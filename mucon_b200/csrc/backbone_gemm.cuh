@@ -226,7 +226,11 @@ using namespace gemm;
 constexpr int CTHREADS = 224;
 constexpr int C = 128;          // channels in = channels out
 constexpr int KB_PER_TAP = C / BK;
-constexpr int CSMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512;
+constexpr int CSTAGES = 4;
+constexpr int EPI_LD = C + 4;   // padded row of the epilogue staging tile (floats): 16-byte aligned, and a
+                                // warp-wide 16-byte store to 32 rows spreads over all banks
+constexpr int EPI_BYTES = 32 * EPI_LD * 4;  // per epilogue warp
+constexpr int CSMEM_BYTES = 1024 + CSTAGES * STAGE_BYTES + 4 * EPI_BYTES + 512;
 
 struct Tile {
   long long row0;  // global row of the video's first time step at this resolution
@@ -243,16 +247,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_mem = base;
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
-  uint64_t* ready = full + STAGES;
-  uint64_t* empty = ready + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  float* epi_mem = reinterpret_cast<float*>(base + CSTAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + CSTAGES * STAGE_BYTES + 4 * EPI_BYTES);
+  uint64_t* ready = full + CSTAGES;
+  uint64_t* empty = ready + CSTAGES;
+  uint64_t* tfull = empty + CSTAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_fence_init();
   }
@@ -285,7 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             unsigned char* a = stage_mem + s * STAGE_BYTES;
             tma_load_2d(a, &tmX, kc * BK, row, &full[s]);
             tma_load_2d(a + A_BYTES, &tmW, kc * BK, tap * C, &full[s]);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (++s == CSTAGES) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -317,7 +322,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&ready[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == CSTAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -350,7 +355,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           __syncwarp();
           ++issued;
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == CSTAGES) { s = 0; ph ^= 1; }
         }
       }
       if (lane == 0) mma_commit(&tfull[acc]);  // the centre tap is always live, so issued > 0
@@ -366,38 +371,53 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
-      const int t = tl.t0 + q * 32 + lane;
-      const long long row = tl.row0 + t;
-      float* orow = out + row * C;
-      const float* rrow = residual ? residual + row * C : nullptr;
+      // phase A: TMEM -> registers (lane = row) -> + bias (ReLU) -> padded shared tile
+      float* et = epi_mem + (warp - 3) * (EPI_BYTES / 4);
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
-        if (t < tl.T) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float v[4];
+        for (int j = 0; j < 32; j += 4) {
+          float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[e] = __uint_as_float(r[j + e]) + __ldg(bias + c * 32 + j + e);
-              if (relu_mid) v[e] = fmaxf(v[e], 0.f);
-            }
-            if (rrow) {
-              const float4 rv = *reinterpret_cast<const float4*>(rrow + c * 32 + j);
-              v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
-            }
-            if (relu_final) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(v[0], v[1], v[2], v[3]);
+          for (int e = 0; e < 4; ++e) {
+            v[e] = __uint_as_float(r[j + e]) + __ldg(bias + c * 32 + j + e);
+            if (relu_mid) v[e] = fmaxf(v[e], 0.f);
           }
+          *reinterpret_cast<float4*>(et + lane * EPI_LD + c * 32 + j) = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
+      // the accumulator is drained: hand it back before the (slower) global phase
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      // phase B: one row per iteration, 32 lanes x 16 bytes = a full 512-byte row: coalesced
+      // residual read and store
+      const int tbase = tl.t0 + q * 32;
+      const long long rbase = tl.row0 + tbase;
+      const int nrow = min(32, tl.T - tbase);  // rows of this warp inside the video (may be <= 0)
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float4 rv[8], v[8];
+        if (residual) {  // eight independent 512-byte row loads in flight
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            rv[e] = (r0 + e < nrow) ? __ldg(reinterpret_cast<const float4*>(residual + (rbase + r0 + e) * C) + lane)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(et + (r0 + e) * EPI_LD + lane * 4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (residual) { v[e].x += rv[e].x; v[e].y += rv[e].y; v[e].z += rv[e].z; v[e].w += rv[e].w; }
+          if (relu_final) {
+            v[e].x = fmaxf(v[e].x, 0.f); v[e].y = fmaxf(v[e].y, 0.f); v[e].z = fmaxf(v[e].z, 0.f); v[e].w = fmaxf(v[e].w, 0.f);
+          }
+          if (r0 + e < nrow) *(reinterpret_cast<float4*>(out + (rbase + r0 + e) * C) + lane) = v[e];
+        }
+      }
+      __syncwarp();
     }
   }
 
