@@ -290,6 +290,49 @@ def main_ours(args, rank, world, local_rank):
     scan_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in sev]))
     dp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in sev]))
 
+    # ---- full test-time inference of the hot path: backbone forward (2048-d features -> log-probs,
+    # tcgen05 projection + conv layers) chained into the fused alignment, all resident in HBM
+    full = None
+    if not args.no_backbone:
+        try:
+            from mucon_b200.temporal import MuConBackbone
+            torch.manual_seed(rank)
+            net = MuConBackbone().eval().to(device)
+            bplan = net.plan(T, device)
+            feats = torch.empty(int(T.sum()), 2048, device=device)
+            feats.normal_(generator=torch.Generator(device).manual_seed(rank)).abs_().mul_(0.5)
+
+            def full_step():
+                lp = net.logprobs_packed(net.encode_packed(feats, bplan), bplan)
+                eng.run(plan, lp, seg0_f32=True, write_bs=False)
+                return lp
+
+            for _ in range(2):
+                full_step()
+            barrier()
+            f0, f1, f2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            nfull = 3
+            f0.record()
+            for _ in range(nfull):
+                lp = net.logprobs_packed(net.encode_packed(feats, bplan), bplan)
+            f1.record()
+            for _ in range(nfull):
+                full_step()
+            f2.record()
+            barrier()
+            bb_ms = f0.elapsed_time(f1) / nfull
+            full_ms = f1.elapsed_time(f2) / nfull
+            full = {"what": "backbone forward (TF32 tcgen05 projection + dilated conv layers, fp32 GN/classifier/"
+                            "log-softmax) -> fused Viterbi alignment, 1712 videos/GPU, features resident in HBM",
+                    "ms_per_step": full_ms, "backbone_ms": bb_ms,
+                    "frames_per_sec_per_gpu": float(T.sum()) / (full_ms * 1e-3),
+                    "feature_bytes": int(feats.numel() * 4),
+                    "feature_read_gbs": feats.numel() * 4 / (bb_ms * 1e-3) / 1e9}
+            del feats, lp, net
+            torch.cuda.empty_cache()
+        except Exception as e:  # the headline number must not depend on this extra leg
+            full = {"error": str(e)[:200]}
+
     # ---- e2e: host API, pinned host log-probs in, labels + scores + segments out ---------------
     host_logp = torch.empty(logp.shape, dtype=logp.dtype, pin_memory=True)
     host_logp.copy_(logp)
@@ -383,6 +426,8 @@ def main_ours(args, rank, world, local_rank):
                                                 "ms_per_launch": scan_ms},
                                 "dp_kernel_ms": dp_ms},
         }
+        if full is not None:
+            out["full_inference"] = full
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
@@ -397,6 +442,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-backbone", action="store_true", help="skip the backbone + alignment leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
