@@ -209,6 +209,16 @@ int mucon_groupnorm_relu(const float* in, float* out, const float* gamma, const 
 int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z, const int64_t* off_t, int V, int max_T,
                             int C, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * vit_mof counters: nearest-neighbour resize of each video's predicted labels
+ * to its ground-truth length (src/core/utils.py:34-47) + MoF counts (src/core/metrics/segmentation.py
+ * :16-44, evaluators.py:225-243).  pred_off / gt_off: [V+1] offsets into pred / gt.  ignore_ids_h:
+ * host array of up to 16 target ids to skip.  counts[2*v] = correct, counts[2*v+1] = total
+ * (zeroed by the call); MoF = sum correct / sum total. */
+int mucon_vit_mof(const int32_t* pred, const int64_t* pred_off, const int32_t* gt, const int64_t* gt_off,
+                  int V, int max_T_gt, const int32_t* ignore_ids_h, int n_ignore,
+                  unsigned long long* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

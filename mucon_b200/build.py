@@ -25,6 +25,7 @@ SOURCES = {
     "viterbi.cu": ["-fmad=false"],
     "masks.cu": ["-fmad=false"],
     "backbone.cu": [],
+    "metrics.cu": [],
 }
 
 
