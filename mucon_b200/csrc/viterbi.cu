@@ -305,7 +305,7 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
   const size_t blk_bytes = (size_t)b.C * sizeof(BST) * b.fs;
   cfg.bps = (int)(env_int("MUCON_FUSED_SLAB_BYTES", 17280) / blk_bytes);
   if (cfg.bps < 1) cfg.bps = 1;
-  cfg.stages = env_int("MUCON_FUSED_STAGES", 3);
+  cfg.stages = env_int("MUCON_FUSED_STAGES", 2);
   cfg.ring_slabs = env_int("MUCON_FUSED_RING", 4);
   if (cfg.stages < 2 || cfg.stages > 8 || cfg.ring_slabs < 2 || cfg.ring_slabs > 8) return MUCON_EINVAL;
   cfg.write_bs = write_bs && b.bs;
@@ -319,11 +319,12 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
   void (*kern)(const mucon_viterbi_batch, const int, const BST*, const int32_t*, const FusedCfg) =
       (b.fs == 30) ? align_fused_kernel<BST, G, SL, 30> : align_fused_kernel<BST, G, SL, 0>;
   if constexpr (sizeof(BST) == 4 && G == 8 && SL == 9) {
-    const int minb = env_int("MUCON_FUSED_MINB", 0);
-    if (b.fs == 30 && cfg.scan_threads + 32 * cfg.dp_warps <= 160 && minb == 4)
-      kern = align_fused_kernel<BST, G, SL, 30, 160, 4>;
-    if (b.fs == 30 && cfg.scan_threads + 32 * cfg.dp_warps <= 160 && minb == 3)
-      kern = align_fused_kernel<BST, G, SL, 30, 160, 3>;
+    // the evaluator's shape (float32, fs = 30, J = 66) with 33..64 classes: one scan warp, two
+    // class columns per lane
+    if (b.fs == 30 && b.C > 32 && b.C <= 64 && b.C % 2 == 0 && env_int("MUCON_FUSED_CPT", 2) == 2) {
+      cfg.scan_threads = 32;
+      kern = align_fused_kernel<BST, G, SL, 30, kFusedMaxThreads, 1, 2>;
+    }
   }
   if (smem > 48 * 1024)
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

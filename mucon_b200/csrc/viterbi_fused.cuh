@@ -39,7 +39,12 @@ __host__ __device__ inline size_t fused_smem_bytes(const FusedCfg& c, int G, int
 // MAXT / MINB: launch bounds.  The generic instantiations allow 256 (512 for G = 32) threads and
 // one CTA per SM; the Breakfast shape (float32, J = 66, fs = 30, <= 13 segments: 160 threads) has a
 // dedicated instantiation whose bounds let the compiler target more resident CTAs.
-template <typename BST, int G, int SL, int FS, int MAXT = (G == 32 ? kFusedMaxThreadsWide : kFusedMaxThreads), int MINB = 1>
+// CPT: class columns per scan thread.  1 = one thread per class (any C <= 128); 2 = one scan WARP
+// walks all columns of a 33..64-class problem, two adjacent classes per lane (two independent
+// running sums per thread, 8-byte shared loads): one warp less per CTA, so four CTAs fit the
+// register file of an SM instead of three.
+template <typename BST, int G, int SL, int FS, int MAXT = (G == 32 ? kFusedMaxThreadsWide : kFusedMaxThreads), int MINB = 1,
+          int CPT = 1>
 __global__ void __launch_bounds__(MAXT, MINB)
 align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restrict__ logp,
                    const int32_t* __restrict__ order, const FusedCfg cfg) {
@@ -91,10 +96,11 @@ align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restri
       const int pre = min(stages, nslabs);
       for (int s = 0; s < pre; ++s) issue(s, s);
     }
-    const int c = threadIdx.x;
+    const int c = threadIdx.x * CPT;
     const bool active = c < C;
-    BST run = neg_zero<BST>();  // -0 is the exact additive identity (F[0] = logp[0])
-    BST prev = 0;
+    BST run[CPT], prev[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { run[j] = neg_zero<BST>(); prev[j] = 0; }  // -0: exact additive identity
     BST* out_g = (cfg.write_bs && b.bs) ? const_cast<BST*>(reinterpret_cast<const BST*>(b.bs)) + b.blk_off[v] * C + c
                                         : nullptr;
     int st = 0, rs = 0;
@@ -110,19 +116,26 @@ align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restri
         for (int bb = 0; bb < nb; ++bb) {
           if (FS) {
 #pragma unroll
-            for (int r = 0; r < (FS ? FS : 1); ++r) run = run + s[r * C];
+            for (int r = 0; r < (FS ? FS : 1); ++r)
+#pragma unroll
+              for (int j = 0; j < CPT; ++j) run[j] = run[j] + s[r * C + j];
           } else {
 #pragma unroll 4
-            for (int r = 0; r < fs; ++r) run = run + s[r * C];
+            for (int r = 0; r < fs; ++r)
+#pragma unroll
+              for (int j = 0; j < CPT; ++j) run[j] = run[j] + s[r * C + j];
           }
           s += fs * C;
-          const BST o = (b0 + bb == 0) ? run : run - prev;
-          prev = run;
-          rp[bb * C] = o;
-          if (out_g) out_g[static_cast<int64_t>(b0 + bb) * C] = o;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            const BST o = (b0 + bb == 0) ? run[j] : run[j] - prev[j];
+            prev[j] = run[j];
+            rp[bb * C + j] = o;
+            if (out_g) out_g[static_cast<int64_t>(b0 + bb) * C + j] = o;
+          }
         }
       }
-      named_bar_sync(15, cfg.scan_threads);  // stage st consumed, ring slab rs written
+      if (cfg.scan_threads == 32) __syncwarp(); else named_bar_sync(15, cfg.scan_threads);  // stage consumed, ring slab written
       if (threadIdx.x == 0) {
         if (feasible) mbar_arrive(&ring_full[rs]);
         if (i + stages < nslabs) issue(i + stages, st);
