@@ -190,6 +190,15 @@ int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const float* W, i
 int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const float* bias,
                          const float* residual, const void* tiles, int num_tiles, int64_t rows, int taps,
                          int dilation, int relu_mid, int relu_final, void* stream);
+/* One whole WaveNet layer (temporal.py:43-53) + optional max_pool1d(2) (temporal.py:137-139) in one
+ * launch, 128 channels, tcgen05 TF32:  out = [pool]( relu_final( conv1x1(relu(conv_k3_dil(x) + bd)) + b1 + x ) ).
+ * The intermediate activation stays in shared memory as the second GEMM's operand.  Wd_kco
+ * [3][128][128], W1_kco [128][128] (Conv1d weights permuted to [k][Cout][Cin]).  tiles: device array
+ * of {int64 row0; int64 row0_out; int32 t0; int32 T} (24 bytes): one entry per 128-row tile; row0_out
+ * is the video's first row in `out` (the pooled resolution when pool != 0, else == row0). */
+int mucon_wavenet_layer_tf32(const float* x, float* out, const float* Wd_kco, const float* bd,
+                             const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
+                             int64_t rows, int dilation, int pool, int relu_final, void* stream);
 /* k = 1 or k = 3 dilated Conv1d with padding = dilation (temporal.py:21-31,48-52), fp32:
  *   out[t, co] = bias[co] + sum_tap sum_ci W_tco[tap][ci][co] * f(in[t + (tap - taps/2)*dilation, ci])
  * f = ReLU when relu_in; ReLU on the result when relu_out; `residual` ([rows, Cout] or NULL) is

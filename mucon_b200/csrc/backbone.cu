@@ -333,6 +333,34 @@ extern "C" int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_
   return MUCON_OK;
 }
 
+extern "C" int mucon_wavenet_layer_tf32(const float* x, float* out, const float* Wd_kco, const float* bd,
+                                        const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
+                                        int64_t rows, int dilation, int pool, int relu_final, void* stream) {
+  if (!x || !out || !Wd_kco || !bd || !W1_kco || !b1 || !tiles || num_tiles < 0 || rows < 0 || dilation < 1)
+    return MUCON_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(Wd_kco) & 15) ||
+      (reinterpret_cast<uintptr_t>(W1_kco) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return MUCON_EALIGN;
+  if (num_tiles == 0 || rows == 0) return MUCON_OK;
+  if (rows > 0x7fffffff - 4096) return MUCON_EUNSUPPORTED;
+  CUtensorMap tx, twd, tw1;
+  int rc = make_map_2d(&tx, x, static_cast<uint64_t>(rows), layer::C, gemm::BM);
+  if (rc != MUCON_OK) return rc;
+  rc = make_map_2d(&twd, Wd_kco, 3ull * layer::C, layer::C, gemm::BN);
+  if (rc != MUCON_OK) return rc;
+  rc = make_map_2d(&tw1, W1_kco, layer::C, layer::C, gemm::BN);
+  if (rc != MUCON_OK) return rc;
+  static int sms = 0;
+  if (!sms) sms = mucon_device_sm_count();
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer::wavenet_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        layer::LSMEM_BYTES));
+  layer::wavenet_layer_kernel<<<grid, layer::LTHREADS, layer::LSMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+      tx, twd, tw1, static_cast<const layer::Tile*>(tiles), num_tiles, dilation, bd, b1, x, out, pool, relu_final);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 extern "C" int mucon_conv1d(const float* in, float* out, const float* W_tco, const float* bias, const float* residual,
                             const int64_t* row_off, int V, int max_T, int Cin, int Cout, int taps, int dilation,
                             int relu_in, int relu_out, void* stream) {

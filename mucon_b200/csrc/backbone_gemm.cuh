@@ -430,4 +430,305 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 }
 
 }  // namespace convgemm
+
+// =============================================================================================
+// One whole WaveNet layer per launch (reference src/core/modules/temporal.py:43-53 + the optional
+// max_pool1d(2) of :137-139):   y = relu(conv_k3_dil(x) + bd);  out = conv_1x1(y) + b1 + x;  [pool]
+//
+// Per 128-row tile: GEMM 1 (3 taps x 4 k-blocks, as conv_gemm_kernel) accumulates into TMEM
+// columns 0-127; the epilogue warps turn that accumulator into relu(. + bd) and write it to shared
+// memory directly in the K-major SWIZZLE_128B layout the tensor core reads (four [128 x 32] sub-tiles),
+// so it becomes the A operand of GEMM 2 (4 k-blocks against the 1x1 weights, TMEM columns 128-255)
+// without ever leaving the SM; the second epilogue adds bias and the residual, optionally max-pools
+// adjacent rows, and writes coalesced 512-byte rows.  The intermediate activation (and the separate
+// pooling pass) cost no HBM traffic.
+// 256 threads: warp 0 producer, warp 1 MMA + TMEM, warp 2 fix-up, warp 3 idle, warps 4-7 epilogue.
+namespace layer {
+
+using namespace gemm;
+constexpr int LTHREADS = 256;
+constexpr int C = 128;
+constexpr int KB_PER_TAP = C / BK;
+constexpr int LSTAGES = 4;
+constexpr int Y_BYTES = BM * C * 4;  // 64 KB: A operand of GEMM 2, later the epilogue staging area
+constexpr int LSMEM_BYTES = 1024 + LSTAGES * STAGE_BYTES + Y_BYTES + 512;
+
+struct Tile {
+  long long row0;      // first row of the video at the input resolution
+  long long row0_out;  // first row of the video in the output tensor (differs when pooling)
+  int t0;              // first time step of the tile within the video
+  int T;               // video length at the input resolution
+};
+
+__device__ __forceinline__ bool tap_live(int shift, int T) { return shift < T && -shift < T; }
+
+__global__ void __launch_bounds__(LTHREADS, 1)
+wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWd,
+                     const __grid_constant__ CUtensorMap tmW1, const Tile* __restrict__ tiles, int num_tiles, int dil,
+                     const float* __restrict__ bd, const float* __restrict__ b1, const float* __restrict__ x,
+                     float* __restrict__ out, int pool, int relu_final) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_mem = base;
+  unsigned char* ybuf = base + LSTAGES * STAGE_BYTES;  // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
+  uint64_t* full = reinterpret_cast<uint64_t*>(ybuf + Y_BYTES);
+  uint64_t* ready = full + LSTAGES;
+  uint64_t* empty = ready + LSTAGES;
+  uint64_t* a1full = empty + LSTAGES;   // accumulator 1 complete
+  uint64_t* a1empty = a1full + 1;       // accumulator 1 drained by the epilogue
+  uint64_t* yready = a1empty + 1;       // Y written and published to the async proxy
+  uint64_t* a2full = yready + 1;        // accumulator 2 complete (Y no longer read)
+  uint64_t* a2empty = a2full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a1full, 1); mbar_init(a1empty, 4); mbar_init(yready, 4); mbar_init(a2full, 1); mbar_init(a2empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWd) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
+        const Tile tl = tiles[ti];
+        for (int tap = 0; tap < 3; ++tap) {
+          const int shift = (tap - 1) * dil;
+          if (!tap_live(shift, tl.T)) continue;
+          const int row = static_cast<int>(tl.row0) + tl.t0 + shift;
+          for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+            unsigned char* a = stage_mem + s * STAGE_BYTES;
+            tma_load_2d(a, &tmX, kc * BK, row, &full[s]);
+            tma_load_2d(a + A_BYTES, &tmWd, kc * BK, tap * C, &full[s]);
+            if (++s == LSTAGES) { s = 0; ph ^= 1; }
+          }
+        }
+        for (int kc = 0; kc < KB_PER_TAP; ++kc) {  // 1x1 weights: B half of the stage only
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], B_BYTES);
+          tma_load_2d(stage_mem + s * STAGE_BYTES + A_BYTES, &tmW1, kc * BK, 0, &full[s]);
+          if (++s == LSTAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ fix-up warp =================================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
+      const Tile tl = tiles[ti];
+      for (int tap = 0; tap < 3; ++tap) {
+        const int shift = (tap - 1) * dil;
+        if (!tap_live(shift, tl.T)) continue;
+        const int lo = -(tl.t0 + shift);
+        const int hi = tl.T - (tl.t0 + shift);
+        const bool fix = lo > 0 || hi < BM;
+        for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+          mbar_wait(&full[s], ph);
+          if (fix) {
+            float4* a4 = reinterpret_cast<float4*>(stage_mem + s * STAGE_BYTES);
+            for (int r = lane; r < BM; r += 32) {
+              if (r < lo || r >= hi) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a4[r * 8 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
+          if (++s == LSTAGES) { s = 0; ph ^= 1; }
+        }
+      }
+      for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+        mbar_wait(&full[s], ph);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+        if (++s == LSTAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    const uint32_t d1 = tmem_base, d2 = tmem_base + BN;
+    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x, ++it) {
+      const Tile tl = tiles[ti];
+      const uint32_t tph = it & 1;
+      // ---- GEMM 1: dilated conv
+      mbar_wait(a1empty, tph ^ 1);
+      tc_fence_after();
+      int issued = 0;
+      for (int tap = 0; tap < 3; ++tap) {
+        const int shift = (tap - 1) * dil;
+        if (!tap_live(shift, tl.T)) continue;
+        for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+          mbar_wait(&ready[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(stage_mem + s * STAGE_BYTES);
+            const uint64_t adesc = smem_desc(a_addr), bdesc = smem_desc(a_addr + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) mma_tf32(d1, adesc + 2 * k, bdesc + 2 * k, idesc, (issued | k) != 0);
+            mma_commit(&empty[s]);
+          }
+          __syncwarp();
+          ++issued;
+          if (++s == LSTAGES) { s = 0; ph ^= 1; }
+        }
+      }
+      if (lane == 0) mma_commit(a1full);
+      __syncwarp();
+      // ---- GEMM 2: 1x1 conv on relu(acc1 + bd), which the epilogue warps wrote to ybuf
+      mbar_wait(yready, tph);
+      mbar_wait(a2empty, tph ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+        mbar_wait(&ready[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = smem_desc(smem_u32(ybuf + kc * A_BYTES));
+          const uint64_t bdesc = smem_desc(smem_u32(stage_mem + s * STAGE_BYTES + A_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) mma_tf32(d2, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+          mma_commit(&empty[s]);
+        }
+        __syncwarp();
+        if (++s == LSTAGES) { s = 0; ph ^= 1; }
+      }
+      if (lane == 0) mma_commit(a2full);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // tile row owned in the TMEM-load phases
+    int it = 0;
+    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x, ++it) {
+      const Tile tl = tiles[ti];
+      const uint32_t tph = it & 1;
+      // ---- epilogue 1: acc1 -> relu(. + bd) -> ybuf in the K-major SWIZZLE_128B operand layout
+      mbar_wait(a1full, tph);
+      tc_fence_after();
+#pragma unroll
+      for (int kc = 0; kc < BN / 32; ++kc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kc * 32, v);
+        unsigned char* rowp = ybuf + kc * A_BYTES + r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = fmaxf(__uint_as_float(v[4 * j + 0]) + __ldg(bd + kc * 32 + 4 * j + 0), 0.f);
+          o.y = fmaxf(__uint_as_float(v[4 * j + 1]) + __ldg(bd + kc * 32 + 4 * j + 1), 0.f);
+          o.z = fmaxf(__uint_as_float(v[4 * j + 2]) + __ldg(bd + kc * 32 + 4 * j + 2), 0.f);
+          o.w = fmaxf(__uint_as_float(v[4 * j + 3]) + __ldg(bd + kc * 32 + 4 * j + 3), 0.f);
+          *reinterpret_cast<float4*>(rowp + ((j ^ (r & 7)) << 4)) = o;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core (async) proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(a1empty); mbar_arrive(yready); }
+      // ---- epilogue 2: acc2 + b1 -> staging (the ybuf bytes, free once GEMM 2 has completed)
+      mbar_wait(a2full, tph);
+      tc_fence_after();
+      float* et = reinterpret_cast<float*>(ybuf) + q * (32 * C);  // [32 rows][128], 16-byte chunks XOR-swizzled by row
+#pragma unroll
+      for (int kc = 0; kc < BN / 32; ++kc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN + kc * 32, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = __uint_as_float(v[4 * j + 0]) + __ldg(b1 + kc * 32 + 4 * j + 0);
+          o.y = __uint_as_float(v[4 * j + 1]) + __ldg(b1 + kc * 32 + 4 * j + 1);
+          o.z = __uint_as_float(v[4 * j + 2]) + __ldg(b1 + kc * 32 + 4 * j + 2);
+          o.w = __uint_as_float(v[4 * j + 3]) + __ldg(b1 + kc * 32 + 4 * j + 3);
+          const int chunk = kc * 8 + j;
+          *reinterpret_cast<float4*>(et + lane * C + ((chunk ^ (lane & 7)) << 2)) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a2empty);
+      // ---- coalesced output: + residual, optional ReLU, optional max-pool of adjacent rows
+      const int tbase = tl.t0 + q * 32;
+      const int nrow = min(32, tl.T - tbase);
+      const long long rbase = tl.row0 + tbase;
+      if (!pool) {
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          float4 rv[8], v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            rv[e] = (r0 + e < nrow) ? __ldg(reinterpret_cast<const float4*>(x + (rbase + r0 + e) * C) + lane)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[e] = *reinterpret_cast<const float4*>(et + (r0 + e) * C + ((lane ^ ((r0 + e) & 7)) << 2));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e].x += rv[e].x; v[e].y += rv[e].y; v[e].z += rv[e].z; v[e].w += rv[e].w;
+            if (relu_final) {
+              v[e].x = fmaxf(v[e].x, 0.f); v[e].y = fmaxf(v[e].y, 0.f); v[e].z = fmaxf(v[e].z, 0.f); v[e].w = fmaxf(v[e].w, 0.f);
+            }
+            if (r0 + e < nrow) *(reinterpret_cast<float4*>(out + (tl.row0_out + tbase + r0 + e) * C) + lane) = v[e];
+          }
+        }
+      } else {
+        const int npool = max(0, nrow) >> 1;  // floor: an odd last row is dropped (max_pool1d)
+        const long long obase = tl.row0_out + (tbase >> 1);
+#pragma unroll
+        for (int p0 = 0; p0 < 16; p0 += 4) {
+          float4 rv[8], v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            rv[e] = (2 * p0 + e < 2 * npool) ? __ldg(reinterpret_cast<const float4*>(x + (rbase + 2 * p0 + e) * C) + lane)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[e] = *reinterpret_cast<const float4*>(et + (2 * p0 + e) * C + ((lane ^ ((2 * p0 + e) & 7)) << 2));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { v[e].x += rv[e].x; v[e].y += rv[e].y; v[e].z += rv[e].z; v[e].w += rv[e].w; }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float4 m;
+            m.x = fmaxf(v[2 * e].x, v[2 * e + 1].x); m.y = fmaxf(v[2 * e].y, v[2 * e + 1].y);
+            m.z = fmaxf(v[2 * e].z, v[2 * e + 1].z); m.w = fmaxf(v[2 * e].w, v[2 * e + 1].w);
+            if (relu_final) { m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f); }
+            if (p0 + e < npool) *(reinterpret_cast<float4*>(out + (obase + p0 + e) * C) + lane) = m;
+          }
+        }
+      }
+      // every epilogue warp must be done with the staging bytes before anyone writes the next Y
+      named_bar_sync(2, 128);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+}  // namespace layer
 }  // namespace mucon

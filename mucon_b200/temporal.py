@@ -50,6 +50,23 @@ class BackbonePlan:
             self.n_tiles.append(int(rec.shape[0]))
             self.tiles.append(torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(self.device)
                               if rec.shape[0] else torch.zeros(16, dtype=torch.uint8, device=self.device))
+        # tiles of the fused layer kernel: {int64 row0, int64 row0_out, int32 t0, int32 T}, for a layer
+        # that keeps the resolution ("same") or is followed by a max-pool ("pool")
+        self.ltiles = {}
+        for lvl, t in enumerate(self.T):
+            nt = (t + 127) // 128
+            vid = np.repeat(np.arange(self.V), nt)
+            first = np.concatenate([[0], np.cumsum(nt)])[:-1]
+            t0 = (np.arange(int(nt.sum())) - np.repeat(first, nt)) * 128
+            for kind in ("same", "pool"):
+                if kind == "pool" and lvl + 1 >= len(self.T):
+                    continue
+                rec = np.zeros(int(nt.sum()), dtype=[("row0", "<i8"), ("row0_out", "<i8"), ("t0", "<i4"), ("T", "<i4")])
+                rec["row0"], rec["t0"], rec["T"] = offs[lvl][:-1][vid], t0, t[vid]
+                rec["row0_out"] = offs[lvl + 1][:-1][vid] if kind == "pool" else rec["row0"]
+                self.ltiles[(lvl, kind)] = (torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(self.device)
+                                            if rec.shape[0] else torch.zeros(24, dtype=torch.uint8, device=self.device),
+                                            int(rec.shape[0]))
 
 
 def _stream(dev):
@@ -84,6 +101,17 @@ def conv_gemm_rows(x, W_kco, bias, plan, level, dilation=1, relu_mid=False, relu
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(W_kco), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(plan.tiles[level]),
         C.c_int(plan.n_tiles[level]), C.c_int64(x.shape[0]), C.c_int(taps), C.c_int(dilation), C.c_int(int(relu_mid)),
         C.c_int(int(relu_final)), _stream(x.device)), "mucon_conv_gemm_tf32")
+    return out
+
+
+def wavenet_layer_rows(x, Wd_kco, bd, W1_kco, b1, plan, level, dilation, pool, relu_final):
+    """One WaveNet layer (+ optional max-pool) in a single tcgen05 launch.  x [rows(level), 128]."""
+    tiles, n_tiles = plan.ltiles[(level, "pool" if pool else "same")]
+    out = torch.empty((plan.rows[level + 1] if pool else x.shape[0], 128), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().mucon_wavenet_layer_tf32(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(Wd_kco), _lib.ptr(bd), _lib.ptr(W1_kco), _lib.ptr(b1), _lib.ptr(tiles),
+        C.c_int(n_tiles), C.c_int64(x.shape[0]), C.c_int(dilation), C.c_int(int(pool)), C.c_int(int(relu_final)),
+        _stream(x.device)), "mucon_wavenet_layer_tf32")
     return out
 
 
@@ -177,7 +205,7 @@ class WaveNetBlock(nn.Module):
             self._cache = (key, w)
         return self._cache[1]
 
-    def forward_packed(self, feats, plan, tensor_cores=True):
+    def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True):
         """feats [sum T, in_channels] float32 rows (time-major, videos concatenated) -> [sum T', out_dims].
         tensor_cores=False keeps the 128->128 convolutions on the fp32 FFMA kernels (exact fp32)."""
         if self.training and self.dropout_rate > 0:
@@ -197,6 +225,14 @@ class WaveNetBlock(nn.Module):
         for i, (wd, bd, w1, b1) in enumerate(w["layers"]):
             off, mt = plan.off[level], plan.max_T[level]
             pooled = self.pooling and i in self.pooling_layers
+            if tc and fused_layers:
+                wdk, w1k = w["layers_k"][i]
+                # dilated conv -> ReLU -> 1x1 -> + x (-> ReLU of temporal.py:144 after the last layer)
+                # (-> max-pool) in one launch
+                x = wavenet_layer_rows(x, wdk, bd, w1k, b1, plan, level, self.stages[i], pooled, relu_final=(i == last))
+                if pooled:
+                    level += 1
+                continue
             if tc:
                 wdk, w1k = w["layers_k"][i]
                 y = conv_gemm_rows(x, wdk, bd, plan, level, dilation=self.stages[i], relu_mid=True)      # temporal.py:48-49
@@ -209,7 +245,7 @@ class WaveNetBlock(nn.Module):
                 x = maxpool2_rows(x, plan, level)                                                          # temporal.py:139
                 level += 1
         if tc:
-            folded = not (self.pooling and last in self.pooling_layers)
+            folded = fused_layers or not (self.pooling and last in self.pooling_layers)
             if not folded:
                 x = torch.relu(x)
             return conv_gemm_rows(x, w["last_k"], w["last_b"], plan, level)                               # temporal.py:144-145
@@ -244,9 +280,9 @@ class MuConBackbone(nn.Module):
         return BackbonePlan(T, self.ft.n_pools(), device or self.conv_classifier.weight.device)
 
     # ---- packed (variable-length batch) API ----------------------------------------------------
-    def encode_packed(self, feats, plan, tensor_cores=True):
+    def encode_packed(self, feats, plan, tensor_cores=True, fused_layers=True):
         """temporal_modeling_forward for a packed batch: [sum T, D] -> [sum Tz, hidden]."""
-        z = self.ft.forward_packed(feats, plan, tensor_cores=tensor_cores)
+        z = self.ft.forward_packed(feats, plan, tensor_cores=tensor_cores, fused_layers=fused_layers)
         lvl = len(plan.off) - 1
         if self.last_gn:
             z = groupnorm_relu_rows(z, self.ft_last_gn.weight.detach().float(), self.ft_last_gn.bias.detach().float(),

@@ -40,7 +40,7 @@ def test_tcgen05_gemm_against_truncated_operands(cuda_device, M, K):
     assert torch.equal(out_r, torch.relu(out))
 
 
-@pytest.mark.parametrize("tensor_cores", [False, True])
+@pytest.mark.parametrize("tensor_cores", [False, True, "fused"])
 def test_layers_against_oracle(cuda_device, tensor_cores):
     """Dilated layers, pools, last conv, GroupNorm, classifier, log-softmax on a ragged batch (video
     lengths from 16 to 1999 frames: every padding / tile-boundary case of the conv kernels).
@@ -59,7 +59,7 @@ def test_layers_against_oracle(cuda_device, tensor_cores):
     mc = m.to(cuda_device)
     plan = mc.plan(Ts)
     packed = torch.cat([f[0] for f in feats]).to(cuda_device)
-    z = mc.encode_packed(packed, plan, tensor_cores=tensor_cores)
+    z = mc.encode_packed(packed, plan, tensor_cores=bool(tensor_cores), fused_layers=(tensor_cores == "fused"))
     logp = mc.logprobs_packed(z, plan)
     zo, lo = plan.off_host[-1], plan.off_host[0]
     for v, t in enumerate(Ts):
