@@ -114,6 +114,16 @@ int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int 
 
 int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 
+/* The same dynamic program for shapes the register-resident kernels reject with
+ * MUCON_EUNSUPPORTED: J = max_len/fs > 128 (the reference class's own defaults, frame_sampling = 1
+ * and max_length = 2000: viterbi.py:34, length_model.py:82) or transcripts beyond 65 segments.
+ * One CTA per unit; hypothesis scores live in the caller's workspace: ws_off[u] (in doubles) is
+ * the start of 2 * N_u * J doubles for unit u.  bp_is_u16 != 0: batch.bp is a uint16 table
+ * (needed when J > 255), bp_off in elements either way.  warp_unit / n_cta / wpc / lanes of the
+ * batch are ignored.  Same outputs, bit for bit, as mucon_viterbi_decode where both apply. */
+int mucon_viterbi_decode_generic(const mucon_viterbi_batch* batch_h, double* ws, const int64_t* ws_off,
+                                 int bp_is_u16, void* stream);
+
 /* One-launch alignment: block-score scan and DP of a unit fused in one CTA (scan warps feed the
  * DP warps through shared memory; block scores do not travel through HBM).  Same inputs and
  * outputs as mucon_viterbi_blockscores + mucon_viterbi_decode; warp_unit / n_cta / wpc of the

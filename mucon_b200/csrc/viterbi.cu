@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "viterbi_dp.cuh"
 #include "viterbi_fused.cuh"
+#include "viterbi_generic.cuh"
 
 namespace mucon {
 namespace {
@@ -403,6 +404,35 @@ extern "C" int mucon_viterbi_decode(const mucon_viterbi_batch* bh, void* stream)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (b.bs_is_f64) return dispatch_sl<double>(b, J, st);
   return dispatch_sl<float>(b, J, st);
+}
+
+extern "C" int mucon_viterbi_decode_generic(const mucon_viterbi_batch* bh, double* ws, const int64_t* ws_off,
+                                            int bp_is_u16, void* stream) {
+  if (!bh || !ws || !ws_off) return MUCON_EINVAL;
+  const mucon_viterbi_batch& b = *bh;
+  if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1) return MUCON_EINVAL;
+  if (!b.bs || !b.vid_off || !b.blk_off || !b.unit_vid || !b.tr || !b.tr_off || !b.score || !b.seg_blocks ||
+      !b.final_j || !b.status || !b.bp || !b.bp_off)
+    return MUCON_EINVAL;
+  if (!b.len_rows && !(b.len_params && b.logfact)) return MUCON_EINVAL;
+  if (b.U == 0) return MUCON_OK;
+  const int J = b.max_len / b.fs;
+  if (!bp_is_u16 && J > 255) return MUCON_EINVAL;
+  if (J > 65535) return MUCON_EUNSUPPORTED;
+  const size_t smem = (size_t)b.max_N * (sizeof(double) + sizeof(int64_t) + 3 * sizeof(int));
+  if (smem > 200 * 1024) return MUCON_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MUCON_GEN(BST, BPT)                                                                                   \
+  do {                                                                                                        \
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(dp_generic_kernel<BST, BPT>,                                        \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    dp_generic_kernel<BST, BPT><<<b.U, kGenThreads, smem, st>>>(b, J, ws, ws_off);                            \
+  } while (0)
+  if (b.bs_is_f64) { if (bp_is_u16) MUCON_GEN(double, uint16_t); else MUCON_GEN(double, uint8_t); }
+  else { if (bp_is_u16) MUCON_GEN(float, uint16_t); else MUCON_GEN(float, uint8_t); }
+#undef MUCON_GEN
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
 }
 
 extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,

@@ -68,6 +68,10 @@ class _Blob:
         return dev, host, {name: base + off for name, off, _ in self.parts}
 
 
+MAX_J_REGISTER = 128  # kDpMaxJ in csrc/viterbi_dp.cuh
+MAX_N_REGISTER = 65   # dp_max_n(8)
+
+
 class AlignPlan:
     """Shapes, offsets and device metadata of one batch of (video, candidate) units.
 
@@ -78,7 +82,8 @@ class AlignPlan:
     """
 
     def __init__(self, T, candidates, n_classes, fs=30, max_len=2000, len_params=None, len_rows=None,
-                 device=None, want_bp=True, labels="best", groups=None, long_K=None, payload_capacity=None):
+                 device=None, want_bp=True, labels="best", groups=None, long_K=None, payload_capacity=None,
+                 force_generic=False):
         self.device = torch.device(device if device is not None else "cuda")
         self.fs, self.max_len, self.C = int(fs), int(max_len), int(n_classes)
         self.J = self.max_len // self.fs
@@ -130,6 +135,9 @@ class AlignPlan:
         # serial chain, so it starts first and gives every transcript segment its own warp.
         self.order_v = np.argsort(-T, kind="stable").astype(np.int32)
         self.max_K = int(uK.max()) if U else 0
+        # shapes outside the register-resident kernels (J > 128, e.g. the reference class's default
+        # frame_sampling = 1, or N > 65) run the generic kernel with its state in a workspace
+        self.generic = bool(force_generic) or self.J > MAX_J_REGISTER or self.max_N > MAX_N_REGISTER
         if groups is None:
             groups = 1  # measured: cutting the scan into groups serialises its long videos
         cumT = np.cumsum(T[self.order_v]) / max(1, T.sum())
@@ -154,16 +162,19 @@ class AlignPlan:
             gmaxK = int(uK[units].max()) if units.size else 0
             want = 32 if (gi == 0 and len(bounds) > 2 and long_K and gmaxK >= long_K) else 0
             wu = np.full(max(units.size, 1) * 16, -1, dtype=np.int32)
-            n_cta, wpc, lanes = C.c_int32(0), C.c_int32(0), C.c_int32(0)
-            _lib.check(lib.mucon_viterbi_pack_h(
-                n32.ctypes.data_as(C.c_void_p), order_u.ctypes.data_as(C.c_void_p), C.c_int(int(units.size)),
-                C.c_int(gmaxN), C.c_int(self.fs), C.c_int(self.max_len), C.c_int(want),
-                wu.ctypes.data_as(C.c_void_p), C.byref(n_cta), C.byref(wpc), C.byref(lanes)),
-                "mucon_viterbi_pack_h")
+            n_cta, wpc, lanes = C.c_int32(0), C.c_int32(4), C.c_int32(0)
+            if not self.generic:
+                _lib.check(lib.mucon_viterbi_pack_h(
+                    n32.ctypes.data_as(C.c_void_p), order_u.ctypes.data_as(C.c_void_p), C.c_int(int(units.size)),
+                    C.c_int(gmaxN), C.c_int(self.fs), C.c_int(self.max_len), C.c_int(want),
+                    wu.ctypes.data_as(C.c_void_p), C.byref(n_cta), C.byref(wpc), C.byref(lanes)),
+                    "mucon_viterbi_pack_h")
             self.groups.append(dict(v0=v0, v1=v1, n_cta=int(n_cta.value), wpc=int(wpc.value), lanes=int(lanes.value),
                                     max_N=gmaxN, max_K=gmaxK, wu_off=sum(len(x) for x in wu_all)))
             wu_all.append(wu[:int(n_cta.value) * int(wpc.value)])
         self.warp_unit = np.concatenate(wu_all) if wu_all else np.full(16, -1, np.int32)
+        if self.warp_unit.size == 0:
+            self.warp_unit = np.full(16, -1, np.int32)
         self.n_cta = sum(g["n_cta"] for g in self.groups)
         self.wpc = self.groups[0]["wpc"] if self.groups else 4
 
@@ -183,6 +194,8 @@ class AlignPlan:
         # (measured slower than one uniform launch on Breakfast-shaped batches, so off by default)
         self.n_long = int((uK >= long_K).sum()) if long_K else 0
         blob.add("vid_lab_off", self.vid_off[:-1])
+        if self.generic:
+            blob.add("ws_off", (2 * self.J * self.tr_off[:-1].astype(np.int64)) if U else np.zeros(1, np.int64))
         self.use_rows = len_rows is not None
         if self.use_rows:
             rows = np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, self.J) for r in len_rows]) \
@@ -214,7 +227,9 @@ class AlignPlan:
         self.status = torch.empty(U, dtype=torch.int32, device=dev)
         self.seg_blocks = self.payload[8 * U:8 * U + 4 * n_pos].view(torch.int32)
         self.labels = torch.empty(self.n_labels, dtype=torch.int32, device=dev)
-        self.bp = torch.empty(max(self.n_bp, 1), dtype=torch.uint8, device=dev)
+        self.bp_u16 = self.J > 255
+        self.bp = torch.empty(max(self.n_bp, 1), dtype=torch.uint16 if self.bp_u16 else torch.uint8, device=dev)
+        self.ws = torch.empty(max(1, 2 * n_pos * self.J), dtype=torch.float64, device=dev) if self.generic else None
         self.best = torch.empty(V, dtype=torch.int32, device=dev)
         self.bs = None  # allocated by the engine once the input dtype is known
 
@@ -281,6 +296,22 @@ class ViterbiEngine:
         self.last_mode = "split"
         if mode not in ("auto", "fused", "split"):
             raise ValueError(mode)
+        if plan.generic:
+            if mode == "fused":
+                raise _lib.MuconError("fused mode does not cover J > %d / N > %d" % (MAX_J_REGISTER, MAX_N_REGISTER))
+            _lib.check(lib.mucon_viterbi_blockscores(
+                _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["vid_off"]), C.c_void_p(p["blk_off"]),
+                C.c_void_p(p["order_v"]), C.c_int(plan.V), C.c_int(plan.C), C.c_int(plan.fs),
+                _lib.ptr(plan.bs), sp), "mucon_viterbi_blockscores")
+            if mid_event is not None:
+                mid_event.record(st)
+            b.max_N, b.max_K, b.n_cta, b.wpc, b.lanes, b.warp_unit = plan.max_N, plan.max_K, 0, 4, 0, None
+            _lib.check(lib.mucon_viterbi_decode_generic(
+                C.byref(b), _lib.ptr(plan.ws), C.c_void_p(p["ws_off"]), C.c_int(int(plan.bp_u16)), sp),
+                "mucon_viterbi_decode_generic")
+            self.launches += 2
+            self.last_mode = "generic"
+            return self._finish(plan, sp)
         if mode == "fused" or (mode == "auto" and plan.single):
             # Long videos are a long serial chain of DP steps: they get their own launch with a
             # warp per transcript segment (fewer instructions per step), on a second stream so

@@ -112,6 +112,17 @@ def main():
     tr = list(map(int, rng.integers(0, 16, 12)))
     lp, _ = synth.planted_logp(rng, 10000, 16, tr, np.float32)
     case("long_T10000_N12", lp, [tr], synth.class_means(rng.dirichlet(np.ones(12)).astype(np.float32), tr, 16, 10000))
+    # 10. shapes beyond the register-resident kernels (generic kernel): J = 200, J = 300 (uint16
+    #     back-pointers; frame_sampling = 1 is the reference class's default), N = 70
+    tr = [3, 0, 2, 5, 1]
+    lp, _ = synth.planted_logp(rng, 700, 6, tr, np.float32)
+    case("generic_fs2_J200", lp, [tr], rng.uniform(60, 220, 6), fs=2, max_len=400)
+    tr = [1, 3, 0, 2]
+    lp, _ = synth.planted_logp(rng, 500, 4, tr, np.float64)
+    case("generic_fs1_J300", lp, [tr], rng.uniform(60, 200, 4), fs=1, max_len=300)
+    tr = list(map(int, rng.integers(0, 20, 70)))
+    lp, _ = synth.planted_logp(rng, 4230, 20, tr, np.float32)
+    case("generic_N70", lp, [tr], rng.uniform(30, 120, 20))
 
 
 if __name__ == "__main__":

@@ -24,7 +24,8 @@ def mode(request):
     return request.param
 
 
-def run_units(eng, logps, cands, means, fs=30, max_len=2000, seg0=None, labels="all", use_rows=False, mode="auto"):
+def run_units(eng, logps, cands, means, fs=30, max_len=2000, seg0=None, labels="all", use_rows=False, mode="auto",
+              force_generic=False):
     """logps: list of [T,C] arrays (one per video); cands: per video list of transcripts; means: per video [C]."""
     from mucon_b200.length_model import poisson_params
     from mucon_b200.viterbi import AlignPlan
@@ -37,7 +38,7 @@ def run_units(eng, logps, cands, means, fs=30, max_len=2000, seg0=None, labels="
     else:
         kw["len_params"] = np.stack([poisson_params(m) for m in means])
     plan = AlignPlan([l.shape[0] for l in logps], cands, C, fs=fs, max_len=max_len, device=eng.device,
-                     labels=labels, **kw)
+                     labels=labels, force_generic=force_generic, **kw)
     packed = torch.from_numpy(np.concatenate(logps)).to(eng.device)
     eng.run(plan, packed, seg0_f32=seg0, mode=mode)
     torch.cuda.synchronize()
@@ -62,7 +63,7 @@ def check_unit(plan, out, u, ref, T):
         assert out["final_j"][u] == ref["jf"]
         K, N = ref["bp"].shape
         bp = out["bp"][plan.bp_off[u]:plan.bp_off[u + 1]].reshape(K, N)
-        assert np.array_equal(bp, ref["bp"].astype(np.uint8))
+        assert np.array_equal(bp.astype(np.uint16), ref["bp"].astype(np.uint16))
     lo = plan.lab_off[u]
     assert np.array_equal(out["labels"][lo:lo + T], ref["labels"])
 
@@ -72,8 +73,6 @@ def test_golden_fixture(eng, name, mode):
     """Frozen outputs of the unmodified reference decoder (tests/golden/make_golden.py)."""
     g = load_golden(name)
     T = g["logp"].shape[0]
-    if g["max_len"] // g["fs"] > 128:
-        pytest.skip("J > 128 is outside the register-resident kernel")
     plan, out = run_units(eng, [g["logp"]], [g["transcripts"]], [g["means"]], g["fs"], g["max_len"],
                           seg0=g["seg0_f32"], labels="best", mode=mode)
     if plan.single:
@@ -87,7 +86,9 @@ def test_golden_fixture(eng, name, mode):
     assert dense_viterbi.segments_from_blocks(sb, tr, g["fs"], T) == g["segments"]
     if plan.single and np.isfinite(g["score"]):
         K = T // g["fs"]
-        assert np.array_equal(out["bp"][:K * len(tr)].reshape(K, len(tr)), g["bp"].astype(np.uint8))
+        assert np.array_equal(out["bp"][:K * len(tr)].reshape(K, len(tr)).astype(np.uint16), g["bp"].astype(np.uint16))
+    if name.startswith("generic"):
+        assert eng.last_mode == "generic"
 
 
 @pytest.mark.parametrize("dtype,seg0", [(np.float32, True), (np.float32, False), (np.float64, False)])
@@ -165,6 +166,64 @@ def test_edge_cases_status(eng, mode):
     assert out["seg_blocks"][plan.tr_off[2]:plan.tr_off[3]].tolist() == [66, 66]
 
 
+@pytest.mark.parametrize("dtype,seg0", [(np.float32, True), (np.float64, False)])
+def test_generic_kernel_equals_register_kernel(eng, dtype, seg0):
+    """The workspace kernel (J > 128 / N > 65) computes the same program: force it on shapes the
+    register-resident kernels also cover and compare every output, edge cases included."""
+    rng = np.random.default_rng(77)
+    C = 12
+    logps, cands, means = [], [], []
+    for i in range(40):
+        N = int(rng.integers(1, 9))
+        T = int(rng.integers(40, 2600))
+        tr = list(map(int, rng.integers(0, C, N)))
+        lp, _ = synth.planted_logp(rng, T, C, tr, dtype)
+        logps.append(lp)
+        cands.append([tr])
+        means.append(synth.class_means(rng.dirichlet(np.ones(N)).astype(np.float32), tr, C, T))
+    mk = lambda T: np.log(rng.dirichlet(np.ones(C), T)).astype(dtype)
+    logps += [mk(3990), mk(100), mk(3960), mk(59)]
+    cands += [[[0, 1]], [[0, 1, 2, 3, 4, 5]], [[1, 2]], [[3]]]
+    means += [np.full(C, 500.0)] * 4
+    pa, a = run_units(eng, logps, cands, means, seg0=seg0, mode="split")
+    pb, b = run_units(eng, logps, cands, means, seg0=seg0, force_generic=True)
+    assert eng.last_mode == "generic"
+    assert a["status"].tolist() == b["status"].tolist()
+    assert np.array_equal(a["score"], b["score"], equal_nan=True)
+    for k in ("final_j", "seg_blocks"):
+        assert np.array_equal(a[k], b[k]), k
+    for u in range(pa.U):  # labels / back-pointers of an infeasible unit are not written
+        if a["status"][u] == 1:
+            continue
+        T = logps[u].shape[0]
+        assert np.array_equal(a["labels"][pa.lab_off[u]:pa.lab_off[u] + T], b["labels"][pb.lab_off[u]:pb.lab_off[u] + T])
+        assert np.array_equal(a["bp"][pa.bp_off[u]:pa.bp_off[u + 1]], b["bp"][pb.bp_off[u]:pb.bp_off[u + 1]])
+
+
+@pytest.mark.parametrize("fs,max_len", [(1, 400), (3, 1000)])
+def test_generic_kernel_large_J_vs_oracle(eng, fs, max_len):
+    rng = np.random.default_rng(78)
+    C = 8
+    logps, cands, means = [], [], []
+    for i in range(6):
+        N = int(rng.integers(1, 7))
+        T = int(rng.integers(5 * fs, 900 * fs // 2))
+        tr = list(map(int, rng.integers(0, C, N)))
+        lp, _ = synth.planted_logp(rng, T, C, tr, np.float32)
+        logps.append(lp)
+        cands.append([tr])
+        means.append(rng.uniform(0.1, 0.6, C) * max_len)
+    plan, out = run_units(eng, logps, cands, means, fs=fs, max_len=max_len, seg0=True)
+    assert eng.last_mode == "generic"
+    for u in range(len(logps)):
+        T = logps[u].shape[0]
+        if T // fs > len(cands[u][0]) * (max_len // fs):
+            assert out["status"][u] == 1
+            continue
+        ref = oracle_unit(logps[u], cands[u][0], means[u], fs, max_len, True)
+        check_unit(plan, out, u, ref, T)
+
+
 def test_candidates_best_equals_argmax_of_singles(eng):
     rng = np.random.default_rng(13)
     logps, cands, means = [], [], []
@@ -221,6 +280,20 @@ def test_drop_in_viterbi_class(eng):
         dec.decode(np.zeros((3990, 48), dtype=np.float32))
     with pytest.raises(IndexError):
         dec.decode(np.zeros((20, 48), dtype=np.float32))
+
+
+def test_drop_in_viterbi_class_default_frame_sampling(eng):
+    """Viterbi(grammar, length_model) with the reference's own default frame_sampling = 1
+    (viterbi.py:34): J = max_length blocks, served by the generic kernel."""
+    from mucon_b200 import PoissonModel, SingleTranscriptGrammar
+    from mucon_b200.viterbi import Viterbi
+    g = load_golden("generic_fs1_J300")
+    dec = Viterbi(SingleTranscriptGrammar(g["transcripts"][0], g["logp"].shape[1]),
+                  PoissonModel(g["means"], max_length=int(g["max_len"])))
+    score, labels, segs = dec.decode(g["logp"])
+    assert same_score(score, g["score"])
+    assert labels == g["labels"].tolist()
+    assert [(s.label, s.length) for s in segs] == g["segments"]
 
 
 def test_breakfast_split_properties_full_size(eng, mode):
