@@ -271,6 +271,10 @@ int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
   const int G = b.lanes;
   const int SL = (J + G - 1) / G;
 #define MUCON_SL_CASE(g, n) case n: return launch_dp<BST, g, n>(b, J, st);
+#ifdef MUCON_ONLY_SL9
+  if (G == 8 && SL == 9) return launch_dp<BST, 8, 9>(b, J, st);
+  return MUCON_EUNSUPPORTED;
+#else
   if (G == 32) {
     switch (SL) {
       MUCON_SL_CASE(32, 1) MUCON_SL_CASE(32, 2) MUCON_SL_CASE(32, 3) MUCON_SL_CASE(32, 4)
@@ -290,6 +294,7 @@ int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
     MUCON_SL_CASE(8, 13) MUCON_SL_CASE(8, 14) MUCON_SL_CASE(8, 15) MUCON_SL_CASE(8, 16)
     default: return MUCON_EUNSUPPORTED;
   }
+#endif
 #undef MUCON_SL_CASE
 }
 
@@ -324,7 +329,7 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
     // class columns per lane
     if (b.fs == 30 && b.C > 32 && b.C <= 64 && b.C % 2 == 0 && env_int("MUCON_FUSED_CPT", 2) == 2) {
       cfg.scan_threads = 32;
-      kern = align_fused_kernel<BST, G, SL, 30, kFusedMaxThreads, 1, 2>;
+      kern = align_fused_kernel<BST, G, SL, 30, kFusedMaxThreads, 2, 2>;  // <= 128 registers: 4 CTAs per SM
     }
   }
   if (smem > 48 * 1024)
@@ -340,6 +345,10 @@ int dispatch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const i
   const int G = b.lanes == 32 ? 32 : (J <= 32 ? 4 : 8);
   const int SL = (J + G - 1) / G;
 #define MUCON_SL_CASE(g, n) case n: return launch_fused<BST, g, n>(b, J, logp, order, write_bs, st);
+#ifdef MUCON_ONLY_SL9  // developer builds: only the evaluator's shape (J = 66)
+  if (G == 8 && SL == 9) return launch_fused<BST, 8, 9>(b, J, logp, order, write_bs, st);
+  return MUCON_EUNSUPPORTED;
+#else
   if (G == 32) {
     switch (SL) {
       MUCON_SL_CASE(32, 1) MUCON_SL_CASE(32, 2) MUCON_SL_CASE(32, 3) MUCON_SL_CASE(32, 4)
@@ -359,6 +368,7 @@ int dispatch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const i
     MUCON_SL_CASE(8, 13) MUCON_SL_CASE(8, 14) MUCON_SL_CASE(8, 15) MUCON_SL_CASE(8, 16)
     default: return MUCON_EUNSUPPORTED;
   }
+#endif
 #undef MUCON_SL_CASE
 }
 

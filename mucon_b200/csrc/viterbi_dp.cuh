@@ -33,6 +33,7 @@ namespace mucon {
 
 constexpr int kDpMaxWarps = 16;  // warps per CTA: 4, 8 or 16 (chosen by mucon_viterbi_pack_h)
 constexpr int kDpChunk = 32;     // DP steps per block-score staging chunk
+constexpr bool kStaged = true;   // hand-interleaved DP step (see dp_unit)
 constexpr int kDpMaxJ = 128;     // ages live in registers: 4 lanes x <= 8 or 8 lanes x <= 16
 
 // Lanes per segment.  A single warp issues roughly one instruction every 3.5 cycles on this
@@ -383,6 +384,11 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
     };
     auto c_step = [&](int k, double& bv, double& inc) {
       int bi;
+      // the shift between lanes does not depend on this step's fold: issue it first, so that the
+      // register holding `out` is dead before A'(k+1) and its shift-adds can fill the butterfly's
+      // latency (a single shuffle after the butterfly serialised the two phases through a WAR hazard)
+      double inc_shift = 0.0;
+      if (SL > 1) inc_shift = __shfl_up_sync(0xffffffffu, out, 1);
       if (SL > 1) {
         R[(SL > 1) ? 1 : 0] = __dadd_rn(R[0], bd);
         const double c0v = __dadd_rn(R[(SL > 1) ? 1 : 0], rowr[0]);
@@ -419,9 +425,18 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
           bage = take ? oa : bage;
         }
       }
-      // shift between lanes; the last lane of a group forwards the group's winner instead
-      const double send = (lig == G - 1) ? bv : out;
-      inc = __shfl_up_sync(0xffffffffu, send, 1);
+      // shift between lanes; the first lane of a group takes the previous group's winner instead
+      if (SL > 1) {
+        if (G < 32) {
+          const double win = __shfl_up_sync(0xffffffffu, bv, 1);
+          inc = (lig == 0) ? win : inc_shift;
+        } else {
+          inc = inc_shift;
+        }
+      } else {
+        const double send = (lig == G - 1) ? bv : out;
+        inc = __shfl_up_sync(0xffffffffu, send, 1);
+      }
       inc = (lane == 0) ? e1 : inc;  // first warp: from segment 0; other warps: patched later
       // a fold whose maximum is -inf is decided by liveness alone: oldest live age or none
       const int jhi = min(J, k - n), jlo = max(1, k - nJ);
@@ -448,11 +463,91 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
       row = src.next(t);  // block scores of step k+1
       const double bdn = static_cast<double>(row[my_col]);
       const BST b0n = row[col0];
-      // C(k) and A'(k+1) in one basic block
       double bv, inc, outn = 0.0, tvn = -INFINITY, e1n;
       int tin = 1;
-      c_step(k, bv, inc);
-      a_prime(k + 1, bdn, b0n, outn, tvn, tin, e1n);
+      if (kStaged && G == 8 && SL > 2) {
+        // C(k) and A'(k+1) interleaved by hand.  A warp issues in order and ptxas schedules the
+        // butterfly (the critical path of the block) first and all of A' after it, so every
+        // shuffle -> compare -> select hop stalls the warp with nothing to issue.  The warp-level
+        // fences below end the scheduling region after each shuffle has been issued together with
+        // a slice of A'(k+1): the slice runs while the shuffle is in flight.
+        const double inc_shift = __shfl_up_sync(0xffffffffu, out, 1);
+        R[1] = __dadd_rn(R[0], bd);
+        const double c0v = __dadd_rn(R[1], rowr[0]);
+        const bool young = c0v > tv;
+        bv = young ? c0v : tv;
+        int bage = a0 + (young ? 0 : ti) + 1;
+        double ov = __shfl_xor_sync(0xffffffffu, bv, 1);
+        int oa = __shfl_xor_sync(0xffffffffu, bage, 1);
+        // slice 0: ageing
+        outn = __dadd_rn(R[SL - 1], bdn);
+#pragma unroll
+        for (int i = SL - 1; i >= 2; --i) R[i] = __dadd_rn(R[i - 1], bdn);
+        __syncwarp();
+        bool take = (ov > bv) || (tie_ok[0] && ov == bv);
+        bv = take ? ov : bv;
+        bage = take ? oa : bage;
+        ov = __shfl_xor_sync(0xffffffffu, bv, 2);
+        oa = __shfl_xor_sync(0xffffffffu, bage, 2);
+        // slice 1: candidates of positions >= 1 and the first level of their fold
+        double cv[SL];
+        int idx[SL];
+#pragma unroll
+        for (int i = 1; i < SL; ++i) {
+          const double a = (i + 1 < SL) ? R[(i + 1 < SL) ? i + 1 : 0] : outn;
+          cv[i] = __dadd_rn(a, rowr[i]);
+          idx[i] = i;
+        }
+#pragma unroll
+        for (int i = 1; i + 1 < SL; i += 2) {
+          const bool older = cv[i + 1] >= cv[i];
+          cv[i] = older ? cv[i + 1] : cv[i];
+          idx[i] = older ? idx[i + 1] : idx[i];
+        }
+        __syncwarp();
+        take = (ov > bv) || (tie_ok[1] && ov == bv);
+        bv = take ? ov : bv;
+        bage = take ? oa : bage;
+        ov = __shfl_xor_sync(0xffffffffu, bv, 4);
+        oa = __shfl_xor_sync(0xffffffffu, bage, 4);
+        // slice 2: the rest of the fold
+#pragma unroll
+        for (int w = 2; w < SL - 1; w <<= 1) {
+#pragma unroll
+          for (int i = 1; i + w < SL; i += 2 * w) {
+            const bool older = cv[i + w] >= cv[i];
+            cv[i] = older ? cv[i + w] : cv[i];
+            idx[i] = older ? idx[i + w] : idx[i];
+          }
+        }
+        tvn = cv[1];
+        tin = idx[1];
+        __syncwarp();
+        take = (ov > bv) || (tie_ok[2] && ov == bv);
+        bv = take ? ov : bv;
+        bage = take ? oa : bage;
+        const double win = __shfl_up_sync(0xffffffffu, bv, 1);
+        // slice 3: segment 0, liveness, back-pointer
+        {
+          double a;
+          if (f32seg0) a = static_cast<double>(__fadd_rn(static_cast<float>(s0), static_cast<float>(b0n)));
+          else a = __dadd_rn(s0, static_cast<double>(b0n));
+          s0 = a;
+          e1n = (k + 1 <= J) ? __dadd_rn(a, rows0[min(k + 1, J) - 1]) : -INFINITY;
+        }
+        const int jhi = min(J, k - n), jlo = max(1, k - nJ);
+        const int dead_age = (jlo <= jhi) ? jhi : 0;
+        bage = (bv == -INFINITY) ? dead_age : bage;
+        if (bp_writer) *bp_w = static_cast<uint8_t>(bage);
+        bp_w += bp_stride;
+        __syncwarp();
+        inc = (lig == 0) ? win : inc_shift;
+        inc = (lane == 0) ? e1 : inc;
+      } else {
+        // C(k) and A'(k+1) in one basic block
+        c_step(k, bv, inc);
+        a_prime(k + 1, bdn, b0n, outn, tvn, tin, e1n);
+      }
       exchange(k, bv, inc);
       R[0] = inc;
       out = outn; tv = tvn; ti = tin; e1 = e1n; bd = bdn;
