@@ -124,6 +124,20 @@ int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 int mucon_viterbi_decode_generic(const mucon_viterbi_batch* batch_h, double* ws, const int64_t* ws_off,
                                  int bp_is_u16, void* stream);
 
+/* Lane-per-segment dynamic program (J <= 66, N <= 33): every lane of a warp owns one transcript
+ * segment with its J hypothesis scores in registers, a warp carries several units side by side.
+ * mucon_viterbi_pack_lanes_h assigns lanes on the host: a unit takes max(1, N-1) consecutive lanes
+ * of one warp (units in order_h, longest first); lane_unit_h needs room for U*32 entries, on
+ * return the first *n_warps_out * 32 are valid (-1 = unused lane).
+ * mucon_viterbi_decode_lanes: same inputs/outputs as mucon_viterbi_decode (warp_unit / n_cta /
+ * wpc / lanes ignored), one 32-thread CTA per warp of the packing.  progress: NULL, or [V]
+ * counters of block-score rows already published per video (mucon_viterbi_blockscores_progress):
+ * the kernel then runs concurrently with the scan and only waits for rows it is about to read. */
+int mucon_viterbi_pack_lanes_h(const int32_t* N_h, const int32_t* order_h, int U, int32_t* lane_unit_h,
+                               int32_t* n_warps_out);
+int mucon_viterbi_decode_lanes(const mucon_viterbi_batch* batch_h, const int32_t* lane_unit, int n_warps,
+                               const int32_t* progress, void* stream);
+
 /* One-launch alignment: block-score scan and DP of a unit fused in one CTA (scan warps feed the
  * DP warps through shared memory; block scores do not travel through HBM).  Same inputs and
  * outputs as mucon_viterbi_blockscores + mucon_viterbi_decode; warp_unit / n_cta / wpc of the

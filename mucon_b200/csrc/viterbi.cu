@@ -24,6 +24,7 @@
 #include "viterbi_dp.cuh"
 #include "viterbi_fused.cuh"
 #include "viterbi_generic.cuh"
+#include "viterbi_lanes.cuh"
 
 namespace mucon {
 namespace {
@@ -441,6 +442,63 @@ extern "C" int mucon_viterbi_decode_generic(const mucon_viterbi_batch* bh, doubl
   if (b.bs_is_f64) { if (bp_is_u16) MUCON_GEN(double, uint16_t); else MUCON_GEN(double, uint8_t); }
   else { if (bp_is_u16) MUCON_GEN(float, uint16_t); else MUCON_GEN(float, uint8_t); }
 #undef MUCON_GEN
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_viterbi_pack_lanes_h(const int32_t* N_h, const int32_t* order_h, int U, int32_t* lane_unit_h,
+                                          int32_t* n_warps_out) {
+  if (!N_h || !lane_unit_h || !n_warps_out || U < 0) return MUCON_EINVAL;
+  // first fit over a window of open warps, units taken in order_h (longest first), so that the
+  // units sharing a warp have similar numbers of steps
+  constexpr int kWindow = 4;
+  int open_warp[kWindow], open_used[kWindow], n_open = 0, n_warps = 0;
+  for (int i = 0; i < U; ++i) {
+    const int u = order_h ? order_h[i] : i;
+    const int need = N_h[u] > 1 ? N_h[u] - 1 : 1;
+    if (need > 32) return MUCON_EUNSUPPORTED;
+    int pick = -1;
+    for (int o = 0; o < n_open; ++o)
+      if (32 - open_used[o] >= need) { pick = o; break; }
+    if (pick < 0) {
+      if (n_open == kWindow) {
+        for (int o = 1; o < kWindow; ++o) { open_warp[o - 1] = open_warp[o]; open_used[o - 1] = open_used[o]; }
+        --n_open;
+      }
+      pick = n_open++;
+      open_warp[pick] = n_warps++;
+      open_used[pick] = 0;
+      for (int l = 0; l < 32; ++l) lane_unit_h[(size_t)open_warp[pick] * 32 + l] = -1;
+    }
+    for (int l = 0; l < need; ++l) lane_unit_h[(size_t)open_warp[pick] * 32 + open_used[pick] + l] = u;
+    open_used[pick] += need;
+  }
+  *n_warps_out = n_warps;
+  return MUCON_OK;
+}
+
+extern "C" int mucon_viterbi_decode_lanes(const mucon_viterbi_batch* bh, const int32_t* lane_unit, int n_warps,
+                                          const int32_t* progress, void* stream) {
+  if (!bh || !lane_unit || n_warps < 0) return MUCON_EINVAL;
+  const mucon_viterbi_batch& b = *bh;
+  if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1) return MUCON_EINVAL;
+  if (!b.bs || !b.vid_off || !b.blk_off || !b.unit_vid || !b.tr || !b.tr_off || !b.score || !b.seg_blocks ||
+      !b.final_j || !b.status || !b.bp || !b.bp_off)
+    return MUCON_EINVAL;
+  if (!b.len_rows && !(b.len_params && b.logfact)) return MUCON_EINVAL;
+  if (b.U == 0 || n_warps == 0) return MUCON_OK;
+  const int J = b.max_len / b.fs;
+  if (J > 66 || b.max_N > 33) return MUCON_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MUCON_LANES(BST)                                                                                     \
+  do {                                                                                                       \
+    const size_t smem = lanes_layout(66, sizeof(BST)).total;                                                 \
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(dp_lanes_kernel<BST, 6, 11>,                                       \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    dp_lanes_kernel<BST, 6, 11><<<n_warps, 32, smem, st>>>(b, J, lane_unit, progress);                       \
+  } while (0)
+  if (b.bs_is_f64) MUCON_LANES(double); else MUCON_LANES(float);
+#undef MUCON_LANES
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

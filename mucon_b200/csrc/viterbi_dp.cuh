@@ -181,6 +181,10 @@ struct DpShared {
 };
 
 // ---- block-score sources --------------------------------------------------------------------
+// Both sources hand out the block scores of one DP step at a time as two shared-memory loads (this
+// lane's transcript label and the label of segment 0) from 32-bit shared addresses that advance by
+// one row per step.
+//
 // StagedSrc: block scores come from HBM/L2 (written by the scan kernel); the team copies the
 // columns of its transcript labels into a double-buffered shared stage, kDpChunk steps at a time.
 template <typename BST>
@@ -190,7 +194,13 @@ struct StagedSrc {
   const int* trl;
   int C, K, N, NS, c0, nchunks;
   int kk, chunk;     // position of the row last handed out
+  uint32_t a_my, a_0, base_s;
+  int off_my, off_0;
   __device__ __forceinline__ int col(int n, const int*) const { return n; }  // staged by segment
+  __device__ __forceinline__ void bind(int my_col, int col0) {
+    off_my = (c0 + my_col) * static_cast<int>(sizeof(BST));
+    off_0 = (c0 + col0) * static_cast<int>(sizeof(BST));
+  }
   __device__ __forceinline__ void stage(const DpTeam& t, int ch) {
     const int k0 = ch * kDpChunk;
     const int nk = min(kDpChunk, K - k0);
@@ -203,25 +213,34 @@ struct StagedSrc {
     cp_async_commit();
   }
   // row 0 (returns after the first chunk has landed for the whole team)
-  __device__ __forceinline__ const BST* begin(const DpTeam& t) {
+  __device__ __forceinline__ void begin(const DpTeam& t) {
     nchunks = (K + kDpChunk - 1) / kDpChunk;
     stage(t, 0);
     if (nchunks > 1) { stage(t, 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     t.sync();
     kk = 0; chunk = 0;
-    return bsS + c0;
+    base_s = smem_u32(bsS);
+    a_my = base_s + off_my;
+    a_0 = base_s + off_0;
   }
   // row of the next step
-  __device__ __forceinline__ const BST* next(const DpTeam& t) {
+  __device__ __forceinline__ void next(const DpTeam& t) {
+    const uint32_t row_bytes = static_cast<uint32_t>(NS) * sizeof(BST);
+    a_my += row_bytes;
+    a_0 += row_bytes;
     if (++kk == kDpChunk) {
       kk = 0;
       ++chunk;
       cp_async_wait<0>();
       t.sync();  // chunk landed for every thread of the team; the other buffer is free
       if (chunk + 1 < nchunks) stage(t, chunk + 1);
+      const uint32_t buf = base_s + static_cast<uint32_t>(chunk & 1) * kDpChunk * row_bytes;
+      a_my = buf + off_my;
+      a_0 = buf + off_0;
     }
-    return bsS + (static_cast<size_t>(chunk & 1) * kDpChunk + kk) * NS + c0;
   }
+  __device__ __forceinline__ BST get_my() const { return ld_shared(a_my, BST()); }
+  __device__ __forceinline__ BST get_0() const { return ld_shared(a_0, BST()); }
   __device__ __forceinline__ void finish(const DpTeam&) {}
 };
 
@@ -235,27 +254,46 @@ struct RingSrc {
   int C, bps, slabs;
   int r, slab;       // row within slab, current slab
   uint32_t phase;    // parity of `full` for the current pass over the ring
+  uint32_t a_my, a_0, ring_s, full_s, empty_s;
+  int off_my, off_0;
   __device__ __forceinline__ int col(int n, const int* trl) const { return trl[n]; }  // by label
-  __device__ __forceinline__ const BST* begin(const DpTeam&) {
-    r = 0; slab = 0; phase = 0;
-    mbar_wait(&full[0], 0);
-    return ring;
+  __device__ __forceinline__ void bind(int my_col, int col0) {
+    off_my = my_col * static_cast<int>(sizeof(BST));
+    off_0 = col0 * static_cast<int>(sizeof(BST));
   }
-  __device__ __forceinline__ const BST* next(const DpTeam& t) {
+  __device__ __forceinline__ void begin(const DpTeam&) {
+    r = 0; slab = 0; phase = 0;
+    ring_s = smem_u32(ring);
+    full_s = smem_u32(full);
+    empty_s = smem_u32(empty);
+    a_my = ring_s + off_my;
+    a_0 = ring_s + off_0;
+    mbar_wait_s(full_s, 0);
+  }
+  __device__ __forceinline__ void next(const DpTeam& t) {
+    const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(BST);
+    a_my += row_bytes;  // rows are contiguous across slabs; only the end of the ring wraps
+    a_0 += row_bytes;
     if (++r == bps) {
       r = 0;
       // every thread of the team is past its reads of the old slab (the step ends with a team
       // barrier / warp sync), so one thread may hand it back
       t.sync();
-      if (t.ltid == 0) mbar_arrive(&empty[slab]);
-      if (++slab == slabs) { slab = 0; phase ^= 1; }
-      mbar_wait(&full[slab], phase);
+      if (t.ltid == 0) mbar_arrive_s(empty_s + 8 * slab);
+      if (++slab == slabs) {
+        slab = 0;
+        phase ^= 1;
+        a_my = ring_s + off_my;
+        a_0 = ring_s + off_0;
+      }
+      mbar_wait_s(full_s + 8 * slab, phase);
     }
-    return ring + (static_cast<size_t>(slab) * bps + r) * C;
   }
+  __device__ __forceinline__ BST get_my() const { return ld_shared(a_my, BST()); }
+  __device__ __forceinline__ BST get_0() const { return ld_shared(a_0, BST()); }
   __device__ __forceinline__ void finish(const DpTeam& t) {
     t.sync();
-    if (t.ltid == 0) mbar_arrive(&empty[slab]);
+    if (t.ltid == 0) mbar_arrive_s(empty_s + 8 * slab);
   }
 };
 
@@ -295,9 +333,9 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
     }
     for (int i = ltid; i < K * N; i += nthr) bp_g[i] = 0;  // not computed
     // drain the source so that a producer never waits for this team
-    const BST* row = src.begin(t);
-    for (int k = 1; k < K; ++k) row = src.next(t);
-    (void)row;
+    src.bind(0, 0);
+    src.begin(t);
+    for (int k = 1; k < K; ++k) src.next(t);
     src.finish(t);
     t.sync();
   } else {
@@ -316,10 +354,11 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
     const int my_col = src.col(has_seg ? n : 0, trl);
     const int col0 = src.col(0, trl);
 
-    const BST* row = src.begin(t);  // block scores of step 0
+    src.bind(my_col, col0);
+    src.begin(t);  // block scores of step 0
     // segment 0: scalar chain; 0.0 + F[fs-1, tr_0]  (viterbi.py:81-90)
     const bool f32seg0 = (sizeof(BST) == 4) && b.seg0_f32;
-    double s0 = __dadd_rn(0.0, static_cast<double>(row[col0]));
+    double s0 = __dadd_rn(0.0, static_cast<double>(src.get_0()));
 
     const unsigned gmask = (G == 32) ? 0xffffffffu : ((0xffffffffu >> (32 - G)) << (g * G));
     bool tie_ok[5];  // butterfly level lv: the partner is the higher lane (older ages), ties go to it
@@ -455,14 +494,14 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
     };
 
     if (K > 1) {
-      row = src.next(t);
-      bd = static_cast<double>(row[my_col]);
-      a_prime(1, bd, row[col0], out, tv, ti, e1);
+      src.next(t);
+      bd = static_cast<double>(src.get_my());
+      a_prime(1, bd, src.get_0(), out, tv, ti, e1);
     }
     for (int k = 1; k + 1 < K; ++k) {
-      row = src.next(t);  // block scores of step k+1
-      const double bdn = static_cast<double>(row[my_col]);
-      const BST b0n = row[col0];
+      src.next(t);  // block scores of step k+1
+      const double bdn = static_cast<double>(src.get_my());
+      const BST b0n = src.get_0();
       double bv, inc, outn = 0.0, tvn = -INFINITY, e1n;
       int tin = 1;
       if (kStaged && G == 8 && SL > 2) {

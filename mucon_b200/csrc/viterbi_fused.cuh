@@ -114,7 +114,18 @@ align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restri
         const BST* s = slabs + static_cast<size_t>(st) * slab_elems + c;
         BST* rp = ring + static_cast<size_t>(rs) * bps * C + c;
         for (int bb = 0; bb < nb; ++bb) {
-          if (FS) {
+          if constexpr (FS != 0 && CPT == 2 && sizeof(BST) == 4) {
+            // two adjacent class columns per lane: one 8-byte shared load and one packed
+            // add.rn.f32x2 (two independent IEEE float32 additions) per frame
+            unsigned long long acc;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(run[0]), "f"(run[1]));
+#pragma unroll
+            for (int r = 0; r < (FS ? FS : 1); ++r) {
+              const unsigned long long x = *reinterpret_cast<const unsigned long long*>(s + r * C);
+              asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(x));
+            }
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(run[0]), "=f"(run[1]) : "l"(acc));
+          } else if (FS) {
 #pragma unroll
             for (int r = 0; r < (FS ? FS : 1); ++r)
 #pragma unroll

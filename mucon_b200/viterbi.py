@@ -70,6 +70,7 @@ class _Blob:
 
 MAX_J_REGISTER = 128  # kDpMaxJ in csrc/viterbi_dp.cuh
 MAX_N_REGISTER = 65   # dp_max_n(8)
+LANES_MIN_WARPS = 1184  # two warps per SM sub-partition on a 148-SM part
 
 
 class AlignPlan:
@@ -178,6 +179,19 @@ class AlignPlan:
         self.n_cta = sum(g["n_cta"] for g in self.groups)
         self.wpc = self.groups[0]["wpc"] if self.groups else 4
 
+        # lane-per-segment packing (J <= 66, N <= 33): see csrc/viterbi_lanes.cuh
+        self.n_lane_warps = 0
+        self.lane_unit = None
+        if U and not self.generic and self.J <= 66 and self.max_N <= 33:
+            order_all = np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32)
+            lu = np.full(U * 32, -1, dtype=np.int32)
+            nw = C.c_int32(0)
+            _lib.check(lib.mucon_viterbi_pack_lanes_h(
+                n32.ctypes.data_as(C.c_void_p), order_all.ctypes.data_as(C.c_void_p), C.c_int(U),
+                lu.ctypes.data_as(C.c_void_p), C.byref(nw)), "mucon_viterbi_pack_lanes_h")
+            self.n_lane_warps = int(nw.value)
+            self.lane_unit = lu[:self.n_lane_warps * 32]
+
         blob = _Blob()
         blob.add("vid_off", self.vid_off)
         blob.add("blk_off", self.blk_off)
@@ -194,6 +208,8 @@ class AlignPlan:
         # (measured slower than one uniform launch on Breakfast-shaped batches, so off by default)
         self.n_long = int((uK >= long_K).sum()) if long_K else 0
         blob.add("vid_lab_off", self.vid_off[:-1])
+        if self.lane_unit is not None:
+            blob.add("lane_unit", self.lane_unit)
         if self.generic:
             blob.add("ws_off", (2 * self.J * self.tr_off[:-1].astype(np.int64)) if U else np.zeros(1, np.int64))
         self.use_rows = len_rows is not None
@@ -294,7 +310,7 @@ class ViterbiEngine:
         b.seg_blocks, b.bp = plan.seg_blocks.data_ptr(), plan.bp.data_ptr()
         b.final_j, b.status = plan.final_j.data_ptr(), plan.status.data_ptr()
         self.last_mode = "split"
-        if mode not in ("auto", "fused", "split"):
+        if mode not in ("auto", "fused", "split", "lanes"):
             raise ValueError(mode)
         if plan.generic:
             if mode == "fused":
@@ -311,6 +327,27 @@ class ViterbiEngine:
                 "mucon_viterbi_decode_generic")
             self.launches += 2
             self.last_mode = "generic"
+            return self._finish(plan, sp)
+        # candidate sets large enough to keep every scheduler busy: the lane-per-segment kernel
+        # needs a third of the instructions (measured 1.66x on 16384 units); small batches are
+        # latency-bound and stay on the shift-register kernel
+        if mode == "auto" and not plan.single and plan.lane_unit is not None and plan.n_lane_warps >= LANES_MIN_WARPS:
+            mode = "lanes"
+        if mode == "lanes":
+            if plan.lane_unit is None:
+                raise _lib.MuconError("lanes mode needs J <= 66 and N <= 33")
+            _lib.check(lib.mucon_viterbi_blockscores(
+                _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["vid_off"]), C.c_void_p(p["blk_off"]),
+                C.c_void_p(p["order_v"]), C.c_int(plan.V), C.c_int(plan.C), C.c_int(plan.fs),
+                _lib.ptr(plan.bs), sp), "mucon_viterbi_blockscores")
+            if mid_event is not None:
+                mid_event.record(st)
+            b.max_N, b.max_K, b.n_cta, b.wpc, b.lanes, b.warp_unit = plan.max_N, plan.max_K, 0, 4, 0, None
+            _lib.check(lib.mucon_viterbi_decode_lanes(
+                C.byref(b), C.c_void_p(p["lane_unit"]), C.c_int(plan.n_lane_warps), None, sp),
+                "mucon_viterbi_decode_lanes")
+            self.launches += 2
+            self.last_mode = "lanes"
             return self._finish(plan, sp)
         if mode == "fused" or (mode == "auto" and plan.single):
             # Long videos are a long serial chain of DP steps: they get their own launch with a

@@ -66,7 +66,19 @@ logp = bench.device_logp(Ts, trs[:nv], 0, dev)
 plan3 = AlignPlan(Ts, cands, 48, device=dev, len_params=poisson_params(np.stack(mlist)), labels="best")
 ms = timeit(lambda: eng.run(plan3, logp, seg0_f32=True), n=5)
 res["c3_subset"] = {"videos": nv, "candidates": 64, "units": plan3.U, "max_N": plan3.max_N, "ms": ms,
+                    "mode": eng.last_mode,
                     "aligned_frames_per_s": plan3.aligned_frames / (ms * 1e-3), "ctas": plan3.n_cta, "wpc": plan3.wpc}
+eng.run(plan3, logp, seg0_f32=True, mode="split")
+torch.cuda.synchronize()
+ref3 = eng.fetch(plan3)
+for m3 in ("split", "lanes"):
+    if m3 == "lanes" and plan3.lane_unit is None:
+        continue
+    ms = timeit(lambda: eng.run(plan3, logp, seg0_f32=True, mode=m3), n=5)
+    o3 = eng.fetch(plan3)
+    res["c3_subset_" + m3] = {"ms": ms, "aligned_frames_per_s": plan3.aligned_frames / (ms * 1e-3),
+                              "lane_warps": plan3.n_lane_warps,
+                              "same_as_split": bool(all(np.array_equal(o3[k], ref3[k]) for k in ("score", "labels", "best", "seg_blocks")))}
 
 # c4: one long video, T = 40000, C = 100, N = 60
 r4 = np.random.default_rng(4)
