@@ -331,6 +331,7 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
     if (b.fs == 30 && b.C > 32 && b.C <= 64 && b.C % 2 == 0 && env_int("MUCON_FUSED_CPT", 2) == 2) {
       cfg.scan_threads = 32;
       kern = align_fused_kernel<BST, G, SL, 30, kFusedMaxThreads, 2, 2>;  // <= 128 registers: 4 CTAs per SM
+      if (b.C == 48) kern = align_fused_kernel<BST, G, SL, 30, kFusedMaxThreads, 2, 2, 48>;  // Breakfast
     }
   }
   if (smem > 48 * 1024)

@@ -43,14 +43,16 @@ __host__ __device__ inline size_t fused_smem_bytes(const FusedCfg& c, int G, int
 // walks all columns of a 33..64-class problem, two adjacent classes per lane (two independent
 // running sums per thread, 8-byte shared loads): one warp less per CTA, so four CTAs fit the
 // register file of an SM instead of three.
+// CT: compile-time class count (0 = runtime): the scan's 30 shared loads per block then use immediate
+// offsets instead of a chain of address additions.
 template <typename BST, int G, int SL, int FS, int MAXT = (G == 32 ? kFusedMaxThreadsWide : kFusedMaxThreads), int MINB = 1,
-          int CPT = 1>
+          int CPT = 1, int CT = 0>
 __global__ void __launch_bounds__(MAXT, MINB)
 align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restrict__ logp,
                    const int32_t* __restrict__ order, const FusedCfg cfg) {
   extern __shared__ __align__(128) unsigned char sm[];
   const int fs = FS ? FS : b.fs;
-  const int C = b.C;
+  const int C = CT ? CT : b.C;  // CT: class count known at compile time (immediate offsets in the scan)
   const int u = order ? order[blockIdx.x] : blockIdx.x;
   const int v = b.unit_vid[u];
   const int64_t r0 = b.vid_off[v];
