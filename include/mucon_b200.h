@@ -214,6 +214,13 @@ int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const float* W, i
 int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const float* bias,
                          const float* residual, const void* tiles, int num_tiles, int64_t rows, int taps,
                          int dilation, int relu_mid, int relu_final, void* stream);
+/* The same kernel with an explicit list of tap row-shifts (<= 6, one of them 0):
+ *   out[t,:] = relu_final( relu_mid( sum_i in[t + shifts_h[i], :] . W[i]^T + bias ) + residual[t,:] )
+ * W_kco: [n_shifts][Cout][Cin].  Used for the MS-TCN++ first stage (temporal.py:150-204), whose two
+ * dilated convolutions and 1x1 fusion conv are linear up to the ReLU and fold into one 5-tap conv. */
+int mucon_conv_gemm_tf32_shifts(const float* in, float* out, const float* W_kco, const float* bias,
+                                const float* residual, const void* tiles, int num_tiles, int64_t rows,
+                                const int32_t* shifts_h, int n_shifts, int relu_mid, int relu_final, void* stream);
 /* One whole WaveNet layer (temporal.py:43-53) + optional max_pool1d(2) (temporal.py:137-139) in one
  * launch, 128 channels, tcgen05 TF32:  out = [pool]( relu_final( conv1x1(relu(conv_k3_dil(x) + bd)) + b1 + x ) ).
  * The intermediate activation stays in shared memory as the second GEMM's operand.  Wd_kco

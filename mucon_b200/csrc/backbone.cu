@@ -306,11 +306,10 @@ extern "C" int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const 
   return MUCON_OK;
 }
 
-extern "C" int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const float* bias,
-                                    const float* residual, const void* tiles, int num_tiles, int64_t rows, int taps,
-                                    int dilation, int relu_mid, int relu_final, void* stream) {
-  if (!in || !out || !W_kco || !bias || !tiles || num_tiles < 0 || rows < 0 || dilation < 1) return MUCON_EINVAL;
-  if (taps != 1 && taps != 3) return MUCON_EUNSUPPORTED;
+static int launch_conv_gemm(const float* in, float* out, const float* W_kco, const float* bias, const float* residual,
+                            const void* tiles, int num_tiles, int64_t rows, const convgemm::TapShifts& ts,
+                            int relu_mid, int relu_final, void* stream) {
+  if (!in || !out || !W_kco || !bias || !tiles || num_tiles < 0 || rows < 0) return MUCON_EINVAL;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(W_kco) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (residual && (reinterpret_cast<uintptr_t>(residual) & 15)))
     return MUCON_EALIGN;
@@ -319,7 +318,7 @@ extern "C" int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_
   CUtensorMap tx, tw;
   int rc = make_map_2d(&tx, in, static_cast<uint64_t>(rows), convgemm::C, gemm::BM);
   if (rc != MUCON_OK) return rc;
-  rc = make_map_2d(&tw, W_kco, static_cast<uint64_t>(taps) * convgemm::C, convgemm::C, gemm::BN);
+  rc = make_map_2d(&tw, W_kco, static_cast<uint64_t>(ts.n) * convgemm::C, convgemm::C, gemm::BN);
   if (rc != MUCON_OK) return rc;
   static int sms = 0;
   if (!sms) sms = mucon_device_sm_count();
@@ -327,10 +326,37 @@ extern "C" int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_
   MUCON_CUDA_CHECK(cudaFuncSetAttribute(convgemm::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         convgemm::CSMEM_BYTES));
   convgemm::conv_gemm_kernel<<<grid, convgemm::CTHREADS, convgemm::CSMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      tx, tw, static_cast<const convgemm::Tile*>(tiles), num_tiles, taps, dilation, bias, residual, out, relu_mid,
-      relu_final);
+      tx, tw, static_cast<const convgemm::Tile*>(tiles), num_tiles, ts, bias, residual, out, relu_mid, relu_final);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
+}
+
+extern "C" int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const float* bias,
+                                    const float* residual, const void* tiles, int num_tiles, int64_t rows, int taps,
+                                    int dilation, int relu_mid, int relu_final, void* stream) {
+  if (dilation < 1) return MUCON_EINVAL;
+  if (taps != 1 && taps != 3) return MUCON_EUNSUPPORTED;
+  convgemm::TapShifts ts{};
+  ts.n = taps;
+  for (int t = 0; t < taps; ++t) ts.s[t] = (t - taps / 2) * dilation;
+  return launch_conv_gemm(in, out, W_kco, bias, residual, tiles, num_tiles, rows, ts, relu_mid, relu_final, stream);
+}
+
+extern "C" int mucon_conv_gemm_tf32_shifts(const float* in, float* out, const float* W_kco, const float* bias,
+                                           const float* residual, const void* tiles, int num_tiles, int64_t rows,
+                                           const int32_t* shifts_h, int n_shifts, int relu_mid, int relu_final,
+                                           void* stream) {
+  if (!shifts_h || n_shifts < 1) return MUCON_EINVAL;
+  if (n_shifts > convgemm::kMaxTaps) return MUCON_EUNSUPPORTED;
+  convgemm::TapShifts ts{};
+  ts.n = n_shifts;
+  bool has_zero = false;
+  for (int t = 0; t < n_shifts; ++t) {
+    ts.s[t] = shifts_h[t];
+    has_zero |= shifts_h[t] == 0;
+  }
+  if (!has_zero) return MUCON_EINVAL;  // the kernel relies on one tap that is live for every tile
+  return launch_conv_gemm(in, out, W_kco, bias, residual, tiles, num_tiles, rows, ts, relu_mid, relu_final, stream);
 }
 
 extern "C" int mucon_wavenet_layer_tf32(const float* x, float* out, const float* Wd_kco, const float* bd,

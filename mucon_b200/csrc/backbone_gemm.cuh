@@ -240,9 +240,18 @@ struct Tile {
 
 __device__ __forceinline__ bool tap_live(int shift, int T) { return shift < T && -shift < T; }
 
+// Row shifts of the taps (time steps relative to the output row); one of them must be 0.  A k = 3
+// dilated Conv1d is {-d, 0, +d}; two dilated convolutions folded through a 1x1 fusion conv (MS-TCN++
+// first stage, temporal.py:150-204) are {-d1, -d2, 0, +d2, +d1}.
+constexpr int kMaxTaps = 6;
+struct TapShifts {
+  int n;
+  int s[kMaxTaps];
+};
+
 __global__ void __launch_bounds__(CTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                 const Tile* __restrict__ tiles, int num_tiles, int taps, int dil, const float* __restrict__ bias,
+                 const Tile* __restrict__ tiles, int num_tiles, const TapShifts ts, const float* __restrict__ bias,
                  const float* __restrict__ residual, float* __restrict__ out, int relu_mid, int relu_final) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -269,7 +278,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int center = taps / 2;
+  const int taps = ts.n;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -281,7 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
         const Tile tl = tiles[ti];
         for (int tap = 0; tap < taps; ++tap) {
-          const int shift = (tap - center) * dil;
+          const int shift = ts.s[tap];
           if (!tap_live(shift, tl.T)) continue;
           const int row = static_cast<int>(tl.row0) + tl.t0 + shift;  // may be negative: TMA zero-fills
           for (int kc = 0; kc < KB_PER_TAP; ++kc) {
@@ -302,7 +311,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
       const Tile tl = tiles[ti];
       for (int tap = 0; tap < taps; ++tap) {
-        const int shift = (tap - center) * dil;
+        const int shift = ts.s[tap];
         if (!tap_live(shift, tl.T)) continue;
         const int lo = -(tl.t0 + shift);          // rows r < lo are before the video
         const int hi = tl.T - (tl.t0 + shift);    // rows r >= hi are after it
@@ -340,7 +349,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const uint32_t d_tmem = tmem_base + acc * BN;
       int issued = 0;
       for (int tap = 0; tap < taps; ++tap) {
-        const int shift = (tap - center) * dil;
+        const int shift = ts.s[tap];
         if (!tap_live(shift, tl.T)) continue;
         for (int kc = 0; kc < KB_PER_TAP; ++kc) {
           mbar_wait(&ready[s], ph);

@@ -2,7 +2,8 @@
 
 Drop-in surface: `WaveNetBlock` with the constructor, parameter names and forward signature of
 reference src/core/modules/temporal.py:77-147 (`first_conv`, `l_{i}.dilated_conv`, `l_{i}.conv_1x1`,
-`last_conv`), so a reference state_dict loads unchanged, and `MuConBackbone` with the attribute
+`last_conv`), so a reference state_dict loads unchanged, the alternates `MSTCNPPFirstStage` (:150-204)
+and `NoFt` (:56-74) selected by `model.ft.type`, and `MuConBackbone` with the attribute
 names the reference model uses around it (`ft`, `ft_last_gn`, `conv_classifier`,
 src/mucon/models.py:160-191,276-278) and its three forward helpers (models.py:360-374,567-582,746-773).
 
@@ -261,18 +262,152 @@ class WaveNetBlock(nn.Module):
         return z.view(B, Tz, self.out_dims).permute(0, 2, 1).contiguous()
 
 
+def conv_gemm_shifts_rows(x, W_kco, bias, shifts, plan, level, relu_mid=False, relu_final=False, residual=None):
+    """128 -> 128 channel conv with explicit tap row-shifts on tcgen05.  W_kco: [len(shifts)*128, 128]."""
+    out = torch.empty_like(x)
+    sh = np.asarray(shifts, dtype=np.int32)
+    _lib.check(_lib.lib().mucon_conv_gemm_tf32_shifts(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(W_kco), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(plan.tiles[level]),
+        C.c_int(plan.n_tiles[level]), C.c_int64(x.shape[0]), sh.ctypes.data_as(C.c_void_p), C.c_int(int(sh.size)),
+        C.c_int(int(relu_mid)), C.c_int(int(relu_final)), _stream(x.device)), "mucon_conv_gemm_tf32_shifts")
+    return out
+
+
+class NoFt(nn.Module):
+    """Drop-in for core.modules.temporal.NoFt (temporal.py:56-74): a single 1x1 projection."""
+
+    def __init__(self, in_chnnels, out_dims, kernel_size=1):
+        super().__init__()
+        if kernel_size != 1:
+            raise NotImplementedError("NoFt with kernel_size != 1")
+        self.in_chnnels, self.out_dims, self.kernel_size = in_chnnels, out_dims, kernel_size
+        self.last_conv = nn.Conv1d(in_channels=in_chnnels, out_channels=out_dims, kernel_size=kernel_size)
+
+    def n_pools(self):
+        return 0
+
+    def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True):
+        if not feats.is_cuda:
+            raise _lib.MuconError("the backbone needs CUDA tensors (there is no CPU fallback)")
+        w = self.last_conv.weight.detach()[:, :, 0].contiguous().float()
+        b = self.last_conv.bias.detach().contiguous().float()
+        if tensor_cores and self.out_dims == 128 and self.in_chnnels % 32 == 0:
+            return gemm_tf32_bias_act(feats, w, b, relu=False)
+        return conv1d_rows(feats, w.t().contiguous()[None], b, plan.off[0], plan.V, plan.max_T[0])
+
+    def forward(self, x):
+        B, _, T = x.shape
+        plan = BackbonePlan([T] * B, 0, x.device)
+        rows = x.detach().permute(0, 2, 1).reshape(B * T, self.in_chnnels).contiguous().float()
+        return self.forward_packed(rows, plan).view(B, T, self.out_dims).permute(0, 2, 1).contiguous()
+
+
+class MSTCNPPFirstStage(nn.Module):
+    """Drop-in for core.modules.temporal.MSTCNPPFirstStage (temporal.py:150-204), forward on the GPU.
+
+    Layer i is  f <- relu(conv_fusion(cat(conv_dilated_1(f), conv_dilated_2(f)))) + f  with dilations
+    2**(L-1-i) and 2**i.  Everything in front of the ReLU is linear, so the three convolutions fold (on
+    the host, in float64) into ONE convolution with taps at {-d1, -d2, 0, +d2, +d1}:
+    W_eff[shift] = Wf[:, :H] @ W1[tap] (+ Wf[:, H:] @ W2[tap] where shifts coincide), and the layer is a
+    single tcgen05 launch (mucon_conv_gemm_tf32_shifts: bias + ReLU + residual fused).  Rounding differs
+    from the reference's two-stage evaluation by less than the TF32 operand rounding."""
+
+    def __init__(self, num_layers, num_f_maps, input_dim, output_dim, pooling_layers=(1, 2, 4, 8)):
+        super().__init__()
+        if num_f_maps != 128 or output_dim != 128:
+            raise NotImplementedError("the tcgen05 conv kernels are built for 128 feature maps")
+        self.num_layers, self.num_f_maps, self.input_dim, self.output_dim = num_layers, num_f_maps, input_dim, output_dim
+        self.conv_1x1_in = nn.Conv1d(input_dim, num_f_maps, 1)
+        self.conv_dilated_1 = nn.ModuleList(
+            nn.Conv1d(num_f_maps, num_f_maps, 3, padding=2 ** (num_layers - 1 - i), dilation=2 ** (num_layers - 1 - i))
+            for i in range(num_layers))
+        self.conv_dilated_2 = nn.ModuleList(
+            nn.Conv1d(num_f_maps, num_f_maps, 3, padding=2 ** i, dilation=2 ** i) for i in range(num_layers))
+        self.conv_fusion = nn.ModuleList(nn.Conv1d(2 * num_f_maps, num_f_maps, 1) for i in range(num_layers))
+        self.dropout = nn.Dropout()
+        self.conv_out = nn.Conv1d(num_f_maps, output_dim, 1)
+        self.pooling_layers = list(pooling_layers)
+        self._cache = None
+
+    def n_pools(self):
+        return sum(1 for i in range(self.num_layers) if i in self.pooling_layers)
+
+    def _weights(self):
+        key = tuple(p._version for p in self.parameters()) + (str(self.conv_out.weight.device),)
+        if self._cache is None or self._cache[0] != key:
+            H = self.num_f_maps
+            layers = []
+            for i in range(self.num_layers):
+                d1, d2 = 2 ** (self.num_layers - 1 - i), 2 ** i
+                W1 = self.conv_dilated_1[i].weight.detach().double()   # [Co, Ci, 3]
+                W2 = self.conv_dilated_2[i].weight.detach().double()
+                Wf = self.conv_fusion[i].weight.detach().double()[:, :, 0]
+                Wf1, Wf2 = Wf[:, :H], Wf[:, H:]
+                taps = {}
+                for t in range(3):
+                    taps[(t - 1) * d1] = taps.get((t - 1) * d1, 0) + Wf1 @ W1[:, :, t]
+                    taps[(t - 1) * d2] = taps.get((t - 1) * d2, 0) + Wf2 @ W2[:, :, t]
+                shifts = sorted(taps)
+                W = torch.cat([taps[sft] for sft in shifts], 0).float().contiguous()   # [n*Co, Ci]
+                bias = (Wf1 @ self.conv_dilated_1[i].bias.detach().double()
+                        + Wf2 @ self.conv_dilated_2[i].bias.detach().double()
+                        + self.conv_fusion[i].bias.detach().double()).float().contiguous()
+                layers.append((shifts, W, bias))
+            w = dict(in_w=self.conv_1x1_in.weight.detach()[:, :, 0].contiguous().float(),
+                     in_b=self.conv_1x1_in.bias.detach().contiguous().float(),
+                     out_k=_kco(self.conv_out), out_b=self.conv_out.bias.detach().contiguous().float(), layers=layers)
+            self._cache = (key, w)
+        return self._cache[1]
+
+    def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True):
+        """feats [sum T, input_dim] float32 rows -> [sum T', output_dim]."""
+        if self.training:
+            raise NotImplementedError("training-mode dropout is not implemented; call .eval()")
+        if not feats.is_cuda:
+            raise _lib.MuconError("the backbone needs CUDA tensors (there is no CPU fallback)")
+        if not tensor_cores:
+            raise NotImplementedError("MSTCNPPFirstStage runs on the tcgen05 (TF32) kernels only")
+        w = self._weights()
+        if self.input_dim % 32 == 0:
+            f = gemm_tf32_bias_act(feats, w["in_w"], w["in_b"], relu=False)                   # temporal.py:187
+        else:
+            f = conv1d_rows(feats, w["in_w"].t().contiguous()[None], w["in_b"], plan.off[0], plan.V, plan.max_T[0])
+        level = 0
+        for i, (shifts, W, bias) in enumerate(w["layers"]):
+            f = conv_gemm_shifts_rows(f, W, bias, shifts, plan, level, relu_mid=True, residual=f)   # :189-196
+            if i in self.pooling_layers:
+                f = maxpool2_rows(f, plan, level)                                               # :198-199
+                level += 1
+        return conv_gemm_rows(f, w["out_k"], w["out_b"], plan, level)                          # :201
+
+    def forward(self, x):
+        B, _, T = x.shape
+        plan = BackbonePlan([T] * B, self.n_pools(), x.device)
+        rows = x.detach().permute(0, 2, 1).reshape(B * T, self.input_dim).contiguous().float()
+        z = self.forward_packed(rows, plan)
+        return z.view(B, int(plan.T[-1][0]), self.output_dim).permute(0, 2, 1).contiguous()
+
+
 class MuConBackbone(nn.Module):
     """The backbone-side members of the reference model, under the reference's attribute names:
     `ft` (models.py:162-171), `ft_last_gn` (:188-191), `conv_classifier` (:276-278)."""
 
     def __init__(self, input_feature_size=2048, num_classes=48, hidden_size=128,
                  stages=(1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024), pooling=True, pooling_layers=(1, 2, 4, 8),
-                 last_gn=True, last_gn_num_groups=32, last_relu=True):
+                 last_gn=True, last_gn_num_groups=32, last_relu=True, ft_type="wavenet"):
         super().__init__()
         self.num_classes, self.hidden_size = num_classes, hidden_size
         self.last_gn, self.last_relu = last_gn, last_relu
-        self.ft = WaveNetBlock(input_feature_size, stages=stages, out_dims=hidden_size, pooling=pooling,
-                               pooling_layers=pooling_layers)
+        if ft_type == "wavenet":      # models.py:160-186
+            self.ft = WaveNetBlock(input_feature_size, stages=stages, out_dims=hidden_size, pooling=pooling,
+                                   pooling_layers=pooling_layers)
+        elif ft_type == "mstcnpp":
+            self.ft = MSTCNPPFirstStage(input_dim=input_feature_size, num_layers=len(stages), output_dim=hidden_size,
+                                        num_f_maps=hidden_size, pooling_layers=pooling_layers)
+        elif ft_type == "noft":
+            self.ft = NoFt(in_chnnels=input_feature_size, out_dims=hidden_size)
+        else:
+            raise Exception(f"Invalid ft type ({ft_type})")
         self.ft_last_gn = nn.GroupNorm(num_groups=last_gn_num_groups, num_channels=hidden_size)
         self.conv_classifier = nn.Conv1d(hidden_size, num_classes, kernel_size=1)
 
