@@ -524,6 +524,35 @@ extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const vo
   return dispatch_fused<float>(b, J, static_cast<const float*>(logp), order, write_bs, st);
 }
 
+extern "C" int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
+                                              const int32_t* order, int n_wide, int write_bs, void* stream,
+                                              void* side_stream, void* ev_fork, void* ev_join) {
+  if (!bh || !order || n_wide < 0 || n_wide > bh->U) return MUCON_EINVAL;
+  if (n_wide > 0 && (!side_stream || !ev_fork || !ev_join)) return MUCON_EINVAL;
+  mucon_viterbi_batch b = *bh;
+  cudaStream_t st = static_cast<cudaStream_t>(stream), side = static_cast<cudaStream_t>(side_stream);
+  int rc = MUCON_OK;
+  if (n_wide > 0) {
+    // the wide launch (a warp per transcript segment) for the first n_wide units of `order`, on the
+    // side stream, concurrent with the main launch
+    MUCON_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_fork), st));
+    MUCON_CUDA_CHECK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(ev_fork), 0));
+    b.U = n_wide;
+    b.lanes = 32;
+    rc = mucon_viterbi_align_fused(&b, logp, in_is_f64, order, write_bs, side);
+    if (rc == MUCON_EUNSUPPORTED) { n_wide = 0; rc = MUCON_OK; }  // shape not covered: everything in the main launch
+    if (rc != MUCON_OK) return rc;
+  }
+  b.U = bh->U - n_wide;
+  b.lanes = 0;
+  if (b.U > 0) rc = mucon_viterbi_align_fused(&b, logp, in_is_f64, order + n_wide, write_bs, st);
+  if (n_wide > 0) {
+    MUCON_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_join), side));
+    MUCON_CUDA_CHECK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(ev_join), 0));
+  }
+  return rc;
+}
+
 extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
                                     int max_len, int lanes, int32_t* warp_unit_h, int32_t* n_cta_out,
                                     int32_t* wpc_out, int32_t* lanes_out) {

@@ -12,6 +12,7 @@ transcript) units in two kernel launches; that is what bench.py and the multi-GP
 All compute happens in libmucon_b200.so (CUDA, sm_100a); there is no CPU fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -70,6 +71,8 @@ class _Blob:
 
 MAX_J_REGISTER = 128  # kDpMaxJ in csrc/viterbi_dp.cuh
 MAX_N_REGISTER = 65   # dp_max_n(8)
+LONG_TAIL_FRACTION = float(os.environ.get("MUCON_LONG_TAIL_FRACTION", "0.85"))
+LONG_TAIL_MAX_UNITS = 40
 LANES_MIN_WARPS = 1184  # two warps per SM sub-partition on a 148-SM part
 
 
@@ -206,6 +209,16 @@ class AlignPlan:
         blob.add("order_u", np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32))
         # optional: videos of >= long_K blocks get a launch of their own with a warp per segment
         # (measured slower than one uniform launch on Breakfast-shaped batches, so off by default)
+        if long_K is None:
+            # auto: the few videos within ~15 % of the longest one set the critical path of the launch
+            # (their DP is a serial chain of K steps); they get a wide launch of their own, a warp per
+            # transcript segment, concurrent with the main one (measured on the 1712-video split:
+            # 171 -> 155 us with the 22 longest videos split off; more than ~40 and it stops paying)
+            long_K = 0
+            if U >= 256 and self.single and self.max_N <= 15 and self.max_K >= 128:
+                thr = max(1, int(LONG_TAIL_FRACTION * self.max_K))
+                if int((uK >= thr).sum()) <= LONG_TAIL_MAX_UNITS:
+                    long_K = thr
         self.n_long = int((uK >= long_K).sum()) if long_K else 0
         blob.add("vid_lab_off", self.vid_off[:-1])
         if self.lane_unit is not None:
@@ -264,6 +277,15 @@ class ViterbiEngine:
         if self._side is None:
             self._side = torch.cuda.Stream(self.device)
         return self._side
+
+    def _raw_event(self, i):
+        """cudaEvent_t handle (timing disabled) owned by this engine, for the library's stream fork/join."""
+        key = ("raw", i)
+        ev = self._events.get(key)
+        if ev is None:
+            ev = self._events[key] = torch.cuda.Event(enable_timing=False)
+            ev.record(torch.cuda.current_stream(self.device))  # torch creates the handle lazily
+        return C.c_void_p(ev.cuda_event)
 
     def _event(self, i):
         ev = self._events.get(i)
@@ -350,40 +372,28 @@ class ViterbiEngine:
             self.last_mode = "lanes"
             return self._finish(plan, sp)
         if mode == "fused" or (mode == "auto" and plan.single):
-            # Long videos are a long serial chain of DP steps: they get their own launch with a
-            # warp per transcript segment (fewer instructions per step), on a second stream so
-            # that both launches share the GPU.  order_u is sorted longest first.
+            # One call: the long tail (plan.n_long longest videos, first in order_u) goes to a wide
+            # launch on a side stream, everything else to the main launch; the fork/join between
+            # the two streams happens inside the library.
             b.n_cta, b.wpc, b.warp_unit = 0, 4, None
+            b.U, b.lanes, b.max_N, b.max_K = plan.U, 0, plan.max_N, plan.max_K
             n_long = plan.n_long if (plan.max_N <= 15 and plan.U >= 64) else 0
-            rc = 0
             if n_long:
                 side = self._side_stream()
-                ev = self._event(0)
-                ev.record(st)
-                side.wait_event(ev)
-                b.U, b.lanes, b.max_N, b.max_K = n_long, 32, plan.max_N, plan.max_K
+                fork, join = self._raw_event(0), self._raw_event(1)
+                rc = lib.mucon_viterbi_align_fused_tail(
+                    C.byref(b), _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["order_u"]), C.c_int(n_long),
+                    C.c_int(int(bool(write_bs))), sp, C.c_void_p(side.cuda_stream), fork, join)
+            else:
                 rc = lib.mucon_viterbi_align_fused(C.byref(b), _lib.ptr(logp), C.c_int(int(is64)),
-                                                   C.c_void_p(p["order_u"]), C.c_int(int(bool(write_bs))),
-                                                   C.c_void_p(side.cuda_stream))
-                if rc == -2:
-                    n_long, rc = 0, 0
-            if rc == 0:
-                b.U, b.lanes, b.max_N, b.max_K = plan.U - n_long, 0, plan.max_N, plan.max_K
-                rc = lib.mucon_viterbi_align_fused(C.byref(b), _lib.ptr(logp), C.c_int(int(is64)),
-                                                   C.c_void_p(p["order_u"] + 4 * n_long),
-                                                   C.c_int(int(bool(write_bs))), sp)
-            if n_long:
-                done = self._event(1)
-                done.record(side)
-                st.wait_event(done)
-            b.U = plan.U
+                                                   C.c_void_p(p["order_u"]), C.c_int(int(bool(write_bs))), sp)
             if rc == 0:
                 self.launches += 2 if n_long else 1
                 self.last_mode = "fused"
                 if mid_event is not None:
                     mid_event.record(st)
                 return self._finish(plan, sp)
-            if rc != -2 or mode == "fused" or n_long:
+            if rc != -2 or mode == "fused":
                 _lib.check(rc, "mucon_viterbi_align_fused")
         overlap = len(plan.groups) > 1
         if overlap:

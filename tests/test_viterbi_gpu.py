@@ -328,8 +328,21 @@ def test_breakfast_split_properties_full_size(eng, mode):
         exp = np.concatenate([np.full(rem, trs[v][-1])] + [np.full(30 * n, l) for l, n in zip(trs[v], out["seg_blocks"][a:b])])
         assert np.array_equal(out["labels"][plan.vid_off[v]:plan.vid_off[v + 1]], exp)
     host = logp.cpu().numpy()
-    for v in rng.choice(V, 25, replace=False):
+    longest = np.argsort(-T)[:6]  # these go through the wide launch (a warp per segment) in auto mode
+    for v in list(rng.choice(V, 25, replace=False)) + list(longest):
         lp = host[plan.vid_off[v]:plan.vid_off[v + 1]]
         ref = oracle_unit(lp, trs[v].tolist(), means[v], 30, 2000, True)
         assert same_score(out["score"][v], ref["score"])
         assert np.array_equal(out["labels"][plan.vid_off[v]:plan.vid_off[v + 1]], ref["labels"])
+    if mode == "auto":
+        # the long-tail split (two concurrent launches) changes nothing in the results
+        assert plan.n_long > 0
+        plan1 = AlignPlan(T, [[tr.tolist()] for tr in trs], C, device=eng.device, len_params=poisson_params(means),
+                          long_K=0)
+        assert plan1.n_long == 0
+        eng.run(plan1, logp, seg0_f32=True, mode=mode)
+        torch.cuda.synchronize()
+        out1 = eng.fetch(plan1, want_bp=True)
+        outb = eng.fetch(plan, want_bp=True)
+        for k in ("score", "labels", "seg_blocks", "final_j", "status", "bp"):
+            assert np.array_equal(outb[k], out1[k]), k
