@@ -153,13 +153,13 @@ int mucon_viterbi_align_fused(const mucon_viterbi_batch* batch_h, const void* lo
                               const int32_t* order, int write_bs, void* stream);
 
 /* mucon_viterbi_align_fused with the long tail split off: the first n_wide units of `order` (the
- * longest videos; their DP is the critical path of the launch) run with a warp per segment on
- * side_stream, the others with the shared-warp kernel on `stream`, concurrently; ev_fork / ev_join are
- * two cudaEvent_t (timing disabled) the call records to order the two streams.  n_wide == 0 is
- * mucon_viterbi_align_fused.  If the wide shape is not covered everything runs in the main launch. */
+ * longest videos; their DP is the critical path of the launch) run with a warp per segment, the
+ * others with the shared-warp kernel, CONCURRENTLY in the same stream: the second kernel is a
+ * programmatic dependent launch that starts as soon as the CTAs of the first are resident (the two
+ * work on disjoint units).  n_wide == 0 is mucon_viterbi_align_fused.  If the wide shape is not
+ * covered everything runs in the main launch. */
 int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* batch_h, const void* logp, int in_is_f64,
-                                   const int32_t* order, int n_wide, int write_bs, void* stream,
-                                   void* side_stream, void* ev_fork, void* ev_join);
+                                   const int32_t* order, int n_wide, int write_bs, void* stream);
 
 /* Arg-max over the candidates of each video: best[v] = unit index with the highest score among
  * units cand_off[v] .. cand_off[v+1] (lowest index wins ties; units with status INFEASIBLE are

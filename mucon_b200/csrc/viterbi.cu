@@ -301,7 +301,7 @@ int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
 
 template <typename BST, int G, int SL>
 int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int32_t* order, int write_bs,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool pdl) {
   FusedCfg cfg;
   cfg.scan_threads = b.C <= 32 ? 32 : (b.C <= 64 ? 64 : 128);
   const int spw = 32 / G;
@@ -336,19 +336,37 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
   }
   if (smem > 48 * 1024)
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<b.U, cfg.scan_threads + 32 * cfg.dp_warps, smem, st>>>(b, J, logp, order, cfg);
+  if (pdl) {
+    // programmatic dependent launch: this grid may start as soon as every CTA of the previous kernel
+    // in the stream has executed griddepcontrol.launch_dependents (align_fused_kernel does so at its
+    // start), i.e. it runs CONCURRENTLY with that kernel.  There is no data dependency between the
+    // two (disjoint units), so this kernel never executes griddepcontrol.wait.
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(b.U);
+    lc.blockDim = dim3(cfg.scan_threads + 32 * cfg.dp_warps);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    MUCON_CUDA_CHECK(cudaLaunchKernelEx(&lc, kern, b, J, logp, order, cfg));
+  } else {
+    kern<<<b.U, cfg.scan_threads + 32 * cfg.dp_warps, smem, st>>>(b, J, logp, order, cfg);
+  }
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
 
 template <typename BST>
 int dispatch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int32_t* order, int write_bs,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool pdl) {
   const int G = b.lanes == 32 ? 32 : (J <= 32 ? 4 : 8);
   const int SL = (J + G - 1) / G;
-#define MUCON_SL_CASE(g, n) case n: return launch_fused<BST, g, n>(b, J, logp, order, write_bs, st);
+#define MUCON_SL_CASE(g, n) case n: return launch_fused<BST, g, n>(b, J, logp, order, write_bs, st, pdl);
 #ifdef MUCON_ONLY_SL9  // developer builds: only the evaluator's shape (J = 66)
-  if (G == 8 && SL == 9) return launch_fused<BST, 8, 9>(b, J, logp, order, write_bs, st);
+  if (G == 8 && SL == 9) return launch_fused<BST, 8, 9>(b, J, logp, order, write_bs, st, pdl);
   return MUCON_EUNSUPPORTED;
 #else
   if (G == 32) {
@@ -504,8 +522,8 @@ extern "C" int mucon_viterbi_decode_lanes(const mucon_viterbi_batch* bh, const i
   return MUCON_OK;
 }
 
-extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
-                                         const int32_t* order, int write_bs, void* stream) {
+static int align_fused_impl(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64, const int32_t* order,
+                            int write_bs, void* stream, bool pdl) {
   if (!bh || !logp) return MUCON_EINVAL;
   const mucon_viterbi_batch& b = *bh;
   if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1 || b.max_K < 0) return MUCON_EINVAL;
@@ -520,36 +538,33 @@ extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const vo
   const size_t row_bytes = (size_t)b.C * (in_is_f64 ? 8 : 4);
   if (row_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(logp) & 15) != 0 || b.C > 128) return MUCON_EUNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (in_is_f64) return dispatch_fused<double>(b, J, static_cast<const double*>(logp), order, write_bs, st);
-  return dispatch_fused<float>(b, J, static_cast<const float*>(logp), order, write_bs, st);
+  if (in_is_f64) return dispatch_fused<double>(b, J, static_cast<const double*>(logp), order, write_bs, st, pdl);
+  return dispatch_fused<float>(b, J, static_cast<const float*>(logp), order, write_bs, st, pdl);
+}
+
+extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
+                                         const int32_t* order, int write_bs, void* stream) {
+  return align_fused_impl(bh, logp, in_is_f64, order, write_bs, stream, false);
 }
 
 extern "C" int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
-                                              const int32_t* order, int n_wide, int write_bs, void* stream,
-                                              void* side_stream, void* ev_fork, void* ev_join) {
+                                              const int32_t* order, int n_wide, int write_bs, void* stream) {
   if (!bh || !order || n_wide < 0 || n_wide > bh->U) return MUCON_EINVAL;
-  if (n_wide > 0 && (!side_stream || !ev_fork || !ev_join)) return MUCON_EINVAL;
   mucon_viterbi_batch b = *bh;
-  cudaStream_t st = static_cast<cudaStream_t>(stream), side = static_cast<cudaStream_t>(side_stream);
   int rc = MUCON_OK;
   if (n_wide > 0) {
-    // the wide launch (a warp per transcript segment) for the first n_wide units of `order`, on the
-    // side stream, concurrent with the main launch
-    MUCON_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_fork), st));
-    MUCON_CUDA_CHECK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(ev_fork), 0));
+    // the wide launch (a warp per transcript segment) for the first n_wide units of `order`
     b.U = n_wide;
     b.lanes = 32;
-    rc = mucon_viterbi_align_fused(&b, logp, in_is_f64, order, write_bs, side);
+    rc = align_fused_impl(&b, logp, in_is_f64, order, write_bs, stream, false);
     if (rc == MUCON_EUNSUPPORTED) { n_wide = 0; rc = MUCON_OK; }  // shape not covered: everything in the main launch
     if (rc != MUCON_OK) return rc;
   }
   b.U = bh->U - n_wide;
   b.lanes = 0;
-  if (b.U > 0) rc = mucon_viterbi_align_fused(&b, logp, in_is_f64, order + n_wide, write_bs, st);
-  if (n_wide > 0) {
-    MUCON_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_join), side));
-    MUCON_CUDA_CHECK(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(ev_join), 0));
-  }
+  // the main launch follows in the same stream as a programmatic dependent launch: it starts once
+  // the wide CTAs are resident and runs concurrently with them
+  if (b.U > 0) rc = align_fused_impl(&b, logp, in_is_f64, order + n_wide, write_bs, stream, n_wide > 0);
   return rc;
 }
 

@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
 align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restrict__ logp,
                    const int32_t* __restrict__ order, const FusedCfg cfg) {
   extern __shared__ __align__(128) unsigned char sm[];
+  // Let a programmatically dependent grid (the main launch that follows the long-tail launch in the
+  // same stream, mucon_viterbi_align_fused_tail) start now; a no-op otherwise.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int fs = FS ? FS : b.fs;
   const int C = CT ? CT : b.C;  // CT: class count known at compile time (immediate offsets in the scan)
   const int u = order ? order[blockIdx.x] : blockIdx.x;

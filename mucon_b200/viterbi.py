@@ -278,15 +278,6 @@ class ViterbiEngine:
             self._side = torch.cuda.Stream(self.device)
         return self._side
 
-    def _raw_event(self, i):
-        """cudaEvent_t handle (timing disabled) owned by this engine, for the library's stream fork/join."""
-        key = ("raw", i)
-        ev = self._events.get(key)
-        if ev is None:
-            ev = self._events[key] = torch.cuda.Event(enable_timing=False)
-            ev.record(torch.cuda.current_stream(self.device))  # torch creates the handle lazily
-        return C.c_void_p(ev.cuda_event)
-
     def _event(self, i):
         ev = self._events.get(i)
         if ev is None:
@@ -373,20 +364,14 @@ class ViterbiEngine:
             return self._finish(plan, sp)
         if mode == "fused" or (mode == "auto" and plan.single):
             # One call: the long tail (plan.n_long longest videos, first in order_u) goes to a wide
-            # launch on a side stream, everything else to the main launch; the fork/join between
-            # the two streams happens inside the library.
+            # launch, everything else to the main launch, which follows in the same stream as a
+            # programmatic dependent launch and runs concurrently with it.
             b.n_cta, b.wpc, b.warp_unit = 0, 4, None
             b.U, b.lanes, b.max_N, b.max_K = plan.U, 0, plan.max_N, plan.max_K
             n_long = plan.n_long if (plan.max_N <= 15 and plan.U >= 64) else 0
-            if n_long:
-                side = self._side_stream()
-                fork, join = self._raw_event(0), self._raw_event(1)
-                rc = lib.mucon_viterbi_align_fused_tail(
-                    C.byref(b), _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["order_u"]), C.c_int(n_long),
-                    C.c_int(int(bool(write_bs))), sp, C.c_void_p(side.cuda_stream), fork, join)
-            else:
-                rc = lib.mucon_viterbi_align_fused(C.byref(b), _lib.ptr(logp), C.c_int(int(is64)),
-                                                   C.c_void_p(p["order_u"]), C.c_int(int(bool(write_bs))), sp)
+            rc = lib.mucon_viterbi_align_fused_tail(
+                C.byref(b), _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["order_u"]), C.c_int(n_long),
+                C.c_int(int(bool(write_bs))), sp)
             if rc == 0:
                 self.launches += 2 if n_long else 1
                 self.last_mode = "fused"
