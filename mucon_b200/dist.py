@@ -40,6 +40,55 @@ def gather_payload(plan, recv=None, group=None):
     return recv.view(world, n)
 
 
+class PipelinedGather:
+    """gather_payload for a stream of batches: the collective of batch i runs on the communicator's
+    stream while batch i+1 is being aligned.  Batches alternate between `depth` (plan, receive buffer)
+    slots; before a slot's plan is run again the gather that still reads its payload is waited for
+    (a stream-side wait, the host does not block).
+
+        pg = PipelinedGather([plan_a, plan_b])
+        for i, logp in enumerate(batches):
+            plan = pg.acquire(i)               # safe to overwrite this slot's payload now
+            engine.run(plan, logp, ...)
+            pg.gather(i)                       # async all_gather of plan.payload
+        rows = pg.result(i)                    # [world, capacity] uint8, waits for batch i's gather
+    """
+
+    def __init__(self, plans, group=None):
+        self.plans, self.group = list(plans), group
+        world = dist.get_world_size(group)
+        n = self.plans[0].payload.numel()
+        if any(p.payload.numel() != n for p in self.plans):
+            raise ValueError("all plans need the same payload_capacity")
+        self.recv = [torch.empty(world * n, dtype=torch.uint8, device=p.payload.device) for p in self.plans]
+        self.work = [None] * len(self.plans)
+        self.world, self.n = world, n
+
+    def acquire(self, i):
+        s = i % len(self.plans)
+        if self.work[s] is not None:
+            self.work[s].wait()
+            self.work[s] = None
+        return self.plans[s]
+
+    def gather(self, i):
+        s = i % len(self.plans)
+        self.work[s] = dist.all_gather_into_tensor(self.recv[s], self.plans[s].payload, group=self.group, async_op=True)
+
+    def result(self, i):
+        s = i % len(self.plans)
+        if self.work[s] is not None:
+            self.work[s].wait()
+            self.work[s] = None
+        return self.recv[s].view(self.world, self.n)
+
+    def drain(self):
+        for s in range(len(self.plans)):
+            if self.work[s] is not None:
+                self.work[s].wait()
+                self.work[s] = None
+
+
 def unpack_payload(row, U, n_pos):
     """(scores [U] float64, seg_blocks [n_pos] int32) views of one rank's gathered payload row."""
     return row[:8 * U].view(torch.float64), row[8 * U:8 * U + 4 * n_pos].view(torch.int32)

@@ -70,6 +70,23 @@ def _worker(rank, world, port, ret):
         segr = rr.integers(1, 66, npos).astype(np.int32)
         sc_v, sg_v = mdist.unpack_payload(rows[r], Ur, npos)
         ok &= np.array_equal(sc_v.numpy(), scr) and np.array_equal(sg_v.numpy(), segr)
+    # pipelined gather: two slots, batch i's collective overlaps batch i+1's work
+    plans = []
+    for _ in range(2):
+        q = P()
+        q.payload = torch.zeros(64, dtype=torch.uint8)
+        plans.append(q)
+    pg = mdist.PipelinedGather(plans)
+    for i in range(5):
+        q = pg.acquire(i)
+        q.payload.fill_(10 * i + rank)           # "the alignment of batch i"
+        pg.gather(i)
+        if i >= 1:                                # batch i-1's result is complete and untouched by batch i
+            rows = pg.result(i - 1)
+            ok &= all(int(rows[r][0]) == 10 * (i - 1) + r and int(rows[r][-1]) == 10 * (i - 1) + r for r in range(world))
+    rows = pg.result(4)
+    ok &= all(int(rows[r][7]) == 40 + r for r in range(world))
+    pg.drain()
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
