@@ -350,6 +350,57 @@ def main_ours(args, rank, world, local_rank):
         except Exception as e:  # the headline number must not depend on this extra leg
             full = {"error": str(e)[:200]}
 
+    # ---- mask generation of the consistency loss for the same split (forward + backward) ----------
+    masks_leg = None
+    try:
+        from mucon_b200.masks import batch_meta, create_masks_batch
+        Ms = [len(t) for t in trs]
+        Tl = [int(t) for t in T]
+        rngm = np.random.default_rng(1000 + rank)
+        Lh = np.concatenate([float(t) * rngm.dirichlet(3 * np.ones(m)) for t, m in zip(T, Ms)]).astype(np.float32)
+        Ld = torch.from_numpy(Lh).to(device).requires_grad_(True)
+        mask_bytes = int(sum(4 * t * m for t, m in zip(Tl, Ms)))
+        meta = batch_meta(Tl, Ms, device)   # offset tables built once, like an AlignPlan
+        for _ in range(3):
+            mo, _off = create_masks_batch(Tl, Ld, Ms, meta=meta)
+        go = torch.ones_like(mo)
+        for _ in range(3):
+            Ld.grad = None
+            mo.backward(go, retain_graph=True)
+        barrier()
+        # through the C ABI with preallocated buffers (the autograd entry point above adds ~60 us of host
+        # time per call, more than the kernels take)
+        from mucon_b200 import masks as mmod
+        n_off_d, T_d, off_d, rv_d, Vm, n_rows, max_Tm, total = meta[0]
+        Lc = Ld.detach().clone()
+        ws = torch.empty(2 * n_rows, dtype=torch.float32, device=device)
+        gL = torch.empty(n_rows, dtype=torch.float32, device=device)
+        mo = mo.detach()
+        for _ in range(3):
+            mmod._launch_fwd(Lc, n_off_d, T_d, off_d, rv_d, Vm, n_rows, max_Tm, 0.0, 0, 0, None, mo)
+            mmod._launch_bwd(Lc, n_off_d, T_d, off_d, rv_d, Vm, n_rows, 0.0, 0, 0, go, ws, gL)
+        barrier()
+        m0, m1, m2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        nm = 20
+        m0.record()
+        for _ in range(nm):
+            mmod._launch_fwd(Lc, n_off_d, T_d, off_d, rv_d, Vm, n_rows, max_Tm, 0.0, 0, 0, None, mo)
+        m1.record()
+        for _ in range(nm):
+            mmod._launch_bwd(Lc, n_off_d, T_d, off_d, rv_d, Vm, n_rows, 0.0, 0, 0, go, ws, gL)
+        m2.record()
+        barrier()
+        fwd_ms, bwd_ms = m0.elapsed_time(m1) / nm, m1.elapsed_time(m2) / nm
+        masks_leg = {"what": "create_masks for all 1712 videos in one launch (box template), %d mask rows" % sum(Ms),
+                     "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "bytes_written_fwd": mask_bytes,
+                     "fwd_gbs": mask_bytes / (fwd_ms * 1e-3) / 1e9, "bwd_read_gbs": mask_bytes / (bwd_ms * 1e-3) / 1e9,
+                     "note": "bound: HBM write (fwd) / read (bwd) of 4*N*T bytes (110 MB: fits the 126 MB L2, so "
+                     "the backward's reads are L2 hits); back-to-back launches through the C ABI"}
+        del mo, go, Ld
+        torch.cuda.empty_cache()
+    except Exception as e:
+        masks_leg = {"error": str(e)[:200]}
+
     # ---- e2e: host API, pinned host log-probs in, labels + scores + segments out ---------------
     host_logp = torch.empty(logp.shape, dtype=logp.dtype, pin_memory=True)
     host_logp.copy_(logp)
@@ -448,6 +499,8 @@ def main_ours(args, rank, world, local_rank):
         }
         if full is not None:
             out["full_inference"] = full
+        if masks_leg is not None:
+            out["masks"] = masks_leg
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))

@@ -188,14 +188,16 @@ int mucon_logfact_h(int fs, int max_len, double* out_h);
  * masks.py:61) are written to L_scaled when non-NULL.
  * template_id: 0 box, 1 gaussian(std=20), 2 trapezoid.  align_corners: 0 (torch >= 1.3 default)
  * or 1 (torch 1.1, the reference's pinned docker).
+ * row_vid: [n_rows] video of every mask row (one CTA per row looks its video up in one load), or NULL
+ * (the kernel then searches n_off).
  */
 int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
-                    int V, int n_rows /* n_off[V] */, int max_T /* max over T[] */, float overlap,
-                    int template_id, int align_corners, float* L_scaled, float* out, void* stream);
+                    const int32_t* row_vid, int V, int n_rows /* n_off[V] */, int max_T /* max over T[] */,
+                    float overlap, int template_id, int align_corners, float* L_scaled, float* out, void* stream);
 /* grad_L[i] = d(sum(grad_out * masks))/dL[i], through pi (cumsum) and the scale.
  * grad_out has the layout of `out`; ws is scratch of 2*n_rows floats. */
 int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
-                    int V, int n_rows, float overlap, int template_id, int align_corners,
+                    const int32_t* row_vid, int V, int n_rows, float overlap, int template_id, int align_corners,
                     const float* grad_out, float* ws, float* grad_L, void* stream);
 /* Host helper: the 100 template taps the kernels use (masks.py:34-54). */
 int mucon_mask_template_h(int template_id, float* out100_h);

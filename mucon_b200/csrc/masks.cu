@@ -2,7 +2,8 @@
 //
 // Replaces reference src/mucon/masks.py:19-74 (create_masks): cumsum -> affine map ->
 // affine_grid + bilinear grid_sample (zero padding) of a 100-tap template, fused into one pass
-// that writes each [M, T] mask row with coalesced float4 stores and never materialises the grid.
+// that writes each [M, T] mask row with coalesced, aligned float4 stores (one CTA per row) and never
+// materialises the grid.
 //
 // Per row i of a video with target size T (all float32, torch's op order):
 //   pi = cumsum(L)[i] - L[i];  Ls = L[i]*(1+2*ov);  pi -= Ls*(ov/2)              masks.py:58-62
@@ -62,10 +63,7 @@ __device__ __forceinline__ int find_video(const int32_t* n_off, int V, int row) 
   return lo;
 }
 
-__device__ __forceinline__ RowGeom row_geom(const float* L, int r0, int i, int T, float overlap) {
-  float cum = 0.f;
-  for (int q = 0; q <= i; ++q) cum = cum + L[r0 + q];  // sequential, like torch.cumsum on 1-D
-  const float Li = L[r0 + i];
+__device__ __forceinline__ RowGeom geom_from(float cum, float Li, int T, float overlap) {
   RowGeom g;
   float pi = cum - Li;
   g.Ls = Li * (1.0f + 2 * overlap);
@@ -77,6 +75,44 @@ __device__ __forceinline__ RowGeom row_geom(const float* L, int r0, int i, int T
   return g;
 }
 
+__device__ __forceinline__ RowGeom row_geom(const float* L, int r0, int i, int T, float overlap) {
+  float cum = 0.f;
+  for (int q = 0; q <= i; ++q) cum = cum + L[r0 + q];  // sequential, like torch.cumsum on 1-D
+  return geom_from(cum, L[r0 + i], T, overlap);
+}
+
+// Per-CTA row context.  Every thread reads the (broadcast) row -> video entry and the video's sizes;
+// the lengths in front of the row are fetched by one thread each into shared memory and summed by
+// thread 0 in order (torch.cumsum on a 1-D tensor is sequential), so the prologue is two dependent
+// global loads deep instead of one per segment.  Must be followed by __syncthreads() before *g is read.
+struct RowCtx {
+  int T;
+  long long base;
+};
+__device__ __forceinline__ RowCtx row_ctx(const float* L, const int32_t* n_off, const int32_t* Tv,
+                                          const int64_t* out_off, const int32_t* row_vid, int V, int row,
+                                          float overlap, RowGeom* g) {
+  __shared__ float Lp[256];
+  const int v = row_vid ? row_vid[row] : find_video(n_off, V, row);
+  const int T = Tv[v];
+  const int r0 = n_off[v], i = row - r0;
+  RowCtx c;
+  c.T = T;
+  c.base = out_off[v] + static_cast<long long>(i) * T;
+  if (i < 256) {
+    if (static_cast<int>(threadIdx.x) <= i) Lp[threadIdx.x] = L[r0 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float cum = 0.f;
+      for (int q = 0; q <= i; ++q) cum = cum + Lp[q];
+      *g = geom_from(cum, Lp[i], T, overlap);
+    }
+  } else if (threadIdx.x == 0) {
+    *g = row_geom(L, r0, i, T, overlap);
+  }
+  return c;
+}
+
 __device__ __forceinline__ float coord_u(const RowGeom& g, int t, int T, int align) {
   const float Tf = static_cast<float>(T);
   float gt;
@@ -86,58 +122,78 @@ __device__ __forceinline__ float coord_u(const RowGeom& g, int t, int T, int ali
   return align ? ((gx + 1.f) / 2.f) * (kW - 1) : ((gx + 1.f) * kW - 1.f) / 2.f;
 }
 
-__device__ __forceinline__ float tap(int tid, int i) { return (i >= 0 && i < kW) ? c_tmpl[tid][i] : 0.f; }
+// The template lives in shared memory, padded with one zero on each side (index i+1 holds tap i), so a
+// per-thread index costs one bank access instead of a serialised constant-cache lookup.
+constexpr int kWP = kW + 2;
+__device__ __forceinline__ void load_template(float* tp, int tmpl) {
+  for (int i = threadIdx.x; i < kWP; i += blockDim.x) tp[i] = (i >= 1 && i <= kW) ? c_tmpl[tmpl][i - 1] : 0.f;
+}
+__device__ __forceinline__ float tap(const float* tp, int i) { return tp[i + 1]; }  // valid for -1 <= i <= kW
 
-__device__ __forceinline__ float sample(int tmpl, float u) {
+__device__ __forceinline__ float sample(const float* tp, float u) {
   const float fl = floorf(u);
   // far outside the template: both taps are padding (also keeps the int conversion in range)
   if (!(fl >= -1.f && fl < (float)kW)) return 0.f;
   const int i0 = static_cast<int>(fl);
   const float w1 = u - fl, w0 = 1.f - w1;
-  return tap(tmpl, i0) * w0 + tap(tmpl, i0 + 1) * w1;
+  return tap(tp, i0) * w0 + tap(tp, i0 + 1) * w1;
 }
 
+// One CTA per mask row.  Thread 0 finds the row's video and geometry once; every thread then writes
+// 16-byte aligned float4 groups (rows start at arbitrary element offsets, so the first <= 3 and last
+// <= 3 elements of a row are scalar stores).
 __global__ void __launch_bounds__(256) masks_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off,
                                                         const int32_t* __restrict__ Tv,
-                                                        const int64_t* __restrict__ out_off, int V, float overlap,
+                                                        const int64_t* __restrict__ out_off,
+                                                        const int32_t* __restrict__ row_vid, int V, float overlap,
                                                         int tmpl, int align, float* __restrict__ L_scaled,
                                                         float* __restrict__ out) {
-  const int row = blockIdx.y;
-  const int v = find_video(n_off, V, row);
-  const int T = Tv[v];
-  const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (t0 >= T && !(blockIdx.x == 0 && threadIdx.x == 0)) return;
-  const int r0 = n_off[v], i = row - r0;
-  const RowGeom g = row_geom(L, r0, i, T, overlap);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && L_scaled) L_scaled[row] = g.Ls;
-  if (t0 >= T) return;
-  float* o = out + out_off[v] + static_cast<int64_t>(i) * T;
-  float val[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) val[e] = (t0 + e < T) ? sample(tmpl, coord_u(g, t0 + e, T, align)) : 0.f;
-  if (t0 + 3 < T && ((reinterpret_cast<uintptr_t>(o + t0) & 15) == 0)) {
-    *reinterpret_cast<float4*>(o + t0) = make_float4(val[0], val[1], val[2], val[3]);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (t0 + e < T) o[t0 + e] = val[e];
+  __shared__ float tp[kWP];
+  __shared__ RowGeom g_s;
+  const int row = blockIdx.x;
+  const RowCtx c = row_ctx(L, n_off, Tv, out_off, row_vid, V, row, overlap, &g_s);
+  if (threadIdx.x == 0 && L_scaled) L_scaled[row] = g_s.Ls;
+  load_template(tp, tmpl);
+  __syncthreads();
+  const int T_s = c.T;
+  const long long base_s = c.base;
+  const RowGeom g = g_s;
+  const int T = T_s;
+  float* o = out + base_s;
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(o) >> 2) & 3);
+  const int head = min(T, (4 - mis) & 3);
+  if (static_cast<int>(threadIdx.x) < head) o[threadIdx.x] = sample(tp, coord_u(g, threadIdx.x, T, align));
+  const int nvec = (T - head) >> 2;
+  float4* o4 = reinterpret_cast<float4*>(o + head);
+  for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
+    const int t = head + 4 * q;
+    o4[q] = make_float4(sample(tp, coord_u(g, t, T, align)), sample(tp, coord_u(g, t + 1, T, align)),
+                        sample(tp, coord_u(g, t + 2, T, align)), sample(tp, coord_u(g, t + 3, T, align)));
   }
+  const int t_tail = head + 4 * nvec + threadIdx.x;
+  if (t_tail < T) o[t_tail] = sample(tp, coord_u(g, t_tail, T, align));
 }
 
 // One CTA per mask row: A = dLoss/dpi, B = dLoss/dLs.
 __global__ void __launch_bounds__(256) masks_bwd_rows_kernel(const float* __restrict__ L,
                                                              const int32_t* __restrict__ n_off,
                                                              const int32_t* __restrict__ Tv,
-                                                             const int64_t* __restrict__ out_off, int V, float overlap,
+                                                             const int64_t* __restrict__ out_off,
+                                                             const int32_t* __restrict__ row_vid, int V, float overlap,
                                                              int tmpl, int align, const float* __restrict__ gout,
                                                              float* __restrict__ ws) {
   __shared__ float redA[8], redB[8];
+  __shared__ float tp[kWP];
+  __shared__ RowGeom g_s;
   const int row = blockIdx.x;
-  const int v = find_video(n_off, V, row);
-  const int T = Tv[v];
-  const int r0 = n_off[v], i = row - r0;
-  const RowGeom g = row_geom(L, r0, i, T, overlap);
-  const float* go = gout + out_off[v] + static_cast<int64_t>(i) * T;
+  const RowCtx c = row_ctx(L, n_off, Tv, out_off, row_vid, V, row, overlap, &g_s);
+  load_template(tp, tmpl);
+  __syncthreads();
+  const int T_s = c.T;
+  const long long base_s = c.base;
+  const RowGeom g = g_s;
+  const int T = T_s;
+  const float* go = gout + base_s;
   // u = a_t * Wn / Ls - c,  a_t = (t + 0.5 - pi) [align 0, Wn = W] or (t*T/(T-1) - pi) [align 1, Wn = W-1]
   const float Wn = align ? (float)(kW - 1) : (float)kW;
   const float Tf = (float)T;
@@ -147,7 +203,7 @@ __global__ void __launch_bounds__(256) masks_bwd_rows_kernel(const float* __rest
     const float fl = floorf(u);
     if (!(fl >= -1.f && fl < (float)kW)) continue;
     const int i0 = static_cast<int>(fl);
-    const float slope = tap(tmpl, i0 + 1) - tap(tmpl, i0);
+    const float slope = tap(tp, i0 + 1) - tap(tp, i0);
     if (slope == 0.f) continue;
     const float at = align ? ((T > 1) ? (float)t * Tf / (Tf - 1.f) : 0.f) - g.pi : ((float)t + 0.5f) - g.pi;
     const float w = go[t] * slope;
@@ -190,32 +246,30 @@ __global__ void masks_bwd_combine_kernel(const int32_t* __restrict__ n_off, int 
 
 using namespace mucon;
 
-extern "C" int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off, int V,
-                               int n_rows, int max_T, float overlap, int template_id, int align_corners,
-                               float* L_scaled, float* out, void* stream) {
+extern "C" int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
+                               const int32_t* row_vid, int V, int n_rows, int max_T, float overlap, int template_id,
+                               int align_corners, float* L_scaled, float* out, void* stream) {
   if (!L || !n_off || !T || !out_off || !out || V < 0 || n_rows < 0 || max_T < 0) return MUCON_EINVAL;
   if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
   if (V == 0 || n_rows == 0 || max_T == 0) return MUCON_OK;
-  if (n_rows > 65535) return MUCON_EUNSUPPORTED;
   int rc = ensure_templates();
   if (rc != MUCON_OK) return rc;
-  dim3 grid((max_T + 1023) / 1024, n_rows);
-  masks_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, n_off, T, out_off, V, overlap, template_id,
+  masks_fwd_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, n_off, T, out_off, row_vid, V, overlap, template_id,
                                                                          align_corners, L_scaled, out);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
 
-extern "C" int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off, int V,
-                               int n_rows, float overlap, int template_id, int align_corners, const float* grad_out,
-                               float* ws, float* grad_L, void* stream) {
+extern "C" int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
+                               const int32_t* row_vid, int V, int n_rows, float overlap, int template_id,
+                               int align_corners, const float* grad_out, float* ws, float* grad_L, void* stream) {
   if (!L || !n_off || !T || !out_off || !grad_out || !ws || !grad_L || V < 0 || n_rows < 0) return MUCON_EINVAL;
   if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
   if (V == 0 || n_rows == 0) return MUCON_OK;
   int rc = ensure_templates();
   if (rc != MUCON_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  masks_bwd_rows_kernel<<<n_rows, 256, 0, st>>>(L, n_off, T, out_off, V, overlap, template_id, align_corners, grad_out,
+  masks_bwd_rows_kernel<<<n_rows, 256, 0, st>>>(L, n_off, T, out_off, row_vid, V, overlap, template_id, align_corners, grad_out,
                                                 ws);
   MUCON_CUDA_CHECK(cudaGetLastError());
   masks_bwd_combine_kernel<<<(V + 127) / 128, 128, 0, st>>>(n_off, V, overlap, ws, grad_L);

@@ -27,18 +27,19 @@ def project_lengths_softmax(T, L):
     return T * torch.softmax(L, dim=0)
 
 
-def _launch_fwd(L, n_off, Ts, out_off, V, n_rows, max_T, overlap, tid, align, L_scaled, out):
+def _launch_fwd(L, n_off, Ts, out_off, row_vid, V, n_rows, max_T, overlap, tid, align, L_scaled, out):
     st = torch.cuda.current_stream(L.device)
     _lib.check(_lib.lib().mucon_masks_fwd(
-        _lib.ptr(L), _lib.ptr(n_off), _lib.ptr(Ts), _lib.ptr(out_off), C.c_int(V), C.c_int(n_rows), C.c_int(max_T),
+        _lib.ptr(L), _lib.ptr(n_off), _lib.ptr(Ts), _lib.ptr(out_off), _lib.ptr(row_vid), C.c_int(V), C.c_int(n_rows),
+        C.c_int(max_T),
         C.c_float(overlap), C.c_int(tid), C.c_int(align), _lib.ptr(L_scaled), _lib.ptr(out),
         C.c_void_p(st.cuda_stream)), "mucon_masks_fwd")
 
 
-def _launch_bwd(L, n_off, Ts, out_off, V, n_rows, overlap, tid, align, gout, ws, gL):
+def _launch_bwd(L, n_off, Ts, out_off, row_vid, V, n_rows, overlap, tid, align, gout, ws, gL):
     st = torch.cuda.current_stream(L.device)
     _lib.check(_lib.lib().mucon_masks_bwd(
-        _lib.ptr(L), _lib.ptr(n_off), _lib.ptr(Ts), _lib.ptr(out_off), C.c_int(V), C.c_int(n_rows),
+        _lib.ptr(L), _lib.ptr(n_off), _lib.ptr(Ts), _lib.ptr(out_off), _lib.ptr(row_vid), C.c_int(V), C.c_int(n_rows),
         C.c_float(overlap), C.c_int(tid), C.c_int(align), _lib.ptr(gout), _lib.ptr(ws), _lib.ptr(gL),
         C.c_void_p(st.cuda_stream)), "mucon_masks_bwd")
 
@@ -46,10 +47,10 @@ def _launch_bwd(L, n_off, Ts, out_off, V, n_rows, overlap, tid, align, gout, ws,
 class _MasksFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, L, meta, overlap, tid, align):
-        n_off, Ts, out_off, V, n_rows, max_T, total = meta
+        n_off, Ts, out_off, row_vid, V, n_rows, max_T, total = meta
         Lc = L.detach().float().clone().contiguous()  # private copy: the caller's L is scaled in place later
         out = torch.empty(total, dtype=torch.float32, device=L.device)
-        _launch_fwd(Lc, n_off, Ts, out_off, V, n_rows, max_T, overlap, tid, align, None, out)
+        _launch_fwd(Lc, n_off, Ts, out_off, row_vid, V, n_rows, max_T, overlap, tid, align, None, out)
         ctx.save_for_backward(Lc)
         ctx.meta, ctx.args = meta, (overlap, tid, align)
         return out
@@ -57,12 +58,12 @@ class _MasksFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         (Lc,) = ctx.saved_tensors
-        n_off, Ts, out_off, V, n_rows, max_T, total = ctx.meta
+        n_off, Ts, out_off, row_vid, V, n_rows, max_T, total = ctx.meta
         overlap, tid, align = ctx.args
         gout = gout.contiguous().float()
         ws = torch.empty(2 * n_rows, dtype=torch.float32, device=Lc.device)
         gL = torch.empty(n_rows, dtype=torch.float32, device=Lc.device)
-        _launch_bwd(Lc, n_off, Ts, out_off, V, n_rows, overlap, tid, align, gout, ws, gL)
+        _launch_bwd(Lc, n_off, Ts, out_off, row_vid, V, n_rows, overlap, tid, align, gout, ws, gL)
         return gL, None, None, None, None
 
 
@@ -72,16 +73,19 @@ def _meta(Ms, Ts, device):
     n_off = np.concatenate([[0], np.cumsum(Ms)]).astype(np.int32)
     sizes = Ms * Ts
     out_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    row_vid = np.repeat(np.arange(Ms.shape[0], dtype=np.int32), Ms)
     blob = np.concatenate([n_off.view(np.uint8), np.zeros((-n_off.nbytes) % 8, np.uint8),
                            Ts.astype(np.int32).view(np.uint8), np.zeros((-Ts.shape[0] * 4) % 8, np.uint8),
-                           out_off[:-1].view(np.uint8)])
+                           out_off[:-1].view(np.uint8), row_vid.view(np.uint8)])
     dev = torch.from_numpy(blob).to(device)
     o1 = n_off.nbytes + (-n_off.nbytes) % 8
     o2 = o1 + Ts.shape[0] * 4 + (-Ts.shape[0] * 4) % 8
+    o3 = o2 + 8 * Ms.shape[0]
     d_noff = dev[:n_off.nbytes].view(torch.int32)
     d_T = dev[o1:o1 + Ts.shape[0] * 4].view(torch.int32)
-    d_off = dev[o2:].view(torch.int64)
-    return (d_noff, d_T, d_off, int(Ms.shape[0]), int(n_off[-1]), int(Ts.max(initial=0)), int(out_off[-1])), out_off
+    d_off = dev[o2:o3].view(torch.int64)
+    d_rv = dev[o3:o3 + 4 * row_vid.shape[0]].view(torch.int32) if row_vid.shape[0] else None
+    return (d_noff, d_T, d_off, d_rv, int(Ms.shape[0]), int(n_off[-1]), int(Ts.max(initial=0)), int(out_off[-1])), out_off
 
 
 def _check(L, template):
@@ -101,11 +105,16 @@ def create_masks(T, L, overlap=0.0, template="box", align_corners=None):
     return out.view(L.shape[0], T)
 
 
-def create_masks_batch(Ts, L, Ms, overlap=0.0, template="box", align_corners=None):
+def batch_meta(Ts, Ms, device):
+    """Offset tables of a batch (one small H2D copy); reusable across calls with the same shapes."""
+    return _meta(Ms, Ts, device)
+
+
+def create_masks_batch(Ts, L, Ms, overlap=0.0, template="box", align_corners=None, meta=None):
     """Masks of V videos in one launch.  L: concatenated lengths [sum Ms] (not modified).
     Returns the flat buffer and the per-video offsets; video v is
-    out[off[v]:off[v+1]].view(Ms[v], Ts[v])."""
+    out[off[v]:off[v+1]].view(Ms[v], Ts[v]).  meta: optional result of batch_meta(Ts, Ms, device)."""
     _check(L, template)
-    meta, out_off = _meta(Ms, Ts, L.device)
+    meta, out_off = meta if meta is not None else _meta(Ms, Ts, L.device)
     out = _MasksFn.apply(L, meta, float(overlap), TEMPLATES[template], int(bool(align_corners)))
     return out, out_off
