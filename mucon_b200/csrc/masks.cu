@@ -21,6 +21,7 @@ namespace mucon {
 namespace {
 
 constexpr int kW = 100;  // TEMPLATE_WIDTH, masks.py:32
+
 __constant__ float c_tmpl[3][kW];
 bool g_tmpl_ready[64] = {false};
 
@@ -81,35 +82,37 @@ __device__ __forceinline__ RowGeom row_geom(const float* L, int r0, int i, int T
   return geom_from(cum, L[r0 + i], T, overlap);
 }
 
-// Per-CTA row context.  Every thread reads the (broadcast) row -> video entry and the video's sizes;
-// the lengths in front of the row are fetched by one thread each into shared memory and summed by
-// thread 0 in order (torch.cumsum on a 1-D tensor is sequential), so the prologue is two dependent
-// global loads deep instead of one per segment.  Must be followed by __syncthreads() before *g is read.
+// Row context of a 64-thread group.  Every thread reads the (broadcast) row -> video entry and the
+// video's sizes; the lengths in front of the row are fetched by one thread each into shared memory and
+// summed by the group's first thread in order (torch.cumsum on a 1-D tensor is sequential), so the
+// prologue is two dependent global loads deep instead of one per segment.  *g is valid on return.
 struct RowCtx {
   int T;
   long long base;
 };
+constexpr int kGroup = 64;            // threads per mask row
+constexpr int kGroupsPerCta = 4;      // rows a CTA works on at a time
 __device__ __forceinline__ RowCtx row_ctx(const float* L, const int32_t* n_off, const int32_t* Tv,
                                           const int64_t* out_off, const int32_t* row_vid, int V, int row,
-                                          float overlap, RowGeom* g) {
-  __shared__ float Lp[256];
+                                          float overlap, RowGeom* g, float* Lp, int gt, int bar_id) {
   const int v = row_vid ? row_vid[row] : find_video(n_off, V, row);
   const int T = Tv[v];
   const int r0 = n_off[v], i = row - r0;
   RowCtx c;
   c.T = T;
   c.base = out_off[v] + static_cast<long long>(i) * T;
-  if (i < 256) {
-    if (static_cast<int>(threadIdx.x) <= i) Lp[threadIdx.x] = L[r0 + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  if (i < kGroup) {
+    if (gt <= i) Lp[gt] = L[r0 + gt];
+    named_bar_sync(bar_id, kGroup);
+    if (gt == 0) {
       float cum = 0.f;
       for (int q = 0; q <= i; ++q) cum = cum + Lp[q];
       *g = geom_from(cum, Lp[i], T, overlap);
     }
-  } else if (threadIdx.x == 0) {
+  } else if (gt == 0) {
     *g = row_geom(L, r0, i, T, overlap);
   }
+  named_bar_sync(bar_id, kGroup);
   return c;
 }
 
@@ -139,90 +142,161 @@ __device__ __forceinline__ float sample(const float* tp, float u) {
   return tap(tp, i0) * w0 + tap(tp, i0 + 1) * w1;
 }
 
-// One CTA per mask row.  Thread 0 finds the row's video and geometry once; every thread then writes
-// 16-byte aligned float4 groups (rows start at arbitrary element offsets, so the first <= 3 and last
-// <= 3 elements of a row are scalar stores).
-__global__ void __launch_bounds__(256) masks_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off,
-                                                        const int32_t* __restrict__ Tv,
-                                                        const int64_t* __restrict__ out_off,
-                                                        const int32_t* __restrict__ row_vid, int V, float overlap,
-                                                        int tmpl, int align, float* __restrict__ L_scaled,
-                                                        float* __restrict__ out) {
-  __shared__ float tp[kWP];
-  __shared__ RowGeom g_s;
-  const int row = blockIdx.x;
-  const RowCtx c = row_ctx(L, n_off, Tv, out_off, row_vid, V, row, overlap, &g_s);
-  if (threadIdx.x == 0 && L_scaled) L_scaled[row] = g_s.Ls;
-  load_template(tp, tmpl);
-  __syncthreads();
-  const int T_s = c.T;
-  const long long base_s = c.base;
-  const RowGeom g = g_s;
-  const int T = T_s;
-  float* o = out + base_s;
-  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(o) >> 2) & 3);
-  const int head = min(T, (4 - mis) & 3);
-  if (static_cast<int>(threadIdx.x) < head) o[threadIdx.x] = sample(tp, coord_u(g, threadIdx.x, T, align));
-  const int nvec = (T - head) >> 2;
-  float4* o4 = reinterpret_cast<float4*>(o + head);
-  for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
-    const int t = head + 4 * q;
-    o4[q] = make_float4(sample(tp, coord_u(g, t, T, align)), sample(tp, coord_u(g, t + 1, T, align)),
-                        sample(tp, coord_u(g, t + 2, T, align)), sample(tp, coord_u(g, t + 3, T, align)));
+// Cheap screen for the box template (the default, masks.py:42-43 / default.py:77): almost every frame
+// of a row is either well inside the window (both taps are 1: the mask is 1 up to the last bit of
+// w0 + w1, far below the stated tolerance) or well outside it (0).  u' is the closed form
+// u = a_t * Wn / Ls - c evaluated with two FMAs; it differs from the reference-order evaluation by at
+// most ~3e-3 (the rounding of pi ~ 1e4 times Wn/Ls), so frames within 0.05 of a template edge -- the
+// ramps, where the value and the gradient live -- take the exact path.
+struct Screen {
+  float k, c0, c1;  // u' = (t * c1 + c0) * k - c
+  float c;
+};
+__device__ __forceinline__ Screen make_screen(const RowGeom& g, int T, int align) {
+  Screen sc;
+  const float Tf = static_cast<float>(T);
+  if (align) { sc.k = (float)(kW - 1) / g.Ls; sc.c1 = (T > 1) ? Tf / (Tf - 1.f) : 0.f; sc.c0 = -g.pi; sc.c = 0.f; }
+  else { sc.k = (float)kW / g.Ls; sc.c1 = 1.f; sc.c0 = 0.5f - g.pi; sc.c = 0.5f; }
+  return sc;
+}
+// 1: inside (mask 1, slope 0), 0: outside (mask 0, slope 0), 2: near an edge -> exact evaluation
+__device__ __forceinline__ int screen_box(const Screen& sc, int t) {
+  const float u = fmaf(fmaf(static_cast<float>(t), sc.c1, sc.c0), sc.k, -sc.c);
+  if (u > 0.05f && u < (float)(kW - 1) - 0.05f) return 1;
+  if (u < -1.05f || u > (float)kW + 0.05f) return 0;
+  return 2;
+}
+// Frame ranges of a row: [0,a0) mask 0, [a0,a1) exact, [a1,b0) mask 1, [b0,b1) exact, [b1,T) mask 0.
+// u' is non-decreasing in t, so each constant range is certified by screening its end points; the
+// inverse map only proposes them.  Other templates: everything is "exact".
+struct Regions {
+  int a0, a1, b0, b1;
+};
+__device__ __forceinline__ Regions make_regions(const Screen& sc, int T, bool box) {
+  Regions r;
+  r.a0 = 0; r.a1 = T; r.b0 = T; r.b1 = T;
+  if (!box || !(sc.c1 > 0.f) || !(sc.k > 0.f) || T < 8) return r;
+  auto inv = [&](float u) { return ((u + sc.c) / sc.k - sc.c0) / sc.c1; };
+  auto clampi = [&](float x) { return x < 0.f ? 0 : (x > (float)T ? T : static_cast<int>(x)); };
+  int a0 = clampi(inv(-1.05f) - 1.f), a1 = clampi(inv(0.05f) + 2.f);
+  int b0 = clampi(inv((float)(kW - 1) - 0.05f) - 1.f), b1 = clampi(inv((float)kW + 0.05f) + 2.f);
+  for (int it = 0; it < 4 && a0 > 0 && screen_box(sc, a0 - 1) != 0; ++it) --a0;
+  if (a0 > 0 && screen_box(sc, a0 - 1) != 0) a0 = 0;
+  for (int it = 0; it < 4 && b1 < T && screen_box(sc, b1) != 0; ++it) ++b1;
+  if (b1 < T && screen_box(sc, b1) != 0) b1 = T;
+  if (a1 < a0) a1 = a0;
+  if (b0 > b1) b0 = b1;
+  if (a1 < b0) {
+    for (int it = 0; it < 4 && a1 < b0 && screen_box(sc, a1) != 1; ++it) ++a1;
+    for (int it = 0; it < 4 && b0 > a1 && screen_box(sc, b0 - 1) != 1; ++it) --b0;
+    if (a1 < b0 && (screen_box(sc, a1) != 1 || screen_box(sc, b0 - 1) != 1)) { a1 = b1; b0 = b1; }  // no certified interior
   }
-  const int t_tail = head + 4 * nvec + threadIdx.x;
-  if (t_tail < T) o[t_tail] = sample(tp, coord_u(g, t_tail, T, align));
+  if (a1 >= b0) { a1 = b1; b0 = b1; }  // one exact range [a0, b1)
+  r.a0 = a0; r.a1 = a1; r.b0 = b0; r.b1 = b1;
+  return r;
+}
+__device__ __forceinline__ float mask_value(const float* tp, const RowGeom& g, const Regions& r, int t, int T, int align) {
+  if (t < r.a0 || t >= r.b1) return 0.f;
+  if (t >= r.a1 && t < r.b0) return 1.f;
+  return sample(tp, coord_u(g, t, T, align));
 }
 
-// One CTA per mask row: A = dLoss/dpi, B = dLoss/dLs.
-__global__ void __launch_bounds__(256) masks_bwd_rows_kernel(const float* __restrict__ L,
-                                                             const int32_t* __restrict__ n_off,
-                                                             const int32_t* __restrict__ Tv,
-                                                             const int64_t* __restrict__ out_off,
-                                                             const int32_t* __restrict__ row_vid, int V, float overlap,
-                                                             int tmpl, int align, const float* __restrict__ gout,
-                                                             float* __restrict__ ws) {
-  __shared__ float redA[8], redB[8];
+// Persistent CTAs of four 64-thread groups; a group takes one mask row at a time (grid-stride over the
+// rows): a row is only ~2000 frames and starts with a chain of dependent loads, so what matters is how
+// many rows are in flight per SM and that CTA launches are not the bottleneck (one CTA per row was
+// bound by the block scheduler at ~280 CTAs/us).  Every thread writes 16-byte aligned float4 groups (rows
+// start at arbitrary element offsets, so the first <= 3 and last <= 3 elements of a row are scalar stores).
+__global__ void __launch_bounds__(kGroup * kGroupsPerCta)
+masks_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                 const int64_t* __restrict__ out_off, const int32_t* __restrict__ row_vid, int V, int n_rows,
+                 float overlap, int tmpl, int align, float* __restrict__ L_scaled, float* __restrict__ out) {
   __shared__ float tp[kWP];
-  __shared__ RowGeom g_s;
-  const int row = blockIdx.x;
-  const RowCtx c = row_ctx(L, n_off, Tv, out_off, row_vid, V, row, overlap, &g_s);
+  __shared__ RowGeom g_s[kGroupsPerCta];
+  __shared__ float Lp[kGroupsPerCta][kGroup];
+  const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup;
   load_template(tp, tmpl);
   __syncthreads();
-  const int T_s = c.T;
-  const long long base_s = c.base;
-  const RowGeom g = g_s;
-  const int T = T_s;
-  const float* go = gout + base_s;
+  const bool box = tmpl == 0;
+  for (int row = blockIdx.x * kGroupsPerCta + grp; row < n_rows; row += gridDim.x * kGroupsPerCta) {
+    const RowCtx c = row_ctx(L, n_off, Tv, out_off, row_vid, V, row, overlap, &g_s[grp], Lp[grp], gt, 1 + grp);
+    const RowGeom g = g_s[grp];
+    if (gt == 0 && L_scaled) L_scaled[row] = g.Ls;
+    const int T = c.T;
+    float* o = out + c.base;
+    const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(o) >> 2) & 3);
+    const int head = min(T, (4 - mis) & 3);
+    const Regions r = make_regions(make_screen(g, T, align), T, box);
+    if (gt < head) o[gt] = mask_value(tp, g, r, gt, T, align);
+    const int nvec = (T - head) >> 2;
+    float4* o4 = reinterpret_cast<float4*>(o + head);
+    for (int q = gt; q < nvec; q += kGroup) {
+      const int t = head + 4 * q;
+      float4 val;
+      if (t >= r.a1 && t + 3 < r.b0) val = make_float4(1.f, 1.f, 1.f, 1.f);
+      else if (t + 3 < r.a0 || t >= r.b1) val = make_float4(0.f, 0.f, 0.f, 0.f);
+      else val = make_float4(mask_value(tp, g, r, t, T, align), mask_value(tp, g, r, t + 1, T, align),
+                             mask_value(tp, g, r, t + 2, T, align), mask_value(tp, g, r, t + 3, T, align));
+      o4[q] = val;
+    }
+    const int t_tail = head + 4 * nvec + gt;
+    if (t_tail < T) o[t_tail] = mask_value(tp, g, r, t_tail, T, align);
+    named_bar_sync(1 + grp, kGroup);  // the group's shared slots are rewritten by the next row
+  }
+}
+
+// Same decomposition: A = dLoss/dpi, B = dLoss/dLs of one row per 64-thread group.
+__global__ void __launch_bounds__(kGroup * kGroupsPerCta)
+masks_bwd_rows_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                      const int64_t* __restrict__ out_off, const int32_t* __restrict__ row_vid, int V, int n_rows,
+                      float overlap, int tmpl, int align, const float* __restrict__ gout, float* __restrict__ ws) {
+  __shared__ float tp[kWP];
+  __shared__ RowGeom g_s[kGroupsPerCta];
+  __shared__ float Lp[kGroupsPerCta][kGroup];
+  __shared__ float redA[kGroupsPerCta][kGroup / 32], redB[kGroupsPerCta][kGroup / 32];
+  const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup;
+  load_template(tp, tmpl);
+  __syncthreads();
+  const bool box = tmpl == 0;
   // u = a_t * Wn / Ls - c,  a_t = (t + 0.5 - pi) [align 0, Wn = W] or (t*T/(T-1) - pi) [align 1, Wn = W-1]
   const float Wn = align ? (float)(kW - 1) : (float)kW;
-  const float Tf = (float)T;
-  float A = 0.f, B = 0.f;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const float u = coord_u(g, t, T, align);
-    const float fl = floorf(u);
-    if (!(fl >= -1.f && fl < (float)kW)) continue;
-    const int i0 = static_cast<int>(fl);
-    const float slope = tap(tp, i0 + 1) - tap(tp, i0);
-    if (slope == 0.f) continue;
-    const float at = align ? ((T > 1) ? (float)t * Tf / (Tf - 1.f) : 0.f) - g.pi : ((float)t + 0.5f) - g.pi;
-    const float w = go[t] * slope;
-    A += w * (-Wn / g.Ls);
-    B += w * (-(at * Wn) / (g.Ls * g.Ls));
-  }
+  for (int row = blockIdx.x * kGroupsPerCta + grp; row < n_rows; row += gridDim.x * kGroupsPerCta) {
+    const RowCtx c = row_ctx(L, n_off, Tv, out_off, row_vid, V, row, overlap, &g_s[grp], Lp[grp], gt, 1 + grp);
+    const RowGeom g = g_s[grp];
+    const int T = c.T;
+    const float* go = gout + c.base;
+    const float Tf = (float)T;
+    float A = 0.f, B = 0.f;
+    const Regions r = make_regions(make_screen(g, T, align), T, box);
+    // the box template has no slope away from its edges: only the two exact ranges contribute
+    for (int pass = 0; pass < 2; ++pass) {
+      const int lo = pass ? r.b0 : r.a0, hi = pass ? r.b1 : r.a1;
+      for (int t = lo + gt; t < hi; t += kGroup) {
+        const float u = coord_u(g, t, T, align);
+        const float fl = floorf(u);
+        if (!(fl >= -1.f && fl < (float)kW)) continue;
+        const int i0 = static_cast<int>(fl);
+        const float slope = tap(tp, i0 + 1) - tap(tp, i0);
+        if (slope == 0.f) continue;
+        const float at = align ? ((T > 1) ? (float)t * Tf / (Tf - 1.f) : 0.f) - g.pi : ((float)t + 0.5f) - g.pi;
+        const float w = go[t] * slope;
+        A += w * (-Wn / g.Ls);
+        B += w * (-(at * Wn) / (g.Ls * g.Ls));
+      }
+    }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    A += __shfl_xor_sync(0xffffffffu, A, off);
-    B += __shfl_xor_sync(0xffffffffu, B, off);
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { redA[warp] = A; redB[warp] = B; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += redA[w]; b += redB[w]; }
-    ws[2 * row] = a;
-    ws[2 * row + 1] = b;
+    for (int off = 16; off > 0; off >>= 1) {
+      A += __shfl_xor_sync(0xffffffffu, A, off);
+      B += __shfl_xor_sync(0xffffffffu, B, off);
+    }
+    if ((gt & 31) == 0) { redA[grp][gt >> 5] = A; redB[grp][gt >> 5] = B; }
+    named_bar_sync(1 + grp, kGroup);
+    if (gt == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < kGroup / 32; ++w) { a += redA[grp][w]; b += redB[grp][w]; }
+      ws[2 * row] = a;
+      ws[2 * row + 1] = b;
+    }
+    named_bar_sync(1 + grp, kGroup);
   }
 }
 
@@ -246,6 +320,14 @@ __global__ void masks_bwd_combine_kernel(const int32_t* __restrict__ n_off, int 
 
 using namespace mucon;
 
+static int mask_grid(int n_rows) {
+  static int sms = 0;
+  if (!sms) sms = mucon_device_sm_count();
+  const int want = (n_rows + kGroupsPerCta - 1) / kGroupsPerCta;
+  const int cap = (sms > 0 ? sms : 148) * 8;  // 8 CTAs x 4 groups x 64 threads = 2048 threads per SM
+  return want < cap ? want : cap;
+}
+
 extern "C" int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
                                const int32_t* row_vid, int V, int n_rows, int max_T, float overlap, int template_id,
                                int align_corners, float* L_scaled, float* out, void* stream) {
@@ -254,7 +336,7 @@ extern "C" int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32
   if (V == 0 || n_rows == 0 || max_T == 0) return MUCON_OK;
   int rc = ensure_templates();
   if (rc != MUCON_OK) return rc;
-  masks_fwd_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, n_off, T, out_off, row_vid, V, overlap, template_id,
+  masks_fwd_kernel<<<mask_grid(n_rows), kGroup * kGroupsPerCta, 0, static_cast<cudaStream_t>(stream)>>>(L, n_off, T, out_off, row_vid, V, n_rows, overlap, template_id,
                                                                          align_corners, L_scaled, out);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
@@ -269,7 +351,7 @@ extern "C" int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32
   int rc = ensure_templates();
   if (rc != MUCON_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  masks_bwd_rows_kernel<<<n_rows, 256, 0, st>>>(L, n_off, T, out_off, row_vid, V, overlap, template_id, align_corners, grad_out,
+  masks_bwd_rows_kernel<<<mask_grid(n_rows), kGroup * kGroupsPerCta, 0, st>>>(L, n_off, T, out_off, row_vid, V, n_rows, overlap, template_id, align_corners, grad_out,
                                                 ws);
   MUCON_CUDA_CHECK(cudaGetLastError());
   masks_bwd_combine_kernel<<<(V + 127) / 128, 128, 0, st>>>(n_off, V, overlap, ws, grad_L);
