@@ -241,6 +241,15 @@ int mucon_conv_gemm_tf32_shifts(const float* in, float* out, const float* W_kco,
 int mucon_wavenet_layer_tf32(const float* x, float* out, const float* Wd_kco, const float* bd,
                              const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
                              int64_t rows, int dilation, int pool, int relu_final, void* stream);
+/* The same layer with the weight traffic shared between the two CTAs of a thread-block cluster: each
+ * CTA loads half of every weight k-block with a TMA multicast to both, so a tile reads 128 KB of
+ * weights from L2 instead of 256 KB.  `tiles` must list the two tiles of a pair next to each other,
+ * both from the same video: pad every video to an even number of tiles with {row0, row0_out,
+ * t0 = 128 * tiles_of_video, T} entries (all rows of such a tile lie beyond T, nothing is stored);
+ * num_tiles is then even. */
+int mucon_wavenet_layer_tf32_pair(const float* x, float* out, const float* Wd_kco, const float* bd,
+                                  const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
+                                  int64_t rows, int dilation, int pool, int relu_final, void* stream);
 /* k = 1 or k = 3 dilated Conv1d with padding = dilation (temporal.py:21-31,48-52), fp32:
  *   out[t, co] = bias[co] + sum_tap sum_ci W_tco[tap][ci][co] * f(in[t + (tap - taps/2)*dilation, ci])
  * f = ReLU when relu_in; ReLU on the result when relu_out; `residual` ([rows, Cout] or NULL) is

@@ -359,32 +359,69 @@ extern "C" int mucon_conv_gemm_tf32_shifts(const float* in, float* out, const fl
   return launch_conv_gemm(in, out, W_kco, bias, residual, tiles, num_tiles, rows, ts, relu_mid, relu_final, stream);
 }
 
-extern "C" int mucon_wavenet_layer_tf32(const float* x, float* out, const float* Wd_kco, const float* bd,
-                                        const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
-                                        int64_t rows, int dilation, int pool, int relu_final, void* stream) {
+static int launch_layer(const float* x, float* out, const float* Wd_kco, const float* bd, const float* W1_kco,
+                        const float* b1, const void* tiles, int num_tiles, int64_t rows, int dilation, int pool,
+                        int relu_final, bool pair, void* stream) {
   if (!x || !out || !Wd_kco || !bd || !W1_kco || !b1 || !tiles || num_tiles < 0 || rows < 0 || dilation < 1)
     return MUCON_EINVAL;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(Wd_kco) & 15) ||
       (reinterpret_cast<uintptr_t>(W1_kco) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return MUCON_EALIGN;
+  if (pair && (num_tiles & 1)) return MUCON_EINVAL;
   if (num_tiles == 0 || rows == 0) return MUCON_OK;
   if (rows > 0x7fffffff - 4096) return MUCON_EUNSUPPORTED;
   CUtensorMap tx, twd, tw1;
+  const uint32_t wbox = pair ? gemm::BN / 2 : gemm::BN;  // paired CTAs load half of every weight k-block each
   int rc = make_map_2d(&tx, x, static_cast<uint64_t>(rows), layer::C, gemm::BM);
   if (rc != MUCON_OK) return rc;
-  rc = make_map_2d(&twd, Wd_kco, 3ull * layer::C, layer::C, gemm::BN);
+  rc = make_map_2d(&twd, Wd_kco, 3ull * layer::C, layer::C, wbox);
   if (rc != MUCON_OK) return rc;
-  rc = make_map_2d(&tw1, W1_kco, layer::C, layer::C, gemm::BN);
+  rc = make_map_2d(&tw1, W1_kco, layer::C, layer::C, wbox);
   if (rc != MUCON_OK) return rc;
   static int sms = 0;
   if (!sms) sms = mucon_device_sm_count();
-  const int grid = num_tiles < sms ? num_tiles : sms;
-  MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer::wavenet_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        layer::LSMEM_BYTES));
-  layer::wavenet_layer_kernel<<<grid, layer::LTHREADS, layer::LSMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      tx, twd, tw1, static_cast<const layer::Tile*>(tiles), num_tiles, dilation, bd, b1, x, out, pool, relu_final);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const layer::Tile* tl = static_cast<const layer::Tile*>(tiles);
+  if (!pair) {
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer::wavenet_layer_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, layer::LSMEM_BYTES));
+    layer::wavenet_layer_kernel<false><<<grid, layer::LTHREADS, layer::LSMEM_BYTES, st>>>(
+        tx, twd, tw1, tl, num_tiles, dilation, bd, b1, x, out, pool, relu_final);
+  } else {
+    const int pairs = num_tiles / 2, max_clusters = (sms > 1 ? sms : 2) / 2;
+    const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer::wavenet_layer_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, layer::LSMEM_BYTES));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(2 * clusters);
+    lc.blockDim = dim3(layer::LTHREADS);
+    lc.dynamicSmemBytes = layer::LSMEM_BYTES;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    MUCON_CUDA_CHECK(cudaLaunchKernelEx(&lc, layer::wavenet_layer_kernel<true>, tx, twd, tw1, tl, num_tiles, dilation, bd,
+                                        b1, x, out, pool, relu_final));
+  }
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
+}
+
+extern "C" int mucon_wavenet_layer_tf32(const float* x, float* out, const float* Wd_kco, const float* bd,
+                                        const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
+                                        int64_t rows, int dilation, int pool, int relu_final, void* stream) {
+  return launch_layer(x, out, Wd_kco, bd, W1_kco, b1, tiles, num_tiles, rows, dilation, pool, relu_final, false, stream);
+}
+
+extern "C" int mucon_wavenet_layer_tf32_pair(const float* x, float* out, const float* Wd_kco, const float* bd,
+                                             const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
+                                             int64_t rows, int dilation, int pool, int relu_final, void* stream) {
+  return launch_layer(x, out, Wd_kco, bd, W1_kco, b1, tiles, num_tiles, rows, dilation, pool, relu_final, true, stream);
 }
 
 extern "C" int mucon_conv1d(const float* in, float* out, const float* W_tco, const float* bias, const float* residual,

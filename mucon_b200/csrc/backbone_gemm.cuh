@@ -67,6 +67,30 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// The same load delivered to every CTA of the cluster named in cta_mask, at the same shared-memory
+// offset, signalling the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -471,6 +495,15 @@ struct Tile {
 
 __device__ __forceinline__ bool tap_live(int shift, int T) { return shift < T && -shift < T; }
 
+// PAIR: two CTAs of a cluster work on adjacent tiles of the same video in lockstep and share the
+// weight traffic: each loads half of every weight k-block (64 of the 128 output-channel rows) and
+// multicasts it to both (tmWd / tmW1 are then maps with 64-row boxes), so a tile costs 128 KB of
+// weight reads from L2 instead of 256 KB next to its 64 KB of activations.  A stage may be refilled
+// only when BOTH CTAs' MMAs have released it: the stage-release commit is multicast to both CTAs
+// and the `empty` barriers count two arrivals.  The tile list holds the two tiles of a pair next to
+// each other (the host pads every video to an even number of tiles; a padding tile starts at t0 >= T,
+// so all of its rows are zeroed by the fix-up warp and none is stored).
+template <bool PAIR>
 __global__ void __launch_bounds__(LTHREADS, 1)
 wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWd,
                      const __grid_constant__ CUtensorMap tmW1, const Tile* __restrict__ tiles, int num_tiles, int dil,
@@ -492,7 +525,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < LSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < LSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], PAIR ? 2 : 1); }
     mbar_init(a1full, 1); mbar_init(a1empty, 4); mbar_init(yready, 4); mbar_init(a2full, 1); mbar_init(a2empty, 4);
     mbar_fence_init();
   }
@@ -504,6 +537,11 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // tile walk: alone, CTA b takes tiles b, b + grid, ...; paired, cluster c takes tile pairs c, c + clusters, ...
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile_first = PAIR ? 2 * static_cast<int>(blockIdx.x >> 1) + rank : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x & ~1u) : static_cast<int>(gridDim.x);
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -513,7 +551,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
       int s = 0;
       uint32_t ph = 0;
-      for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
+      for (int ti = tile_first; ti < num_tiles; ti += tile_step) {
         const Tile tl = tiles[ti];
         for (int tap = 0; tap < 3; ++tap) {
           const int shift = (tap - 1) * dil;
@@ -524,14 +562,17 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
             unsigned char* a = stage_mem + s * STAGE_BYTES;
             tma_load_2d(a, &tmX, kc * BK, row, &full[s]);
-            tma_load_2d(a + A_BYTES, &tmWd, kc * BK, tap * C, &full[s]);
+            if (PAIR) tma_load_2d_mc(a + A_BYTES + rank * (B_BYTES / 2), &tmWd, kc * BK, tap * C + rank * (BN / 2), &full[s], 3);
+            else tma_load_2d(a + A_BYTES, &tmWd, kc * BK, tap * C, &full[s]);
             if (++s == LSTAGES) { s = 0; ph ^= 1; }
           }
         }
         for (int kc = 0; kc < KB_PER_TAP; ++kc) {  // 1x1 weights: B half of the stage only
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], B_BYTES);
-          tma_load_2d(stage_mem + s * STAGE_BYTES + A_BYTES, &tmW1, kc * BK, 0, &full[s]);
+          unsigned char* bdst = stage_mem + s * STAGE_BYTES + A_BYTES;
+          if (PAIR) tma_load_2d_mc(bdst + rank * (B_BYTES / 2), &tmW1, kc * BK, rank * (BN / 2), &full[s], 3);
+          else tma_load_2d(bdst, &tmW1, kc * BK, 0, &full[s]);
           if (++s == LSTAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -540,7 +581,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ================================ fix-up warp =================================
     int s = 0;
     uint32_t ph = 0;
-    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
+    for (int ti = tile_first; ti < num_tiles; ti += tile_step) {
       const Tile tl = tiles[ti];
       for (int tap = 0; tap < 3; ++tap) {
         const int shift = (tap - 1) * dil;
@@ -578,7 +619,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     int s = 0, it = 0;
     uint32_t ph = 0;
     const uint32_t d1 = tmem_base, d2 = tmem_base + BN;
-    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x, ++it) {
+    for (int ti = tile_first; ti < num_tiles; ti += tile_step, ++it) {
       const Tile tl = tiles[ti];
       const uint32_t tph = it & 1;
       // ---- GEMM 1: dilated conv
@@ -596,7 +637,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             const uint64_t adesc = smem_desc(a_addr), bdesc = smem_desc(a_addr + A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) mma_tf32(d1, adesc + 2 * k, bdesc + 2 * k, idesc, (issued | k) != 0);
-            mma_commit(&empty[s]);
+            if (PAIR) mma_commit_mc(&empty[s], 3); else mma_commit(&empty[s]);
           }
           __syncwarp();
           ++issued;
@@ -617,7 +658,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint64_t bdesc = smem_desc(smem_u32(stage_mem + s * STAGE_BYTES + A_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) mma_tf32(d2, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
-          mma_commit(&empty[s]);
+          if (PAIR) mma_commit_mc(&empty[s], 3); else mma_commit(&empty[s]);
         }
         __syncwarp();
         if (++s == LSTAGES) { s = 0; ph ^= 1; }
@@ -630,7 +671,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int q = warp & 3;
     const int r = q * 32 + lane;  // tile row owned in the TMEM-load phases
     int it = 0;
-    for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x, ++it) {
+    for (int ti = tile_first; ti < num_tiles; ti += tile_step, ++it) {
       const Tile tl = tiles[ti];
       const uint32_t tph = it & 1;
       // ---- epilogue 1: acc1 -> relu(. + bd) -> ybuf in the K-major SWIZZLE_128B operand layout
@@ -733,6 +774,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));

@@ -13,6 +13,7 @@ offsets of a batch of variable-length videos.  Forward only: training-mode dropo
 not implemented here (the reference trains with its own PyTorch layers).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -59,15 +60,22 @@ class BackbonePlan:
             vid = np.repeat(np.arange(self.V), nt)
             first = np.concatenate([[0], np.cumsum(nt)])[:-1]
             t0 = (np.arange(int(nt.sum())) - np.repeat(first, nt)) * 128
+            # the paired kernel walks tiles two at a time, both from the same video: every video is padded
+            # to an even number of tiles (a padding tile starts at t0 = 128 * tiles >= T: nothing is stored)
+            nt2 = (nt + 1) // 2 * 2
+            vid2 = np.repeat(np.arange(self.V), nt2)
+            first2 = np.concatenate([[0], np.cumsum(nt2)])[:-1]
+            t02 = (np.arange(int(nt2.sum())) - np.repeat(first2, nt2)) * 128
             for kind in ("same", "pool"):
                 if kind == "pool" and lvl + 1 >= len(self.T):
                     continue
-                rec = np.zeros(int(nt.sum()), dtype=[("row0", "<i8"), ("row0_out", "<i8"), ("t0", "<i4"), ("T", "<i4")])
-                rec["row0"], rec["t0"], rec["T"] = offs[lvl][:-1][vid], t0, t[vid]
-                rec["row0_out"] = offs[lvl + 1][:-1][vid] if kind == "pool" else rec["row0"]
-                self.ltiles[(lvl, kind)] = (torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(self.device)
-                                            if rec.shape[0] else torch.zeros(24, dtype=torch.uint8, device=self.device),
-                                            int(rec.shape[0]))
+                for suffix, (vv, tt0) in (("", (vid, t0)), ("2", (vid2, t02))):
+                    rec = np.zeros(int(vv.shape[0]), dtype=[("row0", "<i8"), ("row0_out", "<i8"), ("t0", "<i4"), ("T", "<i4")])
+                    rec["row0"], rec["t0"], rec["T"] = offs[lvl][:-1][vv], tt0, t[vv]
+                    rec["row0_out"] = offs[lvl + 1][:-1][vv] if kind == "pool" else rec["row0"]
+                    self.ltiles[(lvl, kind + suffix)] = (
+                        torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(self.device)
+                        if rec.shape[0] else torch.zeros(24, dtype=torch.uint8, device=self.device), int(rec.shape[0]))
 
 
 def _stream(dev):
@@ -105,11 +113,20 @@ def conv_gemm_rows(x, W_kco, bias, plan, level, dilation=1, relu_mid=False, relu
     return out
 
 
-def wavenet_layer_rows(x, Wd_kco, bd, W1_kco, b1, plan, level, dilation, pool, relu_final):
+# Cluster pairs sharing the weight traffic through TMA multicast (mucon_wavenet_layer_tf32_pair).  Bit-identical
+# results, but measured slower on B200 (level-0 layer 2.04 vs 1.91 ms, whole encode 14.5 vs 13.0 ms on the
+# 1712-video batch): the layer kernel is bound by its per-tile GEMM -> epilogue -> GEMM -> epilogue chain, not
+# by L2 -> shared-memory weight reads, and the lockstep between the two CTAs adds to that chain.  Off by default.
+LAYER_PAIRS = os.environ.get("MUCON_LAYER_PAIRS", "0") != "0"
+
+
+def wavenet_layer_rows(x, Wd_kco, bd, W1_kco, b1, plan, level, dilation, pool, relu_final, pair=None):
     """One WaveNet layer (+ optional max-pool) in a single tcgen05 launch.  x [rows(level), 128]."""
-    tiles, n_tiles = plan.ltiles[(level, "pool" if pool else "same")]
+    pair = LAYER_PAIRS if pair is None else pair
+    tiles, n_tiles = plan.ltiles[(level, ("pool" if pool else "same") + ("2" if pair else ""))]
     out = torch.empty((plan.rows[level + 1] if pool else x.shape[0], 128), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().mucon_wavenet_layer_tf32(
+    fn = _lib.lib().mucon_wavenet_layer_tf32_pair if pair else _lib.lib().mucon_wavenet_layer_tf32
+    _lib.check(fn(
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(Wd_kco), _lib.ptr(bd), _lib.ptr(W1_kco), _lib.ptr(b1), _lib.ptr(tiles),
         C.c_int(n_tiles), C.c_int64(x.shape[0]), C.c_int(dilation), C.c_int(int(pool)), C.c_int(int(relu_final)),
         _stream(x.device)), "mucon_wavenet_layer_tf32")

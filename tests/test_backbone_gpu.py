@@ -113,3 +113,22 @@ def test_wavenet_block_reference_signature(cuda_device):
     assert (out - ref).abs().max().item() <= 1e-2 * rms(ref.numpy()) * 4
     with pytest.raises(NotImplementedError):
         blk.train()(x.to(cuda_device))
+
+
+def test_cluster_pair_layer_kernel_is_bit_identical(cuda_device):
+    """mucon_wavenet_layer_tf32_pair (two CTAs of a cluster share every weight k-block through a TMA
+    multicast; tile list padded to pairs) against the single-CTA kernel on a ragged batch, with and
+    without the fused max-pool."""
+    from mucon_b200.temporal import BackbonePlan, wavenet_layer_rows
+    g = torch.Generator().manual_seed(11)
+    Ts = [700, 333, 64, 1999, 16, 128, 129, 127, 256, 257, 1024, 17, 2048, 300, 1]
+    plan = BackbonePlan(Ts, 1, cuda_device)
+    x = torch.randn(sum(Ts), 128, generator=g).to(cuda_device)
+    wd = (torch.randn(3 * 128, 128, generator=g) / 20).to(cuda_device)
+    w1 = (torch.randn(128, 128, generator=g) / 11).to(cuda_device)
+    bd, b1 = torch.randn(128, generator=g).to(cuda_device), torch.randn(128, generator=g).to(cuda_device)
+    for dil in (1, 4, 64, 1024):
+        for pool in (False, True):
+            a = wavenet_layer_rows(x, wd, bd, w1, b1, plan, 0, dil, pool, relu_final=pool, pair=False)
+            b = wavenet_layer_rows(x, wd, bd, w1, b1, plan, 0, dil, pool, relu_final=pool, pair=True)
+            assert torch.equal(a, b), (dil, pool)
