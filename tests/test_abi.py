@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -62,3 +63,70 @@ def test_host_helpers(built_lib):
     lf = np.zeros(67)
     assert l.mucon_logfact_h(30, 2000, lf.ctypes.data_as(ctypes.c_void_p)) == 0
     assert np.allclose(lf, log_factorial_prefix(1999)[np.arange(67) * 30], rtol=1e-15, atol=0)
+
+
+def _pack_h(lib, N, order, max_N, lanes=0, fs=30, max_len=2000):
+    N = np.ascontiguousarray(N, dtype=np.int32)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    wu = np.full(max(len(N), 1) * 16, -1, dtype=np.int32)
+    n_cta, wpc, lanes_out = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+    rc = lib.mucon_viterbi_pack_h(N.ctypes.data_as(ctypes.c_void_p), order.ctypes.data_as(ctypes.c_void_p),
+                                  ctypes.c_int(len(N)), ctypes.c_int(max_N), ctypes.c_int(fs), ctypes.c_int(max_len),
+                                  ctypes.c_int(lanes), wu.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n_cta),
+                                  ctypes.byref(wpc), ctypes.byref(lanes_out))
+    return rc, wu[:n_cta.value * max(wpc.value, 1)].reshape(n_cta.value, max(wpc.value, 1)), wpc.value, lanes_out.value
+
+
+def test_pack_h_assigns_every_unit_a_contiguous_run_of_warps(built_lib):
+    """Host packing of units into DP bins (no GPU needed): every unit appears exactly once, on
+    ceil((N-1)/segments_per_warp) consecutive warps of one bin; bins hold 4, 8 or 16 warps."""
+    lib = ctypes.CDLL(built_lib)
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        U = int(rng.integers(1, 200))
+        max_N = int(rng.integers(1, 60))
+        N = rng.integers(1, max_N + 1, U)
+        order = np.argsort(-N, kind="stable")
+        rc, wu, wpc, lanes = _pack_h(lib, N, order, int(N.max()))
+        assert rc == 0 and wpc in (4, 8, 16) and lanes == 8  # J = 66 -> 8 lanes per segment
+        spw = 32 // lanes
+        seen = {}
+        for b in range(wu.shape[0]):
+            row = wu[b]
+            for u in set(row[row >= 0].tolist()):
+                pos = np.nonzero(row == u)[0]
+                assert u not in seen and np.array_equal(pos, np.arange(pos[0], pos[0] + len(pos)))
+                assert len(pos) == max(1, -(-(int(N[u]) - 1) // spw))
+                seen[u] = b
+        assert sorted(seen) == list(range(U))
+    # shapes the register kernels do not cover are refused, not mis-packed
+    assert _pack_h(lib, [3], [0], 3, max_len=6000)[0] == -2      # J = 200 > 128
+    assert _pack_h(lib, [70], [0], 70)[0] == -2                  # N > 65
+
+
+def test_pack_lanes_h_packs_units_side_by_side(built_lib):
+    """Lane-per-segment packing: a unit takes max(1, N-1) consecutive lanes of one warp."""
+    lib = ctypes.CDLL(built_lib)
+    rng = np.random.default_rng(1)
+    for trial in range(20):
+        U = int(rng.integers(1, 300))
+        N = rng.integers(1, 34, U).astype(np.int32)
+        order = np.argsort(-N, kind="stable").astype(np.int32)
+        lu = np.full(U * 32, -1, dtype=np.int32)
+        nw = ctypes.c_int32(0)
+        assert lib.mucon_viterbi_pack_lanes_h(N.ctypes.data_as(ctypes.c_void_p), order.ctypes.data_as(ctypes.c_void_p),
+                                              ctypes.c_int(U), lu.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nw)) == 0
+        lanes = lu[:nw.value * 32].reshape(nw.value, 32)
+        seen = set()
+        for w in range(nw.value):
+            row = lanes[w]
+            for u in set(row[row >= 0].tolist()):
+                pos = np.nonzero(row == u)[0]
+                assert u not in seen and np.array_equal(pos, np.arange(pos[0], pos[0] + len(pos)))
+                assert len(pos) == max(1, int(N[u]) - 1)
+                seen.add(u)
+        assert seen == set(range(U))
+        assert nw.value <= U and (lanes >= 0).sum() == np.maximum(N - 1, 1).sum()
+    big = np.array([40], dtype=np.int32)
+    assert lib.mucon_viterbi_pack_lanes_h(big.ctypes.data_as(ctypes.c_void_p), None, ctypes.c_int(1),
+                                          lu.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nw)) == -2
