@@ -199,6 +199,21 @@ int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, cons
 int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
                     const int32_t* row_vid, int V, int n_rows, float overlap, int template_id, int align_corners,
                     const float* grad_out, float* ws, float* grad_L, void* stream);
+/* Fused "flint" evidence of the mutual-consistency loss (models.py:456-468):
+ *   E[r, c] = sum_t mask_r[t] * seg[t, c]        r = mask row (video v, segment i), c < C <= 128
+ * without materialising the masks; seg is the packed [sum T, C] frame-logit tensor, seg_off[v] the
+ * first frame of video v.  A row only reads the frames of its own window.
+ * Backward: grad_seg[t, :] = sum_r mask_r[t] * grad_E[r, :] (skipped when grad_seg is NULL; chunks:
+ * device array of {int32 video, int32 t0}, one entry per 512 frames of a video) and grad_L through
+ * d mask_r[t] = grad_E[r, :] . seg[t, :] (ws: 2*n_rows floats; max_rows = most rows of a video, <= 64;
+ * C a multiple of 4). */
+int mucon_flint_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
+                    const int32_t* row_vid, int V, int n_rows, int C, float overlap, int template_id,
+                    int align_corners, const float* seg, float* E, void* stream);
+int mucon_flint_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
+                    const int32_t* row_vid, int V, int n_rows, int max_rows, int C, float overlap, int template_id,
+                    int align_corners, const float* seg, const float* grad_E, const void* chunks, int n_chunks,
+                    float* grad_seg, float* ws, float* grad_L, void* stream);
 /* Host helper: the 100 template taps the kernels use (masks.py:34-54). */
 int mucon_mask_template_h(int template_id, float* out100_h);
 

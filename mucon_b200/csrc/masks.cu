@@ -87,7 +87,7 @@ __device__ __forceinline__ RowGeom row_geom(const float* L, int r0, int i, int T
 // summed by the group's first thread in order (torch.cumsum on a 1-D tensor is sequential), so the
 // prologue is two dependent global loads deep instead of one per segment.  *g is valid on return.
 struct RowCtx {
-  int T;
+  int T, v, i;
   long long base;
 };
 constexpr int kGroup = 64;            // threads per mask row
@@ -100,6 +100,8 @@ __device__ __forceinline__ RowCtx row_ctx(const float* L, const int32_t* n_off, 
   const int r0 = n_off[v], i = row - r0;
   RowCtx c;
   c.T = T;
+  c.v = v;
+  c.i = i;
   c.base = out_off[v] + static_cast<long long>(i) * T;
   if (i < kGroup) {
     if (gt <= i) Lp[gt] = L[r0 + gt];
@@ -175,24 +177,27 @@ struct Regions {
 __device__ __forceinline__ Regions make_regions(const Screen& sc, int T, bool box) {
   Regions r;
   r.a0 = 0; r.a1 = T; r.b0 = T; r.b1 = T;
-  if (!box || !(sc.c1 > 0.f) || !(sc.k > 0.f) || T < 8) return r;
+  if (!(sc.c1 > 0.f) || !(sc.k > 0.f) || T < 8) return r;
   auto inv = [&](float u) { return ((u + sc.c) / sc.k - sc.c0) / sc.c1; };
   auto clampi = [&](float x) { return x < 0.f ? 0 : (x > (float)T ? T : static_cast<int>(x)); };
-  int a0 = clampi(inv(-1.05f) - 1.f), a1 = clampi(inv(0.05f) + 2.f);
-  int b0 = clampi(inv((float)(kW - 1) - 0.05f) - 1.f), b1 = clampi(inv((float)kW + 0.05f) + 2.f);
+  // every template is zero outside (-1, W): [0,a0) and [b1,T)
+  int a0 = clampi(inv(-1.05f) - 1.f), b1 = clampi(inv((float)kW + 0.05f) + 2.f);
   for (int it = 0; it < 4 && a0 > 0 && screen_box(sc, a0 - 1) != 0; ++it) --a0;
   if (a0 > 0 && screen_box(sc, a0 - 1) != 0) a0 = 0;
   for (int it = 0; it < 4 && b1 < T && screen_box(sc, b1) != 0; ++it) ++b1;
   if (b1 < T && screen_box(sc, b1) != 0) b1 = T;
+  if (b1 < a0) b1 = a0;
+  r.a0 = a0; r.a1 = b1; r.b0 = b1; r.b1 = b1;  // one exact range [a0, b1)
+  if (!box) return r;
+  // the box template is 1 (slope 0) well inside the window: [a1,b0)
+  int a1 = clampi(inv(0.05f) + 2.f), b0 = clampi(inv((float)(kW - 1) - 0.05f) - 1.f);
   if (a1 < a0) a1 = a0;
   if (b0 > b1) b0 = b1;
   if (a1 < b0) {
     for (int it = 0; it < 4 && a1 < b0 && screen_box(sc, a1) != 1; ++it) ++a1;
     for (int it = 0; it < 4 && b0 > a1 && screen_box(sc, b0 - 1) != 1; ++it) --b0;
-    if (a1 < b0 && (screen_box(sc, a1) != 1 || screen_box(sc, b0 - 1) != 1)) { a1 = b1; b0 = b1; }  // no certified interior
+    if (a1 < b0 && screen_box(sc, a1) == 1 && screen_box(sc, b0 - 1) == 1) { r.a1 = a1; r.b0 = b0; }
   }
-  if (a1 >= b0) { a1 = b1; b0 = b1; }  // one exact range [a0, b1)
-  r.a0 = a0; r.a1 = a1; r.b0 = b0; r.b1 = b1;
   return r;
 }
 __device__ __forceinline__ float mask_value(const float* tp, const RowGeom& g, const Regions& r, int t, int T, int align) {
@@ -300,6 +305,158 @@ masks_bwd_rows_kernel(const float* __restrict__ L, const int32_t* __restrict__ n
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused "flint" evidence (models.py:456-468): E[r, c] = sum_t mask_r[t] * seg[t, c] without the masks
+// ever being written: a row only reads the frames of its own window (4*T*C bytes per video in total).
+// One 64-thread group per mask row: a thread owns four class columns and every (64 / (C/4))-th frame
+// of the window (float4 loads, several in flight), partial sums meet in shared memory.
+__global__ void __launch_bounds__(kGroup * kGroupsPerCta)
+flint_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                 const int64_t* __restrict__ seg_off, const int32_t* __restrict__ row_vid, int V, int n_rows, int C,
+                 float overlap, int tmpl, int align, const float* __restrict__ seg, float* __restrict__ E) {
+  __shared__ float tp[kWP];
+  __shared__ RowGeom g_s[kGroupsPerCta];
+  __shared__ float Lp[kGroupsPerCta][kGroup];
+  __shared__ float4 part[kGroupsPerCta][kGroup];
+  const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup;
+  load_template(tp, tmpl);
+  __syncthreads();
+  const bool box = tmpl == 0;
+  const int C4 = C >> 2;
+  const int lanes_t = kGroup / C4;            // frames in flight per group (>= 2 for C <= 128)
+  const int tq = gt / C4, c4 = gt - tq * C4;
+  const bool worker = tq < lanes_t;
+  for (int row = blockIdx.x * kGroupsPerCta + grp; row < n_rows; row += gridDim.x * kGroupsPerCta) {
+    const RowCtx c = row_ctx(L, n_off, Tv, seg_off, row_vid, V, row, overlap, &g_s[grp], Lp[grp], gt, 1 + grp);
+    const RowGeom g = g_s[grp];
+    const int T = c.T;
+    const Regions r = make_regions(make_screen(g, T, align), T, box);
+    const float4* sv = reinterpret_cast<const float4*>(seg + seg_off[c.v] * C);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (worker) {
+#pragma unroll 4
+      for (int t = r.a0 + tq; t < r.b1; t += lanes_t) {
+        const float m = mask_value(tp, g, r, t, T, align);
+        const float4 v = __ldg(sv + static_cast<long long>(t) * C4 + c4);
+        acc.x = fmaf(m, v.x, acc.x); acc.y = fmaf(m, v.y, acc.y); acc.z = fmaf(m, v.z, acc.z); acc.w = fmaf(m, v.w, acc.w);
+      }
+    }
+    part[grp][gt] = acc;
+    named_bar_sync(1 + grp, kGroup);
+    if (gt < C4) {
+      float4 sum = part[grp][gt];
+      for (int q = 1; q < lanes_t; ++q) {
+        const float4 p = part[grp][q * C4 + gt];
+        sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+      }
+      reinterpret_cast<float4*>(E + static_cast<long long>(row) * C)[gt] = sum;
+    }
+    named_bar_sync(1 + grp, kGroup);
+  }
+}
+
+// d seg[t, :] = sum_r mask_r[t] * gE[r, :] over the rows of the frame's video.  One CTA per chunk of
+// kFlintChunk frames of one video (host-built chunk list {video, t0}); the video's row geometry is
+// set up once per CTA, then a thread owns one (frame, 4 classes) item at a time: coalesced stores.
+constexpr int kFlintChunk = 512;
+constexpr int kFlintMaxRows = 64;
+struct FlintChunk {
+  int v, t0;
+};
+__global__ void __launch_bounds__(256)
+flint_bwd_seg_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                     const int64_t* __restrict__ seg_off, const FlintChunk* __restrict__ chunks, int C, float overlap,
+                     int tmpl, int align, const float* __restrict__ gE, float* __restrict__ gseg) {
+  __shared__ float tp[kWP];
+  __shared__ RowGeom g_s[kFlintMaxRows];
+  __shared__ Regions r_s[kFlintMaxRows];
+  const FlintChunk ck = chunks[blockIdx.x];
+  const int T = Tv[ck.v], r0 = n_off[ck.v], N = n_off[ck.v + 1] - r0;
+  load_template(tp, tmpl);
+  if (static_cast<int>(threadIdx.x) < N) {
+    const RowGeom g = row_geom(L, r0, threadIdx.x, T, overlap);
+    g_s[threadIdx.x] = g;
+    r_s[threadIdx.x] = make_regions(make_screen(g, T, align), T, tmpl == 0);
+  }
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int nt = min(kFlintChunk, T - ck.t0);
+  float4* out = reinterpret_cast<float4*>(gseg + (seg_off[ck.v] + ck.t0) * C);
+  const float4* g4 = reinterpret_cast<const float4*>(gE + static_cast<long long>(r0) * C);
+  for (int idx = threadIdx.x; idx < nt * C4; idx += blockDim.x) {
+    const int tl = idx / C4, c4 = idx - tl * C4;
+    const int t = ck.t0 + tl;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < N; ++r) {
+      const Regions rg = r_s[r];
+      if (t < rg.a0 || t >= rg.b1) continue;
+      const float m = mask_value(tp, g_s[r], rg, t, T, align);
+      const float4 gv = __ldg(g4 + r * C4 + c4);
+      acc.x = fmaf(m, gv.x, acc.x); acc.y = fmaf(m, gv.y, acc.y); acc.z = fmaf(m, gv.z, acc.z); acc.w = fmaf(m, gv.w, acc.w);
+    }
+    out[idx] = acc;
+  }
+}
+
+// dLoss/dpi and dLoss/dLs of one row per 64-thread group, with d mask[t] = sum_c gE[r, c] * seg[t, c]
+// formed on the fly for the frames that have a slope (the ramps of the box template).
+__global__ void __launch_bounds__(kGroup * kGroupsPerCta)
+flint_bwd_rows_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                      const int64_t* __restrict__ seg_off, const int32_t* __restrict__ row_vid, int V, int n_rows,
+                      int C, float overlap, int tmpl, int align, const float* __restrict__ seg,
+                      const float* __restrict__ gE, float* __restrict__ ws) {
+  __shared__ float tp[kWP];
+  __shared__ RowGeom g_s[kGroupsPerCta];
+  __shared__ float Lp[kGroupsPerCta][kGroup];
+  __shared__ float red[kGroupsPerCta][kGroup / 32];
+  const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup;
+  load_template(tp, tmpl);
+  __syncthreads();
+  const bool box = tmpl == 0;
+  const float Wn = align ? (float)(kW - 1) : (float)kW;
+  for (int row = blockIdx.x * kGroupsPerCta + grp; row < n_rows; row += gridDim.x * kGroupsPerCta) {
+    const RowCtx c = row_ctx(L, n_off, Tv, seg_off, row_vid, V, row, overlap, &g_s[grp], Lp[grp], gt, 1 + grp);
+    const RowGeom g = g_s[grp];
+    const int T = c.T;
+    const float Tf = (float)T;
+    const Regions r = make_regions(make_screen(g, T, align), T, box);
+    const float* sv = seg + seg_off[c.v] * C;
+    const float ge0 = gt < C ? gE[static_cast<long long>(row) * C + gt] : 0.f;
+    const float ge1 = gt + kGroup < C ? gE[static_cast<long long>(row) * C + gt + kGroup] : 0.f;
+    float A = 0.f, B = 0.f;  // accumulated by the group's first thread
+    for (int pass = 0; pass < 2; ++pass) {
+      const int lo = pass ? r.b0 : r.a0, hi = pass ? r.b1 : r.a1;
+      for (int t = lo; t < hi; ++t) {
+        const float u = coord_u(g, t, T, align);
+        const float fl = floorf(u);
+        if (!(fl >= -1.f && fl < (float)kW)) continue;  // uniform over the group
+        const int i0 = static_cast<int>(fl);
+        const float slope = tap(tp, i0 + 1) - tap(tp, i0);
+        if (slope == 0.f) continue;
+        const float* sr = sv + static_cast<long long>(t) * C;
+        float d = 0.f;
+        if (gt < C) d = ge0 * sr[gt];
+        if (gt + kGroup < C) d = fmaf(ge1, sr[gt + kGroup], d);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        if ((gt & 31) == 0) red[grp][gt >> 5] = d;
+        named_bar_sync(1 + grp, kGroup);
+        if (gt == 0) {
+          float dm = 0.f;
+          for (int w = 0; w < kGroup / 32; ++w) dm += red[grp][w];
+          const float at = align ? ((T > 1) ? (float)t * Tf / (Tf - 1.f) : 0.f) - g.pi : ((float)t + 0.5f) - g.pi;
+          const float w = dm * slope;
+          A += w * (-Wn / g.Ls);
+          B += w * (-(at * Wn) / (g.Ls * g.Ls));
+        }
+        named_bar_sync(1 + grp, kGroup);
+      }
+    }
+    if (gt == 0) { ws[2 * row] = A; ws[2 * row + 1] = B; }
+    named_bar_sync(1 + grp, kGroup);
+  }
+}
+
 // grad_L[j] = sum_{i>j} A_i - A_j*(1+2ov)*(ov/2) + B_j*(1+2ov)
 __global__ void masks_bwd_combine_kernel(const int32_t* __restrict__ n_off, int V, float overlap,
                                          const float* __restrict__ ws, float* __restrict__ grad_L) {
@@ -364,5 +521,49 @@ extern "C" int mucon_mask_template_h(int template_id, float* out100_h) {
   float h[3][kW];
   fill_templates(h);
   for (int i = 0; i < kW; ++i) out100_h[i] = h[template_id][i];
+  return MUCON_OK;
+}
+
+extern "C" int mucon_flint_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
+                               const int32_t* row_vid, int V, int n_rows, int C, float overlap, int template_id,
+                               int align_corners, const float* seg, float* E, void* stream) {
+  if (!L || !n_off || !T || !seg_off || !seg || !E || V < 0 || n_rows < 0 || C < 1) return MUCON_EINVAL;
+  if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
+  if (C > 2 * kGroup || (C & 3)) return MUCON_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(seg) & 15) || (reinterpret_cast<uintptr_t>(E) & 15)) return MUCON_EALIGN;
+  if (V == 0 || n_rows == 0) return MUCON_OK;
+  int rc = ensure_templates();
+  if (rc != MUCON_OK) return rc;
+  flint_fwd_kernel<<<mask_grid(n_rows), kGroup * kGroupsPerCta, 0, static_cast<cudaStream_t>(stream)>>>(
+      L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, E);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_flint_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
+                               const int32_t* row_vid, int V, int n_rows, int max_rows, int C, float overlap,
+                               int template_id, int align_corners, const float* seg, const float* grad_E,
+                               const void* chunks, int n_chunks, float* grad_seg, float* ws, float* grad_L,
+                               void* stream) {
+  if (!L || !n_off || !T || !seg_off || !seg || !grad_E || !ws || !grad_L || V < 0 || n_rows < 0 || C < 1)
+    return MUCON_EINVAL;
+  if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
+  if (grad_seg && (!chunks || n_chunks < 0)) return MUCON_EINVAL;
+  if (C > 2 * kGroup || (C & 3) || max_rows > kFlintMaxRows) return MUCON_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(grad_E) & 15) || (grad_seg && (reinterpret_cast<uintptr_t>(grad_seg) & 15))) return MUCON_EALIGN;
+  if (V == 0 || n_rows == 0) return MUCON_OK;
+  int rc = ensure_templates();
+  if (rc != MUCON_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (grad_seg && n_chunks > 0) {
+    flint_bwd_seg_kernel<<<n_chunks, 256, 0, st>>>(L, n_off, T, seg_off, static_cast<const FlintChunk*>(chunks), C,
+                                                   overlap, template_id, align_corners, grad_E, grad_seg);
+    MUCON_CUDA_CHECK(cudaGetLastError());
+  }
+  flint_bwd_rows_kernel<<<mask_grid(n_rows), kGroup * kGroupsPerCta, 0, st>>>(
+      L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, grad_E, ws);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  masks_bwd_combine_kernel<<<(V + 127) / 128, 128, 0, st>>>(n_off, V, overlap, ws, grad_L);
+  MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

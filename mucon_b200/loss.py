@@ -6,10 +6,90 @@ Mirrors reference src/mucon/models.py:414-450 (`MuCon.mucon_loss`) and :452-525
 class evidence -> NLL.  Everything after the masks is the same handful of torch ops the reference
 uses, so gradients w.r.t. both the lengths and the frame logits flow as they do there.
 """
+import ctypes as C
+
+import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .masks import create_masks, project_lengths_softmax
+from . import _lib
+from .masks import TEMPLATES, create_masks, project_lengths_softmax
+
+FLINT_CHUNK = 512  # kFlintChunk in csrc/masks.cu
+
+
+def _flint_meta(Ms, Ts, device):
+    """Offset tables for the fused evidence kernels (one small H2D copy)."""
+    Ms, Ts = np.asarray(Ms, dtype=np.int64), np.asarray(Ts, dtype=np.int64)
+    n_off = np.concatenate([[0], np.cumsum(Ms)]).astype(np.int32)
+    seg_off = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
+    row_vid = np.repeat(np.arange(Ms.shape[0], dtype=np.int32), Ms)
+    nch = (Ts + FLINT_CHUNK - 1) // FLINT_CHUNK
+    cv = np.repeat(np.arange(Ms.shape[0], dtype=np.int32), nch)
+    first = np.concatenate([[0], np.cumsum(nch)])[:-1]
+    ct0 = ((np.arange(int(nch.sum())) - np.repeat(first, nch)) * FLINT_CHUNK).astype(np.int32)
+    chunks = np.stack([cv, ct0], 1).astype(np.int32).reshape(-1)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return dict(n_off=dev(n_off), T=dev(Ts.astype(np.int32)), seg_off=dev(seg_off[:-1].copy()), row_vid=dev(row_vid),
+                chunks=dev(chunks) if chunks.size else torch.zeros(2, dtype=torch.int32, device=device),
+                n_chunks=int(nch.sum()), V=int(Ms.shape[0]), n_rows=int(n_off[-1]), max_rows=int(Ms.max(initial=0)),
+                total_T=int(seg_off[-1]))
+
+
+class _EvidenceFn(torch.autograd.Function):
+    """E[r, c] = sum_t mask_r[t] * seg[t, c]  (mucon_flint_fwd / mucon_flint_bwd)."""
+
+    @staticmethod
+    def forward(ctx, L, seg, meta, overlap, tid, align):
+        Lc = L.detach().float().contiguous()
+        sg = seg.detach().float().contiguous()
+        Cn = sg.shape[1]
+        E = torch.empty((meta["n_rows"], Cn), dtype=torch.float32, device=sg.device)
+        st = C.c_void_p(torch.cuda.current_stream(sg.device).cuda_stream)
+        _lib.check(_lib.lib().mucon_flint_fwd(
+            _lib.ptr(Lc), _lib.ptr(meta["n_off"]), _lib.ptr(meta["T"]), _lib.ptr(meta["seg_off"]), _lib.ptr(meta["row_vid"]),
+            C.c_int(meta["V"]), C.c_int(meta["n_rows"]), C.c_int(Cn), C.c_float(overlap), C.c_int(tid), C.c_int(align),
+            _lib.ptr(sg), _lib.ptr(E), st), "mucon_flint_fwd")
+        ctx.save_for_backward(Lc, sg)
+        ctx.meta, ctx.args = meta, (overlap, tid, align)
+        return E
+
+    @staticmethod
+    def backward(ctx, gE):
+        Lc, sg = ctx.saved_tensors
+        meta = ctx.meta
+        overlap, tid, align = ctx.args
+        gE = gE.contiguous().float()
+        Cn = sg.shape[1]
+        gseg = torch.empty_like(sg) if ctx.needs_input_grad[1] else None
+        ws = torch.empty(2 * meta["n_rows"], dtype=torch.float32, device=sg.device)
+        gL = torch.empty(meta["n_rows"], dtype=torch.float32, device=sg.device)
+        st = C.c_void_p(torch.cuda.current_stream(sg.device).cuda_stream)
+        _lib.check(_lib.lib().mucon_flint_bwd(
+            _lib.ptr(Lc), _lib.ptr(meta["n_off"]), _lib.ptr(meta["T"]), _lib.ptr(meta["seg_off"]), _lib.ptr(meta["row_vid"]),
+            C.c_int(meta["V"]), C.c_int(meta["n_rows"]), C.c_int(meta["max_rows"]), C.c_int(Cn), C.c_float(overlap),
+            C.c_int(tid), C.c_int(align), _lib.ptr(sg), _lib.ptr(gE), _lib.ptr(meta["chunks"]), C.c_int(meta["n_chunks"]),
+            _lib.ptr(gseg), _lib.ptr(ws), _lib.ptr(gL), st), "mucon_flint_bwd")
+        return gL, gseg, None, None, None, None
+
+
+def flint_evidence(L, seg, Ms, Ts, overlap=0.0, template="box", align_corners=None, meta=None):
+    """Masked class evidence of a batch without materialising the masks: L concatenated absolute
+    lengths [sum Ms] (unscaled), seg packed frame logits [sum Ts, C] -> E [sum Ms, C].
+    Differentiable w.r.t. both.  Needs C % 4 == 0, C <= 128, at most 64 segments per video."""
+    if template not in TEMPLATES:
+        raise NameError(f"Invalid template name ({template})")
+    if not (L.is_cuda and seg.is_cuda):
+        raise _lib.MuconError("flint_evidence needs CUDA tensors (there is no CPU fallback)")
+    meta = meta if meta is not None else _flint_meta(Ms, Ts, seg.device)
+    if seg.shape[0] != meta["total_T"] or L.shape[0] != meta["n_rows"]:
+        raise ValueError("L / seg do not match Ms / Ts")
+    return _EvidenceFn.apply(L, seg, meta, float(overlap), TEMPLATES[template], int(bool(align_corners)))
+
+
+def flint_fusable(segmentation, n_segments):
+    return (segmentation.is_cuda and segmentation.dtype == torch.float32 and segmentation.shape[1] % 4 == 0
+            and segmentation.shape[1] <= 128 and n_segments <= 64)
 
 
 def loss_from_masks(absolute_lengths, masks, segmentation, target_transcript, mucon_type="flint", class_weight=None):
@@ -29,10 +109,21 @@ def loss_from_masks(absolute_lengths, masks, segmentation, target_transcript, mu
 
 
 def mucon_loss(lengths, segmentation, target_transcript, template="box", overlap=0.0, mucon_type="flint",
-               class_weight=None, align_corners=None):
+               class_weight=None, align_corners=None, fused=None):
     """models.py:414-450 given the s-head length logits [N], the frame logits [T, C] and the target
-    transcript [N]."""
+    transcript [N].  fused: None = use the fused evidence kernel when it applies (flint, float32
+    CUDA logits, C % 4 == 0), False = materialise the masks like the reference."""
     T = segmentation.shape[0]
     absolute_lengths = project_lengths_softmax(T=T, L=lengths)
+    if fused is None:
+        fused = mucon_type == "flint" and flint_fusable(segmentation, lengths.shape[0])
+    if fused:
+        if mucon_type != "flint":
+            raise ValueError("the fused kernel implements the flint loss only")
+        E = flint_evidence(absolute_lengths, segmentation, [lengths.shape[0]], [T], overlap=overlap, template=template,
+                           align_corners=align_corners)
+        scaled = absolute_lengths * (1.0 + 2 * overlap)  # the in-place scaling of create_masks (masks.py:61)
+        evidence = E / scaled[:, None]
+        return F.nll_loss(F.log_softmax(evidence, dim=1), target_transcript, weight=class_weight, reduction="mean")
     masks = create_masks(T=T, L=absolute_lengths, template=template, overlap=overlap, align_corners=align_corners)
     return loss_from_masks(absolute_lengths, masks, segmentation, target_transcript, mucon_type, class_weight)

@@ -31,13 +31,18 @@ def test_oracle_matches_reference(i):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, None])
 @pytest.mark.parametrize("i", range(len(CASES)))
-def test_cuda_loss_matches_reference(cuda_device, i):
-    from mucon_b200.loss import mucon_loss
+def test_cuda_loss_matches_reference(cuda_device, i, fused):
+    """fused=False materialises the masks like the reference; None lets the flint cases go through the
+    fused evidence kernel (mucon_flint_fwd / _bwd), which never writes the masks."""
+    from mucon_b200.loss import flint_fusable, mucon_loss
     T, N, C, mtype, tmpl, ov = _case(i)
     lengths = torch.from_numpy(G[f"c{i}_lengths"].copy()).to(cuda_device).requires_grad_(True)
     seg = torch.from_numpy(G[f"c{i}_seg"].copy()).to(cuda_device).requires_grad_(True)
-    loss = mucon_loss(lengths, seg, torch.from_numpy(G[f"c{i}_tr"]).to(cuda_device), tmpl, ov, mtype)
+    if fused is None and not (mtype == "flint" and flint_fusable(seg, N)):
+        pytest.skip("not a fused-kernel case")
+    loss = mucon_loss(lengths, seg, torch.from_numpy(G[f"c{i}_tr"]).to(cuda_device), tmpl, ov, mtype, fused=fused)
     loss.backward()
     want = float(G[f"c{i}_loss"])
     assert abs(loss.item() - want) <= 2e-4 * max(1.0, abs(want))
@@ -46,3 +51,38 @@ def test_cuda_loss_matches_reference(cuda_device, i):
     gs = seg.grad.cpu().numpy()
     assert np.allclose(gs[::37], G[f"c{i}_gseg_rows"], rtol=1e-3, atol=1e-3 * np.abs(G[f"c{i}_gseg_rows"]).max())
     assert abs(np.abs(gs).astype(np.float64).sum() - float(G[f"c{i}_gseg_sum"])) <= 1e-3 * float(G[f"c{i}_gseg_sum"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tmpl,ov,align", [("box", 0.0, False), ("box", 0.15, False), ("gaussian", 0.1, False),
+                                           ("trapezoid", 0.0, True), ("box", 0.0, True)])
+def test_fused_evidence_equals_masks_times_logits(cuda_device, tmpl, ov, align):
+    """flint_evidence on a ragged batch against (create_masks @ seg) per video: values and both gradients."""
+    from mucon_b200.loss import flint_evidence
+    from mucon_b200.masks import create_masks
+    rng = np.random.default_rng(23)
+    Ts = [2000, 317, 64, 5003, 9, 1000, 513, 512]
+    Ms = [6, 3, 2, 12, 1, 30, 4, 5]
+    Cn = 48
+    Ls = [(rng.dirichlet(2 * np.ones(m)) * t * rng.uniform(0.9, 0.99)).astype(np.float32) for t, m in zip(Ts, Ms)]
+    seg0 = rng.standard_normal((sum(Ts), Cn)).astype(np.float32)
+    gE = rng.standard_normal((sum(Ms), Cn)).astype(np.float32)
+    L = torch.from_numpy(np.concatenate(Ls)).to(cuda_device).requires_grad_(True)
+    seg = torch.from_numpy(seg0).to(cuda_device).requires_grad_(True)
+    E = flint_evidence(L, seg, Ms, Ts, overlap=ov, template=tmpl, align_corners=align)
+    (E * torch.from_numpy(gE).to(cuda_device)).sum().backward()
+    Lr = torch.from_numpy(np.concatenate(Ls)).to(cuda_device).requires_grad_(True)
+    segr = torch.from_numpy(seg0).to(cuda_device).requires_grad_(True)
+    outs, so, lo = [], 0, 0
+    for t, m in zip(Ts, Ms):
+        masks = create_masks(t, Lr[lo:lo + m] * 1.0, overlap=ov, template=tmpl, align_corners=align)
+        outs.append(masks @ segr[so:so + t])
+        so, lo = so + t, lo + m
+    Er = torch.cat(outs)
+    (Er * torch.from_numpy(gE).to(cuda_device)).sum().backward()
+    scale = Er.abs().max().item()
+    assert torch.allclose(E, Er, rtol=2e-4, atol=2e-4 * scale), (E - Er).abs().max().item()
+    gs, gsr = seg.grad, segr.grad
+    assert torch.allclose(gs, gsr, rtol=1e-4, atol=1e-4 * gsr.abs().max().item())
+    gl, glr = L.grad.cpu().numpy(), Lr.grad.cpu().numpy()
+    assert np.allclose(gl, glr, rtol=3e-3, atol=3e-3 * np.abs(glr).max()), np.abs(gl - glr).max()
