@@ -308,50 +308,66 @@ masks_bwd_rows_kernel(const float* __restrict__ L, const int32_t* __restrict__ n
 // ---------------------------------------------------------------------------------------------
 // Fused "flint" evidence (models.py:456-468): E[r, c] = sum_t mask_r[t] * seg[t, c] without the masks
 // ever being written: a row only reads the frames of its own window (4*T*C bytes per video in total).
-// One 64-thread group per mask row: a thread owns four class columns and every (64 / (C/4))-th frame
-// of the window (float4 loads, several in flight), partial sums meet in shared memory.
-__global__ void __launch_bounds__(kGroup * kGroupsPerCta)
+// One 256-thread CTA per mask row at a time (grid-stride): a thread owns four class columns and every
+// (256 / (C/4))-th frame of the row's window (float4 loads, several in flight), partial sums meet in
+// shared memory.  Windows range from a few to thousands of frames, so the frames of one row are
+// spread over the whole CTA rather than over a 64-thread group (the longest window was the tail).
+constexpr int kFlintThreads = 256;
+__global__ void __launch_bounds__(kFlintThreads)
 flint_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
                  const int64_t* __restrict__ seg_off, const int32_t* __restrict__ row_vid, int V, int n_rows, int C,
                  float overlap, int tmpl, int align, const float* __restrict__ seg, float* __restrict__ E) {
   __shared__ float tp[kWP];
-  __shared__ RowGeom g_s[kGroupsPerCta];
-  __shared__ float Lp[kGroupsPerCta][kGroup];
-  __shared__ float4 part[kGroupsPerCta][kGroup];
-  const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup;
+  __shared__ RowGeom g_s;
+  __shared__ float Lp[kFlintThreads];
+  __shared__ float4 part[kFlintThreads];
+  const int tid = threadIdx.x;
   load_template(tp, tmpl);
   __syncthreads();
   const bool box = tmpl == 0;
   const int C4 = C >> 2;
-  const int lanes_t = kGroup / C4;            // frames in flight per group (>= 2 for C <= 128)
-  const int tq = gt / C4, c4 = gt - tq * C4;
+  const int lanes_t = kFlintThreads / C4;
+  const int tq = tid / C4, c4 = tid - tq * C4;
   const bool worker = tq < lanes_t;
-  for (int row = blockIdx.x * kGroupsPerCta + grp; row < n_rows; row += gridDim.x * kGroupsPerCta) {
-    const RowCtx c = row_ctx(L, n_off, Tv, seg_off, row_vid, V, row, overlap, &g_s[grp], Lp[grp], gt, 1 + grp);
-    const RowGeom g = g_s[grp];
-    const int T = c.T;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int v = row_vid ? row_vid[row] : find_video(n_off, V, row);
+    const int T = Tv[v];
+    const int r0 = n_off[v], i = row - r0;
+    if (i < kFlintThreads) {
+      if (tid <= i) Lp[tid] = L[r0 + tid];
+      __syncthreads();
+      if (tid == 0) {
+        float cum = 0.f;
+        for (int q = 0; q <= i; ++q) cum = cum + Lp[q];
+        g_s = geom_from(cum, Lp[i], T, overlap);
+      }
+    } else if (tid == 0) {
+      g_s = row_geom(L, r0, i, T, overlap);
+    }
+    __syncthreads();
+    const RowGeom g = g_s;
     const Regions r = make_regions(make_screen(g, T, align), T, box);
-    const float4* sv = reinterpret_cast<const float4*>(seg + seg_off[c.v] * C);
+    const float4* sv = reinterpret_cast<const float4*>(seg + seg_off[v] * C);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (worker) {
 #pragma unroll 4
       for (int t = r.a0 + tq; t < r.b1; t += lanes_t) {
         const float m = mask_value(tp, g, r, t, T, align);
-        const float4 v = __ldg(sv + static_cast<long long>(t) * C4 + c4);
-        acc.x = fmaf(m, v.x, acc.x); acc.y = fmaf(m, v.y, acc.y); acc.z = fmaf(m, v.z, acc.z); acc.w = fmaf(m, v.w, acc.w);
+        const float4 x = __ldg(sv + static_cast<long long>(t) * C4 + c4);
+        acc.x = fmaf(m, x.x, acc.x); acc.y = fmaf(m, x.y, acc.y); acc.z = fmaf(m, x.z, acc.z); acc.w = fmaf(m, x.w, acc.w);
       }
     }
-    part[grp][gt] = acc;
-    named_bar_sync(1 + grp, kGroup);
-    if (gt < C4) {
-      float4 sum = part[grp][gt];
+    part[tid] = acc;
+    __syncthreads();
+    if (tid < C4) {
+      float4 sum = part[tid];
       for (int q = 1; q < lanes_t; ++q) {
-        const float4 p = part[grp][q * C4 + gt];
+        const float4 p = part[q * C4 + tid];
         sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
       }
-      reinterpret_cast<float4*>(E + static_cast<long long>(row) * C)[gt] = sum;
+      reinterpret_cast<float4*>(E + static_cast<long long>(row) * C)[tid] = sum;
     }
-    named_bar_sync(1 + grp, kGroup);
+    __syncthreads();
   }
 }
 
@@ -534,7 +550,10 @@ extern "C" int mucon_flint_fwd(const float* L, const int32_t* n_off, const int32
   if (V == 0 || n_rows == 0) return MUCON_OK;
   int rc = ensure_templates();
   if (rc != MUCON_OK) return rc;
-  flint_fwd_kernel<<<mask_grid(n_rows), kGroup * kGroupsPerCta, 0, static_cast<cudaStream_t>(stream)>>>(
+  static int sms = 0;
+  if (!sms) sms = mucon_device_sm_count();
+  const int grid = n_rows < 8 * sms ? n_rows : 8 * sms;
+  flint_fwd_kernel<<<grid, kFlintThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, E);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
