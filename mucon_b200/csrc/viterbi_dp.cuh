@@ -36,19 +36,18 @@ constexpr int kDpChunk = 32;     // DP steps per block-score staging chunk
 constexpr bool kStaged = true;   // hand-interleaved DP step (see dp_unit)
 constexpr int kDpMaxJ = 128;     // ages live in registers: 4 lanes x <= 8 or 8 lanes x <= 16
 
-// Lanes per segment.  A single warp issues roughly one instruction every 3.5 cycles on this
+// Lanes per segment.  A single warp issues roughly one instruction every 3.8 cycles on this
 // dependent code (measured), so the per-step latency of a unit is set by the instructions per
-// warp-step: 8 lanes x 9 ages for J = 66 keeps a step near 150 instructions while still packing
-// four segments into a warp.
-// Units of up to 17 segments (everything Breakfast-shaped) get a whole warp per segment: the
-// lane butterfly is replaced by three REDUX instructions and a step is ~70 instructions.
-// Longer transcripts share a warp between 4 (or 8) segments.
+// warp-step: 8 lanes x 9 ages for J = 66 keeps a step near 220 instructions while still packing
+// four segments into a warp (4 lanes x 17 ages halves the warps but was measured slower overall).
+// want == 32 gives every segment a warp of its own: the lane butterfly becomes three REDUX
+// instructions and a step is ~70 instructions -- a third of the latency for three to four times the
+// warps.  The host asks for it only for the few longest videos of a batch, whose serial chain of
+// steps is the critical path (AlignPlan.n_long, mucon_viterbi_align_fused_tail).
 __host__ __device__ inline int dp_group(int J, int max_N, int want) {
   const int shared = J <= 32 ? 4 : 8;  // segments sharing a warp
   if (want == 32) return (max_N <= 1 + kDpMaxWarps) ? 32 : shared;
   if (want == 4 || want == 8) return shared;
-  // auto: a warp per segment costs ~25% more instructions per segment-step but a third less
-  // latency per step; the host asks for it explicitly for its long units
   return shared;
 }
 __host__ __device__ inline int dp_max_n(int G) { return 1 + kDpMaxWarps * (32 / G); }

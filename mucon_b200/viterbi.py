@@ -207,8 +207,8 @@ class AlignPlan:
         blob.add("order_v", self.order_v)
         blob.add("warp_unit", self.warp_unit)
         blob.add("order_u", np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32))
-        # optional: videos of >= long_K blocks get a launch of their own with a warp per segment
-        # (measured slower than one uniform launch on Breakfast-shaped batches, so off by default)
+        # long_K: videos of >= long_K blocks go to a wide launch of their own, a warp per transcript segment
+        # (None = choose automatically, 0 = never)
         if long_K is None:
             # auto: the few videos within ~15 % of the longest one set the critical path of the launch
             # (their DP is a serial chain of K steps); they get a wide launch of their own, a warp per
