@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .grammar import lower_grammar
-from .length_model import PoissonModel, log_factorial_prefix, poisson_params
+from .length_model import PoissonModel, log_factorial_prefix
 
 __all__ = ["Viterbi", "ViterbiEngine", "AlignPlan", "Segment", "default_seg0_f32"]
 
