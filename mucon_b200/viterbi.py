@@ -60,7 +60,9 @@ class _Blob:
         return off
 
     def upload(self, device, stream=None):
-        host = torch.empty(max(self.size, 16), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        # pinning costs a cudaHostAlloc (~100 us): worth it for a batch plan, not for one video
+        host = torch.empty(max(self.size, 16), dtype=torch.uint8,
+                           pin_memory=torch.cuda.is_available() and self.size >= (1 << 18))
         hv = host.numpy()
         for _, off, arr in self.parts:
             hv[off:off + arr.nbytes] = arr.view(np.uint8).reshape(-1)
@@ -469,7 +471,18 @@ class Viterbi(object):
         self.np_mode = np_mode
         self._engine = None
         self._device = device
-        self.last = None  # raw outputs of the last decode (back-pointers etc.), for tests
+        self._last = None
+
+    @property
+    def last(self):
+        """Raw outputs of the last decode (scores, segment lengths, status, labels, back-pointer table,
+        block scores), fetched from the device on demand."""
+        if self._last is None:
+            return None
+        eng, plan, out = self._last
+        if "bp" not in out:
+            out.update(eng.fetch(plan, want_bp=True))
+        return out
 
     def set_multi_length(self, mode=True):  # viterbi.py:40-41 -- a no-op there too
         pass
@@ -508,8 +521,15 @@ class Viterbi(object):
         else:
             seg0 = logp.dtype == np.float32 and self.np_mode == "numpy2"
         eng.run(plan, dev_logp, seg0_f32=seg0)
-        out = eng.fetch(plan, want_bp=True)
-        self.last = out
+        # three device->host reads: [scores | segment lengths] (one buffer), status, labels
+        payload = plan.payload.cpu()
+        n_pos = int(plan.tr_off[-1])
+        out = dict(score=payload[:8 * plan.U].view(torch.float64).numpy(),
+                   seg_blocks=payload[8 * plan.U:8 * plan.U + 4 * n_pos].view(torch.int32).numpy(),
+                   status=plan.status.cpu().numpy(), labels=plan.labels.cpu().numpy())
+        if not plan.single:
+            out["best"] = plan.best.cpu().numpy()
+        self._last = (eng, plan, out)
         u = 0 if plan.single else int(out["best"][0])
         if u < 0 or out["status"][u] == _lib.UNIT_INFEASIBLE:
             # the reference dies with AttributeError in traceback when every hypothesis has been
