@@ -346,3 +346,24 @@ def test_breakfast_split_properties_full_size(eng, mode):
         outb = eng.fetch(plan, want_bp=True)
         for k in ("score", "labels", "seg_blocks", "final_j", "status", "bp"):
             assert np.array_equal(outb[k], out1[k]), k
+
+
+def test_empty_batch_and_single_frame_blocks(eng):
+    """Degenerate batches: no videos at all; videos of exactly one block; a one-segment transcript."""
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan
+    plan = AlignPlan([], [], 8, device=eng.device, len_params=np.zeros((0, 8, 3)))
+    eng.run(plan, torch.zeros((0, 8), device=eng.device))
+    torch.cuda.synchronize()
+    out = eng.fetch(plan)
+    assert out["score"].shape == (0,) and out["labels"].shape == (0,)
+    rng = np.random.default_rng(4)
+    logps = [np.log(rng.dirichlet(np.ones(8), t)).astype(np.float32) for t in (30, 59, 31, 1980)]
+    cands = [[[3]], [[5]], [[0]], [[7]]]
+    means = [np.full(8, 40.0)] * 4
+    for m in ("auto", "split", "lanes"):
+        plan, out = run_units(eng, logps, cands, means, seg0=True, mode=m)
+        assert out["status"].tolist() == [0, 0, 0, 0]
+        for u in range(4):
+            ref = oracle_unit(logps[u], cands[u][0], means[u], 30, 2000, True)
+            check_unit(plan, out, u, ref, logps[u].shape[0])
