@@ -475,11 +475,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // without ever leaving the SM; the second epilogue adds bias and the residual, optionally max-pools
 // adjacent rows, and writes coalesced 512-byte rows.  The intermediate activation (and the separate
 // pooling pass) cost no HBM traffic.
-// 256 threads: warp 0 producer, warp 1 MMA + TMEM, warp 2 fix-up, warp 3 idle, warps 4-7 epilogue.
+// 384 threads: warp 0 producer, warp 1 MMA + TMEM, warp 2 fix-up, warp 3 idle, warps 4-11 epilogue.
 namespace layer {
 
 using namespace gemm;
-constexpr int LTHREADS = 256;
+constexpr int LTHREADS = 384;  // producer, MMA, fix-up, (idle), 8 epilogue warps
+constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, 64 accumulator columns each
 constexpr int C = 128;
 constexpr int KB_PER_TAP = C / BK;
 constexpr int LSTAGES = 4;
@@ -526,7 +527,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < LSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], PAIR ? 2 : 1); }
-    mbar_init(a1full, 1); mbar_init(a1empty, 4); mbar_init(yready, 4); mbar_init(a2full, 1); mbar_init(a2empty, 4);
+    mbar_init(a1full, 1); mbar_init(a1empty, EPI_WARPS); mbar_init(yready, EPI_WARPS); mbar_init(a2full, 1); mbar_init(a2empty, EPI_WARPS);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -668,8 +669,14 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // tile row owned in the TMEM-load phases
+    // Eight epilogue warps: the per-tile timeline (clock stamps, scratch build) showed the four epilogue
+    // warps busy ~12.5 k of the 14.4 k cycles of a tile (8.5 k of it in the residual-load / store phase)
+    // while the MMA and TMA warps waited for them.  Two warps now share a TMEM lane quarter: each takes
+    // 64 of the 128 accumulator columns in the TMEM phases and 16 of the quarter's 32 rows in the
+    // coalesced phase.
+    const int q = warp & 3;            // TMEM lane quarter (a warp may only touch lanes 32*(warp%4) ..)
+    const int half = (warp - 4) >> 2;  // which 64 accumulator columns / which 16 rows of the quarter
+    const int r = q * 32 + lane;       // tile row owned in the TMEM-load phases
     int it = 0;
     for (int ti = tile_first; ti < num_tiles; ti += tile_step, ++it) {
       const Tile tl = tiles[ti];
@@ -678,7 +685,8 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       mbar_wait(a1full, tph);
       tc_fence_after();
 #pragma unroll
-      for (int kc = 0; kc < BN / 32; ++kc) {
+      for (int kh = 0; kh < BN / 64; ++kh) {
+        const int kc = half * (BN / 64) + kh;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kc * 32, v);
         unsigned char* rowp = ybuf + kc * A_BYTES + r * 128;
@@ -701,7 +709,8 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc_fence_after();
       float* et = reinterpret_cast<float*>(ybuf) + q * (32 * C);  // [32 rows][128], 16-byte chunks XOR-swizzled by row
 #pragma unroll
-      for (int kc = 0; kc < BN / 32; ++kc) {
+      for (int kh = 0; kh < BN / 64; ++kh) {
+        const int kc = half * (BN / 64) + kh;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN + kc * 32, v);
 #pragma unroll
@@ -718,13 +727,16 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a2empty);
-      // ---- coalesced output: + residual, optional ReLU, optional max-pool of adjacent rows
+      // both warps of a quarter have staged their 64 columns before either reads whole rows
+      named_bar_sync(3 + q, 64);
+      // ---- coalesced output: + residual, optional ReLU, optional max-pool of adjacent rows;
+      // the quarter's 32 rows are split between its two warps
       const int tbase = tl.t0 + q * 32;
       const int nrow = min(32, tl.T - tbase);
       const long long rbase = tl.row0 + tbase;
       if (!pool) {
 #pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += 8) {
+        for (int r0 = half * 16; r0 < half * 16 + 16; r0 += 8) {
           float4 rv[8], v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e)
@@ -746,7 +758,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int npool = max(0, nrow) >> 1;  // floor: an odd last row is dropped (max_pool1d)
         const long long obase = tl.row0_out + (tbase >> 1);
 #pragma unroll
-        for (int p0 = 0; p0 < 16; p0 += 4) {
+        for (int p0 = half * 8; p0 < half * 8 + 8; p0 += 4) {
           float4 rv[8], v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e)
@@ -768,7 +780,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
       // every epilogue warp must be done with the staging bytes before anyone writes the next Y
-      named_bar_sync(2, 128);
+      named_bar_sync(2, 32 * EPI_WARPS);
     }
   }
 
