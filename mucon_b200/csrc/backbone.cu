@@ -16,6 +16,8 @@
 #include <math.h>
 
 #include "backbone_gemm.cuh"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mucon {
@@ -382,7 +384,22 @@ static int launch_layer(const float* x, float* out, const float* Wd_kco, const f
   if (!sms) sms = mucon_device_sm_count();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const layer::Tile* tl = static_cast<const layer::Tile*>(tiles);
-  if (!pair) {
+  static int use_slab = -1;
+  if (use_slab < 0) {
+    const char* e = getenv("MUCON_LAYER_SLAB");
+    use_slab = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!pair && use_slab && dilation <= layer::kSlabMaxDil) {
+    // small dilations: one activation slab of 128 + 2*dilation rows per k-block serves all three taps
+    CUtensorMap txs;
+    rc = make_map_2d(&txs, x, static_cast<uint64_t>(rows), layer::C, gemm::BM + 2 * dilation);
+    if (rc != MUCON_OK) return rc;
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer::wavenet_layer_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          layer::SSMEM_BYTES));
+    layer::wavenet_layer_slab_kernel<<<grid, layer::LTHREADS, layer::SSMEM_BYTES, st>>>(
+        txs, twd, tw1, tl, num_tiles, dilation, bd, b1, x, out, pool, relu_final);
+  } else if (!pair) {
     const int grid = num_tiles < sms ? num_tiles : sms;
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer::wavenet_layer_kernel<false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, layer::LSMEM_BYTES));

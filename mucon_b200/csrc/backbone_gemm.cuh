@@ -793,5 +793,303 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
+// Slab variant for small dilations (dil <= kSlabMaxDil): the three taps of the dilated conv read
+// overlapping rows, so per k-block ONE activation slab of 128 + 2*dil rows is loaded and the taps are
+// row-shifted SWIZZLE_128B views of it: GEMM 1 takes in 272 KB instead of 384 KB per tile, and with
+// eight epilogue warps GEMM 1's operand supply is what the tile time hangs on.  Two rings keep the
+// pipeline deep: activation slabs (3 x 20 KB) and weight tiles (6 x 16 KB; the 1x1 weights of GEMM 2
+// travel through the same ring).  Everything after the MMAs (epilogues, pooling, stores) is the code
+// of wavenet_layer_kernel.
+constexpr int kSlabMaxDil = 16;
+constexpr int SLAB_BYTES = (BM + 2 * kSlabMaxDil) * 128;   // 20 KB, a multiple of the 1024-byte swizzle atom
+constexpr int SLAB_STAGES = 3;
+constexpr int W_STAGES = 6;
+constexpr int SSMEM_BYTES = 1024 + SLAB_STAGES * SLAB_BYTES + W_STAGES * B_BYTES + Y_BYTES + 512;
+static_assert(SLAB_BYTES % 1024 == 0 && B_BYTES % 1024 == 0 && SSMEM_BYTES <= 227 * 1024, "slab kernel shared memory");
+
+__global__ void __launch_bounds__(LTHREADS, 1)
+wavenet_layer_slab_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWd,
+                     const __grid_constant__ CUtensorMap tmW1, const Tile* __restrict__ tiles, int num_tiles, int dil,
+                     const float* __restrict__ bd, const float* __restrict__ b1, const float* __restrict__ x,
+                     float* __restrict__ out, int pool, int relu_final) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* slab_mem = base;                              // [SLAB_STAGES][SLAB_BYTES] activation slabs
+  unsigned char* w_mem = base + SLAB_STAGES * SLAB_BYTES;      // [W_STAGES][B_BYTES] weight tiles
+  unsigned char* ybuf = w_mem + W_STAGES * B_BYTES;            // all three regions are multiples of 1024 bytes
+  uint64_t* fullS = reinterpret_cast<uint64_t*>(ybuf + Y_BYTES);
+  uint64_t* readyS = fullS + SLAB_STAGES;
+  uint64_t* emptyS = readyS + SLAB_STAGES;
+  uint64_t* fullW = emptyS + SLAB_STAGES;
+  uint64_t* emptyW = fullW + W_STAGES;
+  uint64_t* a1full = emptyW + W_STAGES;  // accumulator 1 complete
+  uint64_t* a1empty = a1full + 1;       // accumulator 1 drained by the epilogue
+  uint64_t* yready = a1empty + 1;       // Y written and published to the async proxy
+  uint64_t* a2full = yready + 1;        // accumulator 2 complete (Y no longer read)
+  uint64_t* a2empty = a2full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SLAB_STAGES; ++s) { mbar_init(&fullS[s], 1); mbar_init(&readyS[s], 1); mbar_init(&emptyS[s], 1); }
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1); }
+    mbar_init(a1full, 1); mbar_init(a1empty, EPI_WARPS); mbar_init(yready, EPI_WARPS); mbar_init(a2full, 1); mbar_init(a2empty, EPI_WARPS);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // tile walk: alone, CTA b takes tiles b, b + grid, ...; paired, cluster c takes tile pairs c, c + clusters, ...
+  const int tile_first = static_cast<int>(blockIdx.x);
+  const int tile_step = static_cast<int>(gridDim.x);
+  const uint32_t slab_bytes = static_cast<uint32_t>(BM + 2 * dil) * 128u;  // rows of 32 floats
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWd) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+      int ss = 0, ws = 0;
+      uint32_t phs = 0, phw = 0;
+      for (int ti = tile_first; ti < num_tiles; ti += tile_step) {
+        const Tile tl = tiles[ti];
+        // GEMM 1: per k-block ONE activation slab of 128 + 2*dil rows (the three taps are row-shifted
+        // views of it) into the slab ring, and the three taps' weight tiles into the weight ring
+        const int row = static_cast<int>(tl.row0) + tl.t0 - dil;  // may be negative: TMA zero-fills
+        for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+          mbar_wait(&emptyS[ss], phs ^ 1);
+          mbar_arrive_expect_tx(&fullS[ss], slab_bytes);
+          tma_load_2d(slab_mem + ss * SLAB_BYTES, &tmX, kc * BK, row, &fullS[ss]);
+          if (++ss == SLAB_STAGES) { ss = 0; phs ^= 1; }
+          for (int tap = 0; tap < 3; ++tap) {
+            mbar_wait(&emptyW[ws], phw ^ 1);
+            mbar_arrive_expect_tx(&fullW[ws], B_BYTES);
+            tma_load_2d(w_mem + ws * B_BYTES, &tmWd, kc * BK, tap * C, &fullW[ws]);
+            if (++ws == W_STAGES) { ws = 0; phw ^= 1; }
+          }
+        }
+        // GEMM 2: the 1x1 weights, through the weight ring
+        for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+          mbar_wait(&emptyW[ws], phw ^ 1);
+          mbar_arrive_expect_tx(&fullW[ws], B_BYTES);
+          tma_load_2d(w_mem + ws * B_BYTES, &tmW1, kc * BK, 0, &fullW[ws]);
+          if (++ws == W_STAGES) { ws = 0; phw ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ fix-up warp =================================
+    int ss = 0;
+    uint32_t phs = 0;
+    for (int ti = tile_first; ti < num_tiles; ti += tile_step) {
+      const Tile tl = tiles[ti];
+      // slab row r holds time step t0 - dil + r: rows outside [0, T) are Conv1d's zero padding
+      const int rows = BM + 2 * dil;
+      const int lo = dil - tl.t0;            // rows below lo are before the video
+      const int hi = tl.T - tl.t0 + dil;     // rows from hi on are after it
+      const bool fix = lo > 0 || hi < rows;
+      for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+        mbar_wait(&fullS[ss], phs);
+        if (fix) {
+          float4* a4 = reinterpret_cast<float4*>(slab_mem + ss * SLAB_BYTES);
+          for (int r = lane; r < rows; r += 32) {
+            if (r < lo || r >= hi) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) a4[r * 8 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&readyS[ss]);
+        if (++ss == SLAB_STAGES) { ss = 0; phs ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
+    int ss = 0, ws = 0, it = 0;
+    uint32_t phs = 0, phw = 0;
+    const uint32_t d1 = tmem_base, d2 = tmem_base + BN;
+    for (int ti = tile_first; ti < num_tiles; ti += tile_step, ++it) {
+      const uint32_t tph = it & 1;
+      // ---- GEMM 1: dilated conv
+      mbar_wait(a1empty, tph ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+        mbar_wait(&readyS[ss], phs);
+        const uint32_t a_addr = smem_u32(slab_mem + ss * SLAB_BYTES);
+        for (int tap = 0; tap < 3; ++tap) {
+          mbar_wait(&fullW[ws], phw);
+          tc_fence_after();
+          if (lane == 0) {
+            // tap `tap` reads slab rows tap*dil .. tap*dil + 127: the same SWIZZLE_128B descriptor with its
+            // start address moved by whole 128-byte rows (the swizzle is a function of the absolute
+            // shared-memory address, so a row shift needs no base-offset field; checked on the device)
+            const uint64_t adesc = smem_desc(a_addr + static_cast<uint32_t>(tap * dil) * 128u);
+            const uint64_t bdesc = smem_desc(smem_u32(w_mem + ws * B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) mma_tf32(d1, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0);
+            mma_commit(&emptyW[ws]);
+            if (tap == 2) mma_commit(&emptyS[ss]);
+          }
+          __syncwarp();
+          if (++ws == W_STAGES) { ws = 0; phw ^= 1; }
+        }
+        if (++ss == SLAB_STAGES) { ss = 0; phs ^= 1; }
+      }
+      if (lane == 0) mma_commit(a1full);
+      __syncwarp();
+      // ---- GEMM 2: 1x1 conv on relu(acc1 + bd), which the epilogue warps wrote to ybuf
+      mbar_wait(yready, tph);
+      mbar_wait(a2empty, tph ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < KB_PER_TAP; ++kc) {
+        mbar_wait(&fullW[ws], phw);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = smem_desc(smem_u32(ybuf + kc * A_BYTES));
+          const uint64_t bdesc = smem_desc(smem_u32(w_mem + ws * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) mma_tf32(d2, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+          mma_commit(&emptyW[ws]);
+        }
+        __syncwarp();
+        if (++ws == W_STAGES) { ws = 0; phw ^= 1; }
+      }
+      if (lane == 0) mma_commit(a2full);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    // Eight epilogue warps: the per-tile timeline (clock stamps, scratch build) showed the four epilogue
+    // warps busy ~12.5 k of the 14.4 k cycles of a tile (8.5 k of it in the residual-load / store phase)
+    // while the MMA and TMA warps waited for them.  Two warps now share a TMEM lane quarter: each takes
+    // 64 of the 128 accumulator columns in the TMEM phases and 16 of the quarter's 32 rows in the
+    // coalesced phase.
+    const int q = warp & 3;            // TMEM lane quarter (a warp may only touch lanes 32*(warp%4) ..)
+    const int half = (warp - 4) >> 2;  // which 64 accumulator columns / which 16 rows of the quarter
+    const int r = q * 32 + lane;       // tile row owned in the TMEM-load phases
+    int it = 0;
+    for (int ti = tile_first; ti < num_tiles; ti += tile_step, ++it) {
+      const Tile tl = tiles[ti];
+      const uint32_t tph = it & 1;
+      // ---- epilogue 1: acc1 -> relu(. + bd) -> ybuf in the K-major SWIZZLE_128B operand layout
+      mbar_wait(a1full, tph);
+      tc_fence_after();
+#pragma unroll
+      for (int kh = 0; kh < BN / 64; ++kh) {
+        const int kc = half * (BN / 64) + kh;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kc * 32, v);
+        unsigned char* rowp = ybuf + kc * A_BYTES + r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = fmaxf(__uint_as_float(v[4 * j + 0]) + __ldg(bd + kc * 32 + 4 * j + 0), 0.f);
+          o.y = fmaxf(__uint_as_float(v[4 * j + 1]) + __ldg(bd + kc * 32 + 4 * j + 1), 0.f);
+          o.z = fmaxf(__uint_as_float(v[4 * j + 2]) + __ldg(bd + kc * 32 + 4 * j + 2), 0.f);
+          o.w = fmaxf(__uint_as_float(v[4 * j + 3]) + __ldg(bd + kc * 32 + 4 * j + 3), 0.f);
+          *reinterpret_cast<float4*>(rowp + ((j ^ (r & 7)) << 4)) = o;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core (async) proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(a1empty); mbar_arrive(yready); }
+      // ---- epilogue 2: acc2 + b1 -> staging (the ybuf bytes, free once GEMM 2 has completed)
+      mbar_wait(a2full, tph);
+      tc_fence_after();
+      float* et = reinterpret_cast<float*>(ybuf) + q * (32 * C);  // [32 rows][128], 16-byte chunks XOR-swizzled by row
+#pragma unroll
+      for (int kh = 0; kh < BN / 64; ++kh) {
+        const int kc = half * (BN / 64) + kh;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN + kc * 32, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = __uint_as_float(v[4 * j + 0]) + __ldg(b1 + kc * 32 + 4 * j + 0);
+          o.y = __uint_as_float(v[4 * j + 1]) + __ldg(b1 + kc * 32 + 4 * j + 1);
+          o.z = __uint_as_float(v[4 * j + 2]) + __ldg(b1 + kc * 32 + 4 * j + 2);
+          o.w = __uint_as_float(v[4 * j + 3]) + __ldg(b1 + kc * 32 + 4 * j + 3);
+          const int chunk = kc * 8 + j;
+          *reinterpret_cast<float4*>(et + lane * C + ((chunk ^ (lane & 7)) << 2)) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a2empty);
+      // both warps of a quarter have staged their 64 columns before either reads whole rows
+      named_bar_sync(3 + q, 64);
+      // ---- coalesced output: + residual, optional ReLU, optional max-pool of adjacent rows;
+      // the quarter's 32 rows are split between its two warps
+      const int tbase = tl.t0 + q * 32;
+      const int nrow = min(32, tl.T - tbase);
+      const long long rbase = tl.row0 + tbase;
+      if (!pool) {
+#pragma unroll
+        for (int r0 = half * 16; r0 < half * 16 + 16; r0 += 8) {
+          float4 rv[8], v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            rv[e] = (r0 + e < nrow) ? __ldg(reinterpret_cast<const float4*>(x + (rbase + r0 + e) * C) + lane)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[e] = *reinterpret_cast<const float4*>(et + (r0 + e) * C + ((lane ^ ((r0 + e) & 7)) << 2));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e].x += rv[e].x; v[e].y += rv[e].y; v[e].z += rv[e].z; v[e].w += rv[e].w;
+            if (relu_final) {
+              v[e].x = fmaxf(v[e].x, 0.f); v[e].y = fmaxf(v[e].y, 0.f); v[e].z = fmaxf(v[e].z, 0.f); v[e].w = fmaxf(v[e].w, 0.f);
+            }
+            if (r0 + e < nrow) *(reinterpret_cast<float4*>(out + (tl.row0_out + tbase + r0 + e) * C) + lane) = v[e];
+          }
+        }
+      } else {
+        const int npool = max(0, nrow) >> 1;  // floor: an odd last row is dropped (max_pool1d)
+        const long long obase = tl.row0_out + (tbase >> 1);
+#pragma unroll
+        for (int p0 = half * 8; p0 < half * 8 + 8; p0 += 4) {
+          float4 rv[8], v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            rv[e] = (2 * p0 + e < 2 * npool) ? __ldg(reinterpret_cast<const float4*>(x + (rbase + 2 * p0 + e) * C) + lane)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[e] = *reinterpret_cast<const float4*>(et + (2 * p0 + e) * C + ((lane ^ ((2 * p0 + e) & 7)) << 2));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { v[e].x += rv[e].x; v[e].y += rv[e].y; v[e].z += rv[e].z; v[e].w += rv[e].w; }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float4 m;
+            m.x = fmaxf(v[2 * e].x, v[2 * e + 1].x); m.y = fmaxf(v[2 * e].y, v[2 * e + 1].y);
+            m.z = fmaxf(v[2 * e].z, v[2 * e + 1].z); m.w = fmaxf(v[2 * e].w, v[2 * e + 1].w);
+            if (relu_final) { m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f); }
+            if (p0 + e < npool) *(reinterpret_cast<float4*>(out + (obase + p0 + e) * C) + lane) = m;
+          }
+        }
+      }
+      // every epilogue warp must be done with the staging bytes before anyone writes the next Y
+      named_bar_sync(2, 32 * EPI_WARPS);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
 }  // namespace layer
 }  // namespace mucon
