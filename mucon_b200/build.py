@@ -57,6 +57,10 @@ def build(force=False, verbose=False):
         if not os.path.exists(sp):
             continue
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if src == "backbone.cu" and os.environ.get("MUCON_LAYER_TRACE") == "1":
+            obj = os.path.join(OBJ_DIR, "backbone_trace.o")  # developer build with clock stamps (scripts/trace_layer.py)
+            extra = list(extra) + ["-DMUCON_LAYER_TRACE"]
+            fast = True  # mark the library as a developer build
         if fast and src == "viterbi.cu":
             obj = os.path.join(OBJ_DIR, "viterbi_fast.o")
             extra = list(extra) + ["-DMUCON_ONLY_SL9"]

@@ -495,3 +495,10 @@ extern "C" int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
+
+#ifdef MUCON_LAYER_TRACE
+// developer builds only (not part of include/mucon_b200.h): the clock stamps of the last wavenet_layer_kernel launch
+extern "C" int mucon_debug_layer_trace(long long* out_h) {
+  return cudaMemcpyFromSymbol(out_h, mucon::layer::g_trace, sizeof(long long) * 16 * 128) == cudaSuccess ? 0 : -3;
+}
+#endif

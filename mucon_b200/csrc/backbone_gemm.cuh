@@ -478,6 +478,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // 384 threads: warp 0 producer, warp 1 MMA + TMEM, warp 2 fix-up, warp 3 idle, warps 4-11 epilogue.
 namespace layer {
 
+// Optional per-role timeline of CTA 0 (developer builds with -DMUCON_LAYER_TRACE, see scripts/trace_layer.py):
+// clock64() stamps per tile for the MMA warp and epilogue warp 4 of wavenet_layer_kernel.  This is how the
+// epilogue warps were found to be the bottleneck of the layer kernel.  Compiles to nothing by default.
+#ifdef MUCON_LAYER_TRACE
+__device__ long long g_trace[16][128];
+#define MUCON_TR(ev, it) do { if (blockIdx.x == 0 && (it) < 128) g_trace[ev][it] = clock64(); } while (0)
+#else
+#define MUCON_TR(ev, it) do { } while (0)
+#endif
+
+
 using namespace gemm;
 constexpr int LTHREADS = 384;  // producer, MMA, fix-up, (idle), 8 epilogue warps
 constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, 64 accumulator columns each
@@ -626,6 +637,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       // ---- GEMM 1: dilated conv
       mbar_wait(a1empty, tph ^ 1);
       tc_fence_after();
+      if (lane == 0) MUCON_TR(2, it);  // GEMM 1 may start
       int issued = 0;
       for (int tap = 0; tap < 3; ++tap) {
         const int shift = (tap - 1) * dil;
@@ -645,12 +657,13 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           if (++s == LSTAGES) { s = 0; ph ^= 1; }
         }
       }
-      if (lane == 0) mma_commit(a1full);
+      if (lane == 0) { mma_commit(a1full); MUCON_TR(3, it); }  // GEMM 1 issued
       __syncwarp();
       // ---- GEMM 2: 1x1 conv on relu(acc1 + bd), which the epilogue warps wrote to ybuf
       mbar_wait(yready, tph);
       mbar_wait(a2empty, tph ^ 1);
       tc_fence_after();
+      if (lane == 0) MUCON_TR(4, it);  // GEMM 2 may start
       for (int kc = 0; kc < KB_PER_TAP; ++kc) {
         mbar_wait(&ready[s], ph);
         tc_fence_after();
@@ -664,7 +677,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         __syncwarp();
         if (++s == LSTAGES) { s = 0; ph ^= 1; }
       }
-      if (lane == 0) mma_commit(a2full);
+      if (lane == 0) { mma_commit(a2full); MUCON_TR(5, it); }  // GEMM 2 issued
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -684,6 +697,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       // ---- epilogue 1: acc1 -> relu(. + bd) -> ybuf in the K-major SWIZZLE_128B operand layout
       mbar_wait(a1full, tph);
       tc_fence_after();
+      if (warp == 4 && lane == 0) MUCON_TR(6, it);  // epilogue 1 starts
 #pragma unroll
       for (int kh = 0; kh < BN / 64; ++kh) {
         const int kc = half * (BN / 64) + kh;
@@ -704,9 +718,11 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(a1empty); mbar_arrive(yready); }
+      if (warp == 4 && lane == 0) MUCON_TR(7, it);  // epilogue 1 done
       // ---- epilogue 2: acc2 + b1 -> staging (the ybuf bytes, free once GEMM 2 has completed)
       mbar_wait(a2full, tph);
       tc_fence_after();
+      if (warp == 4 && lane == 0) MUCON_TR(8, it);  // epilogue 2 starts
       float* et = reinterpret_cast<float*>(ybuf) + q * (32 * C);  // [32 rows][128], 16-byte chunks XOR-swizzled by row
 #pragma unroll
       for (int kh = 0; kh < BN / 64; ++kh) {
@@ -729,6 +745,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (lane == 0) mbar_arrive(a2empty);
       // both warps of a quarter have staged their 64 columns before either reads whole rows
       named_bar_sync(3 + q, 64);
+      if (warp == 4 && lane == 0) MUCON_TR(9, it);  // accumulator 2 staged
       // ---- coalesced output: + residual, optional ReLU, optional max-pool of adjacent rows;
       // the quarter's 32 rows are split between its two warps
       const int tbase = tl.t0 + q * 32;
@@ -780,7 +797,9 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
       // every epilogue warp must be done with the staging bytes before anyone writes the next Y
+      if (warp == 4 && lane == 0) MUCON_TR(11, it);  // this warp's rows stored
       named_bar_sync(2, 32 * EPI_WARPS);
+      if (warp == 4 && lane == 0) MUCON_TR(10, it);  // tile done
     }
   }
 
