@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "backbone_gemm.cuh"
+#include "backbone_bf16.cuh"
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -50,6 +51,20 @@ int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, 
   cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MUCON_OK : MUCON_ECUDA;
+}
+
+// [rows, 128] bf16 row-major, box [box_rows, 64 cols] (128 bytes) with 128-byte swizzle
+int make_map_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MUCON_ECUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MUCON_OK : MUCON_ECUDA;
@@ -282,12 +297,25 @@ __global__ void __launch_bounds__(256) logsoftmax_expand_kernel(const float* __r
 
 using namespace mucon;
 
+static int launch_proj(const float* A, int64_t M, int K, const float* W, int N, const float* bias, void* out, int relu,
+                       int out_bf16, void* stream);
+
 extern "C" int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const float* W, int N, const float* bias,
                                         float* out, int relu, void* stream) {
+  return launch_proj(A, M, K, W, N, bias, out, relu, 0, stream);
+}
+
+extern "C" int mucon_gemm_tf32_bias_act_bf16(const float* A, int64_t M, int K, const float* W, int N,
+                                             const float* bias, void* out_bf16, int relu, void* stream) {
+  return launch_proj(A, M, K, W, N, bias, out_bf16, relu, 1, stream);
+}
+
+static int launch_proj(const float* A, int64_t M, int K, const float* W, int N, const float* bias, void* out, int relu,
+                       int out_bf16, void* stream) {
   if (!A || !W || !bias || !out || M < 0 || K < 1) return MUCON_EINVAL;
   if (N != gemm::BN || K % gemm::BK != 0) return MUCON_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) ||
-      (reinterpret_cast<uintptr_t>(out) & 15))
+      (reinterpret_cast<uintptr_t>(out) & 31))
     return MUCON_EALIGN;
   if (M == 0) return MUCON_OK;
   if (M > 0x7fffffff) return MUCON_EUNSUPPORTED;
@@ -303,7 +331,7 @@ extern "C" int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const 
   MUCON_CUDA_CHECK(cudaFuncSetAttribute(gemm::proj_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         gemm::SMEM_BYTES));
   gemm::proj_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      ta, tb, bias, out, static_cast<int>(M), K, relu);
+      ta, tb, bias, static_cast<float*>(out), static_cast<int>(M), K, relu, out_bf16);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
@@ -441,6 +469,50 @@ extern "C" int mucon_wavenet_layer_tf32_pair(const float* x, float* out, const f
   return launch_layer(x, out, Wd_kco, bd, W1_kco, b1, tiles, num_tiles, rows, dilation, pool, relu_final, true, stream);
 }
 
+extern "C" int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd_kco, const float* bd_h,
+                                        const void* W1_kco, const float* b1_h, const void* tiles, int num_tiles,
+                                        int64_t rows, int64_t rows_out, int dilation, int pool, int relu_final,
+                                        int out_f32, void* stream) {
+  if (num_tiles == 0 || rows == 0 || rows_out == 0) return MUCON_OK;  // nothing to produce
+  if (!x || !out || !Wd_kco || !bd_h || !W1_kco || !b1_h || !tiles || num_tiles < 0 || rows < 0 || rows_out < 0 ||
+      dilation < 1)
+    return MUCON_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) & 31) || (reinterpret_cast<uintptr_t>(Wd_kco) & 15) ||
+      (reinterpret_cast<uintptr_t>(W1_kco) & 15) || (reinterpret_cast<uintptr_t>(out) & 31))
+    return MUCON_EALIGN;
+  if (pool && out_f32) return MUCON_EUNSUPPORTED;
+  if (rows > 0x7fffffff - 4096) return MUCON_EUNSUPPORTED;
+  const int slab = dilation <= layer16::kMaxSlabDil ? 1 : 0;
+  CUtensorMap tx, twd, tw1, to;
+  int rc = make_map_bf16(&tx, x, static_cast<uint64_t>(rows), layer16::C,
+                         slab ? gemm::BM + 2 * dilation : gemm::BM);
+  if (rc != MUCON_OK) return rc;
+  rc = make_map_bf16(&twd, Wd_kco, 3ull * layer16::C, layer16::C, gemm::BN);
+  if (rc != MUCON_OK) return rc;
+  rc = make_map_bf16(&tw1, W1_kco, layer16::C, layer16::C, gemm::BN);
+  if (rc != MUCON_OK) return rc;
+  // output tiles leave through a TMA store of the rows that fit the shared-memory staging area
+  const int S = layer16::staged_rows(dilation, slab, pool, out_f32);
+  if (S > 0) {
+    rc = make_map_bf16(&to, out, static_cast<uint64_t>(rows_out), layer16::C, static_cast<uint32_t>(S));
+    if (rc != MUCON_OK) return rc;
+  } else {
+    to = tx;  // never used by the kernel
+  }
+  layer16::BiasPack bp;
+  for (int c = 0; c < layer16::C; ++c) { bp.bd[c] = bd_h[c]; bp.b1[c] = b1_h[c]; }
+  const int sms = mucon_device_sm_count();
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  const int smem = layer16::smem_bytes_of(dilation, slab, pool, out_f32);
+  MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer16::wavenet_layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        layer16::SMEM_LIMIT));
+  layer16::wavenet_layer_bf16_kernel<<<grid, layer16::LTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      tx, twd, tw1, to, bp, static_cast<const layer16::Tile*>(tiles), num_tiles, dilation, slab, out, pool, relu_final,
+      out_f32 ? 1 : 0);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 extern "C" int mucon_conv1d(const float* in, float* out, const float* W_tco, const float* bias, const float* residual,
                             const int64_t* row_off, int V, int max_T, int Cin, int Cout, int taps, int dilation,
                             int relu_in, int relu_out, void* stream) {
@@ -499,6 +571,6 @@ extern "C" int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z
 #ifdef MUCON_LAYER_TRACE
 // developer builds only (not part of include/mucon_b200.h): the clock stamps of the last wavenet_layer_kernel launch
 extern "C" int mucon_debug_layer_trace(long long* out_h) {
-  return cudaMemcpyFromSymbol(out_h, mucon::layer::g_trace, sizeof(long long) * 16 * 128) == cudaSuccess ? 0 : -3;
+  return cudaMemcpyFromSymbol(out_h, mucon::layer::g_trace, sizeof(long long) * 32 * 128) == cudaSuccess ? 0 : -3;
 }
 #endif

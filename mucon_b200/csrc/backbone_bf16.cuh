@@ -1,0 +1,560 @@
+// backbone_bf16.cuh -- one whole WaveNet layer per launch on tcgen05 `kind::f16` with bf16 operands.
+//
+//   y = relu(conv_k3_dil(x) + bd);  out = conv_1x1(y) + b1 + x;  [max_pool1d(2)]  [relu]
+//   (reference src/core/modules/temporal.py:43-53, pooling :137-139, the ReLU of :144)
+//
+// What changed against the TF32 layer kernels of backbone_gemm.cuh (which moved 448 KB of operand tiles,
+// 57 % of them re-read weights, through the SM per 128-row tile and were bound by that L2 -> SM stream):
+//   * activations travel as bf16 (256 B per time step): half the HBM and L2 bytes of every layer;
+//   * the layer's weights (3 taps + the 1x1: 4 x 128 x 128 bf16 = 128 KB) are loaded ONCE per CTA and stay
+//     resident in shared memory in the K-major SWIZZLE_128B operand layout;
+//   * per tile a single activation slab of 128 + 2*dil rows comes in (two 64-channel k-blocks); the three
+//     taps are row-shifted descriptor views of it;
+//   * nothing but the slab and the weights lives in shared memory.  The first epilogue reads the residual out of
+//     the slab's centre rows and stores `x + b1` (fp32) into accumulator 2 with tcgen05.st, so GEMM 2 simply
+//     accumulates on top of it and the slab is released before GEMM 2 has even started; relu(acc1 + bd) is
+//     rounded to bf16 and stored back IN PLACE over the first 64 columns of accumulator 1, from where GEMM 2
+//     takes it as its A operand (tcgen05.mma with A in tensor memory); the second epilogue is TMEM -> (ReLU)
+//     (max over adjacent rows) -> bf16 -> 32-byte global stores.  32-48 KB in and 16-32 KB out per tile
+//     instead of 576 KB;
+//   * accumulators are double-buffered in TMEM (2 x 128 + 2 x 128 columns); the MMA warp issues GEMM 1 of tile
+//     i+1 before GEMM 2 of tile i and the epilogue warps run epilogue 1 of tile i+1 before epilogue 2 of tile
+//     i, so the tensor pipe and the epilogue warps both stay busy.
+// Dilations above kMaxSlabDil use the same program with the three taps loaded as three separate 128-row
+// tiles into one (single) stage.
+// 384 threads: warp 0 TMA producer, warp 1 MMA + TMEM, warp 2 padding fix-up, warp 3 idle, warps 4-11 epilogue.
+#pragma once
+#include <cuda.h>
+
+#include "backbone_gemm.cuh"
+
+namespace mucon {
+namespace layer16 {
+
+using namespace gemm;  // TMA / mbarrier / tcgen05 helpers, BM = BN = 128
+
+constexpr int C = 128;
+constexpr int NKB = 2;                    // k-blocks of 64 bf16 = one 128-byte swizzle row each
+constexpr int WTILE = BN * 128;           // one [128 x 64] bf16 weight tile: 16 KB
+constexpr int W_BYTES = 8 * WTILE;        // 3 taps x 2 k-blocks + the 1x1's 2 k-blocks: 128 KB
+constexpr int LTHREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int kMaxSlabDil = 32;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = 256;
+
+// shared-memory plan of a launch (host and device agree through these)
+__host__ __device__ inline int stage_rows(int dil, int slab) { return slab ? BM + 2 * dil : 3 * BM; }
+__host__ __device__ inline int kb_bytes_of(int dil, int slab) { return ((stage_rows(dil, slab) + 7) & ~7) * 128; }
+__host__ __device__ inline int num_stages(int slab) { return slab ? 2 : 1; }
+// rows of the (bf16) output tile that are staged in shared memory and leave through a TMA store; the rest of the
+// tile (and every tile that crosses the end of its video, and fp32 output) is stored straight from registers
+__host__ __device__ inline int staged_rows(int dil, int slab, int pool, int out_f32) {
+  if (out_f32) return 0;
+  const int free_bytes = SMEM_LIMIT - W_BYTES - num_stages(slab) * NKB * kb_bytes_of(dil, slab) - BAR_BYTES;
+  int s = (free_bytes / 256) & ~7;
+  const int want = pool ? BM / 2 : BM;
+  if (s > want) s = want;
+  return s < 8 ? 0 : s;
+}
+__host__ __device__ inline int smem_bytes_of(int dil, int slab, int pool, int out_f32) {
+  return W_BYTES + num_stages(slab) * NKB * kb_bytes_of(dil, slab) + staged_rows(dil, slab, pool, out_f32) * 256 + BAR_BYTES;
+}
+
+// both bias vectors travel as a kernel parameter: the epilogue adds them as constant-bank operands
+struct BiasPack {
+  float bd[C];
+  float b1[C];
+};
+
+// developer builds (-DMUCON_LAYER_TRACE, scripts/trace_layer16.py): clock64() stamps per role and tile of CTA 0
+#ifdef MUCON_LAYER_TRACE
+#define MUCON_TR16(ev, it) do { if (blockIdx.x == 0 && (it) < 128) layer::g_trace[ev][it] = clock64(); } while (0)
+#else
+#define MUCON_TR16(ev, it) do { } while (0)
+#endif
+
+struct Tile {
+  long long row0;      // first row of the video at the input resolution
+  long long row0_out;  // first row of the video in the output tensor (differs when pooling)
+  int t0;              // first time step of the tile within the video
+  int T;               // video length at the input resolution
+};
+
+__device__ __forceinline__ bool tap_live(int shift, int T) { return shift < T && -shift < T; }
+
+// instruction descriptor: D = F32, A = B = BF16 (format 1), both K-major
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]: A is a [128 x 16] bf16 block in tensor memory, row m in lane m, elements
+// 2c / 2c+1 of a row in the low / high half of 32-bit column c
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// two independent IEEE fp32 additions in one instruction (Blackwell packed fp32)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tadd.rn.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+struct EpiCtx {
+  const Tile* tiles;
+  unsigned char* stage_mem;
+  unsigned char* staging;
+  uint64_t *emptyS, *a1full, *yready, *a2full;
+  const CUtensorMap* tmO;
+  void* out;
+  uint32_t tmem_base;
+  int n_my, NS, LA, stage_bytes, kb_bytes, tap_rows, S, pool, relu_final, out_f32;
+};
+
+// The eight epilogue warps (H = which 64 accumulator columns / which k-block of the slab this warp owns).
+template <int H>
+__device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& bias) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;            // TMEM lane quarter (a warp may only touch lanes 32*(warp%4) ..)
+  const int r = q * 32 + lane;       // tile row owned by this thread
+  const uint32_t lane_base = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const bool leader = warp == 4 && lane == 0;
+  bool store_pending = false;
+  for (int i = 0; i < c.n_my + c.LA; ++i) {
+    if (i < c.n_my) {
+      // ---- epilogue 1 of tile i
+      const int s = i % c.NS, acc = i & 1;
+      mbar_wait(&c.a1full[acc], (i >> 1) & 1);
+      tc_fence_after();
+      if (leader) MUCON_TR16(6, i);
+      // (a) residual rows out of the slab's centre tap, + b1, as fp32 into accumulator 2 (this thread drained the
+      // same lanes / columns of it two tiles ago: program order)
+      {
+        const int cr = c.tap_rows + r;
+        const unsigned char* cp = c.stage_mem + s * c.stage_bytes + H * c.kb_bytes + cr * 128;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t f[32];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(cp + (((c2 * 4 + jj) ^ (cr & 7)) << 4));
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = H * 64 + c2 * 32 + jj * 8 + 2 * e;
+              f[8 * jj + 2 * e] = __float_as_uint(bf16_lo(rw[e]) + bias.b1[col]);
+              f[8 * jj + 2 * e + 1] = __float_as_uint(bf16_hi(rw[e]) + bias.b1[col + 1]);
+            }
+          }
+          if (c2 == 0 && leader) MUCON_TR16(20, i);
+          tmem_st32(lane_base + 2 * BN + acc * BN + H * 64 + c2 * 32, f);
+          if (c2 == 0 && leader) MUCON_TR16(21, i);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c.emptyS[s]);  // the slab may be refilled
+      if (leader) MUCON_TR16(10, i);
+      // (b) acc1 -> relu(. + bd) -> bf16 -> back over accumulator 1 (columns 32H .. 32H+31): A operand of GEMM 2
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(lane_base + acc * BN + H * 64, v0);
+        tmem_ld32(lane_base + acc * BN + H * 64 + 32, v1);
+        if (leader) MUCON_TR16(11, i);
+        // the other warp of this quarter reads columns that this one overwrites (and vice versa)
+        named_bar_sync(3 + q, 64);
+        if (leader) MUCON_TR16(14, i);
+        uint32_t y[32];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          y[e] = pack_bf16_relu(__uint_as_float(v0[2 * e]) + bias.bd[H * 64 + 2 * e],
+                                __uint_as_float(v0[2 * e + 1]) + bias.bd[H * 64 + 2 * e + 1]);
+          y[16 + e] = pack_bf16_relu(__uint_as_float(v1[2 * e]) + bias.bd[H * 64 + 32 + 2 * e],
+                                     __uint_as_float(v1[2 * e + 1]) + bias.bd[H * 64 + 32 + 2 * e + 1]);
+        }
+        tmem_st32(lane_base + acc * BN + H * 32, y);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c.yready[acc]);
+      if (leader) MUCON_TR16(7, i);
+    }
+    if (i >= c.LA) {
+      // ---- epilogue 2 of tile j: acc2 (-> ReLU) (-> max over adjacent rows) -> bf16 -> shared-memory staging ->
+      // TMA store (rows beyond the staging area, tiles that cross the video's end and fp32 output: 32-byte stores
+      // straight from registers)
+      const int j = i - c.LA;
+      const Tile tl = c.tiles[blockIdx.x + j * gridDim.x];
+      const int acc = j & 1;
+      mbar_wait(&c.a2full[acc], (j >> 1) & 1);
+      tc_fence_after();
+      if (leader) MUCON_TR16(8, j);
+      const int t = tl.t0 + r;
+      const bool row_ok = t < tl.T;
+      const bool pair_ok = (t | 1) < tl.T;  // both rows of the pooling pair inside the video (floor)
+      const bool staged = c.S > 0 && tl.t0 + BM <= tl.T;  // CTA-uniform
+      if (staged) {
+        // the previous TMA store must have read the staging area before it is overwritten
+        if (leader && store_pending) tma_store_wait_read();
+        named_bar_sync(2, 32 * EPI_WARPS);
+      }
+      const int orow = c.pool ? (r >> 1) : r;  // row of the output tile this thread (pair) produces
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + 2 * BN + acc * BN + H * 64 + c2 * 32, v);
+        const int col = H * 64 + c2 * 32;
+        if (c2 == 0 && leader) MUCON_TR16(15, j);
+        if (c2 == 1 && leader) MUCON_TR16(16, j);
+        if (c.out_f32) {
+          // (the host never asks for pooling together with fp32 output)
+          if (c.relu_final) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaxf(__uint_as_float(v[e]), 0.f));
+          }
+          if (row_ok) {
+            float* op = reinterpret_cast<float*>(c.out) + (tl.row0_out + t) * C + col;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) st_global_v8(op + 8 * g, v + 8 * g);
+          }
+        } else {
+          uint32_t p[16];
+          if (c.relu_final) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) p[e] = pack_bf16_relu(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) p[e] = pack_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          }
+          unsigned char* srow = c.staging + H * (c.S * 128) + orow * 128;  // k-block half H, [S rows x 128 B], SWIZZLE_128B
+          if (!c.pool) {
+            if (staged && orow < c.S) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(srow + (((c2 * 4 + g) ^ (orow & 7)) << 4)) =
+                    make_uint4(p[4 * g], p[4 * g + 1], p[4 * g + 2], p[4 * g + 3]);
+            } else if (row_ok) {
+              unsigned short* op = reinterpret_cast<unsigned short*>(c.out) + (tl.row0_out + t) * C + col;
+              st_global_v8(op, p);
+              st_global_v8(op + 16, p + 8);
+            }
+          } else {
+            // rounding to bf16 is monotonic: max of the rounded values = rounded max.  Adjacent rows are adjacent lanes.
+            uint32_t m[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) m[e] = max_bf16x2(p[e], __shfl_xor_sync(0xffffffffu, p[e], 1));
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e] = (lane & 1) ? m[8 + e] : m[e];  // even lane: columns 0-15, odd lane: 16-31
+            if (staged && orow < c.S) {
+              const int ch = c2 * 4 + ((lane & 1) << 1);
+              *reinterpret_cast<uint4*>(srow + ((ch ^ (orow & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ (orow & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+            } else if (pair_ok) {
+              unsigned short* op = reinterpret_cast<unsigned short*>(c.out) + (tl.row0_out + (t >> 1)) * C + col + ((lane & 1) << 4);
+              st_global_v8(op, w);
+            }
+          }
+        }
+      }
+      if (leader) MUCON_TR16(17, j);
+      if (staged) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> the TMA's (async) proxy
+        if (leader) MUCON_TR16(18, j);
+        named_bar_sync(2, 32 * EPI_WARPS);
+        if (leader) MUCON_TR16(19, j);
+        if (leader) {
+          const int orow0 = static_cast<int>(tl.row0_out) + (c.pool ? (tl.t0 >> 1) : tl.t0);
+          tma_store_2d(c.tmO, c.staging, 0, orow0);
+          tma_store_2d(c.tmO, c.staging + c.S * 128, 64, orow0);
+          tma_store_commit();
+        }
+        store_pending = true;
+      }
+      if (leader) MUCON_TR16(9, j);
+    }
+  }
+  if (leader && store_pending) tma_store_wait_all();  // the stores are complete before the CTA exits
+}
+
+__global__ void __launch_bounds__(LTHREADS, 1)
+wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWd,
+                          const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmO,
+                          const __grid_constant__ BiasPack bias, const Tile* __restrict__ tiles, int num_tiles,
+                          int dil, int slab, void* __restrict__ out, int pool, int relu_final, int out_f32) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = smem_raw;  // the launch asks for exactly what it uses: no slack for re-alignment
+  if ((smem_u32(base) & 1023u) != 0) __trap();
+  // stage geometry: a stage holds NKB k-blocks of R rows x 128 bytes.  Slab mode: R = 128 + 2*dil rows starting at
+  // time step t0 - dil, tap `tap` is the 128 rows from row tap*dil.  Otherwise three separate 128-row tap tiles.
+  const int R = stage_rows(dil, slab);
+  const int kb_bytes = kb_bytes_of(dil, slab);
+  const int stage_bytes = NKB * kb_bytes;
+  const int NS = num_stages(slab);         // stages
+  const int LA = NS - 1;                   // GEMM 1 / epilogue 1 run LA tiles ahead of GEMM 2 / epilogue 2
+  const int tap_rows = slab ? dil : BM;    // row offset of tap `tap` inside a k-block = tap * tap_rows
+  const int S = staged_rows(dil, slab, pool, out_f32);
+  unsigned char* w_mem = base;                       // [8][WTILE]: (tap, kb) tiles of the dilated conv, then the 1x1's
+  unsigned char* stage_mem = base + W_BYTES;         // activation stages
+  unsigned char* staging = stage_mem + NS * stage_bytes;  // [2][S rows x 128 B] output tile, SWIZZLE_128B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + S * 256);
+  uint64_t* wfull = bars;          // weights resident
+  uint64_t* fullS = bars + 1;      // [2] slab landed (TMA bytes)
+  uint64_t* readyS = bars + 3;     // [2] slab padded (fix-up warp)
+  uint64_t* emptyS = bars + 5;     // [2] slab no longer read (GEMM 1 retired and the residual rows are in registers)
+  uint64_t* a1full = bars + 7;     // [2] accumulator 1 complete
+  uint64_t* a1free = bars + 9;     // [2] GEMM 2 retired: accumulator 1 / Y may be overwritten
+  uint64_t* yready = bars + 11;    // [2] Y (bf16, over accumulator 1) and x + b1 (accumulator 2) stored
+  uint64_t* a2full = bars + 13;    // [2] accumulator 2 complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&fullS[s], 1); mbar_init(&readyS[s], 1); mbar_init(&emptyS[s], EPI_WARPS);
+      mbar_init(&a1full[s], 1); mbar_init(&a1free[s], 1); mbar_init(&yready[s], EPI_WARPS); mbar_init(&a2full[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // all of TMEM: accumulators 1 at columns 0 / 128, accumulators 2 at 256 / 384
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_my = (static_cast<int>(blockIdx.x) < num_tiles)
+                       ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                       : 0;
+  // does the tile need rows zeroed (Conv1d padding at the video's ends)?  Only then does the MMA warp wait for the
+  // fix-up warp; otherwise it goes straight from the TMA's barrier
+  auto needs_fix = [&](const Tile& tl) {
+    if (slab) return dil - tl.t0 > 0 || tl.T - tl.t0 + dil < R;
+    return tl.t0 - dil < 0 || tl.t0 + BM + dil > tl.T;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWd) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+      if (n_my > 0) {
+        mbar_arrive_expect_tx(wfull, W_BYTES);
+        for (int tap = 0; tap < 3; ++tap)
+          for (int kb = 0; kb < NKB; ++kb) tma_load_2d(w_mem + (tap * NKB + kb) * WTILE, &tmWd, kb * 64, tap * C, wfull);
+        for (int kb = 0; kb < NKB; ++kb) tma_load_2d(w_mem + (3 * NKB + kb) * WTILE, &tmW1, kb * 64, 0, wfull);
+      }
+      for (int i = 0; i < n_my; ++i) {
+        const Tile tl = tiles[blockIdx.x + i * gridDim.x];
+        const int s = i % NS;
+        const uint32_t ph = (i / NS) & 1;
+        unsigned char* st = stage_mem + s * stage_bytes;
+        mbar_wait(&emptyS[s], ph ^ 1);
+        MUCON_TR16(0, i);
+        if (slab) {
+          mbar_arrive_expect_tx(&fullS[s], static_cast<uint32_t>(NKB * R * 128));
+          const int row = static_cast<int>(tl.row0) + tl.t0 - dil;  // may be negative: TMA zero-fills
+          for (int kb = 0; kb < NKB; ++kb) tma_load_2d(st + kb * kb_bytes, &tmX, kb * 64, row, &fullS[s]);
+        } else {
+          int live = 0;
+          for (int tap = 0; tap < 3; ++tap) live += tap_live((tap - 1) * dil, tl.T) ? 1 : 0;
+          mbar_arrive_expect_tx(&fullS[s], static_cast<uint32_t>(live * NKB * BM * 128));
+          for (int tap = 0; tap < 3; ++tap) {
+            const int shift = (tap - 1) * dil;
+            if (!tap_live(shift, tl.T)) continue;
+            const int row = static_cast<int>(tl.row0) + tl.t0 + shift;
+            for (int kb = 0; kb < NKB; ++kb)
+              tma_load_2d(st + kb * kb_bytes + tap * BM * 128, &tmX, kb * 64, row, &fullS[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ fix-up warp =================================
+    // rows that lie outside the video are Conv1d's zero padding (the TMA brought the neighbouring video's rows)
+    for (int i = 0; i < n_my; ++i) {
+      const Tile tl = tiles[blockIdx.x + i * gridDim.x];
+      const int s = i % NS;
+      const uint32_t ph = (i / NS) & 1;
+      unsigned char* st = stage_mem + s * stage_bytes;
+      mbar_wait(&fullS[s], ph);
+      if (lane == 0) MUCON_TR16(1, i);
+      if (needs_fix(tl)) {
+        if (slab) {
+          const int lo = dil - tl.t0;           // rows below lo are before the video
+          const int hi = tl.T - tl.t0 + dil;    // rows from hi on are after it
+          for (int r = lane; r < R; r += 32) {
+            if (r < lo || r >= hi) {
+#pragma unroll
+              for (int kb = 0; kb < NKB; ++kb) {
+                uint4* p = reinterpret_cast<uint4*>(st + kb * kb_bytes + r * 128);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) p[c] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          }
+        } else {
+          for (int tap = 0; tap < 3; ++tap) {
+            const int shift = (tap - 1) * dil;
+            if (!tap_live(shift, tl.T)) continue;
+            const int lo = -(tl.t0 + shift);
+            const int hi = tl.T - (tl.t0 + shift);
+            if (lo <= 0 && hi >= BM) continue;
+            for (int r = lane; r < BM; r += 32) {
+              if (r < lo || r >= hi) {
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
+                  uint4* p = reinterpret_cast<uint4*>(st + kb * kb_bytes + (tap * BM + r) * 128);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) p[c] = make_uint4(0u, 0u, 0u, 0u);
+                }
+              }
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&readyS[s]);
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc = instr_desc_bf16(BM, BN);
+    const uint32_t w_addr = smem_u32(w_mem);
+    if (n_my > 0) mbar_wait(wfull, 0);
+    for (int i = 0; i < n_my + LA; ++i) {
+      if (i < n_my) {
+        // ---- GEMM 1 of tile i: dilated conv, 3 taps x 2 k-blocks x 4 instructions (M128 N128 K16)
+        const Tile tl = tiles[blockIdx.x + i * gridDim.x];
+        const int s = i % NS, acc = i & 1;
+        if (lane == 0) MUCON_TR16(12, i);
+        mbar_wait(needs_fix(tl) ? &readyS[s] : &fullS[s], (i / NS) & 1);
+        mbar_wait(&a1free[acc], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) MUCON_TR16(2, i);
+        if (lane == 0) {
+          const uint32_t st = smem_u32(stage_mem + s * stage_bytes);
+          const uint32_t d1 = tmem_base + acc * BN;
+          int issued = 0;
+          for (int tap = 0; tap < 3; ++tap) {
+            if (!tap_live((tap - 1) * dil, tl.T)) continue;
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+              // tap `tap` = rows tap*tap_rows .. +127 of the k-block: the SWIZZLE_128B descriptor's start address
+              // moved by whole 128-byte rows (the swizzle is a function of the absolute shared-memory address)
+              const uint64_t adesc = smem_desc(st + kb * kb_bytes + static_cast<uint32_t>(tap * tap_rows) * 128u);
+              const uint64_t bdesc = smem_desc(w_addr + (tap * NKB + kb) * WTILE);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma_bf16(d1, adesc + 2 * k, bdesc + 2 * k, idesc, (issued | k) != 0);
+              ++issued;
+            }
+          }
+          mma_commit(&a1full[acc]);
+          MUCON_TR16(3, i);
+        }
+        __syncwarp();
+      }
+      if (i >= LA) {
+        // ---- GEMM 2 of tile j: acc2 (= x + b1, stored by the epilogue) += Y . W1^T, Y = relu(acc1 + bd) as bf16 in
+        // the first 64 columns of accumulator 1
+        const int j = i - LA;
+        const int acc = j & 1;
+        if (lane == 0) MUCON_TR16(13, j);
+        mbar_wait(&yready[acc], (j >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) MUCON_TR16(4, j);
+        if (lane == 0) {
+          const uint32_t d2 = tmem_base + 2 * BN + acc * BN;
+          const uint32_t ya = tmem_base + acc * BN;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 8 x K16: 8 columns of packed bf16 pairs each
+            const uint64_t bdesc = smem_desc(w_addr + (3 * NKB + (k >> 2)) * WTILE) + 2 * (k & 3);
+            mma_bf16_ts(d2, ya + 8 * k, bdesc, idesc, 1u);
+          }
+          mma_commit(&a2full[acc]);
+          mma_commit(&a1free[acc]);
+          MUCON_TR16(5, j);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    EpiCtx c;
+    c.tiles = tiles; c.stage_mem = stage_mem; c.staging = staging;
+    c.emptyS = emptyS; c.a1full = a1full; c.yready = yready; c.a2full = a2full;
+    c.tmO = &tmO; c.out = out; c.tmem_base = tmem_base;
+    c.n_my = n_my; c.NS = NS; c.LA = LA; c.stage_bytes = stage_bytes; c.kb_bytes = kb_bytes; c.tap_rows = tap_rows;
+    c.S = S; c.pool = pool; c.relu_final = relu_final; c.out_f32 = out_f32;
+    if (warp < 8) epilogue_warps<0>(c, bias);
+    else epilogue_warps<1>(c, bias);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace layer16
+}  // namespace mucon

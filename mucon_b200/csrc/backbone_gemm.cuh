@@ -109,7 +109,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const float* __restrict__ bias, float* __restrict__ out, int M, int K, int relu) {
+                 const float* __restrict__ bias, float* __restrict__ out, int M, int K, int relu, int out_bf16) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -201,7 +201,24 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
-        if (row < M) {
+        if (row < M && out_bf16) {
+          // bf16 activations for the bf16 layer kernels (backbone_bf16.cuh): 32 columns = 64 bytes = two 32-byte stores
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float lo = __uint_as_float(r[2 * j + 0]) + __ldg(bias + c * 32 + 2 * j + 0);
+            float hi = __uint_as_float(r[2 * j + 1]) + __ldg(bias + c * 32 + 2 * j + 1);
+            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(hi), "f"(lo));
+          }
+          unsigned short* ob = reinterpret_cast<unsigned short*>(out) + static_cast<int64_t>(row) * BN + c * 32;
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"l"(ob + 16 * g), "r"(pk[8 * g + 0]), "r"(pk[8 * g + 1]), "r"(pk[8 * g + 2]), "r"(pk[8 * g + 3]),
+                           "r"(pk[8 * g + 4]), "r"(pk[8 * g + 5]), "r"(pk[8 * g + 6]), "r"(pk[8 * g + 7])
+                         : "memory");
+        } else if (row < M) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v;
@@ -482,7 +499,7 @@ namespace layer {
 // clock64() stamps per tile for the MMA warp and epilogue warp 4 of wavenet_layer_kernel.  This is how the
 // epilogue warps were found to be the bottleneck of the layer kernel.  Compiles to nothing by default.
 #ifdef MUCON_LAYER_TRACE
-__device__ long long g_trace[16][128];
+__device__ long long g_trace[32][128];
 #define MUCON_TR(ev, it) do { if (blockIdx.x == 0 && (it) < 128) g_trace[ev][it] = clock64(); } while (0)
 #else
 #define MUCON_TR(ev, it) do { } while (0)

@@ -82,10 +82,12 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def gemm_tf32_bias_act(A, W, bias, relu):
-    """act(A @ W.T + bias) on tcgen05 (TF32 operands, fp32 accumulate).  A [M,K], W [128,K]."""
-    out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.float32, device=A.device)
-    _lib.check(_lib.lib().mucon_gemm_tf32_bias_act(
+def gemm_tf32_bias_act(A, W, bias, relu, out_bf16=False):
+    """act(A @ W.T + bias) on tcgen05 (TF32 operands, fp32 accumulate).  A [M,K], W [128,K].
+    out_bf16: store the result as bf16 (the input of the bf16 layer kernel)."""
+    out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
+    fn = _lib.lib().mucon_gemm_tf32_bias_act_bf16 if out_bf16 else _lib.lib().mucon_gemm_tf32_bias_act
+    _lib.check(fn(
         _lib.ptr(A), C.c_int64(A.shape[0]), C.c_int(A.shape[1]), _lib.ptr(W), C.c_int(W.shape[0]), _lib.ptr(bias),
         _lib.ptr(out), C.c_int(int(relu)), _stream(A.device)), "mucon_gemm_tf32_bias_act")
     return out
@@ -130,6 +132,33 @@ def wavenet_layer_rows(x, Wd_kco, bd, W1_kco, b1, plan, level, dilation, pool, r
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(Wd_kco), _lib.ptr(bd), _lib.ptr(W1_kco), _lib.ptr(b1), _lib.ptr(tiles),
         C.c_int(n_tiles), C.c_int64(x.shape[0]), C.c_int(dilation), C.c_int(int(pool)), C.c_int(int(relu_final)),
         _stream(x.device)), "mucon_wavenet_layer_tf32")
+    return out
+
+
+# Arithmetic of the 128 -> 128 layers: "bf16" (bf16 activations and weights, tcgen05 kind::f16, weights resident in
+# shared memory: the fast path), "tf32" (fp32 activations read as TF32) or "fp32" (CUDA cores, exact fp32).
+DEFAULT_PRECISION = os.environ.get("MUCON_BACKBONE_PRECISION", "bf16")
+
+
+def _host_f32(t):
+    """contiguous float32 host copy of a (small) tensor, as a ctypes pointer keeps it alive through the call"""
+    a = np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32) if isinstance(t, torch.Tensor) else \
+        np.ascontiguousarray(t, dtype=np.float32)
+    return a
+
+
+def wavenet_layer_bf16_rows(x, Wd_kco16, bd, W1_kco16, b1, plan, level, dilation, pool, relu_final, out_f32=False):
+    """One WaveNet layer (+ optional max-pool) in a single tcgen05 launch, bf16 operands.  x [rows(level), 128] bf16.
+    bd / b1: biases, as host float32 arrays (numpy) or tensors (copied to the host: pass numpy in hot loops)."""
+    tiles, n_tiles = plan.ltiles[(level, "pool" if pool else "same")]
+    out = torch.empty((plan.rows[level + 1] if pool else x.shape[0], 128),
+                      dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    bd_h, b1_h = _host_f32(bd), _host_f32(b1)
+    _lib.check(_lib.lib().mucon_wavenet_layer_bf16(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(Wd_kco16), bd_h.ctypes.data_as(C.c_void_p), _lib.ptr(W1_kco16),
+        b1_h.ctypes.data_as(C.c_void_p), _lib.ptr(tiles), C.c_int(n_tiles), C.c_int64(x.shape[0]),
+        C.c_int64(out.shape[0]), C.c_int(dilation), C.c_int(int(pool)), C.c_int(int(relu_final)),
+        C.c_int(int(out_f32)), _stream(x.device)), "mucon_wavenet_layer_bf16")
     return out
 
 
@@ -220,18 +249,47 @@ class WaveNetBlock(nn.Module):
             if self.out_dims == 128:  # tensor-core layouts
                 w["last_k"] = _kco(self.last_conv)
                 w["layers_k"] = [(_kco(l.dilated_conv), _kco(l.conv_1x1)) for l in self.layers]
+                w["layers_k16"] = [(a.to(torch.bfloat16).contiguous(), b.to(torch.bfloat16).contiguous())
+                                   for a, b in w["layers_k"]]
+                w["layers_bias_h"] = [(_host_f32(l.dilated_conv.bias), _host_f32(l.conv_1x1.bias)) for l in self.layers]
             self._cache = (key, w)
         return self._cache[1]
 
-    def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True):
+    def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True, precision=None):
         """feats [sum T, in_channels] float32 rows (time-major, videos concatenated) -> [sum T', out_dims].
-        tensor_cores=False keeps the 128->128 convolutions on the fp32 FFMA kernels (exact fp32)."""
+        tensor_cores=False keeps the 128->128 convolutions on the fp32 FFMA kernels (exact fp32);
+        precision: "bf16" | "tf32" (| "fp32" == tensor_cores=False), default DEFAULT_PRECISION."""
         if self.training and self.dropout_rate > 0:
             raise NotImplementedError("training-mode dropout is not implemented; call .eval()")
         if not feats.is_cuda:
             raise _lib.MuconError("the backbone needs CUDA tensors (there is no CPU fallback)")
+        precision = precision or DEFAULT_PRECISION
+        if precision not in ("bf16", "tf32", "fp32"):
+            raise ValueError(f"precision {precision!r}")
+        if precision == "fp32":
+            tensor_cores = False
         w = self._weights()
         V = plan.V
+        last = self.num_stages - 1
+        if precision == "bf16" and tensor_cores and fused_layers and self.out_dims == 128 and self.num_stages > 0:
+            if self.in_channels % 32 == 0:
+                x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True, out_bf16=True)  # temporal.py:133
+            else:
+                x = conv1d_rows(feats, w["first_w"].t().contiguous()[None], w["first_b"], plan.off[0], V, plan.max_T[0],
+                                relu_out=True).to(torch.bfloat16)
+            level = 0
+            for i, (wd, bd, w1, b1) in enumerate(w["layers"]):
+                pooled = self.pooling and i in self.pooling_layers
+                wdk, w1k = w["layers_k16"][i]
+                bd, b1 = w["layers_bias_h"][i]
+                # the last layer hands fp32 to last_conv (with the ReLU of temporal.py:144 folded into its store)
+                x = wavenet_layer_bf16_rows(x, wdk, bd, w1k, b1, plan, level, self.stages[i], pooled,
+                                            relu_final=(i == last), out_f32=(i == last and not pooled))
+                if pooled:
+                    level += 1
+            if x.dtype != torch.float32:
+                x = x.float()
+            return conv_gemm_rows(x, w["last_k"], w["last_b"], plan, level)                          # temporal.py:144-145
         if self.out_dims == 128 and self.in_channels % 32 == 0:
             x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True)       # temporal.py:133
         else:
@@ -239,7 +297,6 @@ class WaveNetBlock(nn.Module):
                             relu_out=True)
         level = 0
         tc = tensor_cores and self.out_dims == 128
-        last = self.num_stages - 1
         for i, (wd, bd, w1, b1) in enumerate(w["layers"]):
             off, mt = plan.off[level], plan.max_T[level]
             pooled = self.pooling and i in self.pooling_layers
@@ -432,9 +489,10 @@ class MuConBackbone(nn.Module):
         return BackbonePlan(T, self.ft.n_pools(), device or self.conv_classifier.weight.device)
 
     # ---- packed (variable-length batch) API ----------------------------------------------------
-    def encode_packed(self, feats, plan, tensor_cores=True, fused_layers=True):
+    def encode_packed(self, feats, plan, tensor_cores=True, fused_layers=True, precision=None):
         """temporal_modeling_forward for a packed batch: [sum T, D] -> [sum Tz, hidden]."""
-        z = self.ft.forward_packed(feats, plan, tensor_cores=tensor_cores, fused_layers=fused_layers)
+        kw = dict(precision=precision) if isinstance(self.ft, WaveNetBlock) else {}
+        z = self.ft.forward_packed(feats, plan, tensor_cores=tensor_cores, fused_layers=fused_layers, **kw)
         lvl = len(plan.off) - 1
         if self.last_gn:
             z = groupnorm_relu_rows(z, self.ft_last_gn.weight.detach().float(), self.ft_last_gn.bias.detach().float(),

@@ -29,7 +29,7 @@ torch.cuda.synchronize()
 lib = _lib.lib()
 if not hasattr(lib, "mucon_debug_layer_trace"):
     sys.exit("build with MUCON_LAYER_TRACE=1 first")
-buf = np.zeros((16, 128), dtype=np.int64)
+buf = np.zeros((32, 128), dtype=np.int64)
 assert lib.mucon_debug_layer_trace(buf.ctypes.data_as(C.c_void_p)) == 0
 d = lambda a, b: float(np.median(buf[a, 10:100] - buf[b, 10:100]))
 print("cycles, medians over tiles 10..99 of CTA 0")

@@ -59,7 +59,8 @@ def test_layers_against_oracle(cuda_device, tensor_cores):
     mc = m.to(cuda_device)
     plan = mc.plan(Ts)
     packed = torch.cat([f[0] for f in feats]).to(cuda_device)
-    z = mc.encode_packed(packed, plan, tensor_cores=bool(tensor_cores), fused_layers=(tensor_cores == "fused"))
+    z = mc.encode_packed(packed, plan, tensor_cores=bool(tensor_cores), fused_layers=(tensor_cores == "fused"),
+                         precision="tf32")
     logp = mc.logprobs_packed(z, plan)
     zo, lo = plan.off_host[-1], plan.off_host[0]
     for v, t in enumerate(Ts):
@@ -77,7 +78,7 @@ def test_layers_against_oracle(cuda_device, tensor_cores):
 
 
 @pytest.mark.parametrize("i", range(len(CASES)))
-def test_reference_golden_end_to_end(cuda_device, i):
+def test_reference_golden_end_to_end(cuda_device, i, monkeypatch):
     from mucon_b200.temporal import MuConBackbone
     (T, D, H, C), (ft, gn, cls), feats, fresh = case_inputs(i)
     if not fresh:
@@ -85,6 +86,7 @@ def test_reference_golden_end_to_end(cuda_device, i):
     m = MuConBackbone(input_feature_size=D, num_classes=C, hidden_size=H).eval()
     m.load_state_dict(state_dict_of(ft, gn, cls))
     m = m.to(cuda_device)
+    monkeypatch.setattr("mucon_b200.temporal.DEFAULT_PRECISION", "tf32")
     enc = m.temporal_modeling_forward(feats.to(cuda_device))  # reference signature: [1, T, D] -> [1, Tz, H]
     want_z = G[f"c{i}_z"]
     assert tuple(enc.shape) == (1,) + want_z.shape
@@ -100,8 +102,9 @@ def test_reference_golden_end_to_end(cuda_device, i):
     assert np.mean(np.argmax(got, 1) == np.argmax(want, 1)) >= 0.98
 
 
-def test_wavenet_block_reference_signature(cuda_device):
+def test_wavenet_block_reference_signature(cuda_device, monkeypatch):
     from mucon_b200.temporal import WaveNetBlock
+    monkeypatch.setattr("mucon_b200.temporal.DEFAULT_PRECISION", "tf32")
     torch.manual_seed(9)
     blk = WaveNetBlock(64, stages=STAGES, out_dims=128, pooling_layers=POOL).eval()
     sd = {"ft." + k: v.clone() for k, v in blk.state_dict().items()}
