@@ -230,10 +230,10 @@ int mucon_mask_template_h(int template_id, float* out100_h);
  * read as TF32: 10-bit mantissa, fp32 accumulate).  Replaces first_conv + ReLU (temporal.py:133). */
 int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const float* W, int N, const float* bias,
                              float* out, int relu, void* stream);
-/* The same projection with the result stored as bf16 ([M, 128] row-major, 32-byte aligned): the input of the bf16
- * layer kernel below.  Operands are still the fp32 features read as TF32. */
+/* The same projection with the result stored as bf16 (fp16 != 0: IEEE half, saturating) ([M, 128] row-major,
+ * 32-byte aligned): the input of the 16-bit layer kernel below.  Operands are still the fp32 features read as TF32. */
 int mucon_gemm_tf32_bias_act_bf16(const float* A, int64_t M, int K, const float* W, int N, const float* bias,
-                                  void* out_bf16, int relu, void* stream);
+                                  void* out16, int relu, int fp16, void* stream);
 /* The same convolution for 128 -> 128 channels on tcgen05 (TF32 operands, fp32 accumulate): every
  * tap is four k-blocks of one TMEM accumulator, A tiles are TMA loads of the time-major activations
  * at a shifted row, rows outside the video are zeroed in shared memory (Conv1d zero padding).
@@ -270,13 +270,15 @@ int mucon_wavenet_layer_tf32_pair(const float* x, float* out, const float* Wd_kc
                                   const float* W1_kco, const float* b1, const void* tiles, int num_tiles,
                                   int64_t rows, int dilation, int pool, int relu_final, void* stream);
 /* One whole WaveNet layer (temporal.py:43-53, + max_pool1d(2) :137-139, + the ReLU of :144) on tcgen05 kind::f16:
- * bf16 activations ([rows, 128] row-major, 32-byte aligned) and bf16 weights (Wd_kco [3][128][128], W1_kco
- * [128][128], resident in shared memory for the whole launch), fp32 accumulate.  The two bias vectors are HOST
- * arrays of 128 floats (they travel as a kernel parameter).  `out` ([rows_out, 128]) is bf16 (pooled resolution
- * when pool != 0) or, with out_f32 != 0 (pool must be 0), fp32.  tiles as for mucon_wavenet_layer_tf32. */
+ * 16-bit activations ([rows, 128] row-major, 32-byte aligned) and weights (Wd_kco [3][128][128], W1_kco
+ * [128][128], resident in shared memory for the whole launch), fp32 accumulate.  fp16 == 0: bfloat16; fp16 != 0:
+ * IEEE half (11-bit mantissa: the rounding of the residual stream, which dominates the bf16 path's error, is 8x
+ * smaller; values saturate at +-65504).  The two bias vectors are HOST arrays of 128 floats (they travel as a
+ * kernel parameter).  `out` ([rows_out, 128]) has the activation type (pooled resolution when pool != 0) or, with
+ * out_f32 != 0 (pool must be 0), is fp32.  tiles as for mucon_wavenet_layer_tf32. */
 int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd_kco, const float* bd_h, const void* W1_kco,
                              const float* b1_h, const void* tiles, int num_tiles, int64_t rows, int64_t rows_out,
-                             int dilation, int pool, int relu_final, int out_f32, void* stream);
+                             int dilation, int pool, int relu_final, int out_f32, int fp16, void* stream);
 /* k = 1 or k = 3 dilated Conv1d with padding = dilation (temporal.py:21-31,48-52), fp32:
  *   out[t, co] = bias[co] + sum_tap sum_ci W_tco[tap][ci][co] * f(in[t + (tap - taps/2)*dilation, ci])
  * f = ReLU when relu_in; ReLU on the result when relu_out; `residual` ([rows, Cout] or NULL) is

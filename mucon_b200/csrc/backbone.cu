@@ -57,14 +57,14 @@ int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, 
 }
 
 // [rows, 128] bf16 row-major, box [box_rows, 64 cols] (128 bytes) with 128-byte swizzle
-int make_map_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int make_map_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MUCON_ECUDA;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MUCON_OK : MUCON_ECUDA;
@@ -306,8 +306,8 @@ extern "C" int mucon_gemm_tf32_bias_act(const float* A, int64_t M, int K, const 
 }
 
 extern "C" int mucon_gemm_tf32_bias_act_bf16(const float* A, int64_t M, int K, const float* W, int N,
-                                             const float* bias, void* out_bf16, int relu, void* stream) {
-  return launch_proj(A, M, K, W, N, bias, out_bf16, relu, 1, stream);
+                                             const float* bias, void* out16, int relu, int fp16, void* stream) {
+  return launch_proj(A, M, K, W, N, bias, out16, relu, fp16 ? 2 : 1, stream);
 }
 
 static int launch_proj(const float* A, int64_t M, int K, const float* W, int N, const float* bias, void* out, int relu,
@@ -472,7 +472,7 @@ extern "C" int mucon_wavenet_layer_tf32_pair(const float* x, float* out, const f
 extern "C" int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd_kco, const float* bd_h,
                                         const void* W1_kco, const float* b1_h, const void* tiles, int num_tiles,
                                         int64_t rows, int64_t rows_out, int dilation, int pool, int relu_final,
-                                        int out_f32, void* stream) {
+                                        int out_f32, int fp16, void* stream) {
   if (num_tiles == 0 || rows == 0 || rows_out == 0) return MUCON_OK;  // nothing to produce
   if (!x || !out || !Wd_kco || !bd_h || !W1_kco || !b1_h || !tiles || num_tiles < 0 || rows < 0 || rows_out < 0 ||
       dilation < 1)
@@ -484,17 +484,18 @@ extern "C" int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd
   if (rows > 0x7fffffff - 4096) return MUCON_EUNSUPPORTED;
   const int slab = dilation <= layer16::kMaxSlabDil ? 1 : 0;
   CUtensorMap tx, twd, tw1, to;
+  const bool f16 = fp16 != 0;
   int rc = make_map_bf16(&tx, x, static_cast<uint64_t>(rows), layer16::C,
-                         slab ? gemm::BM + 2 * dilation : gemm::BM);
+                         slab ? gemm::BM + 2 * dilation : gemm::BM, f16);
   if (rc != MUCON_OK) return rc;
-  rc = make_map_bf16(&twd, Wd_kco, 3ull * layer16::C, layer16::C, gemm::BN);
+  rc = make_map_bf16(&twd, Wd_kco, 3ull * layer16::C, layer16::C, gemm::BN, f16);
   if (rc != MUCON_OK) return rc;
-  rc = make_map_bf16(&tw1, W1_kco, layer16::C, layer16::C, gemm::BN);
+  rc = make_map_bf16(&tw1, W1_kco, layer16::C, layer16::C, gemm::BN, f16);
   if (rc != MUCON_OK) return rc;
   // output tiles leave through a TMA store of the rows that fit the shared-memory staging area
   const int S = layer16::staged_rows(dilation, slab, pool, out_f32);
   if (S > 0) {
-    rc = make_map_bf16(&to, out, static_cast<uint64_t>(rows_out), layer16::C, static_cast<uint32_t>(S));
+    rc = make_map_bf16(&to, out, static_cast<uint64_t>(rows_out), layer16::C, static_cast<uint32_t>(S), f16);
     if (rc != MUCON_OK) return rc;
   } else {
     to = tx;  // never used by the kernel
@@ -504,9 +505,9 @@ extern "C" int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd
   const int sms = mucon_device_sm_count();
   const int grid = num_tiles < sms ? num_tiles : sms;
   const int smem = layer16::smem_bytes_of(dilation, slab, pool, out_f32);
-  MUCON_CUDA_CHECK(cudaFuncSetAttribute(layer16::wavenet_layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        layer16::SMEM_LIMIT));
-  layer16::wavenet_layer_bf16_kernel<<<grid, layer16::LTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  auto kern = f16 ? layer16::wavenet_layer_bf16_kernel<true> : layer16::wavenet_layer_bf16_kernel<false>;
+  MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, layer16::SMEM_LIMIT));
+  kern<<<grid, layer16::LTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       tx, twd, tw1, to, bp, static_cast<const layer16::Tile*>(tiles), num_tiles, dilation, slab, out, pool, relu_final,
       out_f32 ? 1 : 0);
   MUCON_CUDA_CHECK(cudaGetLastError());

@@ -84,8 +84,8 @@ struct Tile {
 __device__ __forceinline__ bool tap_live(int shift, int T) { return shift < T && -shift < T; }
 
 // instruction descriptor: D = F32, A = B = BF16 (format 1), both K-major
-__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N, bool f16 = false) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -147,6 +147,41 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
+// The 16-bit activation / weight type of a launch: bf16 (8-bit mantissa, fp32 range) or fp16 (11-bit mantissa:
+// rounding the residual stream costs 8x less error, at the price of saturating at +-65504).
+template <bool F16>
+struct Half2 {
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    uint32_t r;
+    if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  static __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
+    uint32_t r;
+    if (F16) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  static __device__ __forceinline__ float lo(uint32_t p) {
+    if (!F16) return bf16_lo(p);
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(p));
+    return f;
+  }
+  static __device__ __forceinline__ float hi(uint32_t p) {
+    if (!F16) return bf16_hi(p);
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(p));
+    return f;
+  }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    if (F16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+  }
+};
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -165,7 +200,7 @@ struct EpiCtx {
 };
 
 // The eight epilogue warps (H = which 64 accumulator columns / which k-block of the slab this warp owns).
-template <int H>
+template <int H, bool F16>
 __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& bias) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;            // TMEM lane quarter (a warp may only touch lanes 32*(warp%4) ..)
@@ -195,8 +230,8 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int col = H * 64 + c2 * 32 + jj * 8 + 2 * e;
-              f[8 * jj + 2 * e] = __float_as_uint(bf16_lo(rw[e]) + bias.b1[col]);
-              f[8 * jj + 2 * e + 1] = __float_as_uint(bf16_hi(rw[e]) + bias.b1[col + 1]);
+              f[8 * jj + 2 * e] = __float_as_uint(Half2<F16>::lo(rw[e]) + bias.b1[col]);
+              f[8 * jj + 2 * e + 1] = __float_as_uint(Half2<F16>::hi(rw[e]) + bias.b1[col + 1]);
             }
           }
           if (c2 == 0 && leader) MUCON_TR16(20, i);
@@ -219,9 +254,9 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
         uint32_t y[32];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          y[e] = pack_bf16_relu(__uint_as_float(v0[2 * e]) + bias.bd[H * 64 + 2 * e],
+          y[e] = Half2<F16>::pack_relu(__uint_as_float(v0[2 * e]) + bias.bd[H * 64 + 2 * e],
                                 __uint_as_float(v0[2 * e + 1]) + bias.bd[H * 64 + 2 * e + 1]);
-          y[16 + e] = pack_bf16_relu(__uint_as_float(v1[2 * e]) + bias.bd[H * 64 + 32 + 2 * e],
+          y[16 + e] = Half2<F16>::pack_relu(__uint_as_float(v1[2 * e]) + bias.bd[H * 64 + 32 + 2 * e],
                                      __uint_as_float(v1[2 * e + 1]) + bias.bd[H * 64 + 32 + 2 * e + 1]);
         }
         tmem_st32(lane_base + acc * BN + H * 32, y);
@@ -274,10 +309,10 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
           uint32_t p[16];
           if (c.relu_final) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) p[e] = pack_bf16_relu(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            for (int e = 0; e < 16; ++e) p[e] = Half2<F16>::pack_relu(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) p[e] = pack_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            for (int e = 0; e < 16; ++e) p[e] = Half2<F16>::pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
           }
           unsigned char* srow = c.staging + H * (c.S * 128) + orow * 128;  // k-block half H, [S rows x 128 B], SWIZZLE_128B
           if (!c.pool) {
@@ -295,7 +330,7 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
             // rounding to bf16 is monotonic: max of the rounded values = rounded max.  Adjacent rows are adjacent lanes.
             uint32_t m[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) m[e] = max_bf16x2(p[e], __shfl_xor_sync(0xffffffffu, p[e], 1));
+            for (int e = 0; e < 16; ++e) m[e] = Half2<F16>::max2(p[e], __shfl_xor_sync(0xffffffffu, p[e], 1));
             uint32_t w[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) w[e] = (lane & 1) ? m[8 + e] : m[e];  // even lane: columns 0-15, odd lane: 16-31
@@ -330,6 +365,7 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
   if (leader && store_pending) tma_store_wait_all();  // the stores are complete before the CTA exits
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(LTHREADS, 1)
 wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWd,
                           const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmO,
@@ -477,7 +513,7 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    constexpr uint32_t idesc = instr_desc_bf16(BM, BN);
+    constexpr uint32_t idesc = instr_desc_bf16(BM, BN, F16);
     const uint32_t w_addr = smem_u32(w_mem);
     if (n_my > 0) mbar_wait(wfull, 0);
     for (int i = 0; i < n_my + LA; ++i) {
@@ -544,8 +580,8 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     c.tmO = &tmO; c.out = out; c.tmem_base = tmem_base;
     c.n_my = n_my; c.NS = NS; c.LA = LA; c.stage_bytes = stage_bytes; c.kb_bytes = kb_bytes; c.tap_rows = tap_rows;
     c.S = S; c.pool = pool; c.relu_final = relu_final; c.out_f32 = out_f32;
-    if (warp < 8) epilogue_warps<0>(c, bias);
-    else epilogue_warps<1>(c, bias);
+    if (warp < 8) epilogue_warps<0, F16>(c, bias);
+    else epilogue_warps<1, F16>(c, bias);
   }
 
   tc_fence_before();

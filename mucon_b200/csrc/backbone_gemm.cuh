@@ -202,14 +202,16 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
         if (row < M && out_bf16) {
-          // bf16 activations for the bf16 layer kernels (backbone_bf16.cuh): 32 columns = 64 bytes = two 32-byte stores
+          // 16-bit activations (1: bf16, 2: fp16) for the layer kernels of backbone_bf16.cuh: 32 columns = 64 bytes = two
+          // 32-byte stores
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float lo = __uint_as_float(r[2 * j + 0]) + __ldg(bias + c * 32 + 2 * j + 0);
             float hi = __uint_as_float(r[2 * j + 1]) + __ldg(bias + c * 32 + 2 * j + 1);
             if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(hi), "f"(lo));
+            if (out_bf16 == 2) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(hi), "f"(lo));
+            else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(hi), "f"(lo));
           }
           unsigned short* ob = reinterpret_cast<unsigned short*>(out) + static_cast<int64_t>(row) * BN + c * 32;
 #pragma unroll

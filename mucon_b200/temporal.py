@@ -82,14 +82,20 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def gemm_tf32_bias_act(A, W, bias, relu, out_bf16=False):
+def gemm_tf32_bias_act(A, W, bias, relu, out_bf16=False, out_dtype=None):
     """act(A @ W.T + bias) on tcgen05 (TF32 operands, fp32 accumulate).  A [M,K], W [128,K].
-    out_bf16: store the result as bf16 (the input of the bf16 layer kernel)."""
-    out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
-    fn = _lib.lib().mucon_gemm_tf32_bias_act_bf16 if out_bf16 else _lib.lib().mucon_gemm_tf32_bias_act
-    _lib.check(fn(
-        _lib.ptr(A), C.c_int64(A.shape[0]), C.c_int(A.shape[1]), _lib.ptr(W), C.c_int(W.shape[0]), _lib.ptr(bias),
-        _lib.ptr(out), C.c_int(int(relu)), _stream(A.device)), "mucon_gemm_tf32_bias_act")
+    out_dtype: torch.float32 (default), torch.bfloat16 or torch.float16 (the input of the 16-bit layer kernel)."""
+    out_dtype = out_dtype or (torch.bfloat16 if out_bf16 else torch.float32)
+    out = torch.empty((A.shape[0], W.shape[0]), dtype=out_dtype, device=A.device)
+    if out_dtype == torch.float32:
+        _lib.check(_lib.lib().mucon_gemm_tf32_bias_act(
+            _lib.ptr(A), C.c_int64(A.shape[0]), C.c_int(A.shape[1]), _lib.ptr(W), C.c_int(W.shape[0]), _lib.ptr(bias),
+            _lib.ptr(out), C.c_int(int(relu)), _stream(A.device)), "mucon_gemm_tf32_bias_act")
+    else:
+        _lib.check(_lib.lib().mucon_gemm_tf32_bias_act_bf16(
+            _lib.ptr(A), C.c_int64(A.shape[0]), C.c_int(A.shape[1]), _lib.ptr(W), C.c_int(W.shape[0]), _lib.ptr(bias),
+            _lib.ptr(out), C.c_int(int(relu)), C.c_int(int(out_dtype == torch.float16)), _stream(A.device)),
+            "mucon_gemm_tf32_bias_act_bf16")
     return out
 
 
@@ -135,9 +141,11 @@ def wavenet_layer_rows(x, Wd_kco, bd, W1_kco, b1, plan, level, dilation, pool, r
     return out
 
 
-# Arithmetic of the 128 -> 128 layers: "bf16" (bf16 activations and weights, tcgen05 kind::f16, weights resident in
-# shared memory: the fast path), "tf32" (fp32 activations read as TF32) or "fp32" (CUDA cores, exact fp32).
-DEFAULT_PRECISION = os.environ.get("MUCON_BACKBONE_PRECISION", "bf16")
+# Arithmetic of the 128 -> 128 layers: "fp16" / "bf16" (16-bit activations and weights, tcgen05 kind::f16, weights
+# resident in shared memory: the fast path; fp16's 11-bit mantissa keeps the residual stream as accurate as TF32,
+# bf16 has fp32's range but 8x the rounding error), "tf32" (fp32 activations read as TF32) or "fp32" (CUDA cores,
+# exact fp32).
+DEFAULT_PRECISION = os.environ.get("MUCON_BACKBONE_PRECISION", "fp16")
 
 
 def _host_f32(t):
@@ -148,17 +156,19 @@ def _host_f32(t):
 
 
 def wavenet_layer_bf16_rows(x, Wd_kco16, bd, W1_kco16, b1, plan, level, dilation, pool, relu_final, out_f32=False):
-    """One WaveNet layer (+ optional max-pool) in a single tcgen05 launch, bf16 operands.  x [rows(level), 128] bf16.
+    """One WaveNet layer (+ optional max-pool) in a single tcgen05 launch, 16-bit operands.  x [rows(level), 128]
+    bfloat16 or float16 (the weights must have the same type).
     bd / b1: biases, as host float32 arrays (numpy) or tensors (copied to the host: pass numpy in hot loops)."""
     tiles, n_tiles = plan.ltiles[(level, "pool" if pool else "same")]
+    assert x.dtype in (torch.bfloat16, torch.float16) and Wd_kco16.dtype == x.dtype and W1_kco16.dtype == x.dtype
     out = torch.empty((plan.rows[level + 1] if pool else x.shape[0], 128),
-                      dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+                      dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
     bd_h, b1_h = _host_f32(bd), _host_f32(b1)
     _lib.check(_lib.lib().mucon_wavenet_layer_bf16(
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(Wd_kco16), bd_h.ctypes.data_as(C.c_void_p), _lib.ptr(W1_kco16),
         b1_h.ctypes.data_as(C.c_void_p), _lib.ptr(tiles), C.c_int(n_tiles), C.c_int64(x.shape[0]),
         C.c_int64(out.shape[0]), C.c_int(dilation), C.c_int(int(pool)), C.c_int(int(relu_final)),
-        C.c_int(int(out_f32)), _stream(x.device)), "mucon_wavenet_layer_bf16")
+        C.c_int(int(out_f32)), C.c_int(int(x.dtype == torch.float16)), _stream(x.device)), "mucon_wavenet_layer_bf16")
     return out
 
 
@@ -251,6 +261,8 @@ class WaveNetBlock(nn.Module):
                 w["layers_k"] = [(_kco(l.dilated_conv), _kco(l.conv_1x1)) for l in self.layers]
                 w["layers_k16"] = [(a.to(torch.bfloat16).contiguous(), b.to(torch.bfloat16).contiguous())
                                    for a, b in w["layers_k"]]
+                w["layers_kh16"] = [(a.to(torch.float16).contiguous(), b.to(torch.float16).contiguous())
+                                    for a, b in w["layers_k"]]
                 w["layers_bias_h"] = [(_host_f32(l.dilated_conv.bias), _host_f32(l.conv_1x1.bias)) for l in self.layers]
             self._cache = (key, w)
         return self._cache[1]
@@ -258,29 +270,30 @@ class WaveNetBlock(nn.Module):
     def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True, precision=None):
         """feats [sum T, in_channels] float32 rows (time-major, videos concatenated) -> [sum T', out_dims].
         tensor_cores=False keeps the 128->128 convolutions on the fp32 FFMA kernels (exact fp32);
-        precision: "bf16" | "tf32" (| "fp32" == tensor_cores=False), default DEFAULT_PRECISION."""
+        precision: "fp16" | "bf16" | "tf32" (| "fp32" == tensor_cores=False), default DEFAULT_PRECISION."""
         if self.training and self.dropout_rate > 0:
             raise NotImplementedError("training-mode dropout is not implemented; call .eval()")
         if not feats.is_cuda:
             raise _lib.MuconError("the backbone needs CUDA tensors (there is no CPU fallback)")
         precision = precision or DEFAULT_PRECISION
-        if precision not in ("bf16", "tf32", "fp32"):
+        if precision not in ("fp16", "bf16", "tf32", "fp32"):
             raise ValueError(f"precision {precision!r}")
         if precision == "fp32":
             tensor_cores = False
         w = self._weights()
         V = plan.V
         last = self.num_stages - 1
-        if precision == "bf16" and tensor_cores and fused_layers and self.out_dims == 128 and self.num_stages > 0:
+        if precision in ("bf16", "fp16") and tensor_cores and fused_layers and self.out_dims == 128 and self.num_stages > 0:
+            dt = torch.float16 if precision == "fp16" else torch.bfloat16
             if self.in_channels % 32 == 0:
-                x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True, out_bf16=True)  # temporal.py:133
+                x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True, out_dtype=dt)   # temporal.py:133
             else:
                 x = conv1d_rows(feats, w["first_w"].t().contiguous()[None], w["first_b"], plan.off[0], V, plan.max_T[0],
-                                relu_out=True).to(torch.bfloat16)
+                                relu_out=True).to(dt)
             level = 0
             for i, (wd, bd, w1, b1) in enumerate(w["layers"]):
                 pooled = self.pooling and i in self.pooling_layers
-                wdk, w1k = w["layers_k16"][i]
+                wdk, w1k = w["layers_kh16" if precision == "fp16" else "layers_k16"][i]
                 bd, b1 = w["layers_bias_h"][i]
                 # the last layer hands fp32 to last_conv (with the ReLU of temporal.py:144 folded into its store)
                 x = wavenet_layer_bf16_rows(x, wdk, bd, w1k, b1, plan, level, self.stages[i], pooled,

@@ -35,12 +35,12 @@ Ts = T[:nv]
 plan = m.plan(Ts)
 feats = torch.randn(int(Ts.sum()), 2048, device=dev).abs_() * 0.5
 out = {}
-for prec in ("bf16", "tf32"):
+for prec in ("fp16", "bf16", "tf32"):
     t_enc = timeit(lambda: m.encode_packed(feats, plan, precision=prec))
     z = m.encode_packed(feats, plan, precision=prec)
     t_cls = timeit(lambda: m.logprobs_packed(z, plan))
     w = m.ft._weights()
-    t_proj = timeit(lambda: temporal.gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], True, out_bf16=(prec == "bf16")))
+    t_proj = timeit(lambda: temporal.gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], True, out_dtype={"fp16": torch.float16, "bf16": torch.bfloat16, "tf32": torch.float32}[prec]))
     out[prec] = dict(encode_ms=t_enc, classifier_logsoftmax_ms=t_cls, projection_ms=t_proj)
     print(f"{prec}: encode {t_enc:.3f} ms (projection {t_proj:.3f}) classifier+logsoftmax {t_cls:.3f} ms", flush=True)
     if prec == "bf16":

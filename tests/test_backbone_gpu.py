@@ -2,8 +2,9 @@
 
 Tolerances: everything after the input projection is fp32 FFMA: rtol 1e-4 / atol 1e-4 against the
 oracle given the same projection output.  The projection runs on tcgen05 with TF32 operands (10-bit
-mantissa, fp32 accumulate), so end-to-end activations are compared with atol = 1e-2 * RMS of the
-reference tensor; the GEMM alone is checked against an fp64 matmul of the
+mantissa, fp32 accumulate), so end-to-end activations are compared with max |err| <= 2e-2 * RMS of the
+reference tensor (measured <= 1.1e-2 on the golden cases, printed by tests/test_backbone_bf16.py; SURVEY.md
+8c proposed 1e-2 "to be confirmed by measurement"); the GEMM alone is checked against an fp64 matmul of the
 TF32-truncated operands with rtol 1e-4."""
 import numpy as np
 import pytest
@@ -46,7 +47,7 @@ def test_layers_against_oracle(cuda_device, tensor_cores):
     lengths from 16 to 1999 frames: every padding / tile-boundary case of the conv kernels).
     in_channels = 48 takes the fp32 kernel for the projection, so with tensor_cores=False the whole
     path is fp32 (rtol/atol 1e-4); with tensor_cores=True the 128->128 convolutions run on tcgen05 with
-    TF32 operands (atol = 1e-2 * RMS of the reference tensor)."""
+    TF32 operands (max |err| <= 2e-2 * RMS of the reference tensor)."""
     from mucon_b200.temporal import MuConBackbone
     torch.manual_seed(3)
     m = MuConBackbone(input_feature_size=48, num_classes=20).eval()  # 48 % 32 != 0 -> fp32 projection
@@ -70,8 +71,8 @@ def test_layers_against_oracle(cuda_device, tensor_cores):
         gz = z[zo[v]:zo[v + 1]].cpu()
         gl = logp[lo[v]:lo[v + 1]].cpu()
         if tensor_cores:
-            assert (gz - rz[0]).abs().max().item() <= 1e-2 * rms(rz.numpy()) * 4, (v, t, (gz - rz[0]).abs().max())
-            assert (gl - rl).abs().max().item() <= 1e-2 * rms(rl.numpy()) * 4, (v, t, (gl - rl).abs().max())
+            assert (gz - rz[0]).abs().max().item() <= 2e-2 * rms(rz.numpy()), (v, t, (gz - rz[0]).abs().max())
+            assert (gl - rl).abs().max().item() <= 2e-2 * rms(rl.numpy()), (v, t, (gl - rl).abs().max())
         else:
             assert torch.allclose(gz, rz[0], rtol=1e-4, atol=1e-4), (v, (gz - rz[0]).abs().max())
             assert torch.allclose(gl, rl, rtol=1e-4, atol=1e-4), (v, (gl - rl).abs().max())
@@ -90,7 +91,7 @@ def test_reference_golden_end_to_end(cuda_device, i, monkeypatch):
     enc = m.temporal_modeling_forward(feats.to(cuda_device))  # reference signature: [1, T, D] -> [1, Tz, H]
     want_z = G[f"c{i}_z"]
     assert tuple(enc.shape) == (1,) + want_z.shape
-    assert np.abs(enc[0].cpu().numpy() - want_z).max() <= 1e-2 * rms(want_z) * 4
+    assert np.abs(enc[0].cpu().numpy() - want_z).max() <= 2e-2 * rms(want_z)
     seg = m.frame_classifier_forward(enc.permute(0, 2, 1), T)  # [1, C, T] logits
     logp = torch.log_softmax(seg[0].t(), dim=1).cpu().numpy()
     plan = m.plan([T])
@@ -98,7 +99,7 @@ def test_reference_golden_end_to_end(cuda_device, i, monkeypatch):
     assert np.abs(logp - logp2).max() <= 1e-5
     want = G[f"c{i}_logp"]
     got = logp2 if T <= 800 else logp2[::7]
-    assert np.abs(got - want).max() <= 1e-2 * rms(want) * 4
+    assert np.abs(got - want).max() <= 2e-2 * rms(want)
     assert np.mean(np.argmax(got, 1) == np.argmax(want, 1)) >= 0.98
 
 
@@ -113,7 +114,7 @@ def test_wavenet_block_reference_signature(cuda_device, monkeypatch):
     with torch.no_grad():
         ref = ob.wavenet_block(sd, x, STAGES, POOL)
     assert out.shape == ref.shape == (2, 128, 31)
-    assert (out - ref).abs().max().item() <= 1e-2 * rms(ref.numpy()) * 4
+    assert (out - ref).abs().max().item() <= 2e-2 * rms(ref.numpy())
     with pytest.raises(NotImplementedError):
         blk.train()(x.to(cuda_device))
 
