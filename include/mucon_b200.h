@@ -160,6 +160,16 @@ int mucon_viterbi_align_fused(const mucon_viterbi_batch* batch_h, const void* lo
  * covered everything runs in the main launch. */
 int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* batch_h, const void* logp, int in_is_f64,
                                    const int32_t* order, int n_wide, int write_bs, void* stream);
+/* The same alignment fed from the backbone's POOLED resolution: logp_z holds log-probabilities [sum Tz, C]
+ * (z_off[V+1] row offsets, device) and frame t of video v reads row min(floor(t * (float)Tz_v / T_v), Tz_v - 1)
+ * -- the nearest-neighbour index of F.interpolate (src/mucon/models.py:574-576; the 1x1 classifier and the
+ * log-softmax commute with it).  The scan performs the same sequence of float additions as over the expanded
+ * [sum T, C] array (np.cumsum, viterbi.py:51), so every output is bit-identical to
+ * mucon_logsoftmax_expand + mucon_viterbi_align_fused_tail, without the 4*T*C bytes per video being written
+ * or read. */
+int mucon_viterbi_align_fused_pooled(const mucon_viterbi_batch* batch_h, const void* logp_z, int in_is_f64,
+                                     const int64_t* z_off, const int32_t* order, int n_wide, int write_bs,
+                                     void* stream);
 
 /* Arg-max over the candidates of each video: best[v] = unit index with the highest score among
  * units cand_off[v] .. cand_off[v+1] (lowest index wins ties; units with status INFEASIBLE are
@@ -297,6 +307,9 @@ int mucon_groupnorm_relu(const float* in, float* out, const float* gamma, const 
  * (models.py:574-580 with the 1x1 classifier applied before the upsample, and :368). */
 int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z, const int64_t* off_t, int V, int max_T,
                             int C, float* out, void* stream);
+/* log_softmax over the C classes of every row (same arithmetic as mucon_logsoftmax_expand, no expansion):
+ * the pooled-resolution table mucon_viterbi_align_fused_pooled reads. */
+int mucon_logsoftmax_rows(const float* logits, int64_t rows, int C, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * vit_mof counters: nearest-neighbour resize of each video's predicted labels

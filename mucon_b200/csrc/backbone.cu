@@ -555,6 +555,38 @@ extern "C" int mucon_groupnorm_relu(const float* in, float* out, const float* ga
   return MUCON_OK;
 }
 
+// log_softmax of every row, one warp per row: the same operations in the same order as the rows
+// logsoftmax_expand_kernel prepares in shared memory (max, sum of expf, m + logf(s), x - lse)
+__global__ void __launch_bounds__(256) logsoftmax_rows_kernel(const float* __restrict__ logits, int64_t rows, int C,
+                                                              float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nw = (gridDim.x * static_cast<int64_t>(blockDim.x)) >> 5;
+  for (int64_t r = wid; r < rows; r += nw) {
+    const float* row = logits + r * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = m + logf(s);
+    for (int c = lane; c < C; c += 32) out[r * C + c] = row[c] - lse;
+  }
+}
+
+extern "C" int mucon_logsoftmax_rows(const float* logits, int64_t rows, int C, float* out, void* stream) {
+  if (!logits || !out || rows < 0 || C < 1) return MUCON_EINVAL;
+  if (rows == 0) return MUCON_OK;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  logsoftmax_rows_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, rows, C, out);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 extern "C" int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z, const int64_t* off_t, int V, int max_T,
                                        int C, float* out, void* stream) {
   if (!logits || !off_z || !off_t || !out || V < 0 || C < 1 || max_T < 0) return MUCON_EINVAL;

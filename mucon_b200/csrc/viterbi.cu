@@ -301,8 +301,9 @@ int dispatch_sl(const mucon_viterbi_batch& b, int J, cudaStream_t st) {
 
 template <typename BST, int G, int SL>
 int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int32_t* order, int write_bs,
-                 cudaStream_t st, bool pdl) {
+                 cudaStream_t st, bool pdl, const int64_t* z_off) {
   FusedCfg cfg;
+  cfg.z_off = z_off;
   cfg.scan_threads = b.C <= 32 ? 32 : (b.C <= 64 ? 64 : 128);
   const int spw = 32 / G;
   cfg.dp_warps = (b.max_N - 1 + spw - 1) / spw;
@@ -314,7 +315,8 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
   if (cfg.bps < 1) cfg.bps = 1;
   cfg.stages = env_int("MUCON_FUSED_STAGES", 2);
   cfg.ring_slabs = env_int("MUCON_FUSED_RING", 4);
-  if (cfg.stages < 2 || cfg.stages > 8 || cfg.ring_slabs < 2 || cfg.ring_slabs > 8) return MUCON_EINVAL;
+  if (z_off) cfg.stages = 0;  // pooled source: no TMA ring, the scan reads the small table through L1
+  if ((!z_off && cfg.stages < 2) || cfg.stages > 8 || cfg.ring_slabs < 2 || cfg.ring_slabs > 8) return MUCON_EINVAL;
   cfg.write_bs = write_bs && b.bs;
   cfg.bp_rows = b.max_K;
   size_t smem = fused_smem_bytes(cfg, G, J, b.C, b.fs, sizeof(BST));
@@ -361,12 +363,12 @@ int launch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int
 
 template <typename BST>
 int dispatch_fused(const mucon_viterbi_batch& b, int J, const BST* logp, const int32_t* order, int write_bs,
-                   cudaStream_t st, bool pdl) {
+                   cudaStream_t st, bool pdl, const int64_t* z_off) {
   const int G = b.lanes == 32 ? 32 : (J <= 32 ? 4 : 8);
   const int SL = (J + G - 1) / G;
-#define MUCON_SL_CASE(g, n) case n: return launch_fused<BST, g, n>(b, J, logp, order, write_bs, st, pdl);
+#define MUCON_SL_CASE(g, n) case n: return launch_fused<BST, g, n>(b, J, logp, order, write_bs, st, pdl, z_off);
 #ifdef MUCON_ONLY_SL9  // developer builds: only the evaluator's shape (J = 66)
-  if (G == 8 && SL == 9) return launch_fused<BST, 8, 9>(b, J, logp, order, write_bs, st, pdl);
+  if (G == 8 && SL == 9) return launch_fused<BST, 8, 9>(b, J, logp, order, write_bs, st, pdl, z_off);
   return MUCON_EUNSUPPORTED;
 #else
   if (G == 32) {
@@ -523,7 +525,7 @@ extern "C" int mucon_viterbi_decode_lanes(const mucon_viterbi_batch* bh, const i
 }
 
 static int align_fused_impl(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64, const int32_t* order,
-                            int write_bs, void* stream, bool pdl) {
+                            int write_bs, void* stream, bool pdl, const int64_t* z_off = nullptr) {
   if (!bh || !logp) return MUCON_EINVAL;
   const mucon_viterbi_batch& b = *bh;
   if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1 || b.max_K < 0) return MUCON_EINVAL;
@@ -538,8 +540,8 @@ static int align_fused_impl(const mucon_viterbi_batch* bh, const void* logp, int
   const size_t row_bytes = (size_t)b.C * (in_is_f64 ? 8 : 4);
   if (row_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(logp) & 15) != 0 || b.C > 128) return MUCON_EUNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (in_is_f64) return dispatch_fused<double>(b, J, static_cast<const double*>(logp), order, write_bs, st, pdl);
-  return dispatch_fused<float>(b, J, static_cast<const float*>(logp), order, write_bs, st, pdl);
+  if (in_is_f64) return dispatch_fused<double>(b, J, static_cast<const double*>(logp), order, write_bs, st, pdl, z_off);
+  return dispatch_fused<float>(b, J, static_cast<const float*>(logp), order, write_bs, st, pdl, z_off);
 }
 
 extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
@@ -547,8 +549,8 @@ extern "C" int mucon_viterbi_align_fused(const mucon_viterbi_batch* bh, const vo
   return align_fused_impl(bh, logp, in_is_f64, order, write_bs, stream, false);
 }
 
-extern "C" int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
-                                              const int32_t* order, int n_wide, int write_bs, void* stream) {
+static int align_fused_tail_impl(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64, const int32_t* order,
+                                 int n_wide, int write_bs, void* stream, const int64_t* z_off) {
   if (!bh || !order || n_wide < 0 || n_wide > bh->U) return MUCON_EINVAL;
   mucon_viterbi_batch b = *bh;
   int rc = MUCON_OK;
@@ -556,7 +558,7 @@ extern "C" int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* bh, con
     // the wide launch (a warp per transcript segment) for the first n_wide units of `order`
     b.U = n_wide;
     b.lanes = 32;
-    rc = align_fused_impl(&b, logp, in_is_f64, order, write_bs, stream, false);
+    rc = align_fused_impl(&b, logp, in_is_f64, order, write_bs, stream, false, z_off);
     if (rc == MUCON_EUNSUPPORTED) { n_wide = 0; rc = MUCON_OK; }  // shape not covered: everything in the main launch
     if (rc != MUCON_OK) return rc;
   }
@@ -564,8 +566,20 @@ extern "C" int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* bh, con
   b.lanes = 0;
   // the main launch follows in the same stream as a programmatic dependent launch: it starts once
   // the wide CTAs are resident and runs concurrently with them
-  if (b.U > 0) rc = align_fused_impl(&b, logp, in_is_f64, order + n_wide, write_bs, stream, n_wide > 0);
+  if (b.U > 0) rc = align_fused_impl(&b, logp, in_is_f64, order + n_wide, write_bs, stream, n_wide > 0, z_off);
   return rc;
+}
+
+extern "C" int mucon_viterbi_align_fused_tail(const mucon_viterbi_batch* bh, const void* logp, int in_is_f64,
+                                              const int32_t* order, int n_wide, int write_bs, void* stream) {
+  return align_fused_tail_impl(bh, logp, in_is_f64, order, n_wide, write_bs, stream, nullptr);
+}
+
+extern "C" int mucon_viterbi_align_fused_pooled(const mucon_viterbi_batch* bh, const void* logp_z, int in_is_f64,
+                                                const int64_t* z_off, const int32_t* order, int n_wide,
+                                                int write_bs, void* stream) {
+  if (!z_off) return MUCON_EINVAL;
+  return align_fused_tail_impl(bh, logp_z, in_is_f64, order, n_wide, write_bs, stream, z_off);
 }
 
 extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,

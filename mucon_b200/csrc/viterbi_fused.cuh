@@ -21,6 +21,11 @@ struct FusedCfg {
   int ring_slabs;    // block-score ring depth
   int bp_rows;       // rows of the shared back-pointer stage (0: trace from HBM)
   int write_bs;      // also store the block scores to b.bs
+  // Pooled source (NULL = `logp` holds one row per frame).  Otherwise `logp` holds the log-probabilities at the
+  // backbone's pooled resolution ([sum Tz, C], z_off[V+1] row offsets) and frame t of a video reads row
+  // min(floor(t * (float)Tz / T), Tz - 1) -- F.interpolate(mode="nearest"), reference src/mucon/models.py:574-576:
+  // the scan walks the same float32 sequence as over the expanded [T, C] array, which is never materialised.
+  const int64_t* z_off;
 };
 
 constexpr int kFusedMaxThreads = 256;      // segments sharing a warp (G = 4 / 8)
@@ -97,7 +102,7 @@ align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restri
       bulk_g2s(slabs + static_cast<size_t>(st) * slab_elems, src + static_cast<int64_t>(b0) * fs * row_bytes, bytes,
                &tma_full[st]);
     };
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && cfg.z_off == nullptr) {
       const int pre = min(stages, nslabs);
       for (int s = 0; s < pre; ++s) issue(s, s);
     }
@@ -110,6 +115,62 @@ align_fused_kernel(const mucon_viterbi_batch b, const int J, const BST* __restri
                                         : nullptr;
     int st = 0, rs = 0;
     uint32_t parity = 0, rpass = 0;
+    if (cfg.z_off != nullptr) {
+      // ---- pooled source: every frame's row is looked up in the [Tz, C] table (L1 / L2 resident: a video's table
+      // is at most a few hundred KB and each row serves T/Tz consecutive frames)
+      const int64_t z0 = cfg.z_off[v];
+      const int Tz = static_cast<int>(cfg.z_off[v + 1] - z0);
+      const float scale = static_cast<float>(Tz) / static_cast<float>(T);
+      const BST* tab = logp + z0 * C + (active ? c : 0);
+      constexpr int CH = 10;  // frames whose loads are in flight together
+      for (int i = 0; i < nslabs; ++i) {
+        if (feasible && rpass > 0) mbar_wait(&ring_empty[rs], (rpass & 1) ^ 1);
+        if (active) {
+          const int b0 = i * bps;
+          const int nb = min(bps, K - b0);
+          BST* rp = ring + static_cast<size_t>(rs) * bps * C + c;
+          for (int bb = 0; bb < nb; ++bb) {
+            const int t0 = (b0 + bb) * fs;
+            for (int r0 = 0; r0 < fs; r0 += CH) {
+              BST x[CH][CPT];
+#pragma unroll
+              for (int r = 0; r < CH; ++r) {
+                if (r0 + r < fs) {
+                  int iz = static_cast<int>(floorf(static_cast<float>(t0 + r0 + r) * scale));
+                  iz = iz > Tz - 1 ? Tz - 1 : iz;
+                  const BST* row = tab + static_cast<int64_t>(iz) * C;
+                  if constexpr (CPT == 2 && sizeof(BST) == 4) {
+                    const float2 xv = __ldg(reinterpret_cast<const float2*>(row));
+                    x[r][0] = xv.x;
+                    x[r][1] = xv.y;
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) x[r][j] = __ldg(row + j);
+                  }
+                }
+              }
+#pragma unroll
+              for (int r = 0; r < CH; ++r)
+                if (r0 + r < fs) {
+#pragma unroll
+                  for (int j = 0; j < CPT; ++j) run[j] = run[j] + x[r][j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              const BST o = (b0 + bb == 0) ? run[j] : run[j] - prev[j];
+              prev[j] = run[j];
+              rp[bb * C + j] = o;
+              if (out_g) out_g[static_cast<int64_t>(b0 + bb) * C + j] = o;
+            }
+          }
+        }
+        if (cfg.scan_threads == 32) __syncwarp(); else named_bar_sync(15, cfg.scan_threads);
+        if (threadIdx.x == 0 && feasible) mbar_arrive(&ring_full[rs]);
+        if (++rs == cfg.ring_slabs) { rs = 0; ++rpass; }
+      }
+      return;
+    }
     for (int i = 0; i < nslabs; ++i) {
       mbar_wait(&tma_full[st], parity);
       if (feasible && rpass > 0) mbar_wait(&ring_empty[rs], (rpass & 1) ^ 1);  // DP is done with this ring slab

@@ -522,6 +522,19 @@ class MuConBackbone(nn.Module):
         logits = conv1d_rows(z, w, self.conv_classifier.bias.detach().float(), plan.off[lvl], plan.V, plan.max_T[lvl])
         return logsoftmax_expand_rows(logits, plan, lvl)
 
+    def logprobs_pooled_packed(self, z, plan):
+        """The same log-probabilities at the POOLED resolution, not expanded: [sum Tz, hidden] -> ([sum Tz, classes],
+        row offsets [V+1]).  ViterbiEngine.run(..., z_off=offsets) aligns straight from this table (bit-identical
+        to the expanded path; the [sum T, classes] array is never written or read)."""
+        lvl = len(plan.off) - 1
+        w = self.conv_classifier.weight.detach().permute(2, 1, 0).contiguous().float()
+        logits = conv1d_rows(z, w, self.conv_classifier.bias.detach().float(), plan.off[lvl], plan.V, plan.max_T[lvl])
+        out = torch.empty_like(logits)
+        _lib.check(_lib.lib().mucon_logsoftmax_rows(
+            _lib.ptr(logits), C.c_int64(logits.shape[0]), C.c_int(logits.shape[1]), _lib.ptr(out),
+            _stream(logits.device)), "mucon_logsoftmax_rows")
+        return out, plan.off[lvl]
+
     # ---- the reference's signatures (batch size 1) -----------------------------------------------
     def temporal_modeling_forward(self, input):
         """[B, T, D] -> [B, T', D']  (models.py:746-773), eval mode."""

@@ -286,8 +286,12 @@ class ViterbiEngine:
             ev = self._events[i] = torch.cuda.Event()
         return ev
 
-    def run(self, plan, logp, seg0_f32=None, stream=None, mid_event=None, mode="auto", write_bs=True):
+    def run(self, plan, logp, seg0_f32=None, stream=None, mid_event=None, mode="auto", write_bs=True, z_off=None):
         """logp: CUDA tensor [sum T, C] float32 or float64, videos concatenated.  Asynchronous.
+
+        z_off: int64 CUDA tensor [V+1] -- `logp` is then the table at the backbone's POOLED resolution
+        ([sum Tz, C]) and frame t of a video reads row min(floor(t * (float)Tz / T), Tz - 1) (nearest
+        interpolate, models.py:574-576); bit-identical to running on the expanded array, fused mode only.
 
         mode: "fused"  one launch, scan and DP of a video in the same CTA (one transcript per video)
               "split"  block-score scan kernel + DP kernel (any number of candidates per video)
@@ -297,7 +301,13 @@ class ViterbiEngine:
             raise _lib.MuconError("ViterbiEngine.run needs a CUDA tensor (no CPU fallback)")
         if logp.dtype not in (torch.float32, torch.float64) or not logp.is_contiguous():
             raise TypeError("logp must be contiguous float32/float64")
-        if logp.shape[0] != plan.total_frames or logp.shape[1] != plan.C:
+        if z_off is not None:
+            if mode not in ("auto", "fused") or not plan.single or plan.generic:
+                raise _lib.MuconError("a pooled-resolution source needs the fused kernel (one transcript per video)")
+            if z_off.dtype != torch.int64 or z_off.numel() != plan.V + 1 or not z_off.is_cuda or logp.shape[1] != plan.C:
+                raise ValueError("z_off must be an int64 CUDA tensor [V+1]; logp [sum Tz, C]")
+            mode = "fused"
+        elif logp.shape[0] != plan.total_frames or logp.shape[1] != plan.C:
             raise ValueError(f"logp shape {tuple(logp.shape)} != ({plan.total_frames}, {plan.C})")
         is64 = logp.dtype == torch.float64
         if seg0_f32 is None:
@@ -371,9 +381,14 @@ class ViterbiEngine:
             b.n_cta, b.wpc, b.warp_unit = 0, 4, None
             b.U, b.lanes, b.max_N, b.max_K = plan.U, 0, plan.max_N, plan.max_K
             n_long = plan.n_long if (plan.max_N <= 15 and plan.U >= 64) else 0
-            rc = lib.mucon_viterbi_align_fused_tail(
-                C.byref(b), _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["order_u"]), C.c_int(n_long),
-                C.c_int(int(bool(write_bs))), sp)
+            if z_off is not None:
+                rc = lib.mucon_viterbi_align_fused_pooled(
+                    C.byref(b), _lib.ptr(logp), C.c_int(int(is64)), _lib.ptr(z_off), C.c_void_p(p["order_u"]),
+                    C.c_int(n_long), C.c_int(int(bool(write_bs))), sp)
+            else:
+                rc = lib.mucon_viterbi_align_fused_tail(
+                    C.byref(b), _lib.ptr(logp), C.c_int(int(is64)), C.c_void_p(p["order_u"]), C.c_int(n_long),
+                    C.c_int(int(bool(write_bs))), sp)
             if rc == 0:
                 self.launches += 2 if n_long else 1
                 self.last_mode = "fused"
@@ -382,6 +397,8 @@ class ViterbiEngine:
                 return self._finish(plan, sp)
             if rc != -2 or mode == "fused":
                 _lib.check(rc, "mucon_viterbi_align_fused")
+            if z_off is not None:
+                raise _lib.MuconError("shape not covered by the fused kernel: expand the log-probabilities instead")
         overlap = len(plan.groups) > 1
         if overlap:
             side = self._side_stream()

@@ -121,3 +121,42 @@ def test_bf16_backbone_ragged_batch_matches_single_videos(cuda_device, precision
     for v, t in enumerate(Ts):
         zv = m.encode_packed(feats[v], m.plan([t]), precision=precision)
         assert torch.equal(z[zo[v]:zo[v + 1]], zv), (v, t, (z[zo[v]:zo[v + 1]] - zv).abs().max().item())
+
+
+def test_full_inference_pooled_equals_expanded(cuda_device):
+    """Backbone -> alignment, two ways: (a) classifier + log-softmax expanded to [sum T, C] and aligned from that
+    array (the drop-in's materialising path), (b) log-softmax at the pooled resolution and the fused alignment kernel
+    reading that table through the nearest-neighbour index.  Scores, segments and labels must be bit-identical."""
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.temporal import MuConBackbone
+    from mucon_b200.viterbi import AlignPlan, ViterbiEngine
+    from tests import synth
+    torch.manual_seed(1)
+    rng = np.random.default_rng(1)
+    net = MuConBackbone(input_feature_size=64, num_classes=48).eval().to(cuda_device)
+    Ts = [int(t) for t in rng.integers(300, 3000, 24)] + [16 * 30 + 7, 30, 31]
+    trs, means = [], []
+    for t in Ts:
+        K = t // 30
+        n = int(rng.integers(max(1, -(-K // 66)), min(12, K) + 1))
+        tr = rng.integers(0, 48, n).tolist()
+        trs.append(tr)
+        means.append(synth.class_means(rng.dirichlet(np.ones(n)).astype(np.float32), tr, 48, t))
+    feats = torch.randn(sum(Ts), 64, device=cuda_device).abs()
+    bplan = net.plan(Ts)
+    z = net.encode_packed(feats, bplan)
+    eng = ViterbiEngine(cuda_device)
+    params = np.stack([poisson_params(m) for m in means])
+    res = []
+    for pooled in (False, True):
+        plan = AlignPlan(Ts, [[tr] for tr in trs], 48, device=cuda_device, labels="best", len_params=params)
+        if pooled:
+            lsm, zoff = net.logprobs_pooled_packed(z, bplan)
+            eng.run(plan, lsm, seg0_f32=True, z_off=zoff)
+        else:
+            eng.run(plan, net.logprobs_packed(z, bplan), seg0_f32=True, mode="fused")
+        torch.cuda.synchronize()
+        res.append(eng.fetch(plan))
+    for k in ("score", "status", "seg_blocks", "labels", "final_j"):
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert (res[0]["status"] == 0).all()

@@ -367,3 +367,49 @@ def test_empty_batch_and_single_frame_blocks(eng):
         for u in range(4):
             ref = oracle_unit(logps[u], cands[u][0], means[u], 30, 2000, True)
             check_unit(plan, out, u, ref, logps[u].shape[0])
+
+
+@pytest.mark.parametrize("dtype,C", [(np.float32, 48), (np.float64, 48), (np.float32, 20), (np.float32, 100)])
+def test_pooled_source_is_bit_identical_to_expanded(eng, dtype, C):
+    """mucon_viterbi_align_fused_pooled: the scan reads the [Tz, C] table at the backbone's pooled resolution through
+    the nearest-neighbour index of F.interpolate instead of the expanded [T, C] array.  Block scores, scores,
+    back-pointers and labels must equal, bit for bit, the run on the expanded array (and the oracle on it)."""
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan
+    rng = np.random.default_rng(7)
+    tabs, logps, cands, means, Tzs = [], [], [], [], []
+    for i in range(40):
+        N = int(rng.integers(1, 13))
+        K = int(rng.integers(max(N, 1), min(N * 66, 340) + 1))
+        T = K * 30 + int(rng.integers(0, 30))
+        Tz = max(1, T // 16) if i % 4 else max(1, int(rng.integers(1, T + 1)))   # also odd ratios, incl. Tz == T
+        tr = rng.integers(0, C, N).tolist()
+        lp, _ = synth.planted_logp(rng, Tz, C, tr, dtype)
+        idx = np.minimum(np.floor(np.arange(T, dtype=np.float32) * (np.float32(Tz) / np.float32(T))).astype(np.int64),
+                         Tz - 1)
+        tabs.append(lp)
+        logps.append(np.ascontiguousarray(lp[idx]))
+        Tzs.append(Tz)
+        cands.append([tr])
+        means.append(synth.class_means(rng.dirichlet(np.ones(N)).astype(np.float32), tr, C, T))
+    seg0 = dtype == np.float32
+    params = np.stack([poisson_params(m) for m in means])
+    T_all = [l.shape[0] for l in logps]
+    outs = []
+    for pooled in (False, True):
+        plan = AlignPlan(T_all, cands, C, device=eng.device, labels="all", len_params=params)
+        if pooled:
+            src = torch.from_numpy(np.concatenate(tabs)).to(eng.device)
+            z_off = torch.from_numpy(np.concatenate([[0], np.cumsum(Tzs)]).astype(np.int64)).to(eng.device)
+            eng.run(plan, src, seg0_f32=seg0, z_off=z_off)
+        else:
+            eng.run(plan, torch.from_numpy(np.concatenate(logps)).to(eng.device), seg0_f32=seg0, mode="fused")
+        torch.cuda.synchronize()
+        assert eng.last_mode == "fused"
+        outs.append((plan, eng.fetch(plan, want_bp=True)))
+    (pa, a), (pb, b) = outs
+    for k in ("score", "final_j", "status", "seg_blocks", "labels", "bp", "bs"):
+        assert np.array_equal(a[k], b[k]), k
+    for u in range(0, pa.U, 5):
+        ref = oracle_unit(logps[u], cands[u][0], means[u], 30, 2000, seg0)
+        check_unit(pb, b, u, ref, logps[u].shape[0])
