@@ -321,7 +321,7 @@ def main_ours(args, rank, world, local_rank):
 
             def backbone_step():
                 # features -> pooled-resolution log-probabilities (the [T, C] expansion is never written)
-                return net.logprobs_pooled_packed(net.encode_packed(feats, bplan), bplan)
+                return net.infer_pooled_packed(feats, bplan)
 
             def full_step():
                 lsm, zoff = backbone_step()

@@ -310,6 +310,20 @@ int mucon_logsoftmax_expand(const float* logits, const int64_t* off_z, const int
 /* log_softmax over the C classes of every row (same arithmetic as mucon_logsoftmax_expand, no expansion):
  * the pooled-resolution table mucon_viterbi_align_fused_pooled reads. */
 int mucon_logsoftmax_rows(const float* logits, int64_t rows, int C, float* out, void* stream);
+/* Fused tail at the pooled resolution, 128 hidden channels, up to 64 classes: GroupNorm(groups) over each video
+ * (+ ReLU) (models.py:759-764), the 1x1 classifier (:276-278, :580; Wc_hc = weight permuted to [hidden][classes],
+ * fp32 FFMA) and log_softmax (:368):  x [rows, 128] -> lsm_out [rows, classes] (and z_out [rows, 128] = the
+ * normalised activations, or NULL).  tiles: the 16-byte {int64 row0; int32 t0; int32 T} records of
+ * mucon_conv_gemm_tf32 at this resolution, tile_vid[num_tiles] the video of each tile, stats_ws: 2 * V * groups
+ * floats of workspace.  Two launches (statistics, then everything else). */
+int mucon_tail_logprobs(const float* x, const int64_t* row_off, const void* tiles, const int32_t* tile_vid,
+                        int num_tiles, int V, int H, int groups, float eps, int relu, const float* gamma,
+                        const float* beta, const float* Wc_hc, const float* bc, int num_classes, float* stats_ws,
+                        float* z_out, float* lsm_out, void* stream);
+/* out[t,:] = table[min(floor(t*(float)Tz/T), Tz-1), :] per video: the nearest-neighbour expansion of
+ * F.interpolate (models.py:574-576) alone (the drop-in's materialising path). */
+int mucon_expand_rows(const float* table, const int64_t* off_z, const int64_t* off_t, int V, int max_T, int C,
+                      float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * vit_mof counters: nearest-neighbour resize of each video's predicted labels

@@ -555,6 +555,219 @@ extern "C" int mucon_groupnorm_relu(const float* in, float* out, const float* ga
   return MUCON_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused tail at the pooled resolution (reference src/mucon/models.py:759-768 GroupNorm + ReLU, :574-580 1x1
+// classifier -- applied before the nearest upsample, with which it commutes -- and :368 log_softmax):
+//   gn_stats_kernel      per video and group: mean and 1/sqrt(var + eps) over (T x C/groups) elements
+//   tail_cls_lsm_kernel  per 128-row tile: z = relu(gn(x)), logits = z . Wc^T + bc (fp32 FFMA, k ascending, bias
+//                        last: the order of conv1d_kernel), log-probabilities = logits - logsumexp
+// Replaces groupnorm_kernel + conv1d_kernel<1> + logsoftmax_rows_kernel (146 + 190 + 20 us on the c2 split).
+namespace mucon {
+namespace {
+
+constexpr int kTailH = 128;  // hidden channels
+
+__global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__ in, const int64_t* __restrict__ off,
+                                                       int groups, float eps, float* __restrict__ stats) {
+  __shared__ double s1[4][kTailH], s2[4][kTailH];
+  const int v = blockIdx.x;
+  const int64_t r0 = off[v];
+  const int T = static_cast<int>(off[v + 1] - r0);
+  const int c = threadIdx.x & (kTailH - 1), sl = threadIdx.x >> 7;
+  double a = 0.0, b = 0.0;
+  for (int t = sl; t < T; t += 4) {
+    const double x = in[(r0 + t) * kTailH + c];
+    a += x;
+    b += x * x;
+  }
+  s1[sl][c] = a;
+  s2[sl][c] = b;
+  __syncthreads();
+  const int cpg = kTailH / groups;
+  if (static_cast<int>(threadIdx.x) < groups) {
+    const int g = threadIdx.x;
+    double sa = 0.0, sb = 0.0;
+    for (int k = 0; k < cpg; ++k)
+      for (int q = 0; q < 4; ++q) { sa += s1[q][g * cpg + k]; sb += s2[q][g * cpg + k]; }
+    const double n = static_cast<double>(T) * cpg;
+    const double mean = n > 0 ? sa / n : 0.0;
+    double var = n > 0 ? sb / n - mean * mean : 0.0;
+    if (var < 0.0) var = 0.0;
+    stats[(static_cast<int64_t>(v) * groups + g) * 2 + 0] = static_cast<float>(mean);
+    stats[(static_cast<int64_t>(v) * groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+struct TailTile {  // the 16-byte tile record of convgemm::Tile plus the video index
+  long long row0;
+  int t0;
+  int T;
+};
+
+constexpr int kTailRows = 128;
+constexpr int kTailLd = kTailH + 1;
+template <int CG>  // classes per thread (8 threads share a row): covers num_classes <= 8 * CG
+__global__ void __launch_bounds__(128) tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                           const int32_t* __restrict__ tile_vid,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ Wc /*[H][NC]*/,
+                                                           const float* __restrict__ bc, const TailTile* __restrict__ tiles,
+                                                           int num_tiles, int groups, int relu, int NC,
+                                                           float* __restrict__ z_out, float* __restrict__ lsm_out) {
+  extern __shared__ float tsm[];
+  float* Xs = tsm;                               // [128 rows][129]
+  float* Ws = tsm + kTailRows * kTailLd;         // [128 k][8 * CG] zero padded
+  float* bs = Ws + kTailH * 8 * CG;              // [8 * CG]
+  constexpr int NCP = 8 * CG;
+  for (int i = threadIdx.x; i < kTailH * NCP; i += blockDim.x) {
+    const int k = i / NCP, n = i - k * NCP;
+    Ws[i] = n < NC ? Wc[k * NC + n] : 0.f;
+  }
+  for (int i = threadIdx.x; i < NCP; i += blockDim.x) bs[i] = i < NC ? bc[i] : 0.f;
+  const int cpg = kTailH / groups;
+  const int rg = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  for (int ti = blockIdx.x; ti < num_tiles; ti += gridDim.x) {
+    const TailTile tl = tiles[ti];
+    const int v = tile_vid[ti];
+    const int nrow = min(kTailRows, tl.T - tl.t0);
+    const int64_t rbase = tl.row0 + tl.t0;
+    __syncthreads();  // Xs of the previous tile is no longer read (and Ws / bs are written)
+    // GroupNorm + ReLU of the tile into shared memory (and to z_out)
+    for (int i = threadIdx.x; i < kTailRows * (kTailH / 4); i += blockDim.x) {
+      const int r = i >> 5, c4 = (i & 31) * 4;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrow) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + (rbase + r) * kTailH + c4);
+        const float xin[4] = {xv.x, xv.y, xv.z, xv.w};
+        float y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c4 + e;
+          const float* st = stats + (static_cast<int64_t>(v) * groups + c / cpg) * 2;
+          float t = (xin[e] - st[0]) * st[1] * __ldg(gamma + c) + __ldg(beta + c);
+          y[e] = relu ? fmaxf(t, 0.f) : t;
+        }
+        o = make_float4(y[0], y[1], y[2], y[3]);
+        if (z_out) *reinterpret_cast<float4*>(z_out + (rbase + r) * kTailH + c4) = o;
+      }
+      Xs[r * kTailLd + c4 + 0] = o.x;
+      Xs[r * kTailLd + c4 + 1] = o.y;
+      Xs[r * kTailLd + c4 + 2] = o.z;
+      Xs[r * kTailLd + c4 + 3] = o.w;
+    }
+    __syncthreads();
+    // classifier: thread (rg, cg) computes rows rg*8 .. +7 x classes cg*CG .. +CG-1
+    float acc[8][CG];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < CG; ++j) acc[i][j] = 0.f;
+    const float* xr = Xs + (rg * 8) * kTailLd;
+    const float* wr = Ws + cg * CG;
+#pragma unroll 4
+    for (int k = 0; k < kTailH; ++k) {
+      float xv[8], wv[CG];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = xr[i * kTailLd + k];
+#pragma unroll
+      for (int j = 0; j < CG; ++j) wv[j] = wr[k * NCP + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < CG; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+    }
+    // + bias, log-softmax over the row's classes (8 lanes x CG classes)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < CG; ++j) {
+        acc[i][j] += bs[cg * CG + j];
+        if (cg * CG + j < NC) m = fmaxf(m, acc[i][j]);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sden = 0.f;
+#pragma unroll
+      for (int j = 0; j < CG; ++j)
+        if (cg * CG + j < NC) sden += expf(acc[i][j] - m);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) sden += __shfl_xor_sync(0xffffffffu, sden, o);
+      const float lse = m + logf(sden);
+      const int r = rg * 8 + i;
+      if (r < nrow) {
+#pragma unroll
+        for (int j = 0; j < CG; ++j)
+          if (cg * CG + j < NC) lsm_out[(rbase + r) * NC + cg * CG + j] = acc[i][j] - lse;
+      }
+    }
+  }
+}
+
+// out[t, :] = table[min(floor(t * (float)Tz / T), Tz - 1), :]: the nearest-neighbour expansion alone
+__global__ void __launch_bounds__(256) expand_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ off_z,
+                                                          const int64_t* __restrict__ off_t, int C, float* __restrict__ out) {
+  const int v = blockIdx.y;
+  const int64_t z0 = off_z[v], t0v = off_t[v];
+  const int Tz = static_cast<int>(off_z[v + 1] - z0);
+  const int T = static_cast<int>(off_t[v + 1] - t0v);
+  const float scale = static_cast<float>(Tz) / static_cast<float>(T);
+  const int64_t n = static_cast<int64_t>(T) * C;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<int64_t>(t) * C);
+    int iz = static_cast<int>(floorf(static_cast<float>(t) * scale));
+    iz = iz > Tz - 1 ? Tz - 1 : iz;
+    out[t0v * C + i] = table[(z0 + iz) * C + c];
+  }
+}
+
+}  // namespace
+}  // namespace mucon
+
+extern "C" int mucon_tail_logprobs(const float* x, const int64_t* row_off, const void* tiles, const int32_t* tile_vid,
+                                   int num_tiles, int V, int H, int groups, float eps, int relu, const float* gamma,
+                                   const float* beta, const float* Wc_hc, const float* bc, int num_classes,
+                                   float* stats_ws, float* z_out, float* lsm_out, void* stream) {
+  if (!x || !row_off || !tiles || !tile_vid || !gamma || !beta || !Wc_hc || !bc || !stats_ws || !lsm_out || V < 0 ||
+      num_tiles < 0 || groups < 1 || num_classes < 1)
+    return MUCON_EINVAL;
+  if (H != kTailH || kTailH % groups != 0 || num_classes > 64) return MUCON_EUNSUPPORTED;
+  if (V == 0 || num_tiles == 0) return MUCON_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gn_stats_kernel<<<V, 512, 0, st>>>(x, row_off, groups, eps, stats_ws);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  const int CG = num_classes <= 24 ? 3 : (num_classes <= 48 ? 6 : 8);
+  const size_t smem = sizeof(float) * (kTailRows * kTailLd + kTailH * 8 * CG + 8 * CG);
+  const int sms = mucon_device_sm_count();
+  int grid = 2 * sms;
+  if (grid > num_tiles) grid = num_tiles;
+  const TailTile* tl = static_cast<const TailTile*>(tiles);
+#define MUCON_TAIL(cg)                                                                                           \
+  do {                                                                                                           \
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(tail_cls_lsm_kernel<cg>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          static_cast<int>(smem)));                                              \
+    tail_cls_lsm_kernel<cg><<<grid, 128, smem, st>>>(x, stats_ws, tile_vid, gamma, beta, Wc_hc, bc, tl, num_tiles, \
+                                                     groups, relu, num_classes, z_out, lsm_out);                 \
+  } while (0)
+  if (CG == 3) MUCON_TAIL(3); else if (CG == 6) MUCON_TAIL(6); else MUCON_TAIL(8);
+#undef MUCON_TAIL
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_expand_rows(const float* table, const int64_t* off_z, const int64_t* off_t, int V, int max_T, int C,
+                                 float* out, void* stream) {
+  if (!table || !off_z || !off_t || !out || V < 0 || C < 1 || max_T < 0) return MUCON_EINVAL;
+  if (V == 0 || max_T == 0) return MUCON_OK;
+  if (V > 65535) return MUCON_EUNSUPPORTED;
+  int bx = static_cast<int>((static_cast<int64_t>(max_T) * C + 255) / 256);
+  if (bx > 64) bx = 64;
+  expand_rows_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, off_z, off_t, C, out);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 // log_softmax of every row, one warp per row: the same operations in the same order as the rows
 // logsoftmax_expand_kernel prepares in shared memory (max, sum of expf, m + logf(s), x - lse)
 __global__ void __launch_bounds__(256) logsoftmax_rows_kernel(const float* __restrict__ logits, int64_t rows, int C,

@@ -41,7 +41,7 @@ class BackbonePlan:
         self.off = [flat[i * n:(i + 1) * n] for i in range(len(offs))]
         # 128-row tiles of every video at every level, for the tcgen05 conv kernel:
         # {int64 row0, int32 t0, int32 T} per tile, longest videos first
-        self.tiles, self.n_tiles = [], []
+        self.tiles, self.n_tiles, self.tile_vid = [], [], []
         for lvl, t in enumerate(self.T):
             nt = (t + 127) // 128
             vid = np.repeat(np.arange(self.V), nt)
@@ -50,6 +50,8 @@ class BackbonePlan:
             rec = np.zeros(int(nt.sum()), dtype=[("row0", "<i8"), ("t0", "<i4"), ("T", "<i4")])
             rec["row0"], rec["t0"], rec["T"] = offs[lvl][:-1][vid], t0, t[vid]
             self.n_tiles.append(int(rec.shape[0]))
+            self.tile_vid.append(torch.from_numpy(vid.astype(np.int32)).to(self.device) if rec.shape[0]
+                                 else torch.zeros(1, dtype=torch.int32, device=self.device))
             self.tiles.append(torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(self.device)
                               if rec.shape[0] else torch.zeros(16, dtype=torch.uint8, device=self.device))
         # tiles of the fused layer kernel: {int64 row0, int64 row0_out, int32 t0, int32 T}, for a layer
@@ -516,11 +518,42 @@ class MuConBackbone(nn.Module):
         return z
 
     def logprobs_packed(self, z, plan):
-        """frame_classifier_forward + predict's log_softmax: [sum Tz, hidden] -> [sum T, classes]."""
+        """frame_classifier_forward + predict's log_softmax: [sum Tz, hidden] -> [sum T, classes]: the pooled-resolution
+        table of logprobs_pooled_packed expanded with the nearest-neighbour index of F.interpolate."""
         lvl = len(plan.off) - 1
-        w = self.conv_classifier.weight.detach().permute(2, 1, 0).contiguous().float()
-        logits = conv1d_rows(z, w, self.conv_classifier.bias.detach().float(), plan.off[lvl], plan.V, plan.max_T[lvl])
-        return logsoftmax_expand_rows(logits, plan, lvl)
+        table, _ = self.logprobs_pooled_packed(z, plan)
+        out = torch.empty((plan.rows[0], table.shape[1]), dtype=torch.float32, device=table.device)
+        _lib.check(_lib.lib().mucon_expand_rows(
+            _lib.ptr(table), _lib.ptr(plan.off[lvl]), _lib.ptr(plan.off[0]), C.c_int(plan.V), C.c_int(plan.max_T[0]),
+            C.c_int(table.shape[1]), _lib.ptr(out), _stream(table.device)), "mucon_expand_rows")
+        return out
+
+    def infer_pooled_packed(self, feats, plan, precision=None, want_z=False):
+        """Features -> pooled-resolution log-probabilities in as few launches as the path has: ft (projection + one
+        launch per layer + last_conv), then GroupNorm statistics and ONE launch for GroupNorm + ReLU + classifier +
+        log_softmax (mucon_tail_logprobs).  Returns (table [sum Tz, classes], row offsets [V+1]) (+ z if want_z)."""
+        lvl = len(plan.off) - 1
+        if not (self.last_gn and self.hidden_size == 128 and self.num_classes <= 64):
+            z = self.encode_packed(feats, plan, precision=precision)
+            table, off = self.logprobs_pooled_packed(z, plan)
+            return (table, off, z) if want_z else (table, off)
+        kw = dict(precision=precision) if isinstance(self.ft, WaveNetBlock) else {}
+        x = self.ft.forward_packed(feats, plan, **kw)
+        key = (self.conv_classifier.weight._version, self.conv_classifier.bias._version, str(x.device))
+        if getattr(self, "_cls_cache", None) is None or self._cls_cache[0] != key:
+            self._cls_cache = (key, self.conv_classifier.weight.detach()[:, :, 0].t().contiguous().float(),
+                               self.conv_classifier.bias.detach().contiguous().float())
+        _, wc, bc = self._cls_cache
+        table = torch.empty((x.shape[0], self.num_classes), dtype=torch.float32, device=x.device)
+        z = torch.empty_like(x) if want_z else None
+        stats = torch.empty(2 * plan.V * self.ft_last_gn.num_groups, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().mucon_tail_logprobs(
+            _lib.ptr(x), _lib.ptr(plan.off[lvl]), _lib.ptr(plan.tiles[lvl]), _lib.ptr(plan.tile_vid[lvl]),
+            C.c_int(plan.n_tiles[lvl]), C.c_int(plan.V), C.c_int(self.hidden_size), C.c_int(self.ft_last_gn.num_groups),
+            C.c_float(self.ft_last_gn.eps), C.c_int(int(self.last_relu)), _lib.ptr(self.ft_last_gn.weight.detach()),
+            _lib.ptr(self.ft_last_gn.bias.detach()), _lib.ptr(wc), _lib.ptr(bc), C.c_int(self.num_classes),
+            _lib.ptr(stats), _lib.ptr(z), _lib.ptr(table), _stream(x.device)), "mucon_tail_logprobs")
+        return (table, plan.off[lvl], z) if want_z else (table, plan.off[lvl])
 
     def logprobs_pooled_packed(self, z, plan):
         """The same log-probabilities at the POOLED resolution, not expanded: [sum Tz, hidden] -> ([sum Tz, classes],

@@ -160,3 +160,25 @@ def test_full_inference_pooled_equals_expanded(cuda_device):
     for k in ("score", "status", "seg_blocks", "labels", "final_j"):
         assert np.array_equal(res[0][k], res[1][k]), k
     assert (res[0]["status"] == 0).all()
+
+
+@pytest.mark.parametrize("ncls", [20, 48, 64])
+def test_fused_tail_equals_separate_kernels(cuda_device, ncls):
+    """mucon_tail_logprobs (GroupNorm statistics + one launch for GroupNorm / ReLU / classifier / log_softmax) against
+    the separate GroupNorm, classifier and log-softmax kernels on a ragged batch."""
+    from mucon_b200.temporal import MuConBackbone
+    torch.manual_seed(2)
+    net = MuConBackbone(input_feature_size=64, num_classes=ncls).eval().to(cuda_device)
+    with torch.no_grad():
+        net.ft_last_gn.weight.uniform_(0.5, 1.5)
+        net.ft_last_gn.bias.uniform_(-0.5, 0.5)
+    Ts = [700, 333, 64, 1999, 16, 128, 129, 127, 4100, 257, 1024, 17, 2048, 300]
+    feats = torch.cat([torch.randn(t, 64).abs() for t in Ts]).to(cuda_device)
+    plan = net.plan(Ts)
+    table, off, z = net.infer_pooled_packed(feats, plan, want_z=True)
+    z2 = net.encode_packed(feats, plan)
+    table2, off2 = net.logprobs_pooled_packed(z2, plan)
+    assert torch.equal(off, off2)
+    assert torch.allclose(z, z2, rtol=1e-5, atol=1e-5), (z - z2).abs().max().item()
+    assert torch.allclose(table, table2, rtol=1e-5, atol=2e-5), (table - table2).abs().max().item()
+    assert torch.allclose(torch.logsumexp(table, 1), torch.zeros_like(table[:, 0]), atol=1e-5)
