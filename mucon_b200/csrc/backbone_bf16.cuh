@@ -20,8 +20,11 @@
 //   * accumulators are double-buffered in TMEM (2 x 128 + 2 x 128 columns); the MMA warp issues GEMM 1 of tile
 //     i+1 before GEMM 2 of tile i and the epilogue warps run epilogue 1 of tile i+1 before epilogue 2 of tile
 //     i, so the tensor pipe and the epilogue warps both stay busy.
-// Dilations above kMaxSlabDil use the same program with the three taps loaded as three separate 128-row
-// tiles into one (single) stage.
+// Dilations above kMaxSlabDil use the same program with each live tap as a separate 128-row tile in a ring of
+// three 32 KB slots: side-tap slots are released by the MMA warp's commit as soon as that tap's instructions have
+// retired, the centre tap (issued last) by the epilogue once the residual rows are in registers, so the loads of
+// the next tile overlap this tile's GEMMs (taps that only see padding -- dilation >= video length -- are never
+// loaded: layers 8-10 at Breakfast lengths are three-deep rings of centre tiles).
 // 384 threads: warp 0 TMA producer, warp 1 MMA + TMEM, warp 2 padding fix-up, warp 3 idle, warps 4-11 epilogue.
 #pragma once
 #include <cuda.h>
@@ -46,7 +49,9 @@ constexpr int BAR_BYTES = 256;
 // shared-memory plan of a launch (host and device agree through these)
 __host__ __device__ inline int stage_rows(int dil, int slab) { return slab ? BM + 2 * dil : 3 * BM; }
 __host__ __device__ inline int kb_bytes_of(int dil, int slab) { return ((stage_rows(dil, slab) + 7) & ~7) * 128; }
-__host__ __device__ inline int num_stages(int slab) { return slab ? 2 : 1; }
+__host__ __device__ inline int num_stages(int slab) { return slab ? 2 : 1; }  // x stage bytes = the ring's bytes
+constexpr int kRingSlots = 3;               // ring mode (separate taps): slots of one [128 x 128] tap tile (32 KB) each
+constexpr int kTapBytes = NKB * BM * 128;
 // rows of the (bf16) output tile that are staged in shared memory and leave through a TMA store; the rest of the
 // tile (and every tile that crosses the end of its video, and fp32 output) is stored straight from registers
 __host__ __device__ inline int staged_rows(int dil, int slab, int pool, int out_f32) {
@@ -196,7 +201,7 @@ struct EpiCtx {
   const CUtensorMap* tmO;
   void* out;
   uint32_t tmem_base;
-  int n_my, NS, LA, stage_bytes, kb_bytes, tap_rows, S, pool, relu_final, out_f32;
+  int n_my, nslot, LA, unit_bytes, kb_bytes, crow0, slab, dil, S, pool, relu_final, out_f32;
 };
 
 // The eight epilogue warps (H = which 64 accumulator columns / which k-block of the slab this warp owns).
@@ -208,18 +213,27 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
   const uint32_t lane_base = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   const bool leader = warp == 4 && lane == 0;
   bool store_pending = false;
+  int uslot = 0;  // ring slot of the next tile's first unit
   for (int i = 0; i < c.n_my + c.LA; ++i) {
     if (i < c.n_my) {
       // ---- epilogue 1 of tile i
-      const int s = i % c.NS, acc = i & 1;
+      const int acc = i & 1;
+      // the unit that holds the centre tap: the slab itself, or the last of the tile's live tap tiles
+      int upt = 1;
+      if (!c.slab) {
+        const int Tv = c.tiles[blockIdx.x + i * gridDim.x].T;
+        upt = 1 + (tap_live(-c.dil, Tv) ? 1 : 0) + (tap_live(c.dil, Tv) ? 1 : 0);
+      }
+      const int s = (uslot + upt - 1) % c.nslot;
+      uslot = (uslot + upt) % c.nslot;
       mbar_wait(&c.a1full[acc], (i >> 1) & 1);
       tc_fence_after();
       if (leader) MUCON_TR16(6, i);
       // (a) residual rows out of the slab's centre tap, + b1, as fp32 into accumulator 2 (this thread drained the
       // same lanes / columns of it two tiles ago: program order)
       {
-        const int cr = c.tap_rows + r;
-        const unsigned char* cp = c.stage_mem + s * c.stage_bytes + H * c.kb_bytes + cr * 128;
+        const int cr = c.crow0 + r;
+        const unsigned char* cp = c.stage_mem + s * c.unit_bytes + H * c.kb_bytes + cr * 128;
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t f[32];
@@ -376,32 +390,38 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   if ((smem_u32(base) & 1023u) != 0) __trap();
   // stage geometry: a stage holds NKB k-blocks of R rows x 128 bytes.  Slab mode: R = 128 + 2*dil rows starting at
   // time step t0 - dil, tap `tap` is the 128 rows from row tap*dil.  Otherwise three separate 128-row tap tiles.
-  const int R = stage_rows(dil, slab);
-  const int kb_bytes = kb_bytes_of(dil, slab);
-  const int stage_bytes = NKB * kb_bytes;
-  const int NS = num_stages(slab);         // stages
-  const int LA = NS - 1;                   // GEMM 1 / epilogue 1 run LA tiles ahead of GEMM 2 / epilogue 2
-  const int tap_rows = slab ? dil : BM;    // row offset of tap `tap` inside a k-block = tap * tap_rows
+  // Unit geometry.  Slab mode: a unit is a slab of NKB k-blocks of R = 128 + 2*dil rows x 128 bytes starting at time
+  // step t0 - dil (tap `tap` = the 128 rows from row tap*dil), one unit per tile, two slots.  Ring mode: a unit is
+  // one live tap's [128 rows] x NKB k-blocks tile, up to three units per tile (side taps first, the centre last),
+  // three slots.
+  const int R = slab ? BM + 2 * dil : BM;
+  const int kb_bytes = slab ? kb_bytes_of(dil, 1) : BM * 128;
+  const int unit_bytes = NKB * kb_bytes;
+  const int nslot = slab ? 2 : kRingSlots;
+  const int LA = 1;                        // GEMM 1 / epilogue 1 run one tile ahead of GEMM 2 / epilogue 2
   const int S = staged_rows(dil, slab, pool, out_f32);
   unsigned char* w_mem = base;                       // [8][WTILE]: (tap, kb) tiles of the dilated conv, then the 1x1's
-  unsigned char* stage_mem = base + W_BYTES;         // activation stages
-  unsigned char* staging = stage_mem + NS * stage_bytes;  // [2][S rows x 128 B] output tile, SWIZZLE_128B
+  unsigned char* stage_mem = base + W_BYTES;         // the unit ring
+  unsigned char* staging = stage_mem + num_stages(slab) * NKB * kb_bytes_of(dil, slab);  // [2][S rows x 128 B], SWIZZLE_128B
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + S * 256);
   uint64_t* wfull = bars;          // weights resident
-  uint64_t* fullS = bars + 1;      // [2] slab landed (TMA bytes)
-  uint64_t* readyS = bars + 3;     // [2] slab padded (fix-up warp)
-  uint64_t* emptyS = bars + 5;     // [2] slab no longer read (GEMM 1 retired and the residual rows are in registers)
-  uint64_t* a1full = bars + 7;     // [2] accumulator 1 complete
-  uint64_t* a1free = bars + 9;     // [2] GEMM 2 retired: accumulator 1 / Y may be overwritten
-  uint64_t* yready = bars + 11;    // [2] Y (bf16, over accumulator 1) and x + b1 (accumulator 2) stored
-  uint64_t* a2full = bars + 13;    // [2] accumulator 2 complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* fullS = bars + 1;      // [3] unit landed (TMA bytes)
+  uint64_t* readyS = bars + 4;     // [3] unit padded (fix-up warp)
+  uint64_t* emptyS = bars + 7;     // [3] unit released by the epilogue (GEMM 1 retired, residual rows in registers)
+  uint64_t* emptyM = bars + 10;    // [3] side-tap unit released by the MMA warp's commit
+  uint64_t* a1full = bars + 13;    // [2] accumulator 1 complete
+  uint64_t* a1free = bars + 15;    // [2] GEMM 2 retired: accumulator 1 / Y may be overwritten
+  uint64_t* yready = bars + 17;    // [2] Y (16-bit, over accumulator 1) and x + b1 (accumulator 2) stored
+  uint64_t* a2full = bars + 19;    // [2] accumulator 2 complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1);
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&fullS[s], 1); mbar_init(&readyS[s], 1); mbar_init(&emptyS[s], EPI_WARPS); mbar_init(&emptyM[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&fullS[s], 1); mbar_init(&readyS[s], 1); mbar_init(&emptyS[s], EPI_WARPS);
       mbar_init(&a1full[s], 1); mbar_init(&a1free[s], 1); mbar_init(&yready[s], EPI_WARPS); mbar_init(&a2full[s], 1);
     }
     mbar_fence_init();
@@ -418,11 +438,23 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   const int n_my = (static_cast<int>(blockIdx.x) < num_tiles)
                        ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                        : 0;
-  // does the tile need rows zeroed (Conv1d padding at the video's ends)?  Only then does the MMA warp wait for the
+  // The units of a tile, in the order they are loaded and consumed, packed two bits per unit (no local arrays in
+  // the single-thread roles): tap of unit k = (code >> 2k) & 3 (slab mode: one unit, tap code 3 = "the slab").
+  auto tile_units = [&](const Tile& tl, uint32_t& code) {
+    if (slab) { code = 3u; return 1; }
+    int n = 0;
+    code = 0u;
+    if (tap_live(-dil, tl.T)) { code |= 0u << (2 * n); ++n; }
+    if (tap_live(dil, tl.T)) { code |= 2u << (2 * n); ++n; }
+    code |= 1u << (2 * n);  // the centre tap is always live and comes last: its slot is the one the epilogue releases
+    return n + 1;
+  };
+  // does the unit need rows zeroed (Conv1d padding at the video's ends)?  Only then does the MMA warp wait for the
   // fix-up warp; otherwise it goes straight from the TMA's barrier
-  auto needs_fix = [&](const Tile& tl) {
-    if (slab) return dil - tl.t0 > 0 || tl.T - tl.t0 + dil < R;
-    return tl.t0 - dil < 0 || tl.t0 + BM + dil > tl.T;
+  auto needs_fix = [&](const Tile& tl, int tap) {
+    if (tap == 3) return dil - tl.t0 > 0 || tl.T - tl.t0 + dil < R;
+    const int start = tl.t0 + (tap - 1) * dil;
+    return start < 0 || start + BM > tl.T;
   };
 
   if (warp == 0) {
@@ -438,45 +470,50 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           for (int kb = 0; kb < NKB; ++kb) tma_load_2d(w_mem + (tap * NKB + kb) * WTILE, &tmWd, kb * 64, tap * C, wfull);
         for (int kb = 0; kb < NKB; ++kb) tma_load_2d(w_mem + (3 * NKB + kb) * WTILE, &tmW1, kb * 64, 0, wfull);
       }
+      int s = 0;
+      uint32_t used = 0, by_epi = 0, phE = 0, phM = 0;  // per slot: used before / last occupant's releaser / phases
       for (int i = 0; i < n_my; ++i) {
         const Tile tl = tiles[blockIdx.x + i * gridDim.x];
-        const int s = i % NS;
-        const uint32_t ph = (i / NS) & 1;
-        unsigned char* st = stage_mem + s * stage_bytes;
-        mbar_wait(&emptyS[s], ph ^ 1);
-        MUCON_TR16(0, i);
-        if (slab) {
-          mbar_arrive_expect_tx(&fullS[s], static_cast<uint32_t>(NKB * R * 128));
-          const int row = static_cast<int>(tl.row0) + tl.t0 - dil;  // may be negative: TMA zero-fills
-          for (int kb = 0; kb < NKB; ++kb) tma_load_2d(st + kb * kb_bytes, &tmX, kb * 64, row, &fullS[s]);
-        } else {
-          int live = 0;
-          for (int tap = 0; tap < 3; ++tap) live += tap_live((tap - 1) * dil, tl.T) ? 1 : 0;
-          mbar_arrive_expect_tx(&fullS[s], static_cast<uint32_t>(live * NKB * BM * 128));
-          for (int tap = 0; tap < 3; ++tap) {
-            const int shift = (tap - 1) * dil;
-            if (!tap_live(shift, tl.T)) continue;
-            const int row = static_cast<int>(tl.row0) + tl.t0 + shift;
-            for (int kb = 0; kb < NKB; ++kb)
-              tma_load_2d(st + kb * kb_bytes + tap * BM * 128, &tmX, kb * 64, row, &fullS[s]);
+        uint32_t code;
+        const int nu = tile_units(tl, code);
+        for (int k = 0; k < nu; ++k) {
+          const int tap = static_cast<int>((code >> (2 * k)) & 3u);
+          const uint32_t bit = 1u << s;
+          if (used & bit) {  // wait for whoever releases the slot's previous occupant
+            if (by_epi & bit) { mbar_wait(&emptyS[s], (phE >> s) & 1); phE ^= bit; }
+            else { mbar_wait(&emptyM[s], (phM >> s) & 1); phM ^= bit; }
           }
+          used |= bit;
+          const bool centre = k == nu - 1;
+          by_epi = centre ? (by_epi | bit) : (by_epi & ~bit);
+          unsigned char* st = stage_mem + s * unit_bytes;
+          if (k == 0) MUCON_TR16(0, i);
+          mbar_arrive_expect_tx(&fullS[s], static_cast<uint32_t>(NKB * R * 128));
+          const int row = static_cast<int>(tl.row0) + tl.t0 + (slab ? -dil : (tap - 1) * dil);  // may be negative: TMA zero-fills
+          for (int kb = 0; kb < NKB; ++kb) tma_load_2d(st + kb * kb_bytes, &tmX, kb * 64, row, &fullS[s]);
+          if (++s == nslot) s = 0;
         }
       }
     }
   } else if (warp == 2) {
     // ================================ fix-up warp =================================
     // rows that lie outside the video are Conv1d's zero padding (the TMA brought the neighbouring video's rows)
+    int s = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < n_my; ++i) {
       const Tile tl = tiles[blockIdx.x + i * gridDim.x];
-      const int s = i % NS;
-      const uint32_t ph = (i / NS) & 1;
-      unsigned char* st = stage_mem + s * stage_bytes;
-      mbar_wait(&fullS[s], ph);
-      if (lane == 0) MUCON_TR16(1, i);
-      if (needs_fix(tl)) {
-        if (slab) {
-          const int lo = dil - tl.t0;           // rows below lo are before the video
-          const int hi = tl.T - tl.t0 + dil;    // rows from hi on are after it
+      uint32_t code;
+      const int nu = tile_units(tl, code);
+      for (int k = 0; k < nu; ++k) {
+        const int tap = static_cast<int>((code >> (2 * k)) & 3u);
+        unsigned char* st = stage_mem + s * unit_bytes;
+        mbar_wait(&fullS[s], ph);
+        if (lane == 0 && k == 0) MUCON_TR16(1, i);
+        if (needs_fix(tl, tap)) {
+          // unit row r holds time step t0 + first + r
+          const int first = slab ? -dil : (tap - 1) * dil;
+          const int lo = -(tl.t0 + first);          // rows below lo are before the video
+          const int hi = tl.T - (tl.t0 + first);    // rows from hi on are after it
           for (int r = lane; r < R; r += 32) {
             if (r < lo || r >= hi) {
 #pragma unroll
@@ -487,62 +524,71 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
               }
             }
           }
-        } else {
-          for (int tap = 0; tap < 3; ++tap) {
-            const int shift = (tap - 1) * dil;
-            if (!tap_live(shift, tl.T)) continue;
-            const int lo = -(tl.t0 + shift);
-            const int hi = tl.T - (tl.t0 + shift);
-            if (lo <= 0 && hi >= BM) continue;
-            for (int r = lane; r < BM; r += 32) {
-              if (r < lo || r >= hi) {
-#pragma unroll
-                for (int kb = 0; kb < NKB; ++kb) {
-                  uint4* p = reinterpret_cast<uint4*>(st + kb * kb_bytes + (tap * BM + r) * 128);
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) p[c] = make_uint4(0u, 0u, 0u, 0u);
-                }
-              }
-            }
-          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&readyS[s]);
+        if (++s == nslot) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&readyS[s]);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     constexpr uint32_t idesc = instr_desc_bf16(BM, BN, F16);
     const uint32_t w_addr = smem_u32(w_mem);
+    const uint64_t b0 = smem_desc(w_addr);
     if (n_my > 0) mbar_wait(wfull, 0);
+    int us = 0;
+    uint32_t uph = 0;
     for (int i = 0; i < n_my + LA; ++i) {
       if (i < n_my) {
         // ---- GEMM 1 of tile i: dilated conv, 3 taps x 2 k-blocks x 4 instructions (M128 N128 K16)
         const Tile tl = tiles[blockIdx.x + i * gridDim.x];
-        const int s = i % NS, acc = i & 1;
+        const int acc = i & 1;
         if (lane == 0) MUCON_TR16(12, i);
-        mbar_wait(needs_fix(tl) ? &readyS[s] : &fullS[s], (i / NS) & 1);
         mbar_wait(&a1free[acc], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        if (lane == 0) MUCON_TR16(2, i);
-        if (lane == 0) {
-          const uint32_t st = smem_u32(stage_mem + s * stage_bytes);
-          const uint32_t d1 = tmem_base + acc * BN;
-          int issued = 0;
-          for (int tap = 0; tap < 3; ++tap) {
-            if (!tap_live((tap - 1) * dil, tl.T)) continue;
+        uint32_t code;
+        const int nu = tile_units(tl, code);
+        const uint32_t d1 = tmem_base + acc * BN;
+        uint32_t issued = 0;
+        for (int ku = 0; ku < nu; ++ku) {
+          const int utap = static_cast<int>((code >> (2 * ku)) & 3u);
+          mbar_wait(needs_fix(tl, utap) ? &readyS[us] : &fullS[us], uph);
+          tc_fence_after();
+          if (lane == 0 && ku == 0) MUCON_TR16(2, i);
+          if (lane == 0) {
+            // A descriptors: the constant fields plus the start address >> 4.  Slab mode: tap `tap` = rows tap*dil ..
+            // +127 of the slab: the SWIZZLE_128B descriptor's start address moved by whole 128-byte rows (the swizzle
+            // is a function of the absolute shared-memory address)
+            const uint64_t a0 = smem_desc(smem_u32(stage_mem + us * unit_bytes));
+            if (slab) {
 #pragma unroll
-            for (int kb = 0; kb < NKB; ++kb) {
-              // tap `tap` = rows tap*tap_rows .. +127 of the k-block: the SWIZZLE_128B descriptor's start address
-              // moved by whole 128-byte rows (the swizzle is a function of the absolute shared-memory address)
-              const uint64_t adesc = smem_desc(st + kb * kb_bytes + static_cast<uint32_t>(tap * tap_rows) * 128u);
-              const uint64_t bdesc = smem_desc(w_addr + (tap * NKB + kb) * WTILE);
+              for (int tap = 0; tap < 3; ++tap) {
+                if (!tap_live((tap - 1) * dil, tl.T)) continue;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma_bf16(d1, adesc + 2 * k, bdesc + 2 * k, idesc, (issued | k) != 0);
-              ++issued;
+                for (int kb = 0; kb < NKB; ++kb) {
+                  const uint64_t adesc = a0 + static_cast<uint32_t>((kb * kb_bytes + tap * dil * 128) >> 4);
+                  const uint64_t bdesc = b0 + static_cast<uint32_t>(((tap * NKB + kb) * WTILE) >> 4);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) mma_bf16(d1, adesc + 2 * k, bdesc + 2 * k, idesc, issued | k);
+                  issued = 1;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int kb = 0; kb < NKB; ++kb) {
+                const uint64_t adesc = a0 + static_cast<uint32_t>((kb * kb_bytes) >> 4);
+                const uint64_t bdesc = b0 + static_cast<uint32_t>(((utap * NKB + kb) * WTILE) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_bf16(d1, adesc + 2 * k, bdesc + 2 * k, idesc, issued | k);
+                issued = 1;
+              }
+              if (ku != nu - 1) mma_commit(&emptyM[us]);  // a side tap's tile is free as soon as these MMAs retire
             }
           }
+          __syncwarp();
+          if (++us == nslot) { us = 0; uph ^= 1; }
+        }
+        if (lane == 0) {
           mma_commit(&a1full[acc]);
           MUCON_TR16(3, i);
         }
@@ -562,7 +608,7 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           const uint32_t ya = tmem_base + acc * BN;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // 8 x K16: 8 columns of packed bf16 pairs each
-            const uint64_t bdesc = smem_desc(w_addr + (3 * NKB + (k >> 2)) * WTILE) + 2 * (k & 3);
+            const uint64_t bdesc = b0 + static_cast<uint32_t>(((3 * NKB + (k >> 2)) * WTILE) >> 4) + 2 * (k & 3);
             mma_bf16_ts(d2, ya + 8 * k, bdesc, idesc, 1u);
           }
           mma_commit(&a2full[acc]);
@@ -578,7 +624,8 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     c.tiles = tiles; c.stage_mem = stage_mem; c.staging = staging;
     c.emptyS = emptyS; c.a1full = a1full; c.yready = yready; c.a2full = a2full;
     c.tmO = &tmO; c.out = out; c.tmem_base = tmem_base;
-    c.n_my = n_my; c.NS = NS; c.LA = LA; c.stage_bytes = stage_bytes; c.kb_bytes = kb_bytes; c.tap_rows = tap_rows;
+    c.n_my = n_my; c.nslot = nslot; c.LA = LA; c.unit_bytes = unit_bytes; c.kb_bytes = kb_bytes; c.crow0 = slab ? dil : 0;
+    c.slab = slab; c.dil = dil;
     c.S = S; c.pool = pool; c.relu_final = relu_final; c.out_f32 = out_f32;
     if (warp < 8) epilogue_warps<0, F16>(c, bias);
     else epilogue_warps<1, F16>(c, bias);

@@ -518,15 +518,13 @@ class MuConBackbone(nn.Module):
         return z
 
     def logprobs_packed(self, z, plan):
-        """frame_classifier_forward + predict's log_softmax: [sum Tz, hidden] -> [sum T, classes]: the pooled-resolution
-        table of logprobs_pooled_packed expanded with the nearest-neighbour index of F.interpolate."""
+        """frame_classifier_forward + predict's log_softmax: [sum Tz, hidden] -> [sum T, classes].  The rows are those
+        of logprobs_pooled_packed (same kernel arithmetic), written for every frame through the nearest-neighbour
+        index of F.interpolate."""
         lvl = len(plan.off) - 1
-        table, _ = self.logprobs_pooled_packed(z, plan)
-        out = torch.empty((plan.rows[0], table.shape[1]), dtype=torch.float32, device=table.device)
-        _lib.check(_lib.lib().mucon_expand_rows(
-            _lib.ptr(table), _lib.ptr(plan.off[lvl]), _lib.ptr(plan.off[0]), C.c_int(plan.V), C.c_int(plan.max_T[0]),
-            C.c_int(table.shape[1]), _lib.ptr(out), _stream(table.device)), "mucon_expand_rows")
-        return out
+        w = self.conv_classifier.weight.detach().permute(2, 1, 0).contiguous().float()
+        logits = conv1d_rows(z, w, self.conv_classifier.bias.detach().float(), plan.off[lvl], plan.V, plan.max_T[lvl])
+        return logsoftmax_expand_rows(logits, plan, lvl)
 
     def infer_pooled_packed(self, feats, plan, precision=None, want_z=False):
         """Features -> pooled-resolution log-probabilities in as few launches as the path has: ft (projection + one

@@ -19,7 +19,8 @@ torch.manual_seed(0)
 m = temporal.MuConBackbone().eval().to(dev)
 T, trs, _ = bench.make_split(0)
 plan = m.plan(T)
-x = torch.randn(int(T.sum()), 128, device=dev).to(torch.bfloat16)
+LEVEL = int(os.environ.get("LEVEL", "0"))
+x = torch.randn(plan.rows[LEVEL], 128, device=dev).to(torch.bfloat16)
 w = m.ft._weights()
 lib = _lib.lib()
 if not hasattr(lib, "mucon_debug_layer_trace"):
@@ -28,11 +29,17 @@ POOL = os.environ.get("POOL", "0") == "1"
 for dil in [int(a) for a in sys.argv[1:]] or [1, 64]:
     wdk, w1k = w["layers_k16"][0]
     for _ in range(3):
-        temporal.wavenet_layer_bf16_rows(x, wdk, w["layers_bias_h"][0][0], w1k, w["layers_bias_h"][0][1], plan, 0, dil, POOL, False)
+        temporal.wavenet_layer_bf16_rows(x, wdk, w["layers_bias_h"][0][0], w1k, w["layers_bias_h"][0][1], plan, LEVEL, dil, POOL, False)
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    temporal.wavenet_layer_bf16_rows(x, wdk, w["layers_bias_h"][0][0], w1k, w["layers_bias_h"][0][1], plan, LEVEL, dil, POOL, False)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"launch: {e0.elapsed_time(e1) * 1e3:.1f} us, {plan.ltiles[(LEVEL, 'same')][1]} tiles")
     buf = np.zeros((32, 128), dtype=np.int64)
     assert lib.mucon_debug_layer_trace(buf.ctypes.data_as(C.c_void_p)) == 0
-    lo, hi = 10, 100
+    lo, hi = (10, 100) if LEVEL == 0 else (3, 22)
     d = lambda a, b, sa=0, sb=0: float(np.median(buf[a, lo + sa:hi + sa] - buf[b, lo + sb:hi + sb]))
     print(f"--- dil {dil}: cycles, medians over tiles {lo}..{hi - 1} of CTA 0")
     print("tile period (epilogue 2 done)        ", float(np.median(np.diff(buf[9, lo:hi]))))
@@ -60,6 +67,7 @@ for dil in [int(a) for a in sys.argv[1:]] or [1, 64]:
     print("GEMM 2 issued -> epilogue 2 starts   ", d(8, 5))
     print("epilogue 2                           ", d(9, 8))
     print("GEMM 2 issued(i) -> stage free(i+2)  ", d(0, 5, 2, 0))
+    print("CTA 0 span: first slab request -> last epilogue 2:", int(buf[9].max() - buf[0, 0]), "cycles")
     print("first tiles, relative to producer tile 0:")
     for ev in (0, 1, 12, 2, 3, 6, 7, 13, 4, 5, 8, 9):
         print(f"  ev{ev:2d}", (buf[ev, :6] - buf[0, 0]).tolist())
