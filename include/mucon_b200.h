@@ -335,6 +335,19 @@ int mucon_vit_mof(const int32_t* pred, const int64_t* pred_off, const int32_t* g
                   int V, int max_T_gt, const int32_t* ignore_ids_h, int n_ignore,
                   unsigned long long* counts, void* stream);
 
+/* Segment-level metrics of the Viterbi head, one CTA per video: the predicted labels are
+ * resized to the ground truth's length (src/core/utils.py:34-47), both vectors are cut into maximal runs whose
+ * label is not in ignore_ids, then IoD / IoU (src/core/metrics/isba_code.py:22-109), the normalised edit score and
+ * the F1 matching counts at overlaps 0.1 / 0.25 / 0.5 (mstcn_code.py:27-81) as consumed at
+ * src/mucon/evaluators.py:230-243.  out[v][12] = {iod, iou, edit, tp, fp, fn, tp, fp, fn, tp, fp, fn} (doubles;
+ * iod / iou / edit are NaN where the reference divides by zero).  ws: 8-byte aligned workspace of
+ * mucon_vit_segment_metrics_ws_words(sum of ground-truth frames, V) int32 words.  Only 96 bytes per video leave
+ * the GPU. */
+int mucon_vit_segment_metrics(const int32_t* pred, const int64_t* pred_off, const int32_t* gt, const int64_t* gt_off,
+                              int V, const int32_t* ignore_ids_h, int n_ignore, int32_t* ws, double* out,
+                              void* stream);
+int64_t mucon_vit_segment_metrics_ws_words(int64_t total_gt_frames, int V);
+
 #ifdef __cplusplus
 }
 #endif

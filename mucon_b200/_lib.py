@@ -18,7 +18,7 @@ SYMBOLS = [
     "mucon_poisson_params_h", "mucon_logfact_h",
     "mucon_masks_fwd", "mucon_masks_bwd", "mucon_flint_fwd", "mucon_flint_bwd", "mucon_mask_template_h",
     "mucon_gemm_tf32_bias_act", "mucon_gemm_tf32_bias_act_bf16", "mucon_wavenet_layer_bf16", "mucon_conv_gemm_tf32", "mucon_conv_gemm_tf32_shifts", "mucon_wavenet_layer_tf32", "mucon_wavenet_layer_tf32_pair", "mucon_conv1d", "mucon_maxpool2", "mucon_groupnorm_relu", "mucon_logsoftmax_expand", "mucon_logsoftmax_rows", "mucon_tail_logprobs", "mucon_expand_rows",
-    "mucon_vit_mof",
+    "mucon_vit_mof", "mucon_vit_segment_metrics", "mucon_vit_segment_metrics_ws_words",
 ]
 
 
@@ -57,7 +57,7 @@ def lib():
         for name in SYMBOLS:
             if name in ("mucon_strerror", "mucon_last_cuda_error"):
                 continue
-            getattr(l, name).restype = C.c_int
+            getattr(l, name).restype = C.c_int64 if name.endswith("_ws_words") else C.c_int
         _lib = l
     return _lib
 

@@ -33,3 +33,42 @@ def mof(counts):
     """MoFAccuracyMetric.summary(): sum(correct) / sum(total), 0.0 when nothing was counted."""
     c = counts.sum(0)
     return float(c[0]) / float(c[1]) if int(c[1]) else 0.0
+
+
+def segment_metrics(pred, pred_off, gt, gt_off, ignore_ids=()):
+    """IoD / IoU / Edit / F1-matching counts of every video on the device (isba_code.py:22-109, mstcn_code.py:27-81
+    after make_same_size_interpolate; evaluators.py:225-243).  Same arguments as mof_counts.  Returns a float64 CUDA
+    tensor [V, 12]: iod, iou, edit, then (tp, fp, fn) at overlaps 0.1, 0.25, 0.5."""
+    if not pred.is_cuda or not gt.is_cuda:
+        raise _lib.MuconError("segment_metrics needs CUDA tensors (there is no CPU fallback)")
+    po_h = np.asarray(pred_off, dtype=np.int64)
+    go_h = np.asarray(gt_off, dtype=np.int64)
+    V = int(po_h.shape[0]) - 1
+    dev = pred.device
+    po, go = torch.from_numpy(po_h).to(dev), torch.from_numpy(go_h).to(dev)
+    lib = _lib.lib()
+    words = int(lib.mucon_vit_segment_metrics_ws_words(C.c_int64(int(go_h[-1])), C.c_int(V)))
+    ws = torch.empty((words + 1) // 2, dtype=torch.int64, device=dev)  # 8-byte aligned
+    out = torch.empty((V, 12), dtype=torch.float64, device=dev)
+    ign = np.asarray(list(ignore_ids), dtype=np.int32)
+    _lib.check(lib.mucon_vit_segment_metrics(
+        _lib.ptr(pred), _lib.ptr(po), _lib.ptr(gt), _lib.ptr(go), C.c_int(V),
+        ign.ctypes.data_as(C.c_void_p) if ign.size else None, C.c_int(int(ign.size)), _lib.ptr(ws), _lib.ptr(out),
+        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "mucon_vit_segment_metrics")
+    return out
+
+
+def summarize(seg):
+    """The evaluator's summaries of a [V, 12] segment_metrics tensor: IoDMetric / IoUMetric / Edit .summary() are means
+    over videos (segmentation.py:78-82, fully_supervised.py:29-33), F1Score.summary() pools the counts
+    (fully_supervised.py:64-88)."""
+    s = seg.detach().cpu().numpy()
+    if s.shape[0] == 0:
+        return {"iod": 0.0, "iou": 0.0, "edit": 0.0, "f1": [0.0, 0.0, 0.0]}
+    f1 = []
+    for k in range(3):
+        tp, fp, fn = (float(s[:, 3 + 3 * k + i].sum()) for i in range(3))
+        prec, rec = (tp / (tp + fp), tp / (tp + fn)) if tp + fp != 0.0 else (0.0, 0.0)
+        f1.append(2.0 * prec * rec / (prec + rec) * 100 if prec + rec != 0.0 else 0.0)
+    return {"iod": float(sum(s[:, 0].tolist()) / s.shape[0]), "iou": float(sum(s[:, 1].tolist()) / s.shape[0]),
+            "edit": float(np.array(s[:, 2]).mean()), "f1": f1}
