@@ -261,6 +261,29 @@ int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const 
 int mucon_conv_gemm_tf32_shifts(const float* in, float* out, const float* W_kco, const float* bias,
                                 const float* residual, const void* tiles, int num_tiles, int64_t rows,
                                 const int32_t* shifts_h, int n_shifts, int relu_mid, int relu_final, void* stream);
+/* conv_gemm with the full epilogue (training step):
+ *   out = gate( relu_final( relu_mid( sum_i in[t + shifts_h[i], :] . W[i]^T (+ bias) ) (* mul) (+ residual) ) )
+ * bias, residual, mul, gate may be NULL.  mul [rows,128]: the dropout mask/scale of WaveNetLayer.drop
+ * (temporal.py:51); gate [rows,128]: out is zeroed where gate <= 0 (the ReLU derivative of the backward pass).
+ * The data gradient of a convolution is this call with the taps' [Cout][Cin] slices transposed and the shifts negated. */
+int mucon_conv_gemm_tf32_ex(const float* in, float* out, const float* W_kco, const float* bias, const float* residual,
+                            const float* mul, const float* gate, const void* tiles, int num_tiles, int64_t rows,
+                            const int32_t* shifts_h, int n_shifts, int relu_mid, int relu_final, void* stream);
+/* Weight and bias gradients of a 128-output-channel convolution over time-major rows on tcgen05 (TF32 operands read
+ * MN-major from the activations as they lie in memory, fp32 accumulation in TMEM), what autograd computes for
+ * temporal.py:43-53,133,145 under trainers.py:125-131:
+ *   dW[out_off_h[j] + co*ldo + ci] += sum_t dY[t, co] * X[t + shifts_h[j], xcol_h[j] + ci]   (both frames in the video)
+ *   dbias[co] += sum_t dY[t, co]                                                              (dbias may be NULL)
+ * dY [rows,128], X [rows,ldx] (ldx a multiple of 32, >= 128), n_jobs <= 16 (three taps of a dilated conv, one tap of a
+ * 1x1 conv, or the sixteen 128-column blocks of the 2048-d features for first_conv).  dW / dbias are ACCUMULATED
+ * (red.global.add): zero them first.  tiles: as mucon_conv_gemm_tf32.  With dbias one of the first four jobs must
+ * have shift 0. */
+int mucon_wgrad_tf32(const float* dY, const float* X, int ldx, const void* tiles, int num_tiles, int64_t rows,
+                     const int32_t* shifts_h, const int32_t* xcol_h, const int64_t* out_off_h, int n_jobs, int ldo,
+                     float* dW, float* dbias, void* stream);
+/* max_pool1d(2) backward (temporal.py:137-139): dx[2t or 2t+1] = dy[t] at the first maximum, 0 elsewhere. */
+int mucon_maxpool2_bwd(const float* x, const float* dy, const int64_t* off_in, const int64_t* off_out, int V,
+                       int max_T_out, int C, float* dx, void* stream);
 /* One whole WaveNet layer (temporal.py:43-53) + optional max_pool1d(2) (temporal.py:137-139) in one
  * launch, 128 channels, tcgen05 TF32:  out = [pool]( relu_final( conv1x1(relu(conv_k3_dil(x) + bd)) + b1 + x ) ).
  * The intermediate activation stays in shared memory as the second GEMM's operand.  Wd_kco

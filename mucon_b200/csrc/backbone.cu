@@ -17,6 +17,7 @@
 
 #include "backbone_gemm.cuh"
 #include "backbone_bf16.cuh"
+#include "backbone_train.cuh"
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -43,7 +44,8 @@ EncodeTiledFn get_encode() {
 }
 
 // [rows, cols] fp32 row-major, box [box_rows, 32 cols] with 128-byte swizzle
-int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MUCON_ECUDA;
   cuuint64_t dims[2] = {cols, rows};
@@ -51,7 +53,7 @@ int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, 
   cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MUCON_OK : MUCON_ECUDA;
 }
@@ -338,10 +340,12 @@ static int launch_proj(const float* A, int64_t M, int K, const float* W, int N, 
 
 static int launch_conv_gemm(const float* in, float* out, const float* W_kco, const float* bias, const float* residual,
                             const void* tiles, int num_tiles, int64_t rows, const convgemm::TapShifts& ts,
-                            int relu_mid, int relu_final, void* stream) {
-  if (!in || !out || !W_kco || !bias || !tiles || num_tiles < 0 || rows < 0) return MUCON_EINVAL;
+                            int relu_mid, int relu_final, void* stream, const float* mul = nullptr,
+                            const float* gate = nullptr, bool bias_optional = false) {
+  if (!in || !out || !W_kco || (!bias && !bias_optional) || !tiles || num_tiles < 0 || rows < 0) return MUCON_EINVAL;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(W_kco) & 15) ||
-      (reinterpret_cast<uintptr_t>(out) & 15) || (residual && (reinterpret_cast<uintptr_t>(residual) & 15)))
+      (reinterpret_cast<uintptr_t>(out) & 15) || (residual && (reinterpret_cast<uintptr_t>(residual) & 15)) ||
+      (mul && (reinterpret_cast<uintptr_t>(mul) & 15)) || (gate && (reinterpret_cast<uintptr_t>(gate) & 15)))
     return MUCON_EALIGN;
   if (num_tiles == 0 || rows == 0) return MUCON_OK;
   if (rows > 0x7fffffff - 4096) return MUCON_EUNSUPPORTED;
@@ -356,7 +360,8 @@ static int launch_conv_gemm(const float* in, float* out, const float* W_kco, con
   MUCON_CUDA_CHECK(cudaFuncSetAttribute(convgemm::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         convgemm::CSMEM_BYTES));
   convgemm::conv_gemm_kernel<<<grid, convgemm::CTHREADS, convgemm::CSMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      tx, tw, static_cast<const convgemm::Tile*>(tiles), num_tiles, ts, bias, residual, out, relu_mid, relu_final);
+      tx, tw, static_cast<const convgemm::Tile*>(tiles), num_tiles, ts, bias, residual, out, relu_mid, relu_final, mul,
+      gate);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
@@ -387,6 +392,86 @@ extern "C" int mucon_conv_gemm_tf32_shifts(const float* in, float* out, const fl
   }
   if (!has_zero) return MUCON_EINVAL;  // the kernel relies on one tap that is live for every tile
   return launch_conv_gemm(in, out, W_kco, bias, residual, tiles, num_tiles, rows, ts, relu_mid, relu_final, stream);
+}
+
+extern "C" int mucon_conv_gemm_tf32_ex(const float* in, float* out, const float* W_kco, const float* bias,
+                                       const float* residual, const float* mul, const float* gate, const void* tiles,
+                                       int num_tiles, int64_t rows, const int32_t* shifts_h, int n_shifts, int relu_mid,
+                                       int relu_final, void* stream) {
+  if (!shifts_h || n_shifts < 1) return MUCON_EINVAL;
+  if (n_shifts > convgemm::kMaxTaps) return MUCON_EUNSUPPORTED;
+  convgemm::TapShifts ts{};
+  ts.n = n_shifts;
+  bool has_zero = false;
+  for (int t = 0; t < n_shifts; ++t) {
+    ts.s[t] = shifts_h[t];
+    has_zero |= shifts_h[t] == 0;
+  }
+  if (!has_zero) return MUCON_EINVAL;
+  return launch_conv_gemm(in, out, W_kco, bias, residual, tiles, num_tiles, rows, ts, relu_mid, relu_final, stream, mul,
+                          gate, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// training step: weight / bias gradients (backbone_train.cuh) and the max-pool backward
+extern "C" int mucon_wgrad_tf32(const float* dY, const float* X, int ldx, const void* tiles, int num_tiles, int64_t rows,
+                                const int32_t* shifts_h, const int32_t* xcol_h, const int64_t* out_off_h, int n_jobs,
+                                int ldo, float* dW, float* dbias, void* stream) {
+  if (!dY || !X || !tiles || !shifts_h || !xcol_h || !out_off_h || !dW || num_tiles < 0 || rows < 0 || n_jobs < 1 ||
+      ldx < 128 || ldo < 128)
+    return MUCON_EINVAL;
+  if (n_jobs > wgrad::kMaxJobs || ldx % 32 != 0 || ldo % 4 != 0) return MUCON_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(dY) & 15) || (reinterpret_cast<uintptr_t>(X) & 15) ||
+      (reinterpret_cast<uintptr_t>(dW) & 15))
+    return MUCON_EALIGN;
+  if (num_tiles == 0 || rows == 0) return MUCON_OK;
+  if (rows > 0x7fffffff - 4096) return MUCON_EUNSUPPORTED;
+  wgrad::Jobs jobs{};
+  jobs.n = n_jobs;
+  jobs.ldo = ldo;
+  bool zero_in_group0 = false;
+  for (int j = 0; j < n_jobs; ++j) {
+    if (xcol_h[j] < 0 || xcol_h[j] % 32 != 0 || xcol_h[j] + 128 > ldx || (out_off_h[j] & 3)) return MUCON_EINVAL;
+    jobs.j[j].shift = shifts_h[j];
+    jobs.j[j].xblk = xcol_h[j] / 32;
+    jobs.j[j].out_off = out_off_h[j];
+    if (j < wgrad::kJobsPerCta && shifts_h[j] == 0) zero_in_group0 = true;
+  }
+  if (dbias && !zero_in_group0) return MUCON_EINVAL;  // the bias sum rides on stages that are always live
+  CUtensorMap tdy, tx;
+  int rc = make_map_2d(&tdy, dY, static_cast<uint64_t>(rows), wgrad::C, wgrad::KT, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != MUCON_OK) return rc;
+  rc = make_map_2d(&tx, X, static_cast<uint64_t>(rows), static_cast<uint64_t>(ldx), wgrad::KT,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != MUCON_OK) return rc;
+  const int groups = (n_jobs + wgrad::kJobsPerCta - 1) / wgrad::kJobsPerCta;
+  const int nj_max = n_jobs < wgrad::kJobsPerCta ? n_jobs : wgrad::kJobsPerCta;
+  const int stage_bytes = (1 + nj_max) * wgrad::OP_BYTES;
+  int stages = (wgrad::WSMEM_MAX - 2048) / stage_bytes;
+  if (stages > wgrad::kMaxStages) stages = wgrad::kMaxStages;
+  const int smem = 1024 + stages * stage_bytes + 512;
+  const int sms = mucon_device_sm_count();
+  int gx = sms / groups;
+  if (gx < 1) gx = 1;
+  if (gx > num_tiles) gx = num_tiles;
+  MUCON_CUDA_CHECK(cudaFuncSetAttribute(wgrad::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  wgrad::wgrad_kernel<<<dim3(gx, groups), wgrad::WTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      tdy, tx, static_cast<const convgemm::Tile*>(tiles), num_tiles, jobs, stages, dW, dbias);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_maxpool2_bwd(const float* x, const float* dy, const int64_t* off_in, const int64_t* off_out, int V,
+                                  int max_T_out, int C, float* dx, void* stream) {
+  if (!x || !dy || !off_in || !off_out || !dx || V < 0 || C < 4 || max_T_out < 0) return MUCON_EINVAL;
+  if (C % 4 != 0 || V > 65535) return MUCON_EUNSUPPORTED;
+  if (V == 0) return MUCON_OK;
+  int bx = static_cast<int>((static_cast<int64_t>(max_T_out) * (C / 4) + 255) / 256);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  wgrad::maxpool2_bwd_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, off_in, off_out, C, dx);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
 }
 
 static int launch_layer(const float* x, float* out, const float* Wd_kco, const float* bd, const float* W1_kco,
@@ -605,18 +690,21 @@ struct TailTile {  // the 16-byte tile record of convgemm::Tile plus the video i
 };
 
 constexpr int kTailRows = 128;
-constexpr int kTailLd = kTailH + 1;
-template <int CG>  // classes per thread (8 threads share a row): covers num_classes <= 8 * CG
-__global__ void __launch_bounds__(128) tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats,
-                                                           const int32_t* __restrict__ tile_vid,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ Wc /*[H][NC]*/,
-                                                           const float* __restrict__ bc, const TailTile* __restrict__ tiles,
-                                                           int num_tiles, int groups, int relu, int NC,
-                                                           float* __restrict__ z_out, float* __restrict__ lsm_out) {
-  extern __shared__ float tsm[];
-  float* Xs = tsm;                               // [128 rows][129]
-  float* Ws = tsm + kTailRows * kTailLd;         // [128 k][8 * CG] zero padded
+constexpr int kTailLd = kTailRows + 4;  // row pitch of the TRANSPOSED tile Xs[k][row]: 16-byte aligned row quads, and
+                                        // 132 = 4 (mod 32) makes the transposing stores below conflict-free
+constexpr int kTailThreads = 256;
+// 256 threads: thread (rg, cg) owns rows rg*4 .. +3 and classes cg*CG .. +CG-1 (8 threads share a row quad: covers
+// num_classes <= 8 * CG).  The activation tile is kept transposed in shared memory, so one LDS.128 fetches the four
+// rows' values of a k and the inner loop is 1 + CG/2 shared loads per 4*CG FFMAs; two CTAs (16 warps) per SM.
+template <int CG>
+__global__ void __launch_bounds__(kTailThreads, 2)
+tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats, const int32_t* __restrict__ tile_vid,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ Wc /*[H][NC]*/,
+                    const float* __restrict__ bc, const TailTile* __restrict__ tiles, int num_tiles, int groups, int relu,
+                    int NC, float* __restrict__ z_out, float* __restrict__ lsm_out) {
+  extern __shared__ __align__(16) float tsm[];
+  float* Xs = tsm;                               // [128 k][132] (transposed: row index contiguous)
+  float* Ws = tsm + kTailH * kTailLd;            // [128 k][8 * CG] zero padded
   float* bs = Ws + kTailH * 8 * CG;              // [8 * CG]
   constexpr int NCP = 8 * CG;
   for (int i = threadIdx.x; i < kTailH * NCP; i += blockDim.x) {
@@ -632,9 +720,12 @@ __global__ void __launch_bounds__(128) tail_cls_lsm_kernel(const float* __restri
     const int nrow = min(kTailRows, tl.T - tl.t0);
     const int64_t rbase = tl.row0 + tl.t0;
     __syncthreads();  // Xs of the previous tile is no longer read (and Ws / bs are written)
-    // GroupNorm + ReLU of the tile into shared memory (and to z_out)
+    // GroupNorm + ReLU of the tile into shared memory (and to z_out).  A warp instruction covers 16 rows x 2 channel
+    // quads: every row is read as one full 32-byte sector, and the four transposed stores of a lane hit banks
+    // (quad*16 + e*4 + row) mod 32: all different across the warp.
     for (int i = threadIdx.x; i < kTailRows * (kTailH / 4); i += blockDim.x) {
-      const int r = i >> 5, c4 = (i & 31) * 4;
+      const int rsub = i & 15, cq = (i >> 4) & 1, rest = i >> 5;
+      const int r = (rest & 7) * 16 + rsub, c4 = ((rest >> 3) * 2 + cq) * 4;
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nrow) {
         const float4 xv = *reinterpret_cast<const float4*>(x + (rbase + r) * kTailH + c4);
@@ -650,35 +741,44 @@ __global__ void __launch_bounds__(128) tail_cls_lsm_kernel(const float* __restri
         o = make_float4(y[0], y[1], y[2], y[3]);
         if (z_out) *reinterpret_cast<float4*>(z_out + (rbase + r) * kTailH + c4) = o;
       }
-      Xs[r * kTailLd + c4 + 0] = o.x;
-      Xs[r * kTailLd + c4 + 1] = o.y;
-      Xs[r * kTailLd + c4 + 2] = o.z;
-      Xs[r * kTailLd + c4 + 3] = o.w;
+      Xs[(c4 + 0) * kTailLd + r] = o.x;
+      Xs[(c4 + 1) * kTailLd + r] = o.y;
+      Xs[(c4 + 2) * kTailLd + r] = o.z;
+      Xs[(c4 + 3) * kTailLd + r] = o.w;
     }
     __syncthreads();
-    // classifier: thread (rg, cg) computes rows rg*8 .. +7 x classes cg*CG .. +CG-1
-    float acc[8][CG];
+    // classifier: one accumulator per (row, class), k ascending, bias last (the order of conv1d_kernel)
+    float acc[4][CG];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < CG; ++j) acc[i][j] = 0.f;
-    const float* xr = Xs + (rg * 8) * kTailLd;
+    const float* xr = Xs + rg * 4;
     const float* wr = Ws + cg * CG;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < kTailH; ++k) {
-      float xv[8], wv[CG];
+      const float4 x4 = *reinterpret_cast<const float4*>(xr + k * kTailLd);
+      const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+      float wv[CG];
+      if constexpr (CG % 2 == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = xr[i * kTailLd + k];
+        for (int j = 0; j < CG; j += 2) {
+          const float2 w2 = *reinterpret_cast<const float2*>(wr + k * NCP + j);
+          wv[j] = w2.x;
+          wv[j + 1] = w2.y;
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < CG; ++j) wv[j] = wr[k * NCP + j];
+        for (int j = 0; j < CG; ++j) wv[j] = wr[k * NCP + j];
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < CG; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
     }
     // + bias, log-softmax over the row's classes (8 lanes x CG classes)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       float m = -INFINITY;
 #pragma unroll
       for (int j = 0; j < CG; ++j) {
@@ -694,7 +794,7 @@ __global__ void __launch_bounds__(128) tail_cls_lsm_kernel(const float* __restri
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) sden += __shfl_xor_sync(0xffffffffu, sden, o);
       const float lse = m + logf(sden);
-      const int r = rg * 8 + i;
+      const int r = rg * 4 + i;
       if (r < nrow) {
 #pragma unroll
         for (int j = 0; j < CG; ++j)
@@ -738,7 +838,7 @@ extern "C" int mucon_tail_logprobs(const float* x, const int64_t* row_off, const
   gn_stats_kernel<<<V, 512, 0, st>>>(x, row_off, groups, eps, stats_ws);
   MUCON_CUDA_CHECK(cudaGetLastError());
   const int CG = num_classes <= 24 ? 3 : (num_classes <= 48 ? 6 : 8);
-  const size_t smem = sizeof(float) * (kTailRows * kTailLd + kTailH * 8 * CG + 8 * CG);
+  const size_t smem = sizeof(float) * (kTailH * kTailLd + kTailH * 8 * CG + 8 * CG);
   const int sms = mucon_device_sm_count();
   int grid = 2 * sms;
   if (grid > num_tiles) grid = num_tiles;
@@ -747,7 +847,7 @@ extern "C" int mucon_tail_logprobs(const float* x, const int64_t* row_off, const
   do {                                                                                                           \
     MUCON_CUDA_CHECK(cudaFuncSetAttribute(tail_cls_lsm_kernel<cg>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           static_cast<int>(smem)));                                              \
-    tail_cls_lsm_kernel<cg><<<grid, 128, smem, st>>>(x, stats_ws, tile_vid, gamma, beta, Wc_hc, bc, tl, num_tiles, \
+    tail_cls_lsm_kernel<cg><<<grid, kTailThreads, smem, st>>>(x, stats_ws, tile_vid, gamma, beta, Wc_hc, bc, tl, num_tiles, \
                                                      groups, relu, num_classes, z_out, lsm_out);                 \
   } while (0)
   if (CG == 3) MUCON_TAIL(3); else if (CG == 6) MUCON_TAIL(6); else MUCON_TAIL(8);

@@ -295,7 +295,11 @@ struct TapShifts {
 __global__ void __launch_bounds__(CTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const Tile* __restrict__ tiles, int num_tiles, const TapShifts ts, const float* __restrict__ bias,
-                 const float* __restrict__ residual, float* __restrict__ out, int relu_mid, int relu_final) {
+                 const float* __restrict__ residual, float* __restrict__ out, int relu_mid, int relu_final,
+                 const float* __restrict__ mul = nullptr, const float* __restrict__ gate = nullptr) {
+  // Epilogue order: v = acc (+ bias) -> ReLU (relu_mid) -> * mul (dropout mask of the forward pass) -> + residual ->
+  // ReLU (relu_final) -> gate (v = gate > 0 ? v : 0: the ReLU derivative of the backward pass).  bias / residual /
+  // mul / gate may be null.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_mem = base;
@@ -434,7 +438,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           float v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            v[e] = __uint_as_float(r[j + e]) + __ldg(bias + c * 32 + j + e);
+            v[e] = __uint_as_float(r[j + e]);
+            if (bias) v[e] += __ldg(bias + c * 32 + j + e);
             if (relu_mid) v[e] = fmaxf(v[e], 0.f);
           }
           *reinterpret_cast<float4*>(et + lane * EPI_LD + c * 32 + j) = make_float4(v[0], v[1], v[2], v[3]);
@@ -460,14 +465,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(et + (r0 + e) * EPI_LD + lane * 4);
+        if (mul) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (r0 + e < nrow) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(mul + (rbase + r0 + e) * C) + lane);
+              v[e].x *= m.x; v[e].y *= m.y; v[e].z *= m.z; v[e].w *= m.w;
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           if (residual) { v[e].x += rv[e].x; v[e].y += rv[e].y; v[e].z += rv[e].z; v[e].w += rv[e].w; }
           if (relu_final) {
             v[e].x = fmaxf(v[e].x, 0.f); v[e].y = fmaxf(v[e].y, 0.f); v[e].z = fmaxf(v[e].z, 0.f); v[e].w = fmaxf(v[e].w, 0.f);
           }
-          if (r0 + e < nrow) *(reinterpret_cast<float4*>(out + (rbase + r0 + e) * C) + lane) = v[e];
         }
+        if (gate) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (r0 + e < nrow) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (rbase + r0 + e) * C) + lane);
+              v[e].x = g.x > 0.f ? v[e].x : 0.f; v[e].y = g.y > 0.f ? v[e].y : 0.f;
+              v[e].z = g.z > 0.f ? v[e].z : 0.f; v[e].w = g.w > 0.f ? v[e].w : 0.f;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (r0 + e < nrow) *(reinterpret_cast<float4*>(out + (rbase + r0 + e) * C) + lane) = v[e];
       }
       __syncwarp();
     }

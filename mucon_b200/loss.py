@@ -127,3 +127,31 @@ def mucon_loss(lengths, segmentation, target_transcript, template="box", overlap
         return F.nll_loss(F.log_softmax(evidence, dim=1), target_transcript, weight=class_weight, reduction="mean")
     masks = create_masks(T=T, L=absolute_lengths, template=template, overlap=overlap, align_corners=align_corners)
     return loss_from_masks(absolute_lengths, masks, segmentation, target_transcript, mucon_type, class_weight)
+
+
+def mucon_loss_batch(lengths, segmentation, transcripts, Ms, Ts, template="box", overlap=0.0, class_weight=None,
+                     align_corners=None, meta=None):
+    """The flint mutual-consistency loss (models.py:414-488) of a packed batch, averaged over its videos: one
+    fused-evidence launch for the whole batch instead of one Python loop per video and segment.
+    lengths [sum Ms] s-head length logits (videos concatenated), segmentation [sum Ts, C] packed frame logits,
+    transcripts [sum Ms] long.  Per video: F.nll_loss(log_softmax(E_v / L_v), transcript_v, reduction="mean")."""
+    Ms_np, Ts_np = np.asarray(Ms, dtype=np.int64), np.asarray(Ts, dtype=np.int64)
+    V, dev = int(Ms_np.shape[0]), segmentation.device
+    meta = meta if meta is not None else _flint_meta(Ms_np, Ts_np, dev)
+    row_vid = meta["row_vid"].long()
+    maxM = int(Ms_np.max(initial=1))
+    col = torch.from_numpy(np.concatenate([np.arange(m) for m in Ms_np]) if V else np.zeros(0, np.int64)).to(dev)
+    # project_lengths_softmax per video (masks.py:8-12): softmax over the video's segments, times T
+    padded = torch.full((V, maxM), float("-inf"), dtype=lengths.dtype, device=dev)
+    padded = padded.index_put((row_vid, col), lengths)
+    Tt = torch.from_numpy(Ts_np.astype(np.float32)).to(dev)
+    absolute = (F.softmax(padded, dim=1) * Tt[:, None])[row_vid, col]
+    E = flint_evidence(absolute, segmentation, Ms_np, Ts_np, overlap=overlap, template=template,
+                       align_corners=align_corners, meta=meta)
+    scaled = absolute * (1.0 + 2 * overlap)  # the in-place scaling of create_masks (masks.py:61)
+    logp = F.log_softmax(E / scaled[:, None], dim=1)
+    nll = -logp.gather(1, transcripts.long()[:, None])[:, 0]
+    w = class_weight[transcripts.long()] if class_weight is not None else torch.ones_like(nll)
+    num = torch.zeros(V, dtype=nll.dtype, device=dev).index_add_(0, row_vid, nll * w)
+    den = torch.zeros(V, dtype=nll.dtype, device=dev).index_add_(0, row_vid, w)
+    return (num / den).mean()

@@ -1,3 +1,5 @@
+"""GPU scratch tool: two backbone forwards on the c2 split through the current fast path (for ncu launch lists).
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/prof_backbone.py"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,5 +14,5 @@ Ts = T[:nv]
 plan = m.plan(Ts)
 feats = torch.randn(int(Ts.sum()), 2048, device=dev).abs_() * 0.5
 for _ in range(2):
-    lp = m.logprobs_packed(m.encode_packed(feats, plan), plan)
+    table, off = m.infer_pooled_packed(feats, plan)
 torch.cuda.synchronize()
