@@ -281,6 +281,15 @@ int mucon_conv_gemm_tf32_ex(const float* in, float* out, const float* W_kco, con
 int mucon_wgrad_tf32(const float* dY, const float* X, int ldx, const void* tiles, int num_tiles, int64_t rows,
                      const int32_t* shifts_h, const int32_t* xcol_h, const int64_t* out_off_h, int n_jobs, int ldo,
                      float* dW, float* dbias, void* stream);
+/* Backward of mucon_groupnorm_relu (models.py:759-768 under autograd), 128 channels: dx, and dgamma / dbeta
+ * ACCUMULATED into zeroed buffers.  x is the GroupNorm input, dy the gradient of relu(gn(x)). */
+int mucon_groupnorm_relu_bwd(const float* x, const float* dy, const float* gamma, const float* beta,
+                             const int64_t* row_off, int V, int C, int groups, float eps, int relu, float* dx,
+                             float* dgamma, float* dbeta, void* stream);
+/* Backward of mucon_expand_rows (F.interpolate(mode="nearest"), models.py:574-577): grad_table[iz,:] = sum of
+ * grad_out[t,:] over the frames whose source row is iz. */
+int mucon_expand_rows_bwd(const float* grad_out, const int64_t* off_z, const int64_t* off_t, int V, int max_Tz, int C,
+                          float* grad_table, void* stream);
 /* max_pool1d(2) backward (temporal.py:137-139): dx[2t or 2t+1] = dy[t] at the first maximum, 0 elsewhere. */
 int mucon_maxpool2_bwd(const float* x, const float* dy, const int64_t* off_in, const int64_t* off_out, int V,
                        int max_T_out, int C, float* dx, void* stream);

@@ -856,6 +856,151 @@ extern "C" int mucon_tail_logprobs(const float* x, const int64_t* row_off, const
   return MUCON_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// training step: backward of the tail (autograd of models.py:759-768 GroupNorm + ReLU and :574-577 nearest upsample)
+namespace mucon {
+namespace {
+
+// One CTA per video, 512 threads = 4 row slices x 128 channels.  y = relu(xhat * gamma + beta), xhat = (x - mean) * rstd:
+//   g = dy * [y > 0];  dgamma[c] += sum_t g * xhat;  dbeta[c] += sum_t g;  dxhat = g * gamma
+//   dx = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat * xhat))      (means over the group's T x C/groups elements)
+__global__ void __launch_bounds__(512) groupnorm_relu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta,
+                                                                 const int64_t* __restrict__ off, int groups, float eps,
+                                                                 int relu, float* __restrict__ dx,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double s1[4][kTailH], s2[4][kTailH];
+  __shared__ float mean_s[kTailH], rstd_s[kTailH], m1_s[kTailH], m2_s[kTailH];
+  const int v = blockIdx.x;
+  const int64_t r0 = off[v];
+  const int T = static_cast<int>(off[v + 1] - r0);
+  if (T == 0) return;
+  const int c = threadIdx.x & (kTailH - 1), sl = threadIdx.x >> 7;
+  const int cpg = kTailH / groups;
+  const double n = static_cast<double>(T) * cpg;
+  // pass 1: statistics (as gn_stats_kernel)
+  double a = 0.0, b = 0.0;
+  for (int t = sl; t < T; t += 4) {
+    const double xv = x[(r0 + t) * kTailH + c];
+    a += xv;
+    b += xv * xv;
+  }
+  s1[sl][c] = a;
+  s2[sl][c] = b;
+  __syncthreads();
+  if (threadIdx.x < kTailH) {
+    const int g = c / cpg;
+    double sa = 0.0, sb = 0.0;
+    for (int k = 0; k < cpg; ++k)
+      for (int q = 0; q < 4; ++q) { sa += s1[q][g * cpg + k]; sb += s2[q][g * cpg + k]; }
+    const double mean = sa / n;
+    double var = sb / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_s[c] = static_cast<float>(mean);
+    rstd_s[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  // pass 2: per-channel sums of g and g * xhat
+  const float mu = mean_s[c], rs = rstd_s[c], ga = gamma[c], be = beta[c];
+  a = 0.0;
+  b = 0.0;
+  for (int t = sl; t < T; t += 4) {
+    const float xh = (x[(r0 + t) * kTailH + c] - mu) * rs;
+    float g = dy[(r0 + t) * kTailH + c];
+    if (relu && xh * ga + be <= 0.f) g = 0.f;
+    a += g;
+    b += static_cast<double>(g) * xh;
+  }
+  s1[sl][c] = a;
+  s2[sl][c] = b;
+  __syncthreads();
+  if (threadIdx.x < kTailH) {
+    const double cg = s1[0][c] + s1[1][c] + s1[2][c] + s1[3][c];
+    const double cgx = s2[0][c] + s2[1][c] + s2[2][c] + s2[3][c];
+    atomicAdd(dbeta + c, static_cast<float>(cg));
+    atomicAdd(dgamma + c, static_cast<float>(cgx));
+    s1[0][c] = cg * ga;    // sum of dxhat over the channel
+    s2[0][c] = cgx * ga;   // sum of dxhat * xhat over the channel
+  }
+  __syncthreads();
+  if (threadIdx.x < kTailH) {
+    const int g = c / cpg;
+    double sa = 0.0, sb = 0.0;
+    for (int k = 0; k < cpg; ++k) { sa += s1[0][g * cpg + k]; sb += s2[0][g * cpg + k]; }
+    m1_s[c] = static_cast<float>(sa / n);
+    m2_s[c] = static_cast<float>(sb / n);
+  }
+  __syncthreads();
+  // pass 3: dx
+  const float m1 = m1_s[c], m2 = m2_s[c];
+  for (int t = sl; t < T; t += 4) {
+    const float xh = (x[(r0 + t) * kTailH + c] - mu) * rs;
+    float g = dy[(r0 + t) * kTailH + c];
+    if (relu && xh * ga + be <= 0.f) g = 0.f;
+    dx[(r0 + t) * kTailH + c] = rs * (g * ga - m1 - xh * m2);
+  }
+}
+
+// grad_table[iz, :] = sum of grad_out[t, :] over the frames t whose nearest-neighbour source row is iz
+// (iz(t) = min(floor(t * (float)Tz / T), Tz - 1) is non-decreasing in t: a contiguous range of frames per row)
+__global__ void __launch_bounds__(256) expand_rows_bwd_kernel(const float* __restrict__ gout,
+                                                              const int64_t* __restrict__ off_z,
+                                                              const int64_t* __restrict__ off_t, int C,
+                                                              float* __restrict__ gtable) {
+  const int v = blockIdx.y;
+  const int64_t z0 = off_z[v], t0v = off_t[v];
+  const int Tz = static_cast<int>(off_z[v + 1] - z0);
+  const int T = static_cast<int>(off_t[v + 1] - t0v);
+  if (Tz == 0) return;
+  const float scale = static_cast<float>(Tz) / static_cast<float>(T);
+  auto src = [&](int t) {
+    int iz = static_cast<int>(floorf(static_cast<float>(t) * scale));
+    return iz > Tz - 1 ? Tz - 1 : iz;
+  };
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int iz = wid; iz < Tz; iz += nw) {
+    // first frame mapping to >= iz: start from the real-valued estimate and correct with the exact formula
+    int lo = static_cast<int>(static_cast<double>(iz) * T / Tz) - 2;
+    if (lo < 0) lo = 0;
+    while (lo < T && src(lo) < iz) ++lo;
+    while (lo > 0 && src(lo - 1) >= iz) --lo;
+    for (int c = lane; c < C; c += 32) {
+      float acc = 0.f;
+      for (int t = lo; t < T && src(t) == iz; ++t) acc += gout[(t0v + t) * C + c];
+      gtable[(z0 + iz) * C + c] = acc;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mucon
+
+extern "C" int mucon_groupnorm_relu_bwd(const float* x, const float* dy, const float* gamma, const float* beta,
+                                        const int64_t* row_off, int V, int C, int groups, float eps, int relu, float* dx,
+                                        float* dgamma, float* dbeta, void* stream) {
+  if (!x || !dy || !gamma || !beta || !row_off || !dx || !dgamma || !dbeta || V < 0 || groups < 1) return MUCON_EINVAL;
+  if (C != kTailH || kTailH % groups != 0) return MUCON_EUNSUPPORTED;
+  if (V == 0) return MUCON_OK;
+  groupnorm_relu_bwd_kernel<<<V, 512, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, gamma, beta, row_off, groups, eps,
+                                                                             relu, dx, dgamma, dbeta);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_expand_rows_bwd(const float* grad_out, const int64_t* off_z, const int64_t* off_t, int V, int max_Tz,
+                                     int C, float* grad_table, void* stream) {
+  if (!grad_out || !off_z || !off_t || !grad_table || V < 0 || C < 1 || max_Tz < 0) return MUCON_EINVAL;
+  if (V == 0 || max_Tz == 0) return MUCON_OK;
+  if (V > 65535) return MUCON_EUNSUPPORTED;
+  int bx = (max_Tz + 7) / 8;
+  if (bx > 64) bx = 64;
+  expand_rows_bwd_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, off_z, off_t, C, grad_table);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 extern "C" int mucon_expand_rows(const float* table, const int64_t* off_z, const int64_t* off_t, int V, int max_T, int C,
                                  float* out, void* stream) {
   if (!table || !off_z || !off_t || !out || V < 0 || C < 1 || max_T < 0) return MUCON_EINVAL;

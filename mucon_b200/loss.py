@@ -138,13 +138,15 @@ def mucon_loss_batch(lengths, segmentation, transcripts, Ms, Ts, template="box",
     Ms_np, Ts_np = np.asarray(Ms, dtype=np.int64), np.asarray(Ts, dtype=np.int64)
     V, dev = int(Ms_np.shape[0]), segmentation.device
     meta = meta if meta is not None else _flint_meta(Ms_np, Ts_np, dev)
-    row_vid = meta["row_vid"].long()
+    if "row_vid64" not in meta:   # small index tables, built once per batch shape (no H2D copies in a captured step)
+        meta["row_vid64"] = meta["row_vid"].long()
+        meta["col"] = torch.from_numpy(np.concatenate([np.arange(m) for m in Ms_np]) if V else np.zeros(0, np.int64)).to(dev)
+        meta["Tf"] = torch.from_numpy(Ts_np.astype(np.float32)).to(dev)
+    row_vid, col, Tt = meta["row_vid64"], meta["col"], meta["Tf"]
     maxM = int(Ms_np.max(initial=1))
-    col = torch.from_numpy(np.concatenate([np.arange(m) for m in Ms_np]) if V else np.zeros(0, np.int64)).to(dev)
     # project_lengths_softmax per video (masks.py:8-12): softmax over the video's segments, times T
     padded = torch.full((V, maxM), float("-inf"), dtype=lengths.dtype, device=dev)
     padded = padded.index_put((row_vid, col), lengths)
-    Tt = torch.from_numpy(Ts_np.astype(np.float32)).to(dev)
     absolute = (F.softmax(padded, dim=1) * Tt[:, None])[row_vid, col]
     E = flint_evidence(absolute, segmentation, Ms_np, Ts_np, overlap=overlap, template=template,
                        align_corners=align_corners, meta=meta)

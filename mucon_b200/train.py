@@ -93,12 +93,19 @@ class _WaveNetBlockFn(torch.autograd.Function):
         saved = dict(x0=x, layers=[])
         level = 0
         last = block.num_stages - 1
+        if block.num_stages:
+            # tensor-core layouts of every layer's weights in four launches: [k][Cout][Cin] for the forward GEMMs,
+            # [k][Cin][Cout] (tap slices transposed) for the data gradients
+            Wd = torch.stack([l.dilated_conv.weight.detach().float() for l in block.layers])          # [L, co, ci, 3]
+            W1 = torch.stack([l.conv_1x1.weight.detach().float()[:, :, 0] for l in block.layers])     # [L, co, ci]
+            kco_d, kco_1 = Wd.permute(0, 3, 1, 2).contiguous(), W1
+            saved["tco_d"], saved["tco_1"] = Wd.permute(0, 3, 2, 1).contiguous(), W1.transpose(1, 2).contiguous()
         for i, l in enumerate(block.layers):
             d = block.stages[i]
             pooled = block.pooling and i in block.pooling_layers
-            h = conv_gemm_ex_rows(x, _kco(l.dilated_conv), plan, level, (-d, 0, d),
+            h = conv_gemm_ex_rows(x, kco_d[i].view(3 * H, H), plan, level, (-d, 0, d),
                                   bias=l.dilated_conv.bias.detach().float().contiguous(), relu_mid=True)
-            y = conv_gemm_ex_rows(h, _kco(l.conv_1x1), plan, level, (0,),
+            y = conv_gemm_ex_rows(h, kco_1[i], plan, level, (0,),
                                   bias=l.conv_1x1.bias.detach().float().contiguous(), mul=drop_masks[i], residual=x,
                                   relu_final=(i == last and not pooled))
             rec = dict(x=x, h=h, level=level, pooled=pooled, y=None)
@@ -146,10 +153,10 @@ class _WaveNetBlockFn(torch.autograd.Function):
             dy = maxpool2_bwd_rows(rec["y"], dx, plan, level) if rec["pooled"] else dx          # temporal.py:137-139
             dym = dy * drop_masks[i] if drop_masks[i] is not None else dy                        # temporal.py:51
             wgrad_rows(dym, rec["h"], plan, level, (0,), (0,), (0,), H, g_w1, g_b1)             # conv_1x1
-            dh = conv_gemm_ex_rows(dym, _tco(l.conv_1x1).view(H, H), plan, level, (0,), gate=rec["h"])   # ReLU of :49
+            dh = conv_gemm_ex_rows(dym, saved["tco_1"][i], plan, level, (0,), gate=rec["h"])    # ReLU of :49
             wgrad_rows(dh, rec["x"], plan, level, (-d, 0, d), (0, 0, 0), (0, H * H, 2 * H * H), H, g_wd, g_bd)
             # dx = dy (skip connection) + dilated^T(dh); the ReLU behind first_conv gates layer 0's result
-            dx = conv_gemm_ex_rows(dh, _tco(l.dilated_conv).view(3 * H, H), plan, level, (d, 0, -d), residual=dy,
+            dx = conv_gemm_ex_rows(dh, saved["tco_d"][i].view(3 * H, H), plan, level, (d, 0, -d), residual=dy,
                                    gate=saved["x0"] if i == 0 else None)
         if L == 0:
             dx = dx * (saved["x0"] > 0)
@@ -173,15 +180,21 @@ def wavenet_forward_train_packed(block: WaveNetBlock, feats, plan: BackbonePlan,
     if not feats.is_cuda:
         raise _lib.MuconError("the backbone needs CUDA tensors (there is no CPU fallback)")
     p = block.dropout_rate if block.training else 0.0
-    masks, level = [], 0
+    levels, level = [], 0
     for i in range(block.num_stages):
-        if p > 0:
-            keep = torch.rand((plan.rows[level], block.out_dims), device=feats.device, generator=generator) >= p
-            masks.append(keep.float() / (1.0 - p))
-        else:
-            masks.append(None)
+        levels.append(level)
         if block.pooling and i in block.pooling_layers:
             level += 1
+    masks = [None] * block.num_stages
+    if p > 0 and block.num_stages:
+        # every layer's inverted-dropout mask from one draw (two launches instead of three per layer)
+        sizes = [plan.rows[lv] * block.out_dims for lv in levels]
+        flat = torch.empty(int(sum(sizes)), dtype=torch.float32, device=feats.device)
+        flat.bernoulli_(1.0 - p, generator=generator).mul_(1.0 / (1.0 - p))
+        o = 0
+        for i, n in enumerate(sizes):
+            masks[i] = flat[o:o + n].view(plan.rows[levels[i]], block.out_dims)
+            o += n
     return _WaveNetBlockFn.apply(block, plan, feats, masks, *_param_list(block))
 
 
@@ -220,11 +233,72 @@ def groupnorm_packed(x, vid, counts, V, weight, bias, groups, eps):
     return xh.reshape(R, Cc) * weight[None, :] + bias[None, :]
 
 
-def tail_logits_packed(model, z_pre, plan):
+class _GroupNormReluFn(torch.autograd.Function):
+    """relu(GroupNorm(x)) per video on packed rows: mucon_groupnorm_relu / mucon_groupnorm_relu_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, plan, groups, eps, relu):
+        from .temporal import groupnorm_relu_rows
+        lvl = len(plan.off) - 1
+        xc, g, b = x.detach().contiguous().float(), gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        ctx.save_for_backward(xc, g, b)
+        ctx.args = (plan, lvl, groups, eps, relu)
+        return groupnorm_relu_rows(xc, g, b, plan.off[lvl], plan.V, groups, eps, relu)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, g, b = ctx.saved_tensors
+        plan, lvl, groups, eps, relu = ctx.args
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(xc)
+        dgb = torch.zeros((2, xc.shape[1]), dtype=torch.float32, device=xc.device)
+        _lib.check(_lib.lib().mucon_groupnorm_relu_bwd(
+            _lib.ptr(xc), _lib.ptr(dy), _lib.ptr(g), _lib.ptr(b), _lib.ptr(plan.off[lvl]), C.c_int(plan.V),
+            C.c_int(xc.shape[1]), C.c_int(groups), C.c_float(eps), C.c_int(int(relu)), _lib.ptr(dx), _lib.ptr(dgb[0]),
+            _lib.ptr(dgb[1]), _stream(xc.device)), "mucon_groupnorm_relu_bwd")
+        return dx, dgb[0], dgb[1], None, None, None, None
+
+
+class _ExpandRowsFn(torch.autograd.Function):
+    """nearest-neighbour expansion of pooled-resolution rows to every frame: mucon_expand_rows / _bwd."""
+
+    @staticmethod
+    def forward(ctx, table, plan):
+        lvl = len(plan.off) - 1
+        tb = table.detach().contiguous().float()
+        out = torch.empty((plan.rows[0], tb.shape[1]), dtype=torch.float32, device=tb.device)
+        _lib.check(_lib.lib().mucon_expand_rows(
+            _lib.ptr(tb), _lib.ptr(plan.off[lvl]), _lib.ptr(plan.off[0]), C.c_int(plan.V), C.c_int(plan.max_T[0]),
+            C.c_int(tb.shape[1]), _lib.ptr(out), _stream(tb.device)), "mucon_expand_rows")
+        ctx.plan, ctx.shape = plan, tb.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        plan = ctx.plan
+        lvl = len(plan.off) - 1
+        gout = gout.contiguous().float()
+        gt = torch.empty(ctx.shape, dtype=torch.float32, device=gout.device)
+        _lib.check(_lib.lib().mucon_expand_rows_bwd(
+            _lib.ptr(gout), _lib.ptr(plan.off[lvl]), _lib.ptr(plan.off[0]), C.c_int(plan.V), C.c_int(plan.max_T[lvl]),
+            C.c_int(gout.shape[1]), _lib.ptr(gt), _stream(gout.device)), "mucon_expand_rows_bwd")
+        return gt, None
+
+
+def tail_logits_packed(model, z_pre, plan, fused=True):
     """ft output [sum Tz, H] -> frame logits [sum T, classes]: GroupNorm + ReLU (models.py:759-768), 1x1 classifier at
-    the pooled resolution and nearest-neighbour expansion (models.py:567-582; the two commute)."""
-    vid, idx, counts = _plan_train_tables(plan, z_pre.device)
+    the pooled resolution and nearest-neighbour expansion (models.py:567-582; the two commute).  fused=True runs
+    GroupNorm(+ReLU) and the expansion, forward and backward, as CUDA kernels; False as packed torch ops."""
     z = z_pre
+    if fused and model.hidden_size == 128 and z_pre.is_cuda:
+        if model.last_gn:
+            z = _GroupNormReluFn.apply(z, model.ft_last_gn.weight, model.ft_last_gn.bias, plan,
+                                       model.ft_last_gn.num_groups, model.ft_last_gn.eps, model.last_relu)
+        elif model.last_relu:
+            z = torch.relu(z)
+        logits_z = torch.addmm(model.conv_classifier.bias, z, model.conv_classifier.weight[:, :, 0].t())
+        return _ExpandRowsFn.apply(logits_z, plan), z
+    vid, idx, counts = _plan_train_tables(plan, z_pre.device)
     if model.last_gn:
         z = groupnorm_packed(z, vid, counts, plan.V, model.ft_last_gn.weight, model.ft_last_gn.bias,
                              model.ft_last_gn.num_groups, model.ft_last_gn.eps)
@@ -239,3 +313,58 @@ def forward_train_packed(model, feats, plan, generator=None):
     backbone / GroupNorm / classifier parameter.  Returns (frame logits [sum T, classes], z [sum Tz, H])."""
     z_pre = wavenet_forward_train_packed(model.ft, feats, plan, generator=generator)
     return tail_logits_packed(model, z_pre, plan)
+
+
+class TrainStep:
+    """One training step of the backbone path for a fixed batch shape, captured in a CUDA graph: forward (tcgen05
+    kernels above) -> GroupNorm / classifier tail -> batched flint loss -> backward -> optimizer step, replayed with
+    one launch per step (trainers.py:125-131 does the same four calls per video from Python).
+
+    The step is launch-bound at reference batch sizes (about 200 small kernels for 32 videos), which is what the
+    graph removes.  Inputs live in static buffers: copy the next batch into `feats`, `lengths`, `transcripts` (same
+    Ts / Ms) and call `run()`; the loss is read from `loss` (a device scalar)."""
+
+    def __init__(self, model, Ts, Ms, optimizer=None, template="box", overlap=0.0, graph=True, warmup=3):
+        from .loss import _flint_meta, mucon_loss_batch
+        self.model, self.optimizer = model, optimizer
+        dev = model.conv_classifier.weight.device
+        self.Ts, self.Ms = [int(t) for t in Ts], [int(m) for m in Ms]
+        self.plan = model.plan(self.Ts, dev)
+        self.meta = _flint_meta(self.Ms, self.Ts, dev)
+        D = model.ft.in_channels
+        self.feats = torch.zeros((int(sum(self.Ts)), D), dtype=torch.float32, device=dev)
+        self.lengths = torch.zeros(int(sum(self.Ms)), dtype=torch.float32, device=dev, requires_grad=True)
+        self.transcripts = torch.zeros(int(sum(self.Ms)), dtype=torch.int64, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self._loss_fn = lambda seg: mucon_loss_batch(self.lengths, seg, self.transcripts, self.Ms, self.Ts,
+                                                     template=template, overlap=overlap, meta=self.meta)
+        self.graph = None
+        self._use_graph, self._warmup = graph, warmup
+
+    def _eager(self):
+        for p in self.model.parameters():
+            p.grad = None
+        self.lengths.grad = None
+        seg, _ = forward_train_packed(self.model, self.feats, self.plan)
+        loss = self._loss_fn(seg)
+        loss.backward()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        self.loss.copy_(loss.detach())
+
+    def run(self):
+        if not self._use_graph:
+            self._eager()
+            return self.loss
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up off the capture stream (allocator, lazy tables, autograd)
+                for _ in range(self._warmup):
+                    self._eager()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._eager()
+        self.graph.replay()
+        return self.loss

@@ -83,6 +83,19 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 frames = sum(Ts)
 print(f"c5 step (32 videos, {frames} frames, dropout 0.25): {ms:.3f} ms  -> {3 * 1.014e6 * frames / ms / 1e9:.1f} TFLOP/s (3 x fwd flops)")
+# the same step captured in a CUDA graph (train.TrainStep), with an SGD step inside
+opt = torch.optim.SGD(m2.parameters(), lr=1e-3)
+ts = train.TrainStep(m2, Ts, Ns, optimizer=opt)
+ts.feats.copy_(f2); ts.transcripts.copy_(t2)
+with torch.no_grad():
+    ts.lengths.copy_(l2)
+ts.run(); torch.cuda.synchronize()
+e0.record()
+for _ in range(20):
+    ts.run()
+e1.record(); torch.cuda.synchronize()
+msg = e0.elapsed_time(e1) / 20
+print(f"c5 step as a CUDA graph (+ SGD): {msg:.3f} ms -> {3 * 1.014e6 * frames / msg / 1e9:.1f} TFLOP/s, loss {ts.loss.item():.4f}")
 # the reference's own way on the same GPU: its modules restated with torch (cudnn), one video at a time
 sd2 = dict(m2.named_parameters())
 def ref_step():

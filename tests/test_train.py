@@ -289,3 +289,73 @@ def test_training_step_random_batch_vs_oracle(cuda_device):
             assert torch.allclose(glen, lens2.grad, rtol=bar, atol=bar * lens2.grad.abs().max().item())
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.gpu
+def test_train_step_graph_replay_matches_eager(cuda_device):
+    """TrainStep: the CUDA-graph replay of forward + loss + backward (+ SGD step) gives the eager step's loss,
+    gradients and updated weights, and a second replay on new inputs follows them"""
+    from mucon_b200 import train
+    from mucon_b200.temporal import MuConBackbone
+    rng = np.random.default_rng(8)
+    Ts, Ms = [900, 260, 1500, 77], [5, 3, 8, 2]
+    states = []
+    for use_graph in (False, True):
+        torch.manual_seed(1)
+        m = MuConBackbone().to(cuda_device).train()
+        m.ft.dropout_rate = 0.0
+        opt = torch.optim.SGD(m.parameters(), lr=0.05)
+        ts = train.TrainStep(m, Ts, Ms, optimizer=opt, graph=use_graph)
+        g = torch.Generator(device="cpu").manual_seed(2)
+        losses = []
+        for it in range(2):
+            ts.feats.copy_(torch.randn(ts.feats.shape, generator=g).abs() * 0.5)
+            with torch.no_grad():
+                ts.lengths.copy_(torch.randn(ts.lengths.shape, generator=g))
+            ts.transcripts.copy_(torch.randint(0, 48, ts.transcripts.shape, generator=g))
+            if use_graph and it == 0:
+                # the capture's warm-up runs take optimizer steps too: restore the initial weights afterwards
+                sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+                ts.run()
+                m.load_state_dict(sd0)
+            losses.append(float(ts.run().item()))
+        states.append((losses, {k: v.detach().clone() for k, v in m.state_dict().items()}))
+    torch.manual_seed(1)
+    init = MuConBackbone().state_dict()
+    (l0, s0), (l1, s1) = states
+    assert abs(l0[0] - l1[0]) <= 1e-5 * abs(l0[0]) and abs(l0[1] - l1[1]) <= 1e-3 * abs(l0[1]), (l0, l1)
+    # the two-step weight UPDATES agree to the run-to-run reproducibility of the gradients (the reductions are
+    # atomic, and the gradient is discontinuous in the activations: see the module docstring)
+    for k in s0:
+        u0, u1 = s0[k].cpu() - init[k], s1[k].cpu() - init[k]
+        if u0.abs().max().item() == 0.0:
+            assert u1.abs().max().item() == 0.0, k
+            continue
+        assert ((u0 - u1).norm() / u0.norm()).item() <= 3e-2, (k, ((u0 - u1).norm() / u0.norm()).item())
+
+
+@pytest.mark.gpu
+def test_fused_tail_backward_equals_torch_ops(cuda_device):
+    """GroupNorm + ReLU and nearest-expansion kernels (forward and backward) against the packed torch-op tail"""
+    from mucon_b200 import train
+    from mucon_b200.temporal import MuConBackbone
+    torch.manual_seed(4)
+    Ts = [900, 260, 1500, 77, 16]
+    m = MuConBackbone().to(cuda_device).train()
+    with torch.no_grad():
+        m.ft_last_gn.weight.uniform_(0.5, 1.5)
+        m.ft_last_gn.bias.uniform_(-0.5, 0.5)
+    plan = m.plan(Ts, cuda_device)
+    z0 = torch.randn(plan.rows[-1], 128, device=cuda_device)
+    R = torch.randn(int(sum(Ts)), 48, device=cuda_device)
+    outs = []
+    for fused in (True, False):
+        for p in m.parameters():
+            p.grad = None
+        z = z0.clone().requires_grad_(True)
+        seg, zz = train.tail_logits_packed(m, z, plan, fused=fused)
+        (seg * R).sum().backward()
+        outs.append((seg.detach(), z.grad.clone(), m.ft_last_gn.weight.grad.clone(), m.ft_last_gn.bias.grad.clone(),
+                     m.conv_classifier.weight.grad.clone(), m.conv_classifier.bias.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-3 * b.abs().max().item()), (a - b).abs().max().item()
