@@ -15,8 +15,8 @@
  *
  * Conventions: plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its name
  * ends in _h.  Every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns
- * 0 or a negative MUCON_E* code, never throws, keeps no global state.  The caller owns all
- * buffers.  There is no CPU fallback: without a CUDA device every compute entry point fails.
+ * 0 or a negative MUCON_E* code, never throws.  Global state is limited to read-only caches (the device's SM
+ * count, the three constant mask templates, the last CUDA error string).  The caller owns all buffers.  There is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef MUCON_B200_H_
 #define MUCON_B200_H_
@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUCON_ABI_VERSION 1
+#define MUCON_ABI_VERSION 2
 
 /* call-level errors (return values) */
 #define MUCON_OK 0
@@ -79,7 +79,7 @@ typedef struct mucon_viterbi_batch {
   int32_t n_cta;      /* number of unit bins, from mucon_viterbi_pack_h */
   int32_t wpc;        /* warps per CTA (4, 8 or 16), from mucon_viterbi_pack_h */
   int32_t lanes;      /* lanes per segment (4, 8 or 32), from mucon_viterbi_pack_h */
-  int32_t reserved_;
+  int32_t n_peers;    /* 0, or the number of valid entries of peer_delta (multi-GPU result exchange, see below) */
   const void* bs;            /* [sum K, C] block scores */
   const int64_t* vid_off;    /* [V+1] frame offsets (T_v = difference) */
   const int64_t* blk_off;    /* [V+1] block offsets into bs */
@@ -98,6 +98,11 @@ typedef struct mucon_viterbi_batch {
   uint8_t* bp;               /* back-pointers: winning predecessor length, 0 = no entry */
   int32_t* final_j;          /* [U] length (blocks) of the last segment */
   int32_t* status;           /* [U] MUCON_UNIT_* */
+  /* Multi-GPU result exchange fused into the kernels' epilogue (replaces the NCCL all_gather of the per-video
+   * scores and segment lengths): `score` and `seg_blocks` live in one payload buffer; every store to
+   * them is repeated at  (char*)address + peer_delta[p]  for p < n_peers -- this rank's slot in the receive buffer
+   * of rank p, mapped into this process with mucon_peer_open (peer-to-peer stores over NVLink). */
+  int64_t peer_delta[8];
 } mucon_viterbi_batch;
 
 /* Host helper: packs units into bins of wpc warps (one CTA each; wpc = 4, 8 or 16, the
@@ -111,6 +116,14 @@ typedef struct mucon_viterbi_batch {
 int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
                          int max_len, int lanes, int32_t* warp_unit_h, int32_t* n_cta_out,
                          int32_t* wpc_out, int32_t* lanes_out);
+
+/* Receive buffers of the result exchange: device memory allocated with cudaMalloc (one allocation = one CUDA IPC
+ * handle), exported as a 64-byte cudaIpcMemHandle_t, opened by the other ranks of the node (peer access is enabled
+ * lazily by the driver), closed / freed at the end.  The handles travel through torch.distributed (or any channel). */
+int mucon_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[64]);
+int mucon_peer_open(const unsigned char handle[64], void** dev_ptr_out);
+int mucon_peer_close(void* dev_ptr);
+int mucon_peer_free(void* dev_ptr);
 
 int mucon_viterbi_decode(const mucon_viterbi_batch* batch_h, void* stream);
 
@@ -130,13 +143,12 @@ int mucon_viterbi_decode_generic(const mucon_viterbi_batch* batch_h, double* ws,
  * of one warp (units in order_h, longest first); lane_unit_h needs room for U*32 entries, on
  * return the first *n_warps_out * 32 are valid (-1 = unused lane).
  * mucon_viterbi_decode_lanes: same inputs/outputs as mucon_viterbi_decode (warp_unit / n_cta /
- * wpc / lanes ignored), one 32-thread CTA per warp of the packing.  progress: NULL, or [V]
- * counters of block-score rows already published per video (mucon_viterbi_blockscores_progress):
- * the kernel then runs concurrently with the scan and only waits for rows it is about to read. */
+ * wpc / lanes ignored), one 32-thread CTA per warp of the packing.  reserved: pass NULL (must be NULL;
+ * a scan-concurrent variant that polled per-video progress counters was never shipped). */
 int mucon_viterbi_pack_lanes_h(const int32_t* N_h, const int32_t* order_h, int U, int32_t* lane_unit_h,
                                int32_t* n_warps_out);
 int mucon_viterbi_decode_lanes(const mucon_viterbi_batch* batch_h, const int32_t* lane_unit, int n_warps,
-                               const int32_t* progress, void* stream);
+                               const int32_t* reserved, void* stream);
 
 /* One-launch alignment: block-score scan and DP of a unit fused in one CTA (scan warps feed the
  * DP warps through shared memory; block scores do not travel through HBM).  Same inputs and

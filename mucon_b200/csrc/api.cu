@@ -32,3 +32,44 @@ extern "C" int mucon_device_sm_count(void) {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   return n;
 }
+
+// ---- receive buffers of the multi-GPU result exchange (CUDA IPC; see mucon_viterbi_batch.peer_delta) ------------
+extern "C" int mucon_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!dev_ptr_out || !handle_out || bytes == 0) return MUCON_EINVAL;
+  void* p = nullptr;
+  MUCON_CUDA_CHECK(cudaMalloc(&p, bytes));
+  MUCON_CUDA_CHECK(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    mucon::set_cuda_error(e, "cudaIpcGetMemHandle");
+    return MUCON_ECUDA;
+  }
+  memcpy(handle_out, &h, 64);
+  *dev_ptr_out = p;
+  return MUCON_OK;
+}
+
+extern "C" int mucon_peer_open(const unsigned char handle[64], void** dev_ptr_out) {
+  if (!handle || !dev_ptr_out) return MUCON_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  MUCON_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr_out = p;
+  return MUCON_OK;
+}
+
+extern "C" int mucon_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return MUCON_EINVAL;
+  MUCON_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+  return MUCON_OK;
+}
+
+extern "C" int mucon_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return MUCON_EINVAL;
+  MUCON_CUDA_CHECK(cudaFree(dev_ptr));
+  return MUCON_OK;
+}

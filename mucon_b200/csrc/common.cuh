@@ -111,6 +111,19 @@ __device__ __forceinline__ float neg_zero<float>() { return -0.0f; }
 template <>
 __device__ __forceinline__ double neg_zero<double>() { return -0.0; }
 
+// Result stores of the alignment kernels: the local payload buffer and, when a multi-GPU result exchange is set up
+// (mucon_viterbi_batch.peer_delta), the same location of this rank's slot in every peer's receive buffer.
+__device__ __forceinline__ void put_score(const mucon_viterbi_batch& b, int64_t u, double v) {
+  b.score[u] = v;
+  for (int p = 0; p < b.n_peers; ++p)
+    *reinterpret_cast<double*>(reinterpret_cast<char*>(b.score + u) + b.peer_delta[p]) = v;
+}
+__device__ __forceinline__ void put_seg(const mucon_viterbi_batch& b, int64_t i, int32_t v) {
+  b.seg_blocks[i] = v;
+  for (int p = 0; p < b.n_peers; ++p)
+    *reinterpret_cast<int32_t*>(reinterpret_cast<char*>(b.seg_blocks + i) + b.peer_delta[p]) = v;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

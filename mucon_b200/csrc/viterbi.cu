@@ -9,11 +9,13 @@
 //                   slabs arrive in shared memory through 1-D TMA bulk copies (UBLKCP) on an
 //                   mbarrier ring; one thread per class column walks the slab.
 //   dp_kernel       per (video, candidate transcript): the K x N x J dynamic program
-//                   (viterbi.py:92-138) with one warp per transcript segment, the J length
-//                   slots of a segment spread over the lanes as a circular buffer indexed by
-//                   entry step (no shifting), a warp-shuffle (value, length) arg-max with the
-//                   reference's "last writer wins" tie rule (viterbi.py:26-28), back-pointers,
-//                   traceback (viterbi.py:140-158) and a vectorised label writer.
+//                   (viterbi.py:92-138).  A transcript segment's J hypothesis scores are a SHIFT
+//                   REGISTER over a group of 8 lanes x 9 registers (or a whole warp for the long
+//                   tail): ageing is a register move + add, the (value, age) arg-max is an in-lane
+//                   tree followed by a lane butterfly with the reference's "last writer wins" tie
+//                   rule (viterbi.py:26-28); back-pointers, traceback (viterbi.py:140-158) and a
+//                   vectorised label writer (viterbi_dp.cuh).  The generic kernel (viterbi_generic.cuh)
+//                   keeps the older circular-buffer form in a global-memory workspace for J > 128.
 //
 // This translation unit is compiled with -fmad=false: every add/sub/mul must round exactly like
 // the NumPy scalar arithmetic it replaces.
@@ -499,8 +501,9 @@ extern "C" int mucon_viterbi_pack_lanes_h(const int32_t* N_h, const int32_t* ord
 }
 
 extern "C" int mucon_viterbi_decode_lanes(const mucon_viterbi_batch* bh, const int32_t* lane_unit, int n_warps,
-                                          const int32_t* progress, void* stream) {
-  if (!bh || !lane_unit || n_warps < 0) return MUCON_EINVAL;
+                                          const int32_t* reserved, void* stream) {
+  if (!bh || !lane_unit || n_warps < 0 || reserved) return MUCON_EINVAL;
+  const int32_t* progress = nullptr;
   const mucon_viterbi_batch& b = *bh;
   if (b.U < 0 || b.C < 1 || b.fs < 1 || b.max_len < b.fs || b.max_N < 1) return MUCON_EINVAL;
   if (!b.bs || !b.vid_off || !b.blk_off || !b.unit_vid || !b.tr || !b.tr_off || !b.score || !b.seg_blocks ||

@@ -327,7 +327,7 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
     for (int n = ltid; n < N; n += nthr) segb[n] = (n < K) ? 1 : 0;
     if (ltid == 0) {
       b.status[u] = MUCON_UNIT_SHORT;
-      b.score[u] = -INFINITY;
+      put_score(b, u, -INFINITY);
       b.final_j[u] = 1;
     }
     for (int i = ltid; i < K * N; i += nthr) bp_g[i] = 0;  // not computed
@@ -642,7 +642,7 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
         k0 -= ln;
         --m;
       }
-      b.score[u] = sc;
+      put_score(b, u, sc);
       b.final_j[u] = jf;
       b.status[u] = (isfinite(sc) || sc == -INFINITY) ? MUCON_UNIT_OK : MUCON_UNIT_NONFINITE;
     }
@@ -670,7 +670,7 @@ __device__ __forceinline__ void dp_unit(const mucon_viterbi_batch& b, const int 
     }
   }
 
-  for (int m = ltid; m < N; m += nthr) b.seg_blocks[tr0 + m] = segb[m];
+  for (int m = ltid; m < N; m += nthr) put_seg(b, tr0 + m, segb[m]);
   const int64_t lo = b.lab_off ? b.lab_off[u] : -1;
   if (lo >= 0) {
     if (ltid == 0) {
@@ -693,10 +693,10 @@ __device__ __forceinline__ bool dp_feasible(const mucon_viterbi_batch& b, int J,
   if (K >= 1 && N >= 1 && K <= static_cast<int64_t>(N) * J) return true;
   if (t.ltid == 0) {
     b.status[u] = MUCON_UNIT_INFEASIBLE;
-    b.score[u] = __longlong_as_double(0x7ff8000000000000ll);
+    put_score(b, u, __longlong_as_double(0x7ff8000000000000ll));
     b.final_j[u] = 0;
   }
-  for (int n = t.ltid; n < N; n += t.nthr) b.seg_blocks[tr0 + n] = 0;
+  for (int n = t.ltid; n < N; n += t.nthr) put_seg(b, tr0 + n, 0);
   return false;
 }
 

@@ -35,10 +35,10 @@ dp_generic_kernel(const mucon_viterbi_batch b, const int J, double* __restrict__
   if (K < 1 || N < 1 || K > static_cast<int64_t>(N) * J) {
     if (tid == 0) {
       b.status[u] = MUCON_UNIT_INFEASIBLE;
-      b.score[u] = __longlong_as_double(0x7ff8000000000000ll);
+      put_score(b, u, __longlong_as_double(0x7ff8000000000000ll));
       b.final_j[u] = 0;
     }
-    for (int n = tid; n < N; n += blockDim.x) b.seg_blocks[tr0 + n] = 0;
+    for (int n = tid; n < N; n += blockDim.x) put_seg(b, tr0 + n, 0);
     return;
   }
   // shared: E[N] entry scores, Ej[N], trl[N], segb[N], segend[N]
@@ -68,7 +68,7 @@ dp_generic_kernel(const mucon_viterbi_batch b, const int J, double* __restrict__
     for (int n = tid; n < N; n += blockDim.x) segb[n] = (n < K) ? 1 : 0;
     if (tid == 0) {
       b.status[u] = MUCON_UNIT_SHORT;
-      b.score[u] = -INFINITY;
+      put_score(b, u, -INFINITY);
       b.final_j[u] = 1;
     }
     __syncthreads();
@@ -164,13 +164,13 @@ dp_generic_kernel(const mucon_viterbi_batch b, const int J, double* __restrict__
         k0 -= ln;
         --n;
       }
-      b.score[u] = sc;
+      put_score(b, u, sc);
       b.final_j[u] = fin_j;
       b.status[u] = (isfinite(sc) || sc == -INFINITY) ? MUCON_UNIT_OK : MUCON_UNIT_NONFINITE;
     }
     __syncthreads();
   }
-  for (int n = tid; n < N; n += blockDim.x) b.seg_blocks[tr0 + n] = segb[n];
+  for (int n = tid; n < N; n += blockDim.x) put_seg(b, tr0 + n, segb[n]);
   const int64_t lo = b.lab_off ? b.lab_off[u] : -1;
   if (lo >= 0) {
     if (tid == 0) {

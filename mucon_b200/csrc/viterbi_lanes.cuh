@@ -11,9 +11,7 @@
 // (video x transcript) of similar length packed side by side by mucon_viterbi_pack_lanes_h; units
 // never straddle warps, warps never synchronise with each other.
 //
-// Block scores are read from HBM/L2 (written by the scan kernel).  With `progress` != NULL the
-// kernel runs CONCURRENTLY with the scan kernel: progress[v] counts the blocks of video v already
-// published, and a lane waits (acquire loads) before it stages block scores beyond that.
+// Block scores are read from HBM/L2 (written by the scan kernel, which precedes this kernel in the stream).
 #pragma once
 #include <math.h>
 
@@ -48,7 +46,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 template <typename BST, int CH, int NCH>
 __global__ void __launch_bounds__(32, 1)
 dp_lanes_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restrict__ lane_unit,
-                const int* __restrict__ progress) {
+                const int* __restrict__ /*reserved*/) {
   constexpr int JT = CH * NCH;
   static_assert(CH % 2 == 0, "rows are read two at a time");
   extern __shared__ __align__(16) unsigned char sm[];
@@ -86,16 +84,16 @@ dp_lanes_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restr
 
   if (active && !feasible && is_first) {
     b.status[u] = MUCON_UNIT_INFEASIBLE;
-    b.score[u] = __longlong_as_double(0x7ff8000000000000ll);
+    put_score(b, u, __longlong_as_double(0x7ff8000000000000ll));
     b.final_j[u] = 0;
-    for (int m = 0; m < N; ++m) b.seg_blocks[tr0 + m] = 0;
+    for (int m = 0; m < N; ++m) put_seg(b, tr0 + m, 0);
   }
   if (is_short && is_first) {
     // nothing reaches the last segment (viterbi.py:125-138)
     b.status[u] = MUCON_UNIT_SHORT;
-    b.score[u] = -INFINITY;
+    put_score(b, u, -INFINITY);
     b.final_j[u] = 1;
-    for (int m = 0; m < N; ++m) b.seg_blocks[tr0 + m] = (m < K) ? 1 : 0;
+    for (int m = 0; m < N; ++m) put_seg(b, tr0 + m, (m < K) ? 1 : 0);
     for (int i = 0; i < K * N; ++i) bp_g[i] = 0;
   }
   if (run && is_first) {  // row 0 and column 0 of the back-pointer table hold no entries
@@ -125,13 +123,6 @@ dp_lanes_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restr
     const int k0 = ch * kLanesChunk;
     if (run && k0 < K) {
       const int k1 = min(K, k0 + kLanesChunk);
-      if (progress) {
-        unsigned spins = 0;
-        while (ld_acquire_gpu(progress + v) < k1) {
-          __nanosleep(64);
-          if (++spins > (1u << 24)) break;  // never hang the GPU on a missing producer
-        }
-      }
       BST* dst = stg + static_cast<size_t>(ch & 1) * kLanesChunk * 64 + lane;
       const BST* src = bs_v + static_cast<int64_t>(k0) * C;
       for (int r = 0; r < k1 - k0; ++r) {
@@ -272,16 +263,16 @@ dp_lanes_kernel(const mucon_viterbi_batch b, const int J, const int32_t* __restr
     }
     int m = N - 1;
     int k0 = K - bage;
-    b.seg_blocks[tr0 + m] = bage;
+    put_seg(b, tr0 + m, bage);
     while (m > 0) {
       int ln;
       if (m == 1) ln = (k0 <= J) ? k0 : 0;
       else ln = static_cast<int>(__ldcg(bp_g + static_cast<int64_t>(k0) * N + m));
-      b.seg_blocks[tr0 + m - 1] = ln;
+      put_seg(b, tr0 + m - 1, ln);
       k0 -= ln;
       --m;
     }
-    b.score[u] = bv;
+    put_score(b, u, bv);
     b.final_j[u] = bage;
     b.status[u] = (isfinite(bv) || bv == -INFINITY) ? MUCON_UNIT_OK : MUCON_UNIT_NONFINITE;
   }

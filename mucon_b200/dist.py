@@ -7,6 +7,8 @@ lengths in blocks -- the run-length form of the frame labels) and path scores ar
 NCCL over NVLink.  All candidates of a video stay on one rank because they share its block-score
 table.  Works with any torch.distributed backend (nccl on GPUs, gloo in the CPU tests).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -122,3 +124,92 @@ def unpack_gathered(all_sc, all_int, max_positions):
         out.append(dict(score=all_sc[r, :U].cpu().numpy(), seg_blocks=row[2:2 + P],
                         tr_off=row[2 + max_positions:2 + max_positions + U + 1]))
     return out
+
+
+def peer_deltas(payload_ptr, peer_recv_ptrs, rank, world, slot, capacity):
+    """Byte offsets from a plan's payload buffer to this rank's slot in every rank's receive buffer (own rank
+    included): receive buffers are laid out [slot][source rank][capacity]."""
+    return [int(base) + (slot * world + rank) * capacity - int(payload_ptr) for base in peer_recv_ptrs]
+
+
+class _DevBuf:
+    """torch view of raw device memory (allocated by mucon_peer_alloc) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """The multi-GPU result exchange without a collective kernel: every rank's alignment kernels store the per-video
+    scores and segment lengths straight into their slot of EVERY rank's receive buffer (peer-to-peer stores over
+    NVLink from the kernel epilogue, mucon_viterbi_batch.peer_delta), so an all_gather of the payloads has happened
+    by the time the kernels of all ranks have finished.  Replaces the NCCL all_gather_into_tensor per step
+    (SURVEY.md 8e), which cost a collective kernel + a stream wait every 150 us step.
+
+        px = PeerExchange([plan_a, plan_b])        # collective: allocates, exchanges IPC handles, opens peers
+        for i, logp in enumerate(batches):
+            engine.run(px.plan(i), logp, ...)      # results land on every rank
+        px.fence()                                 # all ranks' kernels done (stream sync + barrier)
+        rows = px.result(i)                        # [world, capacity] uint8: rank r's payload of batch i
+
+    Slots alternate between the plans: fence() before a slot is read, and before it is overwritten a second time
+    if a consumer is still reading.  Needs one node (CUDA IPC) and the nccl (or any) process group for the handle
+    exchange and the fences."""
+
+    def __init__(self, plans, group=None):
+        from . import _lib
+        self.lib, self.group = _lib.lib(), group
+        self.plans = list(plans)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise _lib.MuconError("peer exchange covers one node (<= 8 ranks)")
+        self.cap = self.plans[0].payload.numel()
+        if any(p.payload.numel() != self.cap for p in self.plans):
+            raise ValueError("all plans need the same payload_capacity")
+        dev = self.plans[0].payload.device
+        nbytes = len(self.plans) * self.world * self.cap
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        _lib.check(self.lib.mucon_peer_alloc(C.c_size_t(nbytes), C.byref(ptr), handle), "mucon_peer_alloc")
+        self._own = ptr.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().reshape(self.world, 64)
+        self._opened, self.ptrs = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs.append(self._own)
+                continue
+            q = C.c_void_p()
+            hb = (C.c_ubyte * 64)(*allh[r].tolist())
+            _lib.check(self.lib.mucon_peer_open(hb, C.byref(q)), "mucon_peer_open")
+            self._opened.append(q.value)
+            self.ptrs.append(q.value)
+        self.recv = torch.as_tensor(_DevBuf(self._own, nbytes), device=dev).view(len(self.plans), self.world, self.cap)
+        for slot, p in enumerate(self.plans):
+            p.peer_delta = peer_deltas(p.payload.data_ptr(), self.ptrs, self.rank, self.world, slot, self.cap)
+        dist.barrier(group=group)
+
+    def plan(self, i):
+        return self.plans[i % len(self.plans)]
+
+    def fence(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def result(self, i):
+        return self.recv[i % len(self.plans)]
+
+    def close(self):
+        for p in self.plans:
+            p.peer_delta = None
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for q in self._opened:
+            self.lib.mucon_peer_close(C.c_void_p(q))
+        self._opened = []
+        dist.barrier(group=self.group)
+        if self._own:
+            self.recv = None
+            self.lib.mucon_peer_free(C.c_void_p(self._own))
+            self._own = None

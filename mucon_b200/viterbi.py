@@ -334,6 +334,11 @@ class ViterbiEngine:
         b.score, b.labels = plan.score.data_ptr(), plan.labels.data_ptr()
         b.seg_blocks, b.bp = plan.seg_blocks.data_ptr(), plan.bp.data_ptr()
         b.final_j, b.status = plan.final_j.data_ptr(), plan.status.data_ptr()
+        deltas = getattr(plan, "peer_delta", None)   # dist.PeerExchange: result stores repeated into peers' buffers
+        if deltas:
+            b.n_peers = len(deltas)
+            for i_, d_ in enumerate(deltas):
+                b.peer_delta[i_] = d_
         self.last_mode = "split"
         if mode not in ("auto", "fused", "split", "lanes"):
             raise ValueError(mode)

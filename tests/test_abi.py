@@ -33,13 +33,13 @@ def test_header_symbols_exported(built_lib):
 def test_loader_symbol_list_matches_header(built_lib):
     from mucon_b200 import _lib
     assert sorted(_lib.SYMBOLS) == _declared()
-    assert _lib.lib().mucon_abi_version() == 1
+    assert _lib.lib().mucon_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     from mucon_b200 import _lib
-    # 12 int32 + 18 pointers
-    assert ctypes.sizeof(_lib.ViterbiBatch) == 12 * 4 + 18 * 8
+    # 12 int32 + 18 pointers + peer_delta[8] (int64)
+    assert ctypes.sizeof(_lib.ViterbiBatch) == 12 * 4 + 18 * 8 + 8 * 8
 
 
 def test_argument_validation_without_gpu(built_lib):

@@ -98,3 +98,10 @@ def test_gather_alignments_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+def test_peer_deltas_layout():
+    """byte offsets from a payload buffer to this rank's slot in every rank's receive buffer ([slot][rank][cap])"""
+    from mucon_b200.dist import peer_deltas
+    d = peer_deltas(payload_ptr=1000, peer_recv_ptrs=[50000, 90000], rank=1, world=2, slot=1, capacity=256)
+    assert d == [50000 + (1 * 2 + 1) * 256 - 1000, 90000 + (1 * 2 + 1) * 256 - 1000]

@@ -1,6 +1,8 @@
 """GPU parity: the CUDA Viterbi path (through the C ABI) against the oracle and the frozen
 reference outputs.  Integer outputs (labels, segments, back-pointers, final j) and block scores
 must be bit-exact; the float64 path score must be equal to the last bit."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -413,3 +415,19 @@ def test_pooled_source_is_bit_identical_to_expanded(eng, dtype, C):
     for u in range(0, pa.U, 5):
         ref = oracle_unit(logps[u], cands[u][0], means[u], 30, 2000, seg0)
         check_unit(pb, b, u, ref, logps[u].shape[0])
+
+
+@pytest.mark.gpu
+def test_peer_exchange_two_gpus():
+    """dist.PeerExchange: result stores repeated into the peers' receive buffers from the kernel epilogue equal an NCCL
+    all_gather of the payloads (needs two GPUs on the node; skipped otherwise)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "scripts", "peer_exchange_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and '"peer_exchange_ok": true' in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
