@@ -67,6 +67,18 @@ def device_logp(T, trs, seed, device):
     return torch.log_softmax(x, dim=1).contiguous()
 
 
+def make_host_logp(T, trs, seed):
+    """The rank's log-probabilities generated on the HOST with the recipe and generator state the reference arm's
+    sample uses (cpu_sample_jobs): both arms see identical arrays (the reference arm the first n videos of them)."""
+    rng = np.random.default_rng(seed + 3000)
+    out = np.empty((int(T.sum()), C), dtype=np.float32)
+    pos = 0
+    for t, tr in zip(T, trs):
+        out[pos:pos + int(t)], _ = synth.planted_logp(rng, int(t), C, tr.tolist(), np.float32)
+        pos += int(t)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -236,26 +248,37 @@ def main_ours(args, rank, world, local_rank):
 
     T, trs, means = make_split(rank)
     cands = [[tr.tolist()] for tr in trs]
-    logp = device_logp(T, trs, rank, device)
+    host_lp = torch.from_numpy(make_host_logp(T, trs, rank)).pin_memory()
+    logp = host_lp.to(device, non_blocking=True)
+    torch.cuda.synchronize()
     eng = ViterbiEngine(device)
     params = poisson_params(means)
     payload_cap = 8 * V_PER_GPU + 4 * V_PER_GPU * 12  # same on every rank: [scores | segment lengths | pad]
     plan = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=params, labels="best",
                      payload_capacity=payload_cap)
-    # N > 1: the gather of step i overlaps the alignment of step i+1 (two plan / receive-buffer slots)
-    pg = None
+    # N > 1: the kernels store every video's score and segment lengths straight into their slot of every rank's
+    # receive buffer (peer-to-peer stores over NVLink, dist.PeerExchange): no collective kernel in the step, the
+    # barrier that ends the timed region is the only synchronisation.  --collective nccl keeps the round-1 form
+    # (an async all_gather_into_tensor per step, overlapped with the next step).
+    pg = px = None
     if world > 1:
         plan_b = AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=params, labels="best",
                            payload_capacity=payload_cap)
-        pg = mdist.PipelinedGather([plan, plan_b])
+        if args.collective == "nccl":
+            pg = mdist.PipelinedGather([plan, plan_b])
+        else:
+            px = mdist.PeerExchange([plan, plan_b])
     step_no = [0]
 
     def step(mode="auto"):
-        if pg is None:
+        if pg is None and px is None:
             eng.run(plan, logp, seg0_f32=True, mode=mode, write_bs=False)
             return
         i = step_no[0]
         step_no[0] += 1
+        if px is not None:
+            eng.run(px.plan(i), logp, seg0_f32=True, mode=mode, write_bs=False)
+            return
         eng.run(pg.acquire(i), logp, seg0_f32=True, mode=mode, write_bs=False)
         pg.gather(i)
 
@@ -285,6 +308,20 @@ def main_ours(args, rank, world, local_rank):
     barrier()
     total_ms = t_all0.elapsed_time(t_all1)
     launches = eng.launches - launches0
+    comm = None
+    if px is not None:
+        # outside the timed region: what the exchange delivered against an NCCL all_gather of the same payloads
+        last = step_no[0] - 1
+        want = mdist.gather_payload(px.plan(last))
+        torch.cuda.synchronize()
+        okt = torch.tensor([int(torch.equal(px.result(last), want))], device=device)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        comm = {"kind": "peer-to-peer stores of scores + segment lengths from the alignment kernels' epilogue into "
+                        "every rank's receive buffer (CUDA IPC over NVLink); no collective kernel in the step",
+                "bytes_per_rank_per_step": int(payload_cap) * world, "equals_nccl_all_gather": bool(okt.item())}
+    elif pg is not None:
+        comm = {"kind": "NCCL all_gather_into_tensor per step, overlapped with the next step",
+                "bytes_per_rank_per_step": int(payload_cap) * world}
     # the alignment launches alone (no collective), same number of steps, for the roofline
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
@@ -473,8 +510,7 @@ def main_ours(args, rank, world, local_rank):
         masks_leg = {"error": str(e)[:200]}
 
     # ---- e2e: host API, pinned host log-probs in, labels + scores + segments out ---------------
-    host_logp = torch.empty(logp.shape, dtype=logp.dtype, pin_memory=True)
-    host_logp.copy_(logp)
+    host_logp = host_lp   # the pinned host array both arms are built from
     n_lab = plan.n_labels
     host_labels = torch.empty(n_lab, dtype=torch.int32, pin_memory=True)
     host_small = torch.empty(plan.U, dtype=torch.float64, pin_memory=True)
@@ -501,13 +537,58 @@ def main_ours(args, rank, world, local_rank):
         p_last = e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # where an e2e step goes: the parts timed one at a time (in the step itself the plan build overlaps the H2D copy)
+    def wall(fn, n=3):
+        torch.cuda.synchronize()
+        t_ = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t_) / n * 1e3
+    plan_ms = wall(lambda: AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device,
+                                     len_params=poisson_params(means), labels="best"))
+    h2d_ms = wall(lambda: dev_in.copy_(host_logp, non_blocking=True))
+    kern_ms = wall(lambda: eng.run(p_last, dev_in, seg0_f32=True, write_bs=False))
+    d2h_ms = wall(lambda: (host_labels.copy_(p_last.labels, non_blocking=True),
+                           host_small.copy_(p_last.score, non_blocking=True),
+                           host_seg.copy_(p_last.seg_blocks, non_blocking=True)))
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     h2d = logp.numel() * logp.element_size() + p_last.h2d_meta_bytes
     d2h = host_labels.numel() * 4 + host_small.numel() * 8 + host_seg.numel() * 4
 
+    # ---- the other configs (bench_legs.py) ---------------------------------------------------------
+    legs = {}
+    if not args.no_legs:
+        import bench_legs
+        del dev_in
+        torch.cuda.empty_cache()
+        try:
+            legs["c3_candidates"] = bench_legs.leg_c3(device, rank, world, make_split, device_logp)
+        except Exception as e:
+            legs["c3_candidates"] = {"error": str(e)[:300]}
+            if world > 1:
+                raise
+        if rank == 0:
+            for name, fn in (("c1_single_video", lambda: bench_legs.leg_c1(device)),
+                             ("c4_long_video", lambda: bench_legs.leg_c4(device)),
+                             ("train_step", lambda: bench_legs.leg_train(device, make_split))):
+                try:
+                    legs[name] = fn()
+                except Exception as e:
+                    legs[name] = {"error": str(e)[:300]}
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
     # max over ranks
+    per_rank_ms = [total_ms / args.steps]
+    per_rank_e2e = [e2e_s * 1e3]
     if world > 1:
+        mine = torch.tensor([total_ms / args.steps, e2e_s * 1e3], dtype=torch.float64, device=device)
+        allr = torch.empty(2 * world, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank_ms, per_rank_e2e = allr.view(world, 2)[:, 0].tolist(), allr.view(world, 2)[:, 1].tolist()
         t = torch.tensor([total_ms, scan_ms, dp_ms, e2e_s, fused_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, scan_ms, dp_ms, e2e_s, fused_ms = t.tolist()
@@ -547,11 +628,22 @@ def main_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "videos_per_gpu": V_PER_GPU, "frames_per_gpu": Tsum,
                        "l2": "inputs (%.0f MB log-probs per GPU) are larger than the 126 MB L2" % (scan_bytes / 1e6),
-                       "collective": "all_gather(scores, segment lengths), overlapped with the next step" if world > 1 else "none"},
+                       "collective": ("none in the step: scores + segment lengths are stored into every rank's receive "
+                                      "buffer by the kernels (NVLink peer stores); one barrier ends the timed region"
+                                      if args.collective == "peer" else
+                                      "all_gather(scores, segment lengths), overlapped with the next step") if world > 1 else "none",
+                       "inputs": "host-generated (numpy, seed rank+3000): the same arrays the reference arm samples from"},
             "clocks": sampler.summary(),
             "e2e": {"value": frames_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                    "what": "AlignPlan build + pinned H2D of log-probs + fused kernel + D2H of labels/scores/segments"},
+                    "what": "AlignPlan build + pinned H2D of log-probs + fused kernel + D2H of labels/scores/segments",
+                    "breakdown_rank0_ms": {"plan_build": plan_ms, "h2d": h2d_ms, "kernel": kern_ms, "d2h": d2h_ms,
+                                           "note": "timed one at a time; in the step the plan build overlaps the H2D copy"},
+                    "h2d_gbs_rank0": h2d / (h2d_ms * 1e-3) / 1e9,
+                    "per_rank_ms": per_rank_e2e,
+                    "limiter": "host-to-device copy of the log-probabilities (740 MB per rank per step over PCIe); with "
+                               "N ranks copying at once the host side is shared, so e2e scales worse than the kernels"},
+            "per_rank_ms_per_step": per_rank_ms,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "align_fused_kernel (scan + DP + traceback + labels)" + (
                              ", %d concurrent launches: the %d longest videos with a warp per segment, the rest "
@@ -568,13 +660,35 @@ def main_ours(args, rank, world, local_rank):
                                                 "ms_per_launch": scan_ms},
                                 "dp_kernel_ms": dp_ms},
         }
+        if comm is not None:
+            out["comm"] = comm
         if full is not None:
             out["full_inference"] = full
         if masks_leg is not None:
+            if "fwd_ms" in masks_leg:
+                masks_leg["roofline"] = {"bound": "hbm", "kernel": "masks_fwd_kernel", "achieved": masks_leg["fwd_gbs"],
+                                         "peak": hbm_peak, "unit": "GB/s", "frac": masks_leg["fwd_gbs"] / hbm_peak,
+                                         "bytes_per_launch": masks_leg["bytes_written_fwd"],
+                                         "algorithmic_bytes": "4*N*T written per video (SURVEY.md 8d)"}
+                ff_ = masks_leg.get("flint_fused", {})
+                if "fwd_read_gbs" in ff_:
+                    ff_["roofline"] = {"bound": "hbm", "kernel": "flint_fwd_kernel", "achieved": ff_["fwd_read_gbs"],
+                                       "peak": hbm_peak, "unit": "GB/s", "frac": ff_["fwd_read_gbs"] / hbm_peak,
+                                       "algorithmic_bytes": "4*T*C read + 4*N*C written per video (SURVEY.md 8d)"}
             out["masks"] = masks_leg
+        out.update(legs)
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
+            if not args.no_legs:
+                import bench_legs
+                for name, fn in (("backbone", bench_legs.cpu_backbone_baseline), ("masks", bench_legs.cpu_masks_baseline)):
+                    try:
+                        out["cpu_baseline"][name] = fn()
+                    except Exception as e:
+                        out["cpu_baseline"][name] = {"error": str(e)[:200]}
         print(json.dumps(out))
+    if px is not None:
+        px.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -587,6 +701,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-backbone", action="store_true", help="skip the backbone + alignment leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip the c1 / c3 / c4 / training-step legs")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: result exchange by peer stores from the kernels (default) or an NCCL all_gather per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
