@@ -116,8 +116,12 @@ def leg_c3(device, rank, world, make_split, device_logp, steps=5):
     if world > 1:
         dist.all_reduce(need, op=dist.ReduceOp.MAX)
     cap = int(need.item())
+    from mucon_b200.viterbi import FlatCandidates
+    flat = FlatCandidates.from_lists(cands)   # candidate sets as arrays (how a beam search would hand them over)
+    AlignPlan(Tm[:8], FlatCandidates.from_lists(cands[:8]), 48, device=device, len_params=params[:8], labels="best")
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    plan = AlignPlan(Tm, cands, 48, device=device, len_params=params, labels="best", payload_capacity=cap)
+    plan = AlignPlan(Tm, flat, 48, device=device, len_params=params, labels="best", payload_capacity=cap)
     torch.cuda.synchronize()
     prep_s = time.perf_counter() - t0
     eng = ViterbiEngine(device)

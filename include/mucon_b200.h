@@ -36,6 +36,7 @@ extern "C" {
 #define MUCON_EUNSUPPORTED (-2) /* shape outside what the kernels cover (J > 128, N > 65, ...) */
 #define MUCON_ECUDA (-3)       /* a CUDA runtime call failed; see mucon_last_cuda_error() */
 #define MUCON_EALIGN (-4)      /* pointer not aligned as documented */
+#define MUCON_ESHAPE (-5)      /* input larger than the session / workspace was created for */
 
 /* per-unit status written by mucon_viterbi_decode (int32 each) */
 #define MUCON_UNIT_OK 0
@@ -116,6 +117,20 @@ typedef struct mucon_viterbi_batch {
 int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
                          int max_len, int lanes, int32_t* warp_unit_h, int32_t* n_cta_out,
                          int32_t* wpc_out, int32_t* lanes_out);
+
+/* Single-video session -- the reference's call pattern (src/mucon/evaluators.py:147-180: one Viterbi.decode per
+ * video, core/viterbi/viterbi.py:49-158) as ONE call from host arrays to host arrays: a pinned staging buffer
+ * carries [metadata | log-probabilities] to the device in one copy, the fused alignment kernel runs, one copy
+ * brings [score | final_j | status | segment lengths | labels] back; the call returns after the stream has been
+ * synchronised.  A session holds buffers for up to max_T frames, C classes, max_N segments of elem_bytes (4 / 8)
+ * log-probabilities; ESHAPE asks the caller for a larger session, EUNSUPPORTED for the general entry points.
+ * len_params_h: [N,3] (ln m, m, norms) of the transcript's classes in transcript order.  Not thread-safe. */
+typedef struct mucon_single mucon_single;
+int mucon_single_create(int max_T, int C, int max_N, int elem_bytes, mucon_single** out);
+int mucon_single_destroy(mucon_single* s);
+int mucon_single_decode_h(mucon_single* s, const void* logp_h, int is_f64, int T, const int32_t* tr_h, int N,
+                          const double* len_params_h, int fs, int max_len, int seg0_f32, double* score_h,
+                          int32_t* labels_h, int32_t* seg_blocks_h, int32_t* status_h, int32_t* final_j_h, void* stream);
 
 /* Receive buffers of the result exchange: device memory allocated with cudaMalloc (one allocation = one CUDA IPC
  * handle), exported as a 64-byte cudaIpcMemHandle_t, opened by the other ranks of the node (peer access is enabled

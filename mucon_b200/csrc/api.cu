@@ -20,6 +20,7 @@ extern "C" const char* mucon_strerror(int code) {
     case MUCON_EUNSUPPORTED: return "shape not supported by the sm_100a kernels";
     case MUCON_ECUDA: return "CUDA runtime error";
     case MUCON_EALIGN: return "misaligned pointer";
+    case MUCON_ESHAPE: return "input larger than the session was created for";
     default: return "unknown error";
   }
 }

@@ -20,6 +20,7 @@
 // This translation unit is compiled with -fmad=false: every add/sub/mul must round exactly like
 // the NumPy scalar arithmetic it replaces.
 #include <math.h>
+#include <string.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -583,6 +584,128 @@ extern "C" int mucon_viterbi_align_fused_pooled(const mucon_viterbi_batch* bh, c
                                                 int write_bs, void* stream) {
   if (!z_off) return MUCON_EINVAL;
   return align_fused_tail_impl(bh, logp_z, in_is_f64, order, n_wide, write_bs, stream, z_off);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-video session: the reference's own call pattern (evaluators.py:147-180 decodes ONE video per call, batch
+// size 1) without per-call allocations or Python-side packing.  One host->device copy carries [metadata | log-
+// probabilities] from a pinned staging buffer, the fused kernel runs, one device->host copy brings back
+// [score | final_j | status | segment lengths | labels].  Not thread-safe per session.
+struct mucon_single {
+  int max_T, C, max_N, elem;
+  size_t off_tr, off_params, off_logfact, off_logp, stage_bytes;
+  size_t out_seg, out_labels, out_bytes;
+  unsigned char *h_stage, *d_stage, *h_out, *d_out;
+  uint8_t* d_bp;
+  int lf_fs, lf_max_len;
+  double logfact[kDpMaxJ + 1];
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int mucon_single_destroy(mucon_single* s) {
+  if (!s) return MUCON_EINVAL;
+  if (s->h_stage) cudaFreeHost(s->h_stage);
+  if (s->h_out) cudaFreeHost(s->h_out);
+  if (s->d_stage) cudaFree(s->d_stage);
+  if (s->d_out) cudaFree(s->d_out);
+  if (s->d_bp) cudaFree(s->d_bp);
+  delete s;
+  return MUCON_OK;
+}
+
+extern "C" int mucon_single_create(int max_T, int C, int max_N, int elem_bytes, mucon_single** out) {
+  if (!out || max_T < 1 || C < 1 || max_N < 1 || (elem_bytes != 4 && elem_bytes != 8)) return MUCON_EINVAL;
+  mucon_single* s = new mucon_single();
+  s->max_T = max_T; s->C = C; s->max_N = max_N; s->elem = elem_bytes;
+  s->lf_fs = s->lf_max_len = -1;
+  // metadata: vid_off[2] blk_off[2] bp_off[1] lab_off[1] (int64) | unit_vid[1] order[1] tr_off[2] (int32) | tr | params | logfact
+  s->off_tr = 64;
+  s->off_params = align_up(s->off_tr + 4 * (size_t)max_N, 16);
+  s->off_logfact = s->off_params + 24 * (size_t)max_N;
+  s->off_logp = align_up(s->off_logfact + 8 * (kDpMaxJ + 1), 128);
+  s->stage_bytes = s->off_logp + (size_t)max_T * C * elem_bytes;
+  s->out_seg = 16;
+  s->out_labels = align_up(s->out_seg + 4 * (size_t)max_N, 16);
+  s->out_bytes = s->out_labels + 4 * (size_t)max_T;
+  bool ok = cudaMallocHost(reinterpret_cast<void**>(&s->h_stage), s->stage_bytes) == cudaSuccess &&
+            cudaMallocHost(reinterpret_cast<void**>(&s->h_out), s->out_bytes) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void**>(&s->d_stage), s->stage_bytes) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void**>(&s->d_out), s->out_bytes) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void**>(&s->d_bp), (size_t)max_T * max_N + 16) == cudaSuccess;
+  if (!ok) {
+    mucon::set_cuda_error(cudaGetLastError(), "mucon_single_create");
+    mucon_single_destroy(s);
+    return MUCON_ECUDA;
+  }
+  *out = s;
+  return MUCON_OK;
+}
+
+extern "C" int mucon_single_decode_h(mucon_single* s, const void* logp_h, int is_f64, int T, const int32_t* tr_h, int N,
+                                     const double* len_params_h, int fs, int max_len, int seg0_f32, double* score_h,
+                                     int32_t* labels_h, int32_t* seg_blocks_h, int32_t* status_h, int32_t* final_j_h,
+                                     void* stream) {
+  if (!s || !logp_h || !tr_h || !len_params_h || !score_h || !labels_h || !seg_blocks_h || !status_h || !final_j_h ||
+      T < 1 || N < 1 || fs < 1 || max_len < fs)
+    return MUCON_EINVAL;
+  if (T > s->max_T || N > s->max_N || (is_f64 ? 8 : 4) != s->elem) return MUCON_ESHAPE;
+  const int J = max_len / fs;
+  if (J > kDpMaxJ) return MUCON_EUNSUPPORTED;
+  if (s->lf_fs != fs || s->lf_max_len != max_len) {
+    int rc = mucon_logfact_h(fs, max_len, s->logfact);
+    if (rc != MUCON_OK) return rc;
+    s->lf_fs = fs;
+    s->lf_max_len = max_len;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = T / fs;
+  int64_t* m64 = reinterpret_cast<int64_t*>(s->h_stage);
+  m64[0] = 0; m64[1] = T;          // vid_off
+  m64[2] = 0; m64[3] = K;          // blk_off
+  m64[4] = 0;                      // bp_off
+  m64[5] = 0;                      // lab_off
+  int32_t* m32 = reinterpret_cast<int32_t*>(s->h_stage + 48);
+  m32[0] = 0;                      // unit_vid
+  m32[1] = 0;                      // order
+  m32[2] = 0; m32[3] = N;          // tr_off
+  memcpy(s->h_stage + s->off_tr, tr_h, 4 * (size_t)N);
+  memcpy(s->h_stage + s->off_params, len_params_h, 24 * (size_t)N);
+  memcpy(s->h_stage + s->off_logfact, s->logfact, 8 * (size_t)(J + 1));
+  const size_t lp_bytes = (size_t)T * s->C * s->elem;
+  memcpy(s->h_stage + s->off_logp, logp_h, lp_bytes);
+  MUCON_CUDA_CHECK(cudaMemcpyAsync(s->d_stage, s->h_stage, s->off_logp + lp_bytes, cudaMemcpyHostToDevice, st));
+  mucon_viterbi_batch b;
+  memset(&b, 0, sizeof(b));
+  b.U = 1; b.C = s->C; b.fs = fs; b.max_len = max_len; b.bs_is_f64 = is_f64 ? 1 : 0; b.seg0_f32 = seg0_f32 ? 1 : 0;
+  b.max_N = N; b.max_K = K; b.n_cta = 0; b.wpc = 4; b.lanes = 0;
+  unsigned char* d = s->d_stage;
+  b.vid_off = reinterpret_cast<const int64_t*>(d);
+  b.blk_off = reinterpret_cast<const int64_t*>(d + 16);
+  b.bp_off = reinterpret_cast<const int64_t*>(d + 32);
+  b.lab_off = reinterpret_cast<const int64_t*>(d + 40);
+  b.unit_vid = reinterpret_cast<const int32_t*>(d + 48);
+  const int32_t* order = reinterpret_cast<const int32_t*>(d + 52);
+  b.tr_off = reinterpret_cast<const int32_t*>(d + 56);
+  b.tr = reinterpret_cast<const int32_t*>(d + s->off_tr);
+  b.len_params = reinterpret_cast<const double*>(d + s->off_params);
+  b.logfact = reinterpret_cast<const double*>(d + s->off_logfact);
+  b.score = reinterpret_cast<double*>(s->d_out);
+  b.final_j = reinterpret_cast<int32_t*>(s->d_out + 8);
+  b.status = reinterpret_cast<int32_t*>(s->d_out + 12);
+  b.seg_blocks = reinterpret_cast<int32_t*>(s->d_out + s->out_seg);
+  b.labels = reinterpret_cast<int32_t*>(s->d_out + s->out_labels);
+  b.bp = s->d_bp;
+  int rc = align_fused_impl(&b, d + s->off_logp, is_f64, order, 0, stream, false);
+  if (rc != MUCON_OK) return rc;
+  MUCON_CUDA_CHECK(cudaMemcpyAsync(s->h_out, s->d_out, s->out_labels + 4 * (size_t)T, cudaMemcpyDeviceToHost, st));
+  MUCON_CUDA_CHECK(cudaStreamSynchronize(st));
+  memcpy(score_h, s->h_out, 8);
+  memcpy(final_j_h, s->h_out + 8, 4);
+  memcpy(status_h, s->h_out + 12, 4);
+  memcpy(seg_blocks_h, s->h_out + s->out_seg, 4 * (size_t)N);
+  memcpy(labels_h, s->h_out + s->out_labels, 4 * (size_t)T);
+  return MUCON_OK;
 }
 
 extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,

@@ -71,6 +71,20 @@ class _Blob:
         return dev, host, {name: base + off for name, off, _ in self.parts}
 
 
+class FlatCandidates:
+    """Candidate transcripts of a batch as three arrays: n_cands [V] (candidates per video), lengths [U]
+    (labels per candidate, videos in order) and labels [sum lengths] (all transcripts concatenated)."""
+
+    def __init__(self, n_cands, lengths, labels):
+        self.n_cands, self.lengths, self.labels = n_cands, lengths, labels
+
+    @classmethod
+    def from_lists(cls, candidates):
+        lengths = np.fromiter((len(t) for cl in candidates for t in cl), dtype=np.int64)
+        labels = np.fromiter((x for cl in candidates for t in cl for x in t), dtype=np.int32, count=int(lengths.sum()))
+        return cls(np.fromiter((len(cl) for cl in candidates), dtype=np.int64, count=len(candidates)), lengths, labels)
+
+
 MAX_J_REGISTER = 128  # kDpMaxJ in csrc/viterbi_dp.cuh
 MAX_N_REGISTER = 65   # dp_max_n(8)
 LONG_TAIL_FRACTION = float(os.environ.get("MUCON_LONG_TAIL_FRACTION", "0.85"))
@@ -99,19 +113,30 @@ class AlignPlan:
         self.K = K = T // self.fs
         self.vid_off = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
         self.blk_off = np.concatenate([[0], np.cumsum(K)]).astype(np.int64)
-        ncand = np.array([len(c) for c in candidates], dtype=np.int64)
-        if len(candidates) != V or (V and ncand.min() < 1):
-            raise ValueError("need at least one candidate transcript per video")
+        if isinstance(candidates, FlatCandidates):
+            # arrays in, no per-transcript Python objects (a 100k-unit plan builds in tens of milliseconds)
+            ncand = np.asarray(candidates.n_cands, dtype=np.int64)
+            nlen = np.asarray(candidates.lengths, dtype=np.int64)
+            tr_all = np.ascontiguousarray(candidates.labels, dtype=np.int32).reshape(-1)
+            if ncand.shape[0] != V or (V and ncand.min() < 1):
+                raise ValueError("need at least one candidate transcript per video")
+            if int(ncand.sum()) != nlen.shape[0] or int(nlen.sum()) != tr_all.shape[0]:
+                raise ValueError("FlatCandidates: n_cands / lengths / labels do not add up")
+        else:
+            ncand = np.array([len(c) for c in candidates], dtype=np.int64)
+            if len(candidates) != V or (V and ncand.min() < 1):
+                raise ValueError("need at least one candidate transcript per video")
+            flat = [np.asarray(tr, dtype=np.int32).reshape(-1) for cl in candidates for tr in cl]
+            nlen = np.array([t.shape[0] for t in flat], dtype=np.int64)
+            tr_all = np.concatenate(flat).astype(np.int32) if flat else np.zeros(0, np.int32)
         self.cand_off = np.concatenate([[0], np.cumsum(ncand)]).astype(np.int32)
         self.U = U = int(self.cand_off[-1])
         self.unit_vid = np.repeat(np.arange(V, dtype=np.int32), ncand)
-        flat = [np.asarray(tr, dtype=np.int32).reshape(-1) for cl in candidates for tr in cl]
-        nlen = np.array([t.shape[0] for t in flat], dtype=np.int64)
         if U and nlen.min() < 1:
             raise ValueError("empty transcript")  # the reference crashes at one_hot (SURVEY V-edge)
         self.N = nlen
         self.tr_off = np.concatenate([[0], np.cumsum(nlen)]).astype(np.int32)
-        self.tr = np.concatenate(flat).astype(np.int32) if U else np.zeros(0, np.int32)
+        self.tr = tr_all
         if U and (self.tr.min() < 0 or self.tr.max() >= self.C):
             raise ValueError("transcript label outside [0, n_classes)")
         self.max_N = int(nlen.max()) if U else 1
@@ -156,6 +181,8 @@ class AlignPlan:
         for gi in range(len(bounds) - 1):
             group_of_video[self.order_v[bounds[gi]:bounds[gi + 1]]] = gi
         unit_group = group_of_video[self.unit_vid]
+        # units longest first (by blocks, then segments): the order of the packers and of the fused launch
+        order_all = np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32)
         self.groups = []
         wu_all = []
         for gi in range(len(bounds) - 1):
@@ -163,7 +190,8 @@ class AlignPlan:
             units = np.nonzero(unit_group == gi)[0]
             if v1 <= v0:
                 continue
-            order_u = units[np.argsort(-(uK[units] * 1024 + nlen[units]), kind="stable")].astype(np.int32)
+            order_u = order_all if len(bounds) == 2 else \
+                units[np.argsort(-(uK[units] * 1024 + nlen[units]), kind="stable")].astype(np.int32)
             gmaxN = int(nlen[units].max()) if units.size else 1
             gmaxK = int(uK[units].max()) if units.size else 0
             want = 32 if (gi == 0 and len(bounds) > 2 and long_K and gmaxK >= long_K) else 0
@@ -188,7 +216,6 @@ class AlignPlan:
         self.n_lane_warps = 0
         self.lane_unit = None
         if U and not self.generic and self.J <= 66 and self.max_N <= 33:
-            order_all = np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32)
             lu = np.full(U * 32, -1, dtype=np.int32)
             nw = C.c_int32(0)
             _lib.check(lib.mucon_viterbi_pack_lanes_h(
@@ -208,7 +235,7 @@ class AlignPlan:
         blob.add("bp_off", self.bp_off[:-1] if U else self.bp_off)
         blob.add("order_v", self.order_v)
         blob.add("warp_unit", self.warp_unit)
-        blob.add("order_u", np.argsort(-(uK * 1024 + nlen), kind="stable").astype(np.int32))
+        blob.add("order_u", order_all)
         # long_K: videos of >= long_K blocks go to a wide launch of their own, a warp per transcript segment
         # (None = choose automatically, 0 = never)
         if long_K is None:
@@ -491,6 +518,9 @@ class Viterbi(object):
         self.frame_sampling = frame_sampling
         self.max_hypotheses = max_hypotheses
         self.np_mode = np_mode
+        # one transcript + PoissonModel: the whole decode is one C call (mucon_single_decode_h).  Set to False to
+        # go through the general AlignPlan path, which keeps the raw tables (back-pointers, block scores) for `last`.
+        self.fast_single = True
         self._engine = None
         self._device = device
         self._last = None
@@ -514,6 +544,53 @@ class Viterbi(object):
             self._engine = ViterbiEngine(self._device)
         return self._engine
 
+    def _decode_single(self, eng, logp, tr, lm, fs, max_len):
+        """One transcript, Poisson lengths: the whole decode is one C call (mucon_single_decode_h: staging copy,
+        fused kernel, result copy).  Returns None when the shape needs the general path."""
+        T, Cn = logp.shape
+        N = len(tr)
+        is64 = logp.dtype == np.float64
+        lib = eng.lib
+        ses = getattr(eng, "_single", None)
+        if ses is None or ses[1] < T or ses[2] != Cn or ses[3] < N or ses[4] != is64:
+            if ses is not None:
+                lib.mucon_single_destroy(ses[0])
+            h = C.c_void_p()
+            cap_T, cap_N = max(T, 4096, 2 * ses[1] if ses and ses[1] < T else 0), max(N, 16)
+            if eng.device.index is not None:
+                torch.cuda.set_device(eng.device)
+            _lib.check(lib.mucon_single_create(C.c_int(cap_T), C.c_int(Cn), C.c_int(cap_N), C.c_int(8 if is64 else 4),
+                                               C.byref(h)), "mucon_single_create")
+            ses = eng._single = (h, cap_T, Cn, cap_N, is64,
+                                 np.empty(cap_T, np.int32), np.empty(cap_N, np.int32), np.zeros(2, np.float64),
+                                 np.zeros(2, np.int32))
+        h, _, _, _, _, labels, segb, score, st_fj = ses
+        lp = logp if logp.flags.c_contiguous else np.ascontiguousarray(logp)
+        tr32 = np.asarray(tr, dtype=np.int32)
+        params = np.ascontiguousarray(lm.params[tr32])
+        if self.np_mode is None:
+            seg0 = default_seg0_f32(logp.dtype)
+        else:
+            seg0 = logp.dtype == np.float32 and self.np_mode == "numpy2"
+        rc = lib.mucon_single_decode_h(
+            h, C.c_void_p(lp.ctypes.data), C.c_int(int(is64)), C.c_int(T), C.c_void_p(tr32.ctypes.data), C.c_int(N),
+            C.c_void_p(params.ctypes.data), C.c_int(fs), C.c_int(max_len), C.c_int(int(bool(seg0))),
+            C.c_void_p(score.ctypes.data), C.c_void_p(labels.ctypes.data), C.c_void_p(segb.ctypes.data),
+            C.c_void_p(st_fj.ctypes.data), C.c_void_p(st_fj.ctypes.data + 4),
+            C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream))
+        if rc == -2:
+            return None
+        _lib.check(rc, "mucon_single_decode_h")
+        eng.launches += 1
+        eng.last_mode = "fused"
+        self._last = None
+        if st_fj[0] == _lib.UNIT_INFEASIBLE:
+            raise AttributeError("no hypothesis survives: sequence too long for this transcript and max_length")
+        K = T // fs
+        segs = [Segment(int(tr32[n]), int(fs * segb[n])) for n in range(N) if segb[n] > 0]
+        segs[-1].length += T - fs * K
+        return np.float64(score[0]), labels[:T].tolist(), segs
+
     def decode(self, log_frame_probs):
         logp = np.asarray(log_frame_probs)
         assert logp.shape[1] == self.grammar.n_classes()  # viterbi.py:50
@@ -536,6 +613,11 @@ class Viterbi(object):
         else:
             kw["len_rows"] = [_length_rows(lm, tr, fs, J) for tr in cands]
         eng = self._eng()
+        if self.fast_single and len(cands) == 1 and isinstance(lm, PoissonModel) and J <= MAX_J_REGISTER \
+                and Cn % 4 == 0 and Cn <= 128:
+            fast = self._decode_single(eng, logp, cands[0], lm, fs, max_len)
+            if fast is not None:
+                return fast
         plan = AlignPlan([T], [cands], Cn, fs=fs, max_len=max_len, device=eng.device, labels="best", **kw)
         dev_logp = torch.from_numpy(np.ascontiguousarray(logp)).to(eng.device)
         if self.np_mode is None:
