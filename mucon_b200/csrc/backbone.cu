@@ -321,19 +321,30 @@ static int launch_proj(const float* A, int64_t M, int K, const float* W, int N, 
     return MUCON_EALIGN;
   if (M == 0) return MUCON_OK;
   if (M > 0x7fffffff) return MUCON_EUNSUPPORTED;
+  static int sms = 0;
+  if (!sms) sms = mucon_device_sm_count();
+  // 256-row CTA tiles (one weight stage feeds two M tiles) once there are enough of them to fill the GPU
+  static const int force_mt = getenv("MUCON_PROJ_MT") ? atoi(getenv("MUCON_PROJ_MT")) : 0;
+  const int mt = force_mt ? force_mt : (M >= static_cast<int64_t>(2) * gemm::BM * sms ? 2 : 1);
   CUtensorMap ta, tb;
-  int rc = make_map_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), gemm::BM);
+  int rc = make_map_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), mt * gemm::BM);
   if (rc != MUCON_OK) return rc;
   rc = make_map_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), gemm::BN);
   if (rc != MUCON_OK) return rc;
-  static int sms = 0;
-  if (!sms) sms = mucon_device_sm_count();
-  const int tiles = static_cast<int>((M + gemm::BM - 1) / gemm::BM);
+  const int tile_m = mt * gemm::BM;
+  const int tiles = static_cast<int>((M + tile_m - 1) / tile_m);
   const int grid = tiles < sms ? tiles : sms;
-  MUCON_CUDA_CHECK(cudaFuncSetAttribute(gemm::proj_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        gemm::SMEM_BYTES));
-  gemm::proj_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      ta, tb, bias, static_cast<float*>(out), static_cast<int>(M), K, relu, out_bf16);
+  if (mt == 2) {
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(gemm::proj_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          gemm::SMEM_BYTES));
+    gemm::proj_gemm_kernel<2><<<grid, gemm::THREADS, gemm::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+        ta, tb, bias, static_cast<float*>(out), static_cast<int>(M), K, relu, out_bf16);
+  } else {
+    MUCON_CUDA_CHECK(cudaFuncSetAttribute(gemm::proj_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          gemm::SMEM_BYTES));
+    gemm::proj_gemm_kernel<1><<<grid, gemm::THREADS, gemm::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+        ta, tb, bias, static_cast<float*>(out), static_cast<int>(M), K, relu, out_bf16);
+  }
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

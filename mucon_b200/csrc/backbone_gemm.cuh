@@ -27,7 +27,7 @@ constexpr int UMMA_K = 8;                     // tf32: 32 bytes of K per instruc
 constexpr int STAGES = 6;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;   // both proj_gemm_kernel variants: 6 x 32 KB = 4 x 48 KB
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -107,30 +107,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// MT = 128-row M tiles per CTA tile.  With MT = 2 a weight k-block staged in shared memory is used for 256 rows:
+// the kernel's traffic from L2 into the SMs drops from 2x to 1.5x the feature bytes.  That matters because the
+// MT = 1 kernel ran AT the L2's total delivery rate (63 GB in 5.3 ms = 11.9 TB/s = 6300 B/cycle at 1.9 GHz, the
+// measured LTS cap), half of it weight tiles that never change, while HBM itself was at 5.9 TB/s.
+template <int MT>
 __global__ void __launch_bounds__(THREADS, 1)
 proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ bias, float* __restrict__ out, int M, int K, int relu, int out_bf16) {
+  constexpr int PSTAGES = MT == 1 ? STAGES : 4;
+  constexpr int PA_BYTES = MT * A_BYTES, PSTAGE_BYTES = PA_BYTES + B_BYTES;
+  constexpr int ACC_COLS = MT * BN;            // TMEM columns of one accumulator set
+  constexpr int TILE_M = MT * BM;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_mem = base;
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + PSTAGES * PSTAGE_BYTES);
+  uint64_t* empty = full + PSTAGES;
+  uint64_t* tfull = empty + PSTAGES;   // [2] accumulator ready
   uint64_t* tempty = tfull + 2;       // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = (M + BM - 1) / BM;
+  const int num_tiles = (M + TILE_M - 1) / TILE_M;
   const int num_kb = K / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_fence_init();
   }
-  if (warp == 1) {  // TMEM: 256 columns = two 128x128 fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+  if (warp == 1) {  // TMEM: two sets of MT 128x128 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * ACC_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -146,14 +155,14 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = tile * BM;
+        const int m0 = tile * TILE_M;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          unsigned char* a = stage_mem + s * STAGE_BYTES;
-          tma_load_2d(a, &tmA, kb * BK, m0, &full[s]);
-          tma_load_2d(a + A_BYTES, &tmB, kb * BK, 0, &full[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          mbar_arrive_expect_tx(&full[s], PSTAGE_BYTES);
+          unsigned char* a = stage_mem + s * PSTAGE_BYTES;
+          tma_load_2d(a, &tmA, kb * BK, m0, &full[s]);          // box = TILE_M rows: MT consecutive [128 x 32] tiles
+          tma_load_2d(a + PA_BYTES, &tmB, kb * BK, 0, &full[s]);
+          if (++s == PSTAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -167,23 +176,27 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tempty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(stage_mem + s * STAGE_BYTES);
-          const uint64_t adesc = smem_desc(a_addr), bdesc = smem_desc(a_addr + A_BYTES);
+          const uint32_t a_addr = smem_u32(stage_mem + s * PSTAGE_BYTES);
+          const uint64_t bdesc = smem_desc(a_addr + PA_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 bytes of K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = smem_desc(a_addr + mt * A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 32 bytes of K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              mma_tf32(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           mma_commit(&empty[s]);                       // frees the stage when these MMAs retire
           if (kb == num_kb - 1) mma_commit(&tfull[acc]);  // accumulator complete
         }
         __syncwarp();
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++s == PSTAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -195,12 +208,14 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
-      const int row = tile * BM + q * 32 + lane;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+      const int row = tile * TILE_M + mt * BM + q * 32 + lane;
       float* orow = out + static_cast<int64_t>(row) * BN;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + mt * BN + c * 32, r);
         if (row < M && out_bf16) {
           // 16-bit activations (1: bf16, 2: fp16) for the layer kernels of backbone_bf16.cuh: 32 columns = 64 bytes = two
           // 32-byte stores
@@ -233,6 +248,7 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -243,7 +259,7 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * ACC_COLS));
   }
 }
 

@@ -24,7 +24,8 @@ def tf32_trunc(x):
     return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
-@pytest.mark.parametrize("M,K", [(128, 32), (300, 2048), (5000, 2048), (77, 256), (148 * 128 * 2 + 5, 64)])
+@pytest.mark.parametrize("M,K", [(128, 32), (300, 2048), (5000, 2048), (77, 256), (148 * 128 * 2 + 5, 64),
+                                 (148 * 256 * 3 + 131, 96)])
 def test_tcgen05_gemm_against_truncated_operands(cuda_device, M, K):
     from mucon_b200.temporal import gemm_tf32_bias_act
     g = torch.Generator().manual_seed(M + K)
