@@ -572,6 +572,7 @@ def main_ours(args, rank, world, local_rank):
         if rank == 0:
             for name, fn in (("c1_single_video", lambda: bench_legs.leg_c1(device)),
                              ("c4_long_video", lambda: bench_legs.leg_c4(device)),
+                             ("length_distributions", lambda: bench_legs.leg_distributions(device)),
                              ("train_step", lambda: bench_legs.leg_train(device, make_split))):
                 try:
                     legs[name] = fn()

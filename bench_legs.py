@@ -246,3 +246,44 @@ def cpu_masks_baseline():
     return {"value": 4.0 * N * T / dt / 1e9, "unit": "GB/s of mask output", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "50 x create_masks(T=2000, N=6, box): oracle/masks.py restatement (cumsum -> affine_grid -> "
                       "grid_sample), %.3f ms per call" % (dt * 1e3)}
+
+
+def leg_distributions(device, steps=20):
+    """The long-tail launch policy on length distributions it was NOT tuned on: the alignment of 1712 videos with equal
+    lengths, a bimodal mix and c2's log-normal, each as one launch (long_K = 0) and with the automatic policy."""
+    import torch
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan, ViterbiEngine
+    from tests import synth
+    eng = ViterbiEngine(device)
+    res = {}
+    V, C = 1712, 48
+    for name in ("lognormal_c2", "equal_2250", "bimodal_650_9000"):
+        rng = np.random.default_rng(23)
+        if name == "lognormal_c2":
+            T, trs = synth.breakfast_split(seed=0, V=V, C=C, fs=30, J=66)
+        else:
+            T = np.full(V, 2250) if name.startswith("equal") else \
+                np.where(rng.random(V) < 0.75, rng.integers(500, 800, V), rng.integers(8500, 9500, V))
+            trs = []
+            for t in T:
+                K = int(t) // 30
+                trs.append(rng.integers(0, C, int(rng.integers(max(2, -(-K // 66)), min(12, K) + 1))))
+        means = np.stack([synth.class_means(rng.dirichlet(np.ones(len(tr))).astype(np.float32), tr, C, int(t))
+                          for tr, t in zip(trs, T)])
+        logp = torch.log_softmax(torch.randn(int(T.sum()), C, device=device), dim=1).contiguous()
+        row = {"frames": int(T.sum())}
+        for pol, long_K in (("single_launch", 0), ("auto", None)):
+            plan = AlignPlan(T, [[tr.tolist()] for tr in trs], C, device=device, len_params=poisson_params(means), long_K=long_K)
+            ms = timed(torch, lambda: eng.run(plan, logp, seg0_f32=True, write_bs=False), steps)
+            bytes_ = 4 * int(T.sum()) * C + 4 * int(T.sum())
+            row[pol] = {"ms": ms, "n_long": int(plan.n_long), "gbs": bytes_ / (ms * 1e-3) / 1e9}
+        res[name] = row
+        del logp
+    hbm, _, _ = peaks()
+    for r in res.values():
+        for pol in ("single_launch", "auto"):
+            r[pol]["frac_of_hbm_peak"] = r[pol]["gbs"] / hbm
+    res["what"] = ("fused alignment of 1712 videos per length distribution: one launch vs the automatic long-tail policy "
+                   "(videos within 15 % of the longest, at most 40, get a wide launch of their own); GB/s counts 4TC + 4T")
+    return res

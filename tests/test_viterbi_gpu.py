@@ -417,6 +417,94 @@ def test_pooled_source_is_bit_identical_to_expanded(eng, dtype, C):
         check_unit(pb, b, u, ref, logps[u].shape[0])
 
 
+def test_c3_full_size_candidate_sets(eng):
+    """config c3 at FULL size: the 1712-video split x 64 candidate transcripts (109 568 units) from array-form
+    candidates (FlatCandidates): per video the winner is the first maximum of its candidates' scores, its labels are
+    the run-length expansion of the winner's segment lengths, and every candidate of six sampled videos (the longest
+    two among them) equals the oracle bit for bit."""
+    import bench
+    import bench_legs
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan, FlatCandidates
+    T, trs, _ = bench.make_split(0)
+    V = len(T)
+    cands, means = bench_legs.c3_candidates(T, trs, range(V))
+    logp = bench.device_logp(T, trs, 0, eng.device)
+    plan = AlignPlan(T, FlatCandidates.from_lists(cands), 48, device=eng.device, len_params=poisson_params(means),
+                     labels="best")
+    assert plan.U == 64 * V
+    eng.run(plan, logp, seg0_f32=True)
+    torch.cuda.synchronize()
+    assert eng.last_mode == "lanes"
+    out = eng.fetch(plan)
+    assert np.isin(out["status"], (0, 2)).all()
+    sc = out["score"].reshape(V, 64)
+    assert np.array_equal(out["best"], np.arange(V) * 64 + np.argmax(sc, axis=1))   # first maximum wins
+    K = T // 30
+    rng = np.random.default_rng(2)
+    sample = list(rng.choice(V, 4, replace=False)) + list(np.argsort(-T)[:2])
+    for v in sample:
+        u = int(out["best"][v])
+        a, b = plan.tr_off[u], plan.tr_off[u + 1]
+        tr = cands[v][u - 64 * v]
+        rem = int(T[v] - 30 * K[v])
+        exp = np.concatenate([np.full(rem, tr[-1])] + [np.full(30 * n, l) for l, n in zip(tr, out["seg_blocks"][a:b])])
+        assert np.array_equal(out["labels"][plan.vid_off[v]:plan.vid_off[v + 1]], exp)
+    host = {int(v): logp[plan.vid_off[v]:plan.vid_off[v + 1]].cpu().numpy() for v in sample}
+    for v in sample:
+        for c in range(64):
+            u = 64 * int(v) + c
+            rows = coracle.poisson_rows(poisson.poisson_params(means[v])[cands[v][c]], 30, 2000)
+            ref = coracle.viterbi(coracle.block_scores(host[int(v)], 30), cands[v][c], rows, True)
+            assert same_score(out["score"][u], ref["score"]), (v, c)
+            assert np.array_equal(out["seg_blocks"][plan.tr_off[u]:plan.tr_off[u + 1]], ref["seg_blocks"]), (v, c)
+
+
+@pytest.mark.parametrize("dist_name", ["equal", "bimodal", "few_long"])
+def test_other_length_distributions(eng, dist_name):
+    """The long-tail launch policy (the videos within 15 % of the longest go to a wide launch of their own) was tuned on
+    the log-normal c2 split: on equal-length, bimodal and few-long-video batches the automatic policy, the forced
+    single launch (long_K = 0) and a forced split must give identical results, equal to the oracle."""
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan
+    rng = np.random.default_rng(17)
+    V, C = 400, 48
+    if dist_name == "equal":
+        T = np.full(V, 2250)
+    elif dist_name == "bimodal":
+        T = np.where(rng.random(V) < 0.5, rng.integers(500, 800, V), rng.integers(8500, 9500, V))
+    else:
+        T = np.concatenate([rng.integers(300, 2000, V - 5), rng.integers(9000, 10000, 5)])
+    trs = []
+    for t in T:
+        K = int(t) // 30
+        n = int(rng.integers(max(2, -(-K // 66)), min(12, K) + 1))
+        trs.append(rng.integers(0, C, n))
+    means = np.stack([synth.class_means(rng.dirichlet(np.ones(len(tr))).astype(np.float32), tr, C, int(t))
+                      for tr, t in zip(trs, T)])
+    logp = torch.log_softmax(torch.randn(int(T.sum()), C, device=eng.device,
+                                         generator=torch.Generator(eng.device).manual_seed(5)), dim=1).contiguous()
+    outs = {}
+    for name, long_K in (("auto", None), ("single", 0), ("split_half", int(0.5 * (T // 30).max()))):
+        plan = AlignPlan(T, [[tr.tolist()] for tr in trs], C, device=eng.device, len_params=poisson_params(means),
+                         long_K=long_K)
+        eng.run(plan, logp, seg0_f32=True, write_bs=False)
+        torch.cuda.synchronize()
+        assert eng.last_mode == "fused"
+        outs[name] = (plan, eng.fetch(plan))
+    ref_plan, ref = outs["single"]
+    assert (ref["status"] == 0).all()
+    for name in ("auto", "split_half"):
+        for k in ("score", "seg_blocks", "labels", "final_j"):
+            assert np.array_equal(outs[name][1][k], ref[k]), (name, k)
+    host = logp.cpu().numpy()
+    for v in list(rng.choice(V, 10, replace=False)) + [int(np.argmax(T))]:
+        lp = host[ref_plan.vid_off[v]:ref_plan.vid_off[v + 1]]
+        o = oracle_unit(lp, trs[v].tolist(), means[v], 30, 2000, True)
+        assert same_score(ref["score"][v], o["score"])
+        assert np.array_equal(ref["labels"][ref_plan.vid_off[v]:ref_plan.vid_off[v + 1]], o["labels"])
+
+
 @pytest.mark.gpu
 def test_peer_exchange_two_gpus():
     """dist.PeerExchange: result stores repeated into the peers' receive buffers from the kernel epilogue equal an NCCL
