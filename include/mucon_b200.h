@@ -118,6 +118,14 @@ int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int 
                          int max_len, int lanes, int32_t* warp_unit_h, int32_t* n_cta_out,
                          int32_t* wpc_out, int32_t* lanes_out);
 
+/* Evaluator glue on the device (src/mucon/evaluators.py:155-165, core/viterbi/length_model.py:54-63): from the
+ * s-head's relative lengths rel [sum N] (float32), one transcript per video (tr, tr_off [V+1]) and the frame offsets
+ * vid_off [V+1], the Poisson parameters (ln m, m, norms) of every transcript position [sum N, 3] -- exactly what
+ * mucon_viterbi_batch.len_params takes.  logtail[i] = sum_{k=2..i} ln k (host-built, logtail_n entries, must cover the
+ * longest video).  ln() is evaluated on the device: scores can differ from host-built parameters in the last bits. */
+int mucon_class_mean_params(const float* rel, const int32_t* tr, const int32_t* tr_off, const int64_t* vid_off, int V,
+                            const double* logtail, int logtail_n, double* len_params_out, void* stream);
+
 /* Single-video session -- the reference's call pattern (src/mucon/evaluators.py:147-180: one Viterbi.decode per
  * video, core/viterbi/viterbi.py:49-158) as ONE call from host arrays to host arrays: a pinned staging buffer
  * carries [metadata | log-probabilities] to the device in one copy, the fused alignment kernel runs, one copy
@@ -288,6 +296,12 @@ int mucon_conv_gemm_tf32(const float* in, float* out, const float* W_kco, const 
 int mucon_conv_gemm_tf32_shifts(const float* in, float* out, const float* W_kco, const float* bias,
                                 const float* residual, const void* tiles, int num_tiles, int64_t rows,
                                 const int32_t* shifts_h, int n_shifts, int relu_mid, int relu_final, void* stream);
+/* max_pool1d(2) (mode 0) or avg_pool1d(2) * 2 = the sum of the pair (mode 1; pooling_type != "max",
+ * temporal.py:139-142) over time-major rows, floor halving per video.  The relu / relu_mid / relu_final / relu_in /
+ * relu_out flags of the backbone entry points are activation modes: 0 none, 1 ReLU, 2 leaky ReLU (slope 0.01,
+ * model.ft.leaky_relu, temporal.py:35-41). */
+int mucon_pool2(const float* in, float* out, const int64_t* off_in, const int64_t* off_out, int V, int max_T_out,
+                int C, int mode, void* stream);
 /* conv_gemm with the full epilogue (training step):
  *   out = gate( relu_final( relu_mid( sum_i in[t + shifts_h[i], :] . W[i]^T (+ bias) ) (* mul) (+ residual) ) )
  * bias, residual, mul, gate may be NULL.  mul [rows,128]: the dropout mask/scale of WaveNetLayer.drop

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const float* __restrict__ i
         float x = 0.f;
         if (t >= 0 && t < T && ci0 + c < Cin) {
           x = in[(r0 + t) * Cin + ci0 + c];
-          if (relu_in) x = fmaxf(x, 0.f);
+          x = act_mode(x, relu_in);
         }
         Xs[r][c] = x;
       }
@@ -141,15 +141,16 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const float* __restrict__ i
       const int co = co0 + tx * 4 + j;
       if (co >= Cout) continue;
       float y = acc[i][j] + bias[co];
-      if (relu_out) y = fmaxf(y, 0.f);
+      y = act_mode(y, relu_out);
       if (residual) y += residual[(r0 + t) * Cout + co];
       out[(r0 + t) * Cout + co] = y;
     }
   }
 }
 
+// mode 0: max_pool1d(2); mode 1: avg_pool1d(2) * 2 = sum of the pair (temporal.py:139-142)
 __global__ void maxpool2_kernel(const float* __restrict__ in, float* __restrict__ out, const int64_t* __restrict__ off_in,
-                                const int64_t* __restrict__ off_out, int C) {
+                                const int64_t* __restrict__ off_out, int C, int mode) {
   const int v = blockIdx.y;
   const int64_t i0 = off_in[v], o0 = off_out[v];
   const int To = static_cast<int>(off_out[v + 1] - o0);
@@ -162,7 +163,8 @@ __global__ void maxpool2_kernel(const float* __restrict__ in, float* __restrict_
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
       const int t = i / c4, q = i - t * c4;
       const float4 a = in4[(2 * t) * c4 + q], b = in4[(2 * t + 1) * c4 + q];
-      out4[i] = make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+      out4[i] = mode ? make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w)
+                     : make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
     }
     return;
   }
@@ -170,7 +172,8 @@ __global__ void maxpool2_kernel(const float* __restrict__ in, float* __restrict_
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t t = i / C;
     const int c = static_cast<int>(i - t * C);
-    out[o0 * C + i] = fmaxf(in[(i0 + 2 * t) * C + c], in[(i0 + 2 * t + 1) * C + c]);
+    const float a = in[(i0 + 2 * t) * C + c], b = in[(i0 + 2 * t + 1) * C + c];
+    out[o0 * C + i] = mode ? a + b : fmaxf(a, b);
   }
 }
 
@@ -628,14 +631,21 @@ extern "C" int mucon_conv1d(const float* in, float* out, const float* W_tco, con
   return MUCON_OK;
 }
 
+extern "C" int mucon_pool2(const float* in, float* out, const int64_t* off_in, const int64_t* off_out, int V,
+                           int max_T_out, int C, int mode, void* stream);
 extern "C" int mucon_maxpool2(const float* in, float* out, const int64_t* off_in, const int64_t* off_out, int V,
                               int max_T_out, int C, void* stream) {
-  if (!in || !out || !off_in || !off_out || V < 0 || C < 1 || max_T_out < 0) return MUCON_EINVAL;
+  return mucon_pool2(in, out, off_in, off_out, V, max_T_out, C, 0, stream);
+}
+
+extern "C" int mucon_pool2(const float* in, float* out, const int64_t* off_in, const int64_t* off_out, int V,
+                           int max_T_out, int C, int mode, void* stream) {
+  if (!in || !out || !off_in || !off_out || V < 0 || C < 1 || max_T_out < 0 || mode < 0 || mode > 1) return MUCON_EINVAL;
   if (V == 0 || max_T_out == 0) return MUCON_OK;
   if (V > 65535) return MUCON_EUNSUPPORTED;
   int bx = static_cast<int>((static_cast<int64_t>(max_T_out) * C + 255) / 256);
   if (bx > 64) bx = 64;
-  maxpool2_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, off_in, off_out, C);
+  maxpool2_kernel<<<dim3(bx, V), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, off_in, off_out, C, mode);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

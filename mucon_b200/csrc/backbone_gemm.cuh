@@ -224,7 +224,7 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 16; ++j) {
             float lo = __uint_as_float(r[2 * j + 0]) + __ldg(bias + c * 32 + 2 * j + 0);
             float hi = __uint_as_float(r[2 * j + 1]) + __ldg(bias + c * 32 + 2 * j + 1);
-            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            lo = act_mode(lo, relu); hi = act_mode(hi, relu);
             if (out_bf16 == 2) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(hi), "f"(lo));
             else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(hi), "f"(lo));
           }
@@ -243,7 +243,7 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v.y = __uint_as_float(r[j + 1]) + __ldg(bias + c * 32 + j + 1);
             v.z = __uint_as_float(r[j + 2]) + __ldg(bias + c * 32 + j + 2);
             v.w = __uint_as_float(r[j + 3]) + __ldg(bias + c * 32 + j + 3);
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            v.x = act_mode(v.x, relu); v.y = act_mode(v.y, relu); v.z = act_mode(v.z, relu); v.w = act_mode(v.w, relu);
             *reinterpret_cast<float4*>(orow + c * 32 + j) = v;
           }
         }
@@ -456,7 +456,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int e = 0; e < 4; ++e) {
             v[e] = __uint_as_float(r[j + e]);
             if (bias) v[e] += __ldg(bias + c * 32 + j + e);
-            if (relu_mid) v[e] = fmaxf(v[e], 0.f);
+            v[e] = act_mode(v[e], relu_mid);
           }
           *reinterpret_cast<float4*>(et + lane * EPI_LD + c * 32 + j) = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -493,7 +493,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int e = 0; e < 8; ++e) {
           if (residual) { v[e].x += rv[e].x; v[e].y += rv[e].y; v[e].z += rv[e].z; v[e].w += rv[e].w; }
           if (relu_final) {
-            v[e].x = fmaxf(v[e].x, 0.f); v[e].y = fmaxf(v[e].y, 0.f); v[e].z = fmaxf(v[e].z, 0.f); v[e].w = fmaxf(v[e].w, 0.f);
+            v[e].x = act_mode(v[e].x, relu_final); v[e].y = act_mode(v[e].y, relu_final);
+            v[e].z = act_mode(v[e].z, relu_final); v[e].w = act_mode(v[e].w, relu_final);
           }
         }
         if (gate) {

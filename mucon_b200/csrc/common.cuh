@@ -111,6 +111,12 @@ __device__ __forceinline__ float neg_zero<float>() { return -0.0f; }
 template <>
 __device__ __forceinline__ double neg_zero<double>() { return -0.0; }
 
+// Activation modes of the backbone kernels' relu flags: 0 none, 1 ReLU, 2 leaky ReLU with torch's default slope 0.01
+// (model.ft.leaky_relu, reference src/core/modules/temporal.py:35-41,98-101).
+__device__ __forceinline__ float act_mode(float v, int mode) {
+  return mode == 0 ? v : (mode == 1 ? fmaxf(v, 0.f) : (v > 0.f ? v : 0.01f * v));
+}
+
 // Result stores of the alignment kernels: the local payload buffer and, when a multi-GPU result exchange is set up
 // (mucon_viterbi_batch.peer_delta), the same location of this rank's slot in every peer's receive buffer.
 __device__ __forceinline__ void put_score(const mucon_viterbi_batch& b, int64_t u, double v) {

@@ -708,6 +708,53 @@ extern "C" int mucon_single_decode_h(mucon_single* s, const void* logp_h, int is
   return MUCON_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Evaluator glue on the device (reference src/mucon/evaluators.py:155-165 + core/viterbi/length_model.py:54-63):
+// class-mean lengths from the s-head's relative lengths and the Poisson parameters (ln m, m, norms) of every
+// transcript position, one warp per video.  lengths[c] = n_frames * sum_{m: tr[m] = c} rel[m] / count(c), exact
+// zeros -> 1 (classes that do not occur never reach the DP: only the transcript's positions are produced).
+// Sums run over the positions in ascending order in float64, like the float32 . float64 one-hot product they
+// replace.  ln() is CUDA's (<= 1 ulp from numpy's): path scores may differ from the host-built parameters in the
+// last bits; mucon_b200/evaluate.py keeps the host path as the bit-exact default.
+__global__ void __launch_bounds__(128) class_mean_params_kernel(const float* __restrict__ rel, const int32_t* __restrict__ tr,
+                                                                const int32_t* __restrict__ tr_off,
+                                                                const int64_t* __restrict__ vid_off, int V,
+                                                                const double* __restrict__ logtail, int logtail_n,
+                                                                double* __restrict__ out) {
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (v >= V) return;
+  const int t0 = tr_off[v], N = tr_off[v + 1] - t0;
+  const double frames = static_cast<double>(vid_off[v + 1] - vid_off[v]);
+  for (int n = lane; n < N; n += 32) {
+    const int c = tr[t0 + n];
+    double s = 0.0;
+    int k = 0;
+    for (int m = 0; m < N; ++m)
+      if (tr[t0 + m] == c) { s += static_cast<double>(rel[t0 + m]); ++k; }
+    double len = s * frames;
+    len = len / static_cast<double>(k);
+    if (len == 0.0) len = 1.0;
+    const double r = rint(len);
+    long long mi = static_cast<long long>(len);
+    if (mi < 0) mi = 0;
+    if (mi >= logtail_n) mi = logtail_n - 1;
+    double* o = out + static_cast<size_t>(t0 + n) * 3;
+    o[0] = log(len);
+    o[1] = len;
+    o[2] = (r * log(r) - r) - logtail[mi];
+  }
+}
+
+extern "C" int mucon_class_mean_params(const float* rel, const int32_t* tr, const int32_t* tr_off, const int64_t* vid_off,
+                                       int V, const double* logtail, int logtail_n, double* len_params_out, void* stream) {
+  if (!rel || !tr || !tr_off || !vid_off || !logtail || !len_params_out || V < 0 || logtail_n < 2) return MUCON_EINVAL;
+  if (V == 0) return MUCON_OK;
+  class_mean_params_kernel<<<(V + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(rel, tr, tr_off, vid_off, V, logtail,
+                                                                                      logtail_n, len_params_out);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 extern "C" int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int max_N, int fs,
                                     int max_len, int lanes, int32_t* warp_unit_h, int32_t* n_cta_out,
                                     int32_t* wpc_out, int32_t* lanes_out) {

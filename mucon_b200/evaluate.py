@@ -32,8 +32,38 @@ def class_mean_lengths(transcript, relative_lengths, n_frames, n_classes):
     return lengths
 
 
+def class_mean_params_device(relative_lengths, transcripts, T, device):
+    """class_mean_lengths + PoissonModel parameters for a batch ON THE DEVICE (mucon_class_mean_params): returns the
+    [sum N, 3] float64 CUDA tensor AlignPlan(len_params_dev=...) takes.  relative_lengths: per video [N_v] (CUDA /
+    CPU tensors or arrays; float32 like the s-head's softmax output) or one concatenated CUDA tensor."""
+    import ctypes as C
+    from .length_model import _log_tail
+    T = np.asarray(T, dtype=np.int64)
+    V = int(T.shape[0])
+    nlen = np.array([len(tr) for tr in transcripts], dtype=np.int64)
+    tr_off = np.concatenate([[0], np.cumsum(nlen)]).astype(np.int32)
+    tr = np.concatenate([np.asarray(t, dtype=np.int32) for t in transcripts]) if V else np.zeros(0, np.int32)
+    if torch.is_tensor(relative_lengths):
+        rel = relative_lengths.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        rel = torch.cat([r.detach().to(device).float() if torch.is_tensor(r) else torch.from_numpy(np.asarray(r, np.float32)).to(device)
+                         for r in relative_lengths]).contiguous() if V else torch.zeros(0, device=device)
+    n_tail = int(T.max(initial=1)) + 2
+    tail = torch.from_numpy(np.ascontiguousarray(_log_tail(n_tail)[:n_tail + 1])).to(device)
+    meta = torch.from_numpy(np.concatenate([np.concatenate([[0], np.cumsum(T)]).astype(np.int64).view(np.int32),
+                                            tr_off, tr])).to(device)
+    vid_off = meta[:2 * (V + 1)].view(torch.int64)
+    tr_off_d, tr_d = meta[2 * (V + 1):2 * (V + 1) + V + 1], meta[2 * (V + 1) + V + 1:]
+    out = torch.empty((int(tr_off[-1]), 3), dtype=torch.float64, device=device)
+    _lib.check(_lib.lib().mucon_class_mean_params(
+        _lib.ptr(rel), _lib.ptr(tr_d), _lib.ptr(tr_off_d), _lib.ptr(vid_off), C.c_int(V), _lib.ptr(tail),
+        C.c_int(int(tail.numel())), _lib.ptr(out), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+        "mucon_class_mean_params")
+    return out
+
+
 def align_videos(engine, log_probs, transcripts, relative_lengths, n_classes, frame_sampling=30,
-                 max_length=2000, np_mode=None, targets=None, ignore_ids=()):
+                 max_length=2000, np_mode=None, targets=None, ignore_ids=(), device_lengths=False):
     """Batched form of the evaluator's decode step.
 
     log_probs: list of [T_v, C] arrays/tensors (float32/float64), or a tuple (packed, T) of an
@@ -63,10 +93,18 @@ def align_videos(engine, log_probs, transcripts, relative_lengths, n_classes, fr
     fs = int(frame_sampling)
     if V and int(T.min()) < fs:
         raise IndexError(f"a sequence is shorter than frame_sampling={fs}")  # viterbi.py:87
-    means = np.stack([class_mean_lengths(tr, _np(rl), int(t), n_classes)
-                      for tr, rl, t in zip(transcripts, relative_lengths, T)]) if V else np.zeros((0, n_classes))
-    plan = AlignPlan(T, [[list(map(int, tr))] for tr in transcripts], n_classes, fs=fs, max_len=int(max_length),
-                     len_params=poisson_params(means), device=dev, labels="best")
+    if device_lengths:
+        # class means and Poisson parameters computed on the device (no per-video host loop; ln() is CUDA's, so path
+        # scores can differ from the default host path in the last bits -- labels only on exact near-ties)
+        means = None
+        plan = AlignPlan(T, [[list(map(int, tr))] for tr in transcripts], n_classes, fs=fs, max_len=int(max_length),
+                         len_params_dev=class_mean_params_device(relative_lengths, transcripts, T, dev), device=dev,
+                         labels="best")
+    else:
+        means = np.stack([class_mean_lengths(tr, _np(rl), int(t), n_classes)
+                          for tr, rl, t in zip(transcripts, relative_lengths, T)]) if V else np.zeros((0, n_classes))
+        plan = AlignPlan(T, [[list(map(int, tr))] for tr in transcripts], n_classes, fs=fs, max_len=int(max_length),
+                         len_params=poisson_params(means), device=dev, labels="best")
     is32 = packed.dtype == torch.float32
     if np_mode is None:
         seg0 = default_seg0_f32(np.float32 if is32 else np.float64)

@@ -174,12 +174,13 @@ def wavenet_layer_bf16_rows(x, Wd_kco16, bd, W1_kco16, b1, plan, level, dilation
     return out
 
 
-def maxpool2_rows(x, plan, level):
+def maxpool2_rows(x, plan, level, mode=0):
+    """mode 0: max_pool1d(2); mode 1: avg_pool1d(2) * 2 (the sum of the pair, temporal.py:141-142)."""
     Cc = x.shape[1]
     out = torch.empty((plan.rows[level + 1], Cc), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().mucon_maxpool2(
+    _lib.check(_lib.lib().mucon_pool2(
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(plan.off[level]), _lib.ptr(plan.off[level + 1]), C.c_int(plan.V),
-        C.c_int(plan.max_T[level + 1]), C.c_int(Cc), _stream(x.device)), "mucon_maxpool2")
+        C.c_int(plan.max_T[level + 1]), C.c_int(Cc), C.c_int(int(mode)), _stream(x.device)), "mucon_pool2")
     return out
 
 
@@ -230,10 +231,9 @@ class WaveNetBlock(nn.Module):
         super().__init__()
         if kernel_size != 3:
             raise NotImplementedError("kernel_size != 3")
-        if leaky:
-            raise NotImplementedError("leaky ReLU variant (model.ft.leaky_relu) is not implemented")
-        if pooling and pooling_type != "max":
-            raise NotImplementedError("only max pooling is implemented")
+        # leaky ReLU (model.ft.leaky_relu) and the non-max pooling type (avg_pool1d * 2, temporal.py:141-142) run on
+        # the TF32 conv GEMM / fp32 kernels with one launch per conv; the fused 16-bit layer kernels cover the
+        # default configuration (ReLU, max pooling)
         self.in_channels, self.stages, self.out_dims = in_channels, list(stages), out_dims
         self.num_stages = len(self.stages)
         self.kernel_size, self.pooling, self.pooling_type = kernel_size, pooling, pooling_type
@@ -282,6 +282,12 @@ class WaveNetBlock(nn.Module):
             raise ValueError(f"precision {precision!r}")
         if precision == "fp32":
             tensor_cores = False
+        act = 2 if self.leaky else 1                       # activation mode of the kernels' relu flags
+        pool_mode = 0 if self.pooling_type == "max" else 1
+        if act != 1 or pool_mode != 0:
+            fused_layers = False
+            if precision in ("fp16", "bf16"):
+                precision = "tf32"
         w = self._weights()
         V = plan.V
         last = self.num_stages - 1
@@ -306,10 +312,10 @@ class WaveNetBlock(nn.Module):
                 x = x.float()
             return conv_gemm_rows(x, w["last_k"], w["last_b"], plan, level)                          # temporal.py:144-145
         if self.out_dims == 128 and self.in_channels % 32 == 0:
-            x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True)       # temporal.py:133
+            x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=act)        # temporal.py:133
         else:
             x = conv1d_rows(feats, w["first_w"].t().contiguous()[None], w["first_b"], plan.off[0], V, plan.max_T[0],
-                            relu_out=True)
+                            relu_out=act)
         level = 0
         tc = tensor_cores and self.out_dims == 128
         for i, (wd, bd, w1, b1) in enumerate(w["layers"]):
@@ -325,21 +331,21 @@ class WaveNetBlock(nn.Module):
                 continue
             if tc:
                 wdk, w1k = w["layers_k"][i]
-                y = conv_gemm_rows(x, wdk, bd, plan, level, dilation=self.stages[i], relu_mid=True)      # temporal.py:48-49
+                y = conv_gemm_rows(x, wdk, bd, plan, level, dilation=self.stages[i], relu_mid=act)      # temporal.py:48-49
                 # the ReLU in front of last_conv (temporal.py:144) is folded into the last layer's store
-                x = conv_gemm_rows(y, w1k, b1, plan, level, residual=x, relu_final=(i == last and not pooled))
+                x = conv_gemm_rows(y, w1k, b1, plan, level, residual=x, relu_final=act * (i == last and not pooled))
             else:
-                y = conv1d_rows(x, wd, bd, off, V, mt, dilation=self.stages[i], relu_out=True)           # temporal.py:48-49
+                y = conv1d_rows(x, wd, bd, off, V, mt, dilation=self.stages[i], relu_out=act)            # temporal.py:48-49
                 x = conv1d_rows(y, w1, b1, off, V, mt, residual=x)                                        # temporal.py:50-52
             if pooled:
-                x = maxpool2_rows(x, plan, level)                                                          # temporal.py:139
+                x = maxpool2_rows(x, plan, level, pool_mode)                                               # temporal.py:139-142
                 level += 1
         if tc:
             folded = fused_layers or not (self.pooling and last in self.pooling_layers)
             if not folded:
-                x = torch.relu(x)
+                x = torch.nn.functional.leaky_relu(x) if self.leaky else torch.relu(x)
             return conv_gemm_rows(x, w["last_k"], w["last_b"], plan, level)                               # temporal.py:144-145
-        return conv1d_rows(x, w["last_w"], w["last_b"], plan.off[level], V, plan.max_T[level], relu_in=True)
+        return conv1d_rows(x, w["last_w"], w["last_b"], plan.off[level], V, plan.max_T[level], relu_in=act)
 
     def forward(self, x):
         """x [B, in_channels, T] -> [B, out_dims, T']  (temporal.py:128-147)."""
@@ -483,13 +489,15 @@ class MuConBackbone(nn.Module):
 
     def __init__(self, input_feature_size=2048, num_classes=48, hidden_size=128,
                  stages=(1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024), pooling=True, pooling_layers=(1, 2, 4, 8),
-                 last_gn=True, last_gn_num_groups=32, last_relu=True, ft_type="wavenet"):
+                 last_gn=True, last_gn_num_groups=32, last_relu=True, ft_type="wavenet", leaky_relu=False,
+                 pooling_type="max", dropout_rate=0.25):
         super().__init__()
         self.num_classes, self.hidden_size = num_classes, hidden_size
         self.last_gn, self.last_relu = last_gn, last_relu
         if ft_type == "wavenet":      # models.py:160-186
             self.ft = WaveNetBlock(input_feature_size, stages=stages, out_dims=hidden_size, pooling=pooling,
-                                   pooling_layers=pooling_layers)
+                                   pooling_layers=pooling_layers, pooling_type=pooling_type, leaky=leaky_relu,
+                                   dropout_rate=dropout_rate)
         elif ft_type == "mstcnpp":
             self.ft = MSTCNPPFirstStage(input_dim=input_feature_size, num_layers=len(stages), output_dim=hidden_size,
                                         num_f_maps=hidden_size, pooling_layers=pooling_layers)

@@ -103,7 +103,7 @@ class AlignPlan:
 
     def __init__(self, T, candidates, n_classes, fs=30, max_len=2000, len_params=None, len_rows=None,
                  device=None, want_bp=True, labels="best", groups=None, long_K=None, payload_capacity=None,
-                 force_generic=False):
+                 force_generic=False, len_params_dev=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.fs, self.max_len, self.C = int(fs), int(max_len), int(n_classes)
         self.J = self.max_len // self.fs
@@ -262,16 +262,24 @@ class AlignPlan:
                 raise ValueError("len_rows must hold one [N_u, J] block per unit")
             blob.add("len_rows", rows)
         else:
-            if len_params is None:
+            if len_params is None and len_params_dev is None:
                 raise ValueError("need len_params (Poisson) or len_rows")
-            lp = np.asarray(len_params, dtype=np.float64).reshape(V, self.C, 3)
-            pos_vid = np.repeat(self.unit_vid, nlen)
-            blob.add("len_params", lp[pos_vid, self.tr])
+            if len_params_dev is None:
+                lp = np.asarray(len_params, dtype=np.float64).reshape(V, self.C, 3)
+                pos_vid = np.repeat(self.unit_vid, nlen)
+                blob.add("len_params", lp[pos_vid, self.tr])
             lf = log_factorial_prefix(self.max_len - 1)
             idx = np.minimum(np.arange(self.J + 1) * self.fs, self.max_len - 1)
             blob.add("logfact", lf[idx])
         self.h2d_meta_bytes = blob.size
         self._meta_dev, self._meta_host, self.p = blob.upload(self.device)
+        if len_params_dev is not None and not self.use_rows:
+            # per-position parameters already on the device (evaluate.class_mean_params_device): [sum N, 3] float64
+            if (not len_params_dev.is_cuda or len_params_dev.dtype != torch.float64 or not len_params_dev.is_contiguous()
+                    or len_params_dev.numel() != 3 * int(self.tr_off[-1])):
+                raise ValueError("len_params_dev must be a contiguous float64 CUDA tensor [sum N, 3]")
+            self._len_params_dev = len_params_dev
+            self.p["len_params"] = len_params_dev.data_ptr()
 
         dev = self.device
         # scores and segment lengths -- what the multi-GPU gather moves -- share one buffer so that

@@ -72,3 +72,46 @@ def test_align_videos_errors(cuda_device):
         align_videos(eng, [np.zeros((3990, 8), np.float32)], [[0, 1]], [np.array([0.5, 0.5], np.float32)], 8)
     with pytest.raises(IndexError):      # T < frame_sampling
         align_videos(eng, [np.zeros((20, 8), np.float32)], [[0]], [np.array([1.0], np.float32)], 8)
+
+
+@pytest.mark.gpu
+def test_device_class_mean_params_match_host(cuda_device):
+    """mucon_class_mean_params (class means + Poisson parameters on the device) against the host statements pinned by
+    eval_lengths.npz: m exactly, ln m and the norms to 2 ulp (ln() is CUDA's); and the batched alignment built on them
+    gives the host path's labels and segments, scores to 1e-12 relative."""
+    import torch
+    from mucon_b200.evaluate import align_videos, class_mean_lengths, class_mean_params_device
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import ViterbiEngine
+    g = np.load(os.path.join(HERE, "golden", "eval_lengths.npz"))
+    n = int(g["n"])
+    trs = [g[f"tr{i}"].astype(np.int64).tolist() for i in range(n)]
+    rels = [g[f"rel{i}"].astype(np.float32) for i in range(n)]
+    Ts = [int(g[f"T{i}"]) for i in range(n)]
+    got = class_mean_params_device(rels, trs, Ts, cuda_device).cpu().numpy()
+    pos = 0
+    for i in range(n):
+        want = poisson_params(g[f"lengths{i}"])[np.asarray(trs[i])]
+        blk = got[pos:pos + len(trs[i])]
+        pos += len(trs[i])
+        assert np.allclose(blk[:, 1], want[:, 1], rtol=4e-16, atol=0), i          # the means (float64 sums)
+        assert np.allclose(blk[:, 0], want[:, 0], rtol=5e-16, atol=1e-15), i
+        ok = np.isfinite(want[:, 2])
+        assert np.allclose(blk[ok, 2], want[ok, 2], rtol=1e-13, atol=1e-10), i
+    rng = np.random.default_rng(21)
+    C = 48
+    logps, trs, rels = [], [], []
+    for i in range(40):
+        N = int(rng.integers(1, 10))
+        T = int(rng.integers(max(60, 30 * N), min(4000, 30 * 66 * N)))
+        tr = list(map(int, rng.integers(0, C, N)))
+        lp, _ = synth.planted_logp(rng, T, C, tr, np.float32)
+        logps.append(lp)
+        trs.append(tr)
+        rels.append(rng.dirichlet(3 * np.ones(N)).astype(np.float32))
+    eng = ViterbiEngine(cuda_device)
+    a = align_videos(eng, logps, trs, rels, C)
+    b = align_videos(eng, logps, trs, rels, C, device_lengths=True)
+    assert np.allclose(a["score"], b["score"], rtol=1e-12, atol=0)
+    assert a["segments"] == b["segments"]
+    assert all(np.array_equal(x, y) for x, y in zip(a["labels"], b["labels"]))
