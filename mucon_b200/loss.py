@@ -130,11 +130,14 @@ def mucon_loss(lengths, segmentation, target_transcript, template="box", overlap
 
 
 def mucon_loss_batch(lengths, segmentation, transcripts, Ms, Ts, template="box", overlap=0.0, class_weight=None,
-                     align_corners=None, meta=None):
-    """The flint mutual-consistency loss (models.py:414-488) of a packed batch, averaged over its videos: one
+                     align_corners=None, meta=None, mucon_type="flint"):
+    """The mutual-consistency loss (models.py:414-525) of a packed batch, averaged over its videos: one
     fused-evidence launch for the whole batch instead of one Python loop per video and segment.
     lengths [sum Ms] s-head length logits (videos concatenated), segmentation [sum Ts, C] packed frame logits,
-    transcripts [sum Ms] long.  Per video: F.nll_loss(log_softmax(E_v / L_v), transcript_v, reduction="mean")."""
+    transcripts [sum Ms] long.
+    flint (:456-488), per video: F.nll_loss(log_softmax(E_v / L_v), transcript_v, reduction="mean"), E = masks @ seg.
+    arithmetic (:489-523), per video: sum_i sum_t CE(seg_t, tr_i) * mask_i[t] / T = -sum_i (masks @ log_softmax(seg))[i,
+    tr_i] / T -- the same evidence kernel applied to the log-probabilities, so the masks are not materialised either."""
     Ms_np, Ts_np = np.asarray(Ms, dtype=np.int64), np.asarray(Ts, dtype=np.int64)
     V, dev = int(Ms_np.shape[0]), segmentation.device
     meta = meta if meta is not None else _flint_meta(Ms_np, Ts_np, dev)
@@ -148,6 +151,16 @@ def mucon_loss_batch(lengths, segmentation, transcripts, Ms, Ts, template="box",
     padded = torch.full((V, maxM), float("-inf"), dtype=lengths.dtype, device=dev)
     padded = padded.index_put((row_vid, col), lengths)
     absolute = (F.softmax(padded, dim=1) * Tt[:, None])[row_vid, col]
+    if mucon_type == "arithmetic":
+        E = flint_evidence(absolute, F.log_softmax(segmentation, dim=1), Ms_np, Ts_np, overlap=overlap,
+                           template=template, align_corners=align_corners, meta=meta)
+        ce = -E.gather(1, transcripts.long()[:, None])[:, 0]
+        if class_weight is not None:
+            ce = ce * class_weight[transcripts.long()]
+        per_video = torch.zeros(V, dtype=ce.dtype, device=dev).index_add_(0, row_vid, ce) / Tt
+        return per_video.mean()
+    if mucon_type != "flint":
+        raise Exception(f"Invalid mucon type ({mucon_type})")
     E = flint_evidence(absolute, segmentation, Ms_np, Ts_np, overlap=overlap, template=template,
                        align_corners=align_corners, meta=meta)
     scaled = absolute * (1.0 + 2 * overlap)  # the in-place scaling of create_masks (masks.py:61)
@@ -157,3 +170,26 @@ def mucon_loss_batch(lengths, segmentation, transcripts, Ms, Ts, template="box",
     num = torch.zeros(V, dtype=nll.dtype, device=dev).index_add_(0, row_vid, nll * w)
     den = torch.zeros(V, dtype=nll.dtype, device=dev).index_add_(0, row_vid, w)
     return (num / den).mean()
+
+
+def smoothing_loss_packed(logits, Ts, log_softmax_before=True, clamp=True, clamp_min=0.0, clamp_max=16.0):
+    """MuCon.calculate_smoothing_loss_for_logits (models.py:398-412) for a packed batch, averaged over its videos.
+    Per video: values = F.mse_loss(x[1:], x[:-1].detach()) -- a scalar mean over (T-1) x C -- clamped (the reference
+    clamps that scalar, not the elements), with x the (log-softmaxed) frame logits.  Frame pairs that straddle two
+    videos are excluded."""
+    Ts_np = np.asarray(Ts, dtype=np.int64)
+    V, dev = int(Ts_np.shape[0]), logits.device
+    x = F.log_softmax(logits, dim=1) if log_softmax_before else logits
+    d = (x[1:] - x[:-1].detach()).pow(2).sum(1)                        # [sum T - 1]
+    ends = np.cumsum(Ts_np)[:-1] - 1                                    # pair index (t, t+1) crossing a boundary
+    keep = np.ones(max(int(Ts_np.sum()) - 1, 0), dtype=bool)
+    keep[ends[ends >= 0]] = False
+    vid = np.repeat(np.arange(V), Ts_np)[:-1] if Ts_np.sum() > 0 else np.zeros(0, np.int64)
+    keep_t = torch.from_numpy(keep).to(dev)
+    vid_t = torch.from_numpy(vid.astype(np.int64)).to(dev)
+    per = torch.zeros(V, dtype=x.dtype, device=dev).index_add_(0, vid_t, d * keep_t)
+    n = torch.from_numpy(np.maximum(Ts_np - 1, 1).astype(np.float32) * x.shape[1]).to(dev)
+    per = per / n
+    if clamp:
+        per = torch.clamp(per, min=clamp_min, max=clamp_max)
+    return per.mean()

@@ -86,3 +86,45 @@ def test_fused_evidence_equals_masks_times_logits(cuda_device, tmpl, ov, align):
     assert torch.allclose(gs, gsr, rtol=1e-4, atol=1e-4 * gsr.abs().max().item())
     gl, glr = L.grad.cpu().numpy(), Lr.grad.cpu().numpy()
     assert np.allclose(gl, glr, rtol=3e-3, atol=3e-3 * np.abs(glr).max()), np.abs(gl - glr).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(CASES)))
+def test_batched_loss_matches_reference_single_videos(cuda_device, i):
+    """mucon_loss_batch (flint and arithmetic through the fused evidence kernel, masks never written) on each frozen
+    reference case as a batch of one"""
+    from mucon_b200.loss import mucon_loss_batch
+    T, N, C, mtype, tmpl, ov = _case(i)
+    lengths = torch.from_numpy(G[f"c{i}_lengths"].copy()).to(cuda_device).requires_grad_(True)
+    seg = torch.from_numpy(G[f"c{i}_seg"].copy()).to(cuda_device).requires_grad_(True)
+    tr = torch.from_numpy(G[f"c{i}_tr"]).to(cuda_device)
+    loss = mucon_loss_batch(lengths, seg, tr, [N], [T], template=tmpl, overlap=ov, mucon_type=mtype)
+    loss.backward()
+    want = float(G[f"c{i}_loss"])
+    assert abs(loss.item() - want) <= 2e-4 * max(1.0, abs(want)), (loss.item(), want)
+    gl, wl = lengths.grad.cpu().numpy(), G[f"c{i}_glen"]
+    assert np.allclose(gl, wl, rtol=2e-3, atol=2e-3 * np.abs(wl).max()), (gl, wl)
+    gs = seg.grad.cpu().numpy()
+    assert np.allclose(gs[::37], G[f"c{i}_gseg_rows"], rtol=1e-3, atol=1e-3 * np.abs(G[f"c{i}_gseg_rows"]).max())
+
+
+@pytest.mark.gpu
+def test_batched_loss_is_mean_of_single_video_losses(cuda_device):
+    from mucon_b200.loss import mucon_loss, mucon_loss_batch, smoothing_loss_packed
+    rng = np.random.default_rng(3)
+    Ts, Ms, C = [700, 333, 1200, 90], [6, 4, 9, 2], 24
+    segs = [torch.from_numpy(rng.standard_normal((t, C)).astype(np.float32) * 2).to(cuda_device) for t in Ts]
+    lens = [torch.from_numpy(rng.standard_normal(m).astype(np.float32)).to(cuda_device) for m in Ms]
+    trs = [torch.from_numpy(rng.integers(0, C, m)).to(cuda_device) for m in Ms]
+    for mtype in ("flint", "arithmetic"):
+        want = sum(mucon_loss(l, s, t, "box", 0.0, mtype, fused=False) for l, s, t in zip(lens, segs, trs)) / len(Ts)
+        got = mucon_loss_batch(torch.cat(lens), torch.cat(segs), torch.cat(trs), Ms, Ts, mucon_type=mtype)
+        assert abs(got.item() - want.item()) <= 2e-4 * max(1.0, abs(want.item())), (mtype, got.item(), want.item())
+    # smoothing loss (models.py:398-412): per video, the reference's statements
+    import torch.nn.functional as F
+    want = 0.0
+    for s in segs:
+        x = F.log_softmax(s, dim=1)
+        want = want + torch.clamp(F.mse_loss(x[1:], x[:-1].detach()), min=0.0, max=16.0)
+    got = smoothing_loss_packed(torch.cat(segs), Ts)
+    assert abs(got.item() - (want / len(Ts)).item()) <= 1e-5 * max(1.0, abs(got.item()))
