@@ -244,6 +244,14 @@ int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, cons
 int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
                     const int32_t* row_vid, int V, int n_rows, float overlap, int template_id, int align_corners,
                     const float* grad_out, float* ws, float* grad_L, void* stream);
+/* mucon_flint_fwd with a warp per (mask row, eighth of its window) instead of a CTA per row: no block barriers, the
+ * long windows no longer set the tail.  ws: mucon_flint_fwd_ws_words(n_rows, C) 4-byte words (16-byte aligned) whose
+ * last n_rows words (row counters) are zero on entry and left zero on return; the eight partial sums of a row are
+ * added in a fixed order by the warp that finishes last, so E does not depend on scheduling. */
+int64_t mucon_flint_fwd_ws_words(int n_rows, int C);
+int mucon_flint_fwd_ws(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
+                       const int32_t* row_vid, int V, int n_rows, int C, float overlap, int template_id,
+                       int align_corners, const float* seg, float* ws, float* E, void* stream);
 /* Fused "flint" evidence of the mutual-consistency loss (models.py:456-468):
  *   E[r, c] = sum_t mask_r[t] * seg[t, c]        r = mask row (video v, segment i), c < C <= 128
  * without materialising the masks; seg is the packed [sum T, C] frame-logit tensor, seg_off[v] the

@@ -13,6 +13,7 @@
 //   u  = ((gx+1)*W - 1)/2 (align_corners=0)  |  (gx+1)/2*(W-1) (align_corners=1) grid_sample
 //   out[i,t] = tmpl[floor u]*(1-frac) + tmpl[floor u + 1]*frac, taps outside [0,W) are 0
 // Backward: d out/d u = tmpl[floor u + 1] - tmpl[floor u]; u depends on L through pi and Ls.
+#include <stdlib.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -371,6 +372,95 @@ flint_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off,
   }
 }
 
+// The same evidence with a WARP per (mask row, part): a row's window is cut into kFlintParts equal parts, item
+// row * kFlintParts + p is taken by one warp, grid-stride -- no block-level barrier anywhere, 64 warps per SM each
+// with several 16-byte loads in flight, and a 5000-frame window is eight items instead of one CTA's tail.  A lane owns
+// four class columns and every (32 / (C/4))-th frame of its part.  The partial sums of a row go to a workspace; the
+// warp that finishes a row's last part (a counter per row) adds the parts in order p = 0..7, so the result does not
+// depend on the order in which the warps ran.
+constexpr int kFlintPartsMax = 8;
+constexpr int kFlintBatch = 8;
+template <int kFlintParts>
+__global__ void __launch_bounds__(256)
+flint_fwd_warp_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                      const int64_t* __restrict__ seg_off, const int32_t* __restrict__ row_vid, int V, int n_rows, int C,
+                      float overlap, int tmpl, int align, const float* __restrict__ seg, float* __restrict__ part_ws,
+                      unsigned int* __restrict__ counters, float* __restrict__ E) {
+  __shared__ float tp[kWP];
+  load_template(tp, tmpl);
+  __syncthreads();
+  const bool box = tmpl == 0;
+  const int C4 = C >> 2;
+  const int FP = 32 / C4;                       // frames per warp iteration
+  const int lane = threadIdx.x & 31;
+  const int fq = lane / C4, c4 = lane - fq * C4;
+  const bool active = fq < FP;
+  const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_items = n_rows * kFlintParts;
+  for (int item = warp_g; item < n_items; item += n_warps) {
+    const int row = item / kFlintParts, p = item - row * kFlintParts;
+    const int v = row_vid ? row_vid[row] : find_video(n_off, V, row);
+    const int T = Tv[v];
+    const int r0 = n_off[v], i = row - r0;
+    const RowGeom g = row_geom(L, r0, i, T, overlap);          // every lane, redundantly: no shuffle, no barrier
+    const Regions r = make_regions(make_screen(g, T, align), T, box);
+    const int len = r.b1 - r.a0;
+    const int t_lo = r.a0 + static_cast<int>(static_cast<long long>(len) * p / kFlintParts);
+    const int t_hi = r.a0 + static_cast<int>(static_cast<long long>(len) * (p + 1) / kFlintParts);
+    const float4* sv = reinterpret_cast<const float4*>(seg + seg_off[v] * C);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+      // batches of kFlintBatch independent 16-byte loads issued before any of them is used (the mask evaluation has
+      // branches the compiler will not move loads across: without the explicit batch one load per warp was in flight)
+      for (int t = t_lo + fq; t < t_hi; t += kFlintBatch * FP) {
+        float4 x[kFlintBatch];
+#pragma unroll
+        for (int k = 0; k < kFlintBatch; ++k) {
+          const int tt = t + k * FP;
+          x[k] = tt < t_hi ? __ldg(sv + static_cast<long long>(tt) * C4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < kFlintBatch; ++k) {
+          const int tt = t + k * FP;
+          if (tt < t_hi) {
+            const float m = mask_value(tp, g, r, tt, T, align);
+            acc.x = fmaf(m, x[k].x, acc.x); acc.y = fmaf(m, x[k].y, acc.y);
+            acc.z = fmaf(m, x[k].z, acc.z); acc.w = fmaf(m, x[k].w, acc.w);
+          }
+        }
+      }
+    }
+    // frames-of-the-iteration groups -> group 0 (fixed order: fq = 0, 1, ...)
+    for (int k = 1; k < FP; ++k) {
+      const int src = lane + k * C4;
+      const float x = __shfl_sync(0xffffffffu, acc.x, src & 31), y = __shfl_sync(0xffffffffu, acc.y, src & 31);
+      const float z = __shfl_sync(0xffffffffu, acc.z, src & 31), w = __shfl_sync(0xffffffffu, acc.w, src & 31);
+      if (fq == 0) { acc.x += x; acc.y += y; acc.z += z; acc.w += w; }
+    }
+    float4* pw = reinterpret_cast<float4*>(part_ws + (static_cast<long long>(row) * kFlintParts + p) * C);
+    if (fq == 0 && c4 < C4) pw[c4] = acc;
+    __threadfence();
+    __syncwarp();
+    unsigned int old = 0;
+    if (lane == 0) old = atomicAdd(counters + row, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == kFlintParts - 1) {   // this warp completed the row: ordered sum of its parts
+      __threadfence();
+      if (lane < C4) {
+        const float4* pr = reinterpret_cast<const float4*>(part_ws + static_cast<long long>(row) * kFlintParts * C);
+        float4 sum = __ldcg(pr + lane);
+        for (int q = 1; q < kFlintParts; ++q) {
+          const float4 a = __ldcg(pr + q * C4 + lane);
+          sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
+        }
+        reinterpret_cast<float4*>(E + static_cast<long long>(row) * C)[lane] = sum;
+      }
+      if (lane == 0) counters[row] = 0;   // ready for the next call
+    }
+  }
+}
+
 // d seg[t, :] = sum_r mask_r[t] * gE[r, :] over the rows of the frame's video.  One CTA per chunk of
 // kFlintChunk frames of one video (host-built chunk list {video, t0}); the video's row geometry is
 // set up once per CTA, then a thread owns one (frame, 4 classes) item at a time: coalesced stores.
@@ -555,6 +645,45 @@ extern "C" int mucon_flint_fwd(const float* L, const int32_t* n_off, const int32
   const int grid = n_rows < 8 * sms ? n_rows : 8 * sms;
   flint_fwd_kernel<<<grid, kFlintThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, E);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int64_t mucon_flint_fwd_ws_words(int n_rows, int C) {
+  if (n_rows < 0 || C < 1) return 0;
+  return static_cast<int64_t>(n_rows) * kFlintPartsMax * C + n_rows;   // float partials + one counter per row
+}
+
+// ws: mucon_flint_fwd_ws_words(n_rows, C) 4-byte words, 16-byte aligned; its counters (the last n_rows words) must be
+// zero on entry -- they are left zero on return, so a workspace zeroed once can be reused call after call.
+extern "C" int mucon_flint_fwd_ws(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
+                                  const int32_t* row_vid, int V, int n_rows, int C, float overlap, int template_id,
+                                  int align_corners, const float* seg, float* ws, float* E, void* stream) {
+  if (!L || !n_off || !T || !seg_off || !seg || !E || !ws || V < 0 || n_rows < 0 || C < 1) return MUCON_EINVAL;
+  if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
+  if (C > 2 * kGroup || (C & 3)) return MUCON_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(seg) & 15) || (reinterpret_cast<uintptr_t>(E) & 15) ||
+      (reinterpret_cast<uintptr_t>(ws) & 15))
+    return MUCON_EALIGN;
+  if (V == 0 || n_rows == 0) return MUCON_OK;
+  int rc = ensure_templates();
+  if (rc != MUCON_OK) return rc;
+  const int sms = mucon_device_sm_count();
+  static const int parts = getenv("MUCON_FLINT_PARTS") ? atoi(getenv("MUCON_FLINT_PARTS")) : 4;
+  const long long items = static_cast<long long>(n_rows) * parts;
+  long long grid = (items + 7) / 8;
+  if (grid > 8LL * sms) grid = 8LL * sms;
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws + static_cast<int64_t>(n_rows) * kFlintPartsMax * C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (parts == 8)
+    flint_fwd_warp_kernel<8><<<static_cast<int>(grid), 256, 0, st>>>(
+        L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, ws, counters, E);
+  else if (parts == 2)
+    flint_fwd_warp_kernel<2><<<static_cast<int>(grid), 256, 0, st>>>(
+        L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, ws, counters, E);
+  else
+    flint_fwd_warp_kernel<4><<<static_cast<int>(grid), 256, 0, st>>>(
+        L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, ws, counters, E);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

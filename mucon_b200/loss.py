@@ -46,10 +46,15 @@ class _EvidenceFn(torch.autograd.Function):
         Cn = sg.shape[1]
         E = torch.empty((meta["n_rows"], Cn), dtype=torch.float32, device=sg.device)
         st = C.c_void_p(torch.cuda.current_stream(sg.device).cuda_stream)
-        _lib.check(_lib.lib().mucon_flint_fwd(
+        lib = _lib.lib()
+        key = ("fwd_ws", Cn)
+        if key not in meta:   # partial sums + row counters; zeroed once, the kernel leaves the counters at zero
+            meta[key] = torch.zeros(int(lib.mucon_flint_fwd_ws_words(C.c_int(meta["n_rows"]), C.c_int(Cn))) + 4,
+                                    dtype=torch.float32, device=sg.device)
+        _lib.check(lib.mucon_flint_fwd_ws(
             _lib.ptr(Lc), _lib.ptr(meta["n_off"]), _lib.ptr(meta["T"]), _lib.ptr(meta["seg_off"]), _lib.ptr(meta["row_vid"]),
             C.c_int(meta["V"]), C.c_int(meta["n_rows"]), C.c_int(Cn), C.c_float(overlap), C.c_int(tid), C.c_int(align),
-            _lib.ptr(sg), _lib.ptr(E), st), "mucon_flint_fwd")
+            _lib.ptr(sg), _lib.ptr(meta[key]), _lib.ptr(E), st), "mucon_flint_fwd_ws")
         ctx.save_for_backward(Lc, sg)
         ctx.meta, ctx.args = meta, (overlap, tid, align)
         return E
