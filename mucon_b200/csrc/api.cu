@@ -28,9 +28,13 @@ extern "C" const char* mucon_strerror(int code) {
 extern "C" const char* mucon_last_cuda_error(void) { return mucon::g_err; }
 
 extern "C" int mucon_device_sm_count(void) {
+  // cached per device (read-only after the first query; a benign race writes the same value twice)
+  static int cache[64] = {0};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
 }
 

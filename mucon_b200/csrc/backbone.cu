@@ -324,8 +324,7 @@ static int launch_proj(const float* A, int64_t M, int K, const float* W, int N, 
     return MUCON_EALIGN;
   if (M == 0) return MUCON_OK;
   if (M > 0x7fffffff) return MUCON_EUNSUPPORTED;
-  static int sms = 0;
-  if (!sms) sms = mucon_device_sm_count();
+  const int sms = mucon_device_sm_count();   // of the current device (cached per device)
   // 256-row CTA tiles (one weight stage feeds two M tiles) once there are enough of them to fill the GPU
   static const int force_mt = getenv("MUCON_PROJ_MT") ? atoi(getenv("MUCON_PROJ_MT")) : 0;
   const int mt = force_mt ? force_mt : (M >= static_cast<int64_t>(2) * gemm::BM * sms ? 2 : 1);
@@ -368,8 +367,7 @@ static int launch_conv_gemm(const float* in, float* out, const float* W_kco, con
   if (rc != MUCON_OK) return rc;
   rc = make_map_2d(&tw, W_kco, static_cast<uint64_t>(ts.n) * convgemm::C, convgemm::C, gemm::BN);
   if (rc != MUCON_OK) return rc;
-  static int sms = 0;
-  if (!sms) sms = mucon_device_sm_count();
+  const int sms = mucon_device_sm_count();   // of the current device (cached per device)
   const int grid = num_tiles < sms ? num_tiles : sms;
   MUCON_CUDA_CHECK(cudaFuncSetAttribute(convgemm::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         convgemm::CSMEM_BYTES));
@@ -507,8 +505,7 @@ static int launch_layer(const float* x, float* out, const float* Wd_kco, const f
   if (rc != MUCON_OK) return rc;
   rc = make_map_2d(&tw1, W1_kco, layer::C, layer::C, wbox);
   if (rc != MUCON_OK) return rc;
-  static int sms = 0;
-  if (!sms) sms = mucon_device_sm_count();
+  const int sms = mucon_device_sm_count();   // of the current device (cached per device)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const layer::Tile* tl = static_cast<const layer::Tile*>(tiles);
   static int use_slab = -1;

@@ -13,6 +13,8 @@
 //   u  = ((gx+1)*W - 1)/2 (align_corners=0)  |  (gx+1)/2*(W-1) (align_corners=1) grid_sample
 //   out[i,t] = tmpl[floor u]*(1-frac) + tmpl[floor u + 1]*frac, taps outside [0,W) are 0
 // Backward: d out/d u = tmpl[floor u + 1] - tmpl[floor u]; u depends on L through pi and Ls.
+#include <atomic>
+#include <mutex>
 #include <stdlib.h>
 #include <math.h>
 
@@ -24,7 +26,8 @@ namespace {
 constexpr int kW = 100;  // TEMPLATE_WIDTH, masks.py:32
 
 __constant__ float c_tmpl[3][kW];
-bool g_tmpl_ready[64] = {false};
+std::atomic<int> g_tmpl_ready[64];   // 0 = not uploaded, 1 = uploaded (per device)
+std::mutex g_tmpl_mutex;
 
 void fill_templates(float (*t)[kW]) {
   for (int i = 0; i < kW; ++i) t[0][i] = 1.0f;  // box, masks.py:42-43
@@ -44,11 +47,13 @@ void fill_templates(float (*t)[kW]) {
 int ensure_templates() {
   int dev = 0;
   MUCON_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 64 && g_tmpl_ready[dev]) return MUCON_OK;
+  if (dev < 64 && g_tmpl_ready[dev].load(std::memory_order_acquire)) return MUCON_OK;
+  std::lock_guard<std::mutex> lock(g_tmpl_mutex);   // two host threads calling for the first time: one upload
+  if (dev < 64 && g_tmpl_ready[dev].load(std::memory_order_acquire)) return MUCON_OK;
   float h[3][kW];
   fill_templates(h);
   MUCON_CUDA_CHECK(cudaMemcpyToSymbol(c_tmpl, h, sizeof(h)));
-  if (dev < 64) g_tmpl_ready[dev] = true;
+  if (dev < 64) g_tmpl_ready[dev].store(1, std::memory_order_release);
   return MUCON_OK;
 }
 
@@ -584,8 +589,7 @@ __global__ void masks_bwd_combine_kernel(const int32_t* __restrict__ n_off, int 
 using namespace mucon;
 
 static int mask_grid(int n_rows) {
-  static int sms = 0;
-  if (!sms) sms = mucon_device_sm_count();
+  const int sms = mucon_device_sm_count();   // per current device (cached per device in api.cu)
   const int want = (n_rows + kGroupsPerCta - 1) / kGroupsPerCta;
   const int cap = (sms > 0 ? sms : 148) * 8;  // 8 CTAs x 4 groups x 64 threads = 2048 threads per SM
   return want < cap ? want : cap;
@@ -640,8 +644,7 @@ extern "C" int mucon_flint_fwd(const float* L, const int32_t* n_off, const int32
   if (V == 0 || n_rows == 0) return MUCON_OK;
   int rc = ensure_templates();
   if (rc != MUCON_OK) return rc;
-  static int sms = 0;
-  if (!sms) sms = mucon_device_sm_count();
+  const int sms = mucon_device_sm_count();   // per current device (cached per device in api.cu)
   const int grid = n_rows < 8 * sms ? n_rows : 8 * sms;
   flint_fwd_kernel<<<grid, kFlintThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, E);

@@ -73,8 +73,14 @@ class PipelinedGather:
             self.work[s] = None
         return self.plans[s]
 
-    def gather(self, i):
+    def gather(self, i, stream=None):
+        """stream: the stream the plan was run on when it is not the current one -- the collective is ordered after
+        the kernels that write the payload through an event on that stream."""
         s = i % len(self.plans)
+        if stream is not None and self.plans[s].payload.is_cuda and stream != torch.cuda.current_stream():
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            torch.cuda.current_stream().wait_event(ev)
         self.work[s] = dist.all_gather_into_tensor(self.recv[s], self.plans[s].payload, group=self.group, async_op=True)
 
     def result(self, i):
@@ -98,8 +104,8 @@ def unpack_payload(row, U, n_pos):
 
 def gather_alignments(score, seg_blocks, tr_off, max_units, max_positions, group=None):
     """all_gather of per-unit scores [U] (float64) and segment lengths [sum N] (int32) plus the
-    transcript offsets, padded to the given maxima.  Returns lists indexed by rank of
-    (score, seg_blocks, tr_off) trimmed back to each rank's true sizes."""
+    transcript offsets, padded to the given maxima.  Returns the raw padded tensors (all_sc [world, max_units],
+    all_int [world, ...]); unpack_gathered(all_sc, all_int, max_positions) trims them to per-rank dicts."""
     world = dist.get_world_size(group)
     dev = score.device
     U, P = score.shape[0], seg_blocks.shape[0]

@@ -67,9 +67,29 @@ class _MasksFn(torch.autograd.Function):
         return gL, None, None, None, None
 
 
+_META_CACHE = {}
+
+
 def _meta(Ms, Ts, device):
+    """Offset tables of a batch on the device.  Single-video shapes (the reference's call pattern: one create_masks
+    per training step) are cached by (M, T, device), so a step does not pay an H2D copy and its implicit sync."""
     Ms = np.asarray(Ms, dtype=np.int64)
     Ts = np.asarray(Ts, dtype=np.int64)
+    key = None
+    if Ms.shape[0] == 1:
+        key = (int(Ms[0]), int(Ts[0]), str(device))
+        hit = _META_CACHE.get(key)
+        if hit is not None:
+            return hit
+    out = _meta_build(Ms, Ts, device)
+    if key is not None:
+        if len(_META_CACHE) > 4096:
+            _META_CACHE.clear()
+        _META_CACHE[key] = out
+    return out
+
+
+def _meta_build(Ms, Ts, device):
     n_off = np.concatenate([[0], np.cumsum(Ms)]).astype(np.int32)
     sizes = Ms * Ts
     out_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
