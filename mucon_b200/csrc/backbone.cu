@@ -721,6 +721,7 @@ tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats
                     const float* __restrict__ bc, const TailTile* __restrict__ tiles, int num_tiles, int groups, int relu,
                     int NC, float* __restrict__ z_out, float* __restrict__ lsm_out) {
   extern __shared__ __align__(16) float tsm[];
+  __shared__ __align__(16) float gn_s[4][kTailH];   // mean, rstd (of the channel's group), gamma, beta of the tile's video
   float* Xs = tsm;                               // [128 k][132] (transposed: row index contiguous)
   float* Ws = tsm + kTailH * kTailLd;            // [128 k][8 * CG] zero padded
   float* bs = Ws + kTailH * 8 * CG;              // [8 * CG]
@@ -738,6 +739,17 @@ tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats
     const int nrow = min(kTailRows, tl.T - tl.t0);
     const int64_t rbase = tl.row0 + tl.t0;
     __syncthreads();  // Xs of the previous tile is no longer read (and Ws / bs are written)
+    // the tile's video: per-channel GroupNorm constants once per tile (the same four operands the element formula
+    // below uses, so the arithmetic -- and the log-probabilities -- stay bit-identical to groupnorm_kernel's)
+    if (threadIdx.x < kTailH) {
+      const int c = threadIdx.x;
+      const float* st = stats + (static_cast<int64_t>(v) * groups + c / cpg) * 2;
+      gn_s[0][c] = st[0];
+      gn_s[1][c] = st[1];
+      gn_s[2][c] = __ldg(gamma + c);
+      gn_s[3][c] = __ldg(beta + c);
+    }
+    __syncthreads();
     // GroupNorm + ReLU of the tile into shared memory (and to z_out).  A warp instruction covers 16 rows x 2 channel
     // quads: every row is read as one full 32-byte sector, and the four transposed stores of a lane hit banks
     // (quad*16 + e*4 + row) mod 32: all different across the warp.
@@ -747,16 +759,13 @@ tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nrow) {
         const float4 xv = *reinterpret_cast<const float4*>(x + (rbase + r) * kTailH + c4);
-        const float xin[4] = {xv.x, xv.y, xv.z, xv.w};
-        float y[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = c4 + e;
-          const float* st = stats + (static_cast<int64_t>(v) * groups + c / cpg) * 2;
-          float t = (xin[e] - st[0]) * st[1] * __ldg(gamma + c) + __ldg(beta + c);
-          y[e] = relu ? fmaxf(t, 0.f) : t;
-        }
-        o = make_float4(y[0], y[1], y[2], y[3]);
+        const float4 mu = *reinterpret_cast<const float4*>(&gn_s[0][c4]), rs = *reinterpret_cast<const float4*>(&gn_s[1][c4]);
+        const float4 ga = *reinterpret_cast<const float4*>(&gn_s[2][c4]), be = *reinterpret_cast<const float4*>(&gn_s[3][c4]);
+        o.x = (xv.x - mu.x) * rs.x * ga.x + be.x;
+        o.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
+        o.z = (xv.z - mu.z) * rs.z * ga.z + be.z;
+        o.w = (xv.w - mu.w) * rs.w * ga.w + be.w;
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         if (z_out) *reinterpret_cast<float4*>(z_out + (rbase + r) * kTailH + c4) = o;
       }
       Xs[(c4 + 0) * kTailLd + r] = o.x;
