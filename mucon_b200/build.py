@@ -26,6 +26,7 @@ SOURCES = {
     "masks.cu": ["-fmad=false"],
     "backbone.cu": [],
     "metrics.cu": [],
+    "shead.cu": [],
 }
 
 

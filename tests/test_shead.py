@@ -1,0 +1,72 @@
+"""The s-head at test time (reference src/mucon/models.py:585-745) against outputs of the UNMODIFIED reference model
+(tests/golden/shead.npz, minted by tests/golden/make_golden_shead.py on a real MuCon built from the reference's default
+configuration).  fp32 arithmetic in a different summation order than torch's LSTM / Linear kernels: log-probabilities
+and length logits within 2e-4 absolute (measured ~1e-5); greedy tokens identical."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shead.npz"))
+N_CASES = int(G["n"])
+
+
+def _load(model):
+    sd = {k[2:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("w.")}
+    missing, unexpected = model.load_state_dict(sd, strict=True), None
+    return model
+
+
+def test_state_dict_names_match_reference():
+    from mucon_b200.shead import SHead
+    m = SHead(num_classes=48)
+    ref = {k[2:]: G[k].shape for k in G.files if k.startswith("w.")}
+    own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert own == {k: tuple(s) for k, s in ref.items()}
+
+
+@pytest.mark.gpu
+def test_shead_matches_reference(cuda_device):
+    from mucon_b200.shead import SHead
+    m = _load(SHead(num_classes=48)).to(cuda_device).eval()
+    zs = [torch.from_numpy(G[f"c{i}_z"]) for i in range(N_CASES)]
+    off_h = np.concatenate([[0], np.cumsum([z.shape[0] for z in zs])]).astype(np.int64)
+    off = torch.from_numpy(off_h).to(cuda_device)
+    z = torch.cat(zs).to(cuda_device)
+    tf = [G[f"c{i}_tf_in"] for i in range(N_CASES)]
+    out = m.forward_packed(z, off, off_h, tf, teacher_forcing=True)
+    for i in range(N_CASES):
+        n = tf[i].shape[0]
+        assert int(out["n_steps"][i]) == n
+        got_lp, got_len = out["logp"][i, :n].cpu().numpy(), out["lengths"][i, :n].cpu().numpy()
+        assert np.abs(got_lp - G[f"c{i}_tf_logp"]).max() <= 2e-4, np.abs(got_lp - G[f"c{i}_tf_logp"]).max()
+        assert np.abs(got_len - G[f"c{i}_tf_len"]).max() <= 2e-4, np.abs(got_len - G[f"c{i}_tf_len"]).max()
+    out = m.forward_packed(z, off, off_h, None, teacher_forcing=False, max_steps=31)
+    for i in range(N_CASES):
+        want_lp = G[f"c{i}_greedy_logp"]
+        n = want_lp.shape[0]
+        assert int(out["n_steps"][i]) == n
+        assert np.array_equal(out["tokens"][i, :n].cpu().numpy(), want_lp.argmax(1))
+        assert np.abs(out["logp"][i, :n].cpu().numpy() - want_lp).max() <= 5e-4
+        assert np.abs(out["lengths"][i, :n].cpu().numpy() - G[f"c{i}_greedy_len"]).max() <= 5e-4
+    # the reference's one-video signature
+    pt, pl = m.sequence_generation_forward(zs[1][None].to(cuda_device), tf[1].shape[0], torch.from_numpy(tf[1]))
+    assert len(pt) == tf[1].shape[0] and pt[0].shape == (1, 49)
+    assert np.abs(torch.cat(pt).cpu().numpy() - G["c1_tf_logp"]).max() <= 2e-4
+
+
+@pytest.mark.gpu
+def test_shead_greedy_stops_at_eos(cuda_device):
+    """an s-head whose transcript head always prefers EOS stops after one step; n_steps and the padding say so"""
+    from mucon_b200.shead import SHead
+    torch.manual_seed(0)
+    m = SHead(num_classes=48).to(cuda_device).eval()
+    with torch.no_grad():
+        m.fs_decoder_transcript[2].bias.zero_()
+        m.fs_decoder_transcript[2].bias[48] = 50.0
+    off_h = np.array([0, 20, 55], dtype=np.int64)
+    z = torch.randn(55, 128, device=cuda_device).relu()
+    out = m.forward_packed(z, torch.from_numpy(off_h).to(cuda_device), off_h, None, teacher_forcing=False)
+    assert out["n_steps"].tolist() == [1, 1] and out["tokens"][:, 0].tolist() == [48, 48]
+    assert (out["tokens"][:, 1:] == -1).all()
