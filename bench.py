@@ -393,6 +393,18 @@ def main_ours(args, rank, world, local_rank):
             from mucon_b200 import temporal as _tm
             proj_ms = timed(lambda: _tm.gemm_tf32_bias_act(feats, w_["first_w"], w_["first_b"], True,
                                                            out_dtype=torch.float16), nfull)
+            # the s-head on the same batch (BiLSTM encoder over the pooled sequence + attention decoder, teacher-forced
+            # with the split's transcripts = the alignment mode of the evaluator): two kernels + three small GEMMs
+            shead_ms = None
+            try:
+                from mucon_b200.shead import SHead
+                sh_ = SHead(num_classes=C).eval().to(device)
+                _, zoff_, z_ = net.infer_pooled_packed(feats, bplan, want_z=True)
+                tf_in_ = [np.concatenate([[C + 1], tr]).astype(np.int32) for tr in trs]
+                shead_ms = timed(lambda: sh_.forward_packed(z_, zoff_, bplan.off_host[-1], tf_in_, teacher_forcing=True), 3)
+                del sh_, z_
+            except Exception as e_:
+                shead_ms = "error: " + str(e_)[:120]
             Tsum_ = int(T.sum())
             # backbone reads 4*T*D bytes of features and writes the log-probabilities (here at the
             # pooled resolution: 4*Tz*C); flops = 1.014 MFLOP per frame
@@ -410,7 +422,7 @@ def main_ours(args, rank, world, local_rank):
                             "fused Viterbi alignment reading the pooled table, 1712 videos/GPU, features resident in HBM",
                     "precision": _tm.DEFAULT_PRECISION,
                     "ms_per_step": full_ms, "backbone_ms": bb_ms, "encode_ms": enc_ms, "projection_ms": proj_ms,
-                    "expanded_path_ms_per_step": exp_ms,
+                    "expanded_path_ms_per_step": exp_ms, "shead_ms": shead_ms,
                     "frames_per_sec_per_gpu": float(T.sum()) / (full_ms * 1e-3),
                     "feature_bytes": int(feats.numel() * 4),
                     "feature_read_gbs": feats.numel() * 4 / (bb_ms * 1e-3) / 1e9,

@@ -70,3 +70,44 @@ def test_shead_greedy_stops_at_eos(cuda_device):
     out = m.forward_packed(z, torch.from_numpy(off_h).to(cuda_device), off_h, None, teacher_forcing=False)
     assert out["n_steps"].tolist() == [1, 1] and out["tokens"][:, 0].tolist() == [48, 48]
     assert (out["tokens"][:, 1:] == -1).all()
+
+
+@pytest.mark.gpu
+def test_full_inference_pipeline(cuda_device):
+    """features -> backbone -> s-head (teacher-forced and greedy) -> predict -> class-mean lengths -> alignment from the
+    pooled table: equal to running the evaluator glue on the host (class_mean_lengths + PoissonModel) over the expanded
+    log-probabilities, video by video through the drop-in Viterbi class"""
+    from mucon_b200 import PoissonModel, SingleTranscriptGrammar
+    from mucon_b200.evaluate import class_mean_lengths
+    from mucon_b200.inference import infer_and_align
+    from mucon_b200.shead import SHead
+    from mucon_b200.temporal import MuConBackbone
+    from mucon_b200.viterbi import Viterbi, ViterbiEngine
+    torch.manual_seed(2)
+    rng = np.random.default_rng(2)
+    net = MuConBackbone(input_feature_size=256).to(cuda_device).eval()
+    sh = _load(SHead(num_classes=48)).to(cuda_device).eval()
+    Ts = [900, 1700, 2400, 640]
+    plan = net.plan(Ts, cuda_device)
+    feats = torch.randn(int(sum(Ts)), 256, device=cuda_device).abs() * 0.5
+    tf = [np.concatenate([[49], rng.integers(0, 48, n)]) for n in (4, 6, 7, 3)]
+    eng = ViterbiEngine(cuda_device)
+    for tfi in (tf, None):
+        out = infer_and_align(net, sh, eng, feats, plan, 48, transcripts_tf_input=tfi)
+        torch.cuda.synchronize()
+        ap = out["plan"]
+        res = eng.fetch(ap)
+        lp = net.logprobs_packed(net.encode_packed(feats, plan), plan).cpu().numpy()
+        dec = Viterbi(None, None, frame_sampling=30, device=cuda_device)
+        off = np.concatenate([[0], np.cumsum(Ts)])
+        for v in range(len(Ts)):
+            tr = out["transcripts"][v]
+            if tfi is not None:
+                assert tr == [int(x) for x in tfi[v][1:]]
+            if res["status"][v] != 0:
+                continue   # K < N for a 30-token greedy transcript of random weights: -inf on both sides
+            dec.grammar = SingleTranscriptGrammar(tr, 48)
+            dec.length_model = PoissonModel(class_mean_lengths(tr, out["rel"][v].cpu().numpy(), Ts[v], 48))
+            score, labels, segs = dec.decode(lp[off[v]:off[v + 1]])
+            assert abs(score - res["score"][v]) <= 1e-9 * abs(score)
+            assert labels == res["labels"][ap.vid_off[v]:ap.vid_off[v + 1]].tolist()
