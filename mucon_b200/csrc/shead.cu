@@ -49,26 +49,31 @@ lstm_recurrent_kernel(const float* __restrict__ xproj_f, const float* __restrict
   if (j < kH) h_s[j] = 0.f;
   float c = 0.f, h = 0.f;
   __syncthreads();
+  // the input projection of step s + 1 is fetched while step s computes (an L2 round trip per step otherwise)
+  float xnext = Tz > 0 ? xproj[(r0 + (dir ? Tz - 1 : 0)) * kG + j] : 0.f;
   for (int s = 0; s < Tz; ++s) {
     const int t = dir ? Tz - 1 - s : s;
-    float acc = xproj[(r0 + t) * kG + j];
+    // four independent partial sums (one dependent chain of 128 FMAs would cost 128 x the FMA latency per step)
+    float a0 = xnext, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (s + 1 < Tz) xnext = xproj[(r0 + (dir ? t - 1 : t + 1)) * kG + j];
     const float4* h4 = reinterpret_cast<const float4*>(h_s);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float4 hv = h4[k];
-      acc = fmaf(w[4 * k + 0], hv.x, acc);
-      acc = fmaf(w[4 * k + 1], hv.y, acc);
-      acc = fmaf(w[4 * k + 2], hv.z, acc);
-      acc = fmaf(w[4 * k + 3], hv.w, acc);
+      a0 = fmaf(w[4 * k + 0], hv.x, a0);
+      a1 = fmaf(w[4 * k + 1], hv.y, a1);
+      a2 = fmaf(w[4 * k + 2], hv.z, a2);
+      a3 = fmaf(w[4 * k + 3], hv.w, a3);
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < 16; ++k) {
       const float4 hv = h4[16 + k];
-      acc = fmaf(Ws[(4 * k + 0) * kG + j], hv.x, acc);
-      acc = fmaf(Ws[(4 * k + 1) * kG + j], hv.y, acc);
-      acc = fmaf(Ws[(4 * k + 2) * kG + j], hv.z, acc);
-      acc = fmaf(Ws[(4 * k + 3) * kG + j], hv.w, acc);
+      a0 = fmaf(Ws[(4 * k + 0) * kG + j], hv.x, a0);
+      a1 = fmaf(Ws[(4 * k + 1) * kG + j], hv.y, a1);
+      a2 = fmaf(Ws[(4 * k + 2) * kG + j], hv.z, a2);
+      a3 = fmaf(Ws[(4 * k + 3) * kG + j], hv.w, a3);
     }
+    const float acc = (a0 + a1) + (a2 + a3);
     g_s[j] = acc;
     __syncthreads();
     if (j < kH) {
