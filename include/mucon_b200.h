@@ -45,6 +45,9 @@ extern "C" {
 #define MUCON_UNIT_NONFINITE 3  /* best score is NaN or +inf */
 
 int mucon_abi_version(void);
+/* Caps the grid of the persistent kernels launched by the calling host thread at n CTAs (0 = no cap); returns the
+ * previous cap.  Two capped kernels on two streams then run side by side on disjoint SMs. */
+int mucon_set_sm_limit(int n);
 const char* mucon_strerror(int code);
 const char* mucon_last_cuda_error(void);
 /* Number of SMs / device name of the current device; 0 / "" without a device. */

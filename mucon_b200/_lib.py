@@ -13,7 +13,7 @@ UNIT_OK, UNIT_INFEASIBLE, UNIT_SHORT, UNIT_NONFINITE = 0, 1, 2, 3
 
 # every symbol include/mucon_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
-    "mucon_abi_version", "mucon_strerror", "mucon_last_cuda_error", "mucon_device_sm_count",
+    "mucon_abi_version", "mucon_strerror", "mucon_last_cuda_error", "mucon_device_sm_count", "mucon_set_sm_limit",
     "mucon_viterbi_blockscores", "mucon_viterbi_decode", "mucon_viterbi_decode_generic", "mucon_viterbi_pack_lanes_h", "mucon_viterbi_decode_lanes", "mucon_viterbi_pack_h", "mucon_viterbi_align_fused", "mucon_viterbi_align_fused_tail", "mucon_viterbi_align_fused_pooled", "mucon_viterbi_select", "mucon_viterbi_labels",
     "mucon_poisson_params_h", "mucon_logfact_h", "mucon_lstm_encoder", "mucon_seq_decoder", "mucon_class_mean_params", "mucon_single_create", "mucon_single_destroy", "mucon_single_decode_h", "mucon_peer_alloc", "mucon_peer_open", "mucon_peer_close", "mucon_peer_free",
     "mucon_masks_fwd", "mucon_masks_bwd", "mucon_flint_fwd", "mucon_flint_fwd_ws", "mucon_flint_fwd_ws_words", "mucon_flint_bwd", "mucon_mask_template_h",

@@ -27,15 +27,28 @@ extern "C" const char* mucon_strerror(int code) {
 
 extern "C" const char* mucon_last_cuda_error(void) { return mucon::g_err; }
 
+// Optional cap on the grid of the persistent kernels (thread-local: set by the launching host thread, read by the
+// launchers through mucon_device_sm_count on the same thread).  Lets two kernels that each want one CTA per SM run
+// SIDE BY SIDE on disjoint SM sets from two streams -- the HBM-bound projection of video chunk k+1 next to the
+// tensor-bound layer kernels of chunk k (MuConBackbone.infer_pooled_pipelined).
+static thread_local int t_sm_limit = 0;
+extern "C" int mucon_set_sm_limit(int n) {
+  const int old = t_sm_limit;
+  t_sm_limit = n > 0 ? n : 0;
+  return old;
+}
+
 extern "C" int mucon_device_sm_count(void) {
   // cached per device (read-only after the first query; a benign race writes the same value twice)
   static int cache[64] = {0};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  if (dev >= 0 && dev < 64) cache[dev] = n;
-  return n;
+  if (dev >= 0 && dev < 64 && cache[dev]) n = cache[dev];
+  else {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+  }
+  return (t_sm_limit > 0 && t_sm_limit < n) ? t_sm_limit : n;
 }
 
 // ---- receive buffers of the multi-GPU result exchange (CUDA IPC; see mucon_viterbi_batch.peer_delta) ------------

@@ -269,8 +269,19 @@ class WaveNetBlock(nn.Module):
             self._cache = (key, w)
         return self._cache[1]
 
-    def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True, precision=None):
+    def project_packed(self, feats, precision=None):
+        """first_conv + ReLU alone (temporal.py:133) in the activation type of the fused layer kernels; hand the result
+        to forward_packed(..., x0=...).  Used by MuConBackbone.infer_pooled_pipelined."""
+        precision = precision or DEFAULT_PRECISION
+        if precision not in ("fp16", "bf16") or self.out_dims != 128 or self.in_channels % 32 != 0 or self.leaky:
+            raise NotImplementedError("project_packed covers the default fast path (fp16 / bf16 layers, 128 channels)")
+        w = self._weights()
+        return gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True,
+                                  out_dtype=torch.float16 if precision == "fp16" else torch.bfloat16)
+
+    def forward_packed(self, feats, plan, tensor_cores=True, fused_layers=True, precision=None, x0=None):
         """feats [sum T, in_channels] float32 rows (time-major, videos concatenated) -> [sum T', out_dims].
+        x0: the projection's output if it has been computed already (project_packed).
         tensor_cores=False keeps the 128->128 convolutions on the fp32 FFMA kernels (exact fp32);
         precision: "fp16" | "bf16" | "tf32" (| "fp32" == tensor_cores=False), default DEFAULT_PRECISION."""
         if self.training and self.dropout_rate > 0:
@@ -293,7 +304,9 @@ class WaveNetBlock(nn.Module):
         last = self.num_stages - 1
         if precision in ("bf16", "fp16") and tensor_cores and fused_layers and self.out_dims == 128 and self.num_stages > 0:
             dt = torch.float16 if precision == "fp16" else torch.bfloat16
-            if self.in_channels % 32 == 0:
+            if x0 is not None:
+                x = x0
+            elif self.in_channels % 32 == 0:
                 x = gemm_tf32_bias_act(feats, w["first_w"], w["first_b"], relu=True, out_dtype=dt)   # temporal.py:133
             else:
                 x = conv1d_rows(feats, w["first_w"].t().contiguous()[None], w["first_b"], plan.off[0], V, plan.max_T[0],
@@ -534,7 +547,54 @@ class MuConBackbone(nn.Module):
         logits = conv1d_rows(z, w, self.conv_classifier.bias.detach().float(), plan.off[lvl], plan.V, plan.max_T[lvl])
         return logsoftmax_expand_rows(logits, plan, lvl)
 
-    def infer_pooled_packed(self, feats, plan, precision=None, want_z=False):
+    def infer_pooled_pipelined(self, feats, T, n_chunks=4, proj_sms=88, precision=None):
+        """infer_pooled_packed with the batch cut into n_chunks contiguous groups of videos and two streams: the
+        projection of chunk k+1 (HBM-bound; it needs about two thirds of the SMs to pull its stream through the L2) runs
+        SIDE BY SIDE with the layer / tail kernels of chunk k (tensor-bound) on disjoint SMs -- every kernel here is
+        persistent with one CTA per SM, so the grids are capped (mucon_set_sm_limit) at proj_sms and SMs - proj_sms.
+        Returns (table [sum Tz, classes], row offsets [V+1]) like infer_pooled_packed (same values)."""
+        dev = feats.device
+        T = np.asarray(T, dtype=np.int64)
+        key = (tuple(T.tolist()), n_chunks, str(dev))
+        pc = getattr(self, "_pipe_cache", None)
+        if pc is None or pc[0] != key:
+            cum = np.cumsum(T)
+            cuts = [0] + [int(np.searchsorted(cum, cum[-1] * (k + 1) / n_chunks, side="left")) + 1 for k in range(n_chunks - 1)]
+            cuts = sorted(set(min(max(c, 0), len(T)) for c in cuts)) + [len(T)]
+            cuts = [c for i, c in enumerate(cuts) if i == 0 or c > cuts[i - 1]]
+            plans = [self.plan(T[a:b], dev) for a, b in zip(cuts[:-1], cuts[1:])]
+            rows = np.concatenate([[0], np.cumsum([int(T[a:b].sum()) for a, b in zip(cuts[:-1], cuts[1:])])])
+            full = self.plan(T, dev)
+            pc = self._pipe_cache = (key, plans, rows, full, torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        _, plans, rows, full, s_proj, s_lay = pc
+        lib = _lib.lib()
+        sms = int(lib.mucon_device_sm_count())
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        s_proj.wait_event(start)
+        s_lay.wait_event(start)
+        tables = []
+        for k, pl in enumerate(plans):
+            with torch.cuda.stream(s_proj):
+                lib.mucon_set_sm_limit(C.c_int(proj_sms))
+                x0 = self.ft.project_packed(feats[int(rows[k]):int(rows[k + 1])], precision)
+                ev = torch.cuda.Event()
+                ev.record(s_proj)
+            x0.record_stream(s_lay)
+            with torch.cuda.stream(s_lay):
+                s_lay.wait_event(ev)
+                lib.mucon_set_sm_limit(C.c_int(max(sms - proj_sms, 8)))
+                tb, _ = self.infer_pooled_packed(None, pl, precision=precision, x0=x0)
+                tb.record_stream(main)
+            tables.append(tb)
+        lib.mucon_set_sm_limit(C.c_int(0))
+        done = torch.cuda.Event()
+        done.record(s_lay)
+        main.wait_event(done)
+        return torch.cat(tables), full.off[len(full.off) - 1]
+
+    def infer_pooled_packed(self, feats, plan, precision=None, want_z=False, x0=None):
         """Features -> pooled-resolution log-probabilities in as few launches as the path has: ft (projection + one
         launch per layer + last_conv), then GroupNorm statistics and ONE launch for GroupNorm + ReLU + classifier +
         log_softmax (mucon_tail_logprobs).  Returns (table [sum Tz, classes], row offsets [V+1]) (+ z if want_z)."""
@@ -544,7 +604,9 @@ class MuConBackbone(nn.Module):
             table, off = self.logprobs_pooled_packed(z, plan)
             return (table, off, z) if want_z else (table, off)
         kw = dict(precision=precision) if isinstance(self.ft, WaveNetBlock) else {}
-        x = self.ft.forward_packed(feats, plan, **kw)
+        if x0 is not None:
+            kw["x0"] = x0
+        x = self.ft.forward_packed(feats if feats is not None else x0, plan, **kw)
         key = (self.conv_classifier.weight._version, self.conv_classifier.bias._version, str(x.device))
         if getattr(self, "_cls_cache", None) is None or self._cls_cache[0] != key:
             self._cls_cache = (key, self.conv_classifier.weight.detach()[:, :, 0].t().contiguous().float(),
