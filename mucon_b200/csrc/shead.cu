@@ -200,7 +200,7 @@ seq_decoder_kernel(const mucon_shead_weights w, const float* __restrict__ enc /*
     __syncthreads();
     ssum = 0.f;
     for (int q = 0; q < nw; ++q) ssum += red[q];
-    const float inv = 1.f / ssum;
+    const float inv = ssum > 0.f ? 1.f / ssum : 0.f;   // Tz == 0 (a video shorter than the pooling factor): zero context
     // context = sum_t a_t * enc[t]  (thread d owns dimension d: coalesced rows)
     {
       float acc = 0.f;

@@ -85,6 +85,12 @@ class SHead(nn.Module):
         Tz = np.diff(np.asarray(row_off_host, dtype=np.int64))
         max_Tz = int(Tz.max(initial=0))
         lib = _lib.lib()
+        if V == 0:
+            e = lambda *shape, dt=torch.float32: torch.zeros(shape, dtype=dt, device=dev)
+            return dict(logp=e(0, 1, self.num_classes + 1), lengths=e(0, 1), tokens=e(0, 1, dt=torch.int32),
+                        n_steps=e(0, dt=torch.int32), encoder_out=e(0, 2 * H))
+        if z.shape[0] == 0:
+            z = torch.zeros((1, H), dtype=torch.float32, device=dev)   # no pooled rows at all: keep the launches valid
         xp_f = conv1d_rows(z, w["wih_f"], w["b_f"], row_off, V, max_Tz)            # [rows, 512]
         xp_b = conv1d_rows(z, w["wih_b"], w["b_b"], row_off, V, max_Tz)
         enc = torch.empty((z.shape[0], 2 * H), dtype=torch.float32, device=dev)

@@ -111,3 +111,22 @@ def test_full_inference_pipeline(cuda_device):
             score, labels, segs = dec.decode(lp[off[v]:off[v + 1]])
             assert abs(score - res["score"][v]) <= 1e-9 * abs(score)
             assert labels == res["labels"][ap.vid_off[v]:ap.vid_off[v + 1]].tolist()
+
+
+@pytest.mark.gpu
+def test_shead_degenerate_lengths(cuda_device):
+    """a video with no pooled rows (T < 16) next to normal ones, and an empty batch: finite outputs, no crash"""
+    from mucon_b200.shead import SHead
+    torch.manual_seed(1)
+    m = SHead(num_classes=48).to(cuda_device).eval()
+    off_h = np.array([0, 7, 7, 30], dtype=np.int64)          # the middle video has Tz = 0
+    z = torch.randn(30, 128, device=cuda_device).relu()
+    tf = [np.array([49, 3, 4]), np.array([49, 5]), np.array([49, 1, 2, 3])]
+    out = m.forward_packed(z, torch.from_numpy(off_h).to(cuda_device), off_h, tf, teacher_forcing=True)
+    assert out["n_steps"].tolist() == [3, 2, 4]
+    for v, n in enumerate((3, 2, 4)):
+        assert torch.isfinite(out["logp"][v, :n]).all() and torch.isfinite(out["lengths"][v, :n]).all()
+    off0 = np.array([0], dtype=np.int64)
+    out = m.forward_packed(torch.zeros(0, 128, device=cuda_device), torch.from_numpy(off0).to(cuda_device), off0, [],
+                           teacher_forcing=True)
+    assert out["logp"].shape[0] == 0
