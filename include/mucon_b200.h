@@ -124,10 +124,12 @@ int mucon_viterbi_pack_h(const int32_t* N_h, const int32_t* order_h, int U, int 
 /* ---- the sequence-generation ("s") head at test time (src/mucon/models.py:585-745) -------------------------------
  * mucon_lstm_encoder: the recurrence of the bidirectional LSTM encoder for a packed batch.  xproj_f / xproj_b
  * [rows, 4H]: W_ih x_t + b_ih + b_hh of every step for the forward / reverse direction (one mucon_conv1d launch each),
- * whh_f / whh_b [4H, H] (torch gate order i, f, g, o), row_off [V+1] -> enc_out [rows, 2H] (= fs_encoder_lstm_out),
- * hn / cn [V, 2, H] (final states).  H = 128.
+ * whh_f / whh_b [4H, H] (torch gate order i, f, g, o), row_off [V+1], order [V] (a permutation of the videos, longest
+ * first: a CTA runs four consecutive entries in lockstep) -> enc_out [rows, 2H] (= fs_encoder_lstm_out), hn / cn
+ * [V, 2, H] (final states).  H = 128.
  * mucon_seq_decoder: the attention decoder, every decoding step of every video in one launch.  enc = enc_out,
- * enc_ready [rows, H] = enc @ fs_decoder_attention_W1; tf_in / tf_off [V+1]: per video SOS + transcript
+ * enc_ready [rows, H] = enc @ fs_decoder_attention_W1; order [V]: a permutation of the videos (a CTA decodes four
+ * consecutive entries in lockstep: sort by the number of steps); tf_in / tf_off [V+1]: per video SOS + transcript
  * (teacher_forcing != 0: step s is fed tf_in[s]; == 0: greedy, the first-maximum argmax of a step feeds the next and
  * the video stops at `eos` or after max_steps -- the reference's per-step .item(), models.py:721, stays on the device).
  * out_logp [V, max_steps, n_words] log-softmaxed transcript logits, out_len [V, max_steps] length logits,
@@ -137,9 +139,10 @@ typedef struct mucon_shead_weights {
       *t1_w, *t1_b, *t2_w, *t2_b, *n1_w, *n1_b, *n2_w, *n2_b;
 } mucon_shead_weights;
 int mucon_lstm_encoder(const float* xproj_f, const float* xproj_b, const float* whh_f, const float* whh_b,
-                       const int64_t* row_off, int V, int H, float* enc_out, float* hn, float* cn, void* stream);
+                       const int64_t* row_off, const int32_t* order, int V, int H, float* enc_out, float* hn, float* cn,
+                       void* stream);
 int mucon_seq_decoder(const mucon_shead_weights* w_h, const float* enc, const float* enc_ready, const float* hn,
-                      const float* cn, const int64_t* row_off, int V, int max_Tz, const int32_t* tf_in,
+                      const float* cn, const int64_t* row_off, const int32_t* order, int V, int max_Tz, const int32_t* tf_in,
                       const int32_t* tf_off, int teacher_forcing, int max_steps, int n_words, int eos, float* out_logp,
                       float* out_len, int32_t* out_tokens, int32_t* n_steps, void* stream);
 

@@ -96,9 +96,10 @@ class SHead(nn.Module):
         enc = torch.empty((z.shape[0], 2 * H), dtype=torch.float32, device=dev)
         hn = torch.empty((V, 2, H), dtype=torch.float32, device=dev)
         cn = torch.empty((V, 2, H), dtype=torch.float32, device=dev)
+        order = torch.from_numpy(np.argsort(-Tz, kind="stable").astype(np.int32)).to(dev)   # similar lengths share a CTA
         _lib.check(lib.mucon_lstm_encoder(_lib.ptr(xp_f), _lib.ptr(xp_b), _lib.ptr(w["whh_f"]), _lib.ptr(w["whh_b"]),
-                                          _lib.ptr(row_off), C.c_int(V), C.c_int(H), _lib.ptr(enc), _lib.ptr(hn),
-                                          _lib.ptr(cn), _stream(dev)), "mucon_lstm_encoder")
+                                          _lib.ptr(row_off), _lib.ptr(order), C.c_int(V), C.c_int(H), _lib.ptr(enc),
+                                          _lib.ptr(hn), _lib.ptr(cn), _stream(dev)), "mucon_lstm_encoder")
         enc_ready = conv1d_rows(enc, w["w1"], w["zero_h"], row_off, V, max_Tz)      # [rows, 128] (models.py:627-629)
         if teacher_forcing:
             if transcripts_tf_input is None:
@@ -116,8 +117,12 @@ class SHead(nn.Module):
         lens = torch.zeros((V, S), dtype=torch.float32, device=dev)
         toks = torch.full((V, S), -1, dtype=torch.int32, device=dev)
         nst = torch.zeros(V, dtype=torch.int32, device=dev)
+        # four videos share a CTA: group by the number of steps (teacher forcing) / by length (greedy)
+        key = np.array([t.shape[0] for t in tf]) * 100000 + Tz if teacher_forcing else Tz
+        dorder = torch.from_numpy(np.argsort(-key, kind="stable").astype(np.int32)).to(dev)
         _lib.check(lib.mucon_seq_decoder(
-            C.byref(ws), _lib.ptr(enc), _lib.ptr(enc_ready), _lib.ptr(hn), _lib.ptr(cn), _lib.ptr(row_off), C.c_int(V),
+            C.byref(ws), _lib.ptr(enc), _lib.ptr(enc_ready), _lib.ptr(hn), _lib.ptr(cn), _lib.ptr(row_off),
+            _lib.ptr(dorder), C.c_int(V),
             C.c_int(max_Tz), _lib.ptr(tf_in_d), _lib.ptr(tf_off_d), C.c_int(int(bool(teacher_forcing))), C.c_int(S),
             C.c_int(nw), C.c_int(self.EOS_token_id), _lib.ptr(logp), _lib.ptr(lens), _lib.ptr(toks), _lib.ptr(nst),
             _stream(dev)), "mucon_seq_decoder")
