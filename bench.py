@@ -666,7 +666,11 @@ def main_ours(args, rank, world, local_rank):
                              ", %d concurrent launches: the %d longest videos with a warp per segment, the rest "
                              "with 8 lanes per segment" % (2, plan.n_long) if plan.n_long else ", one launch"),
                          "achieved": fused_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fused_gbs / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": path_bytes,
+                         "traffic": traffic,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of both launches from the ncu --set "
+                                           "full capture profiles/r1d_align_fused_pair_c2.md (profiles/traffic.json); not "
+                                           "re-measured in this run -- ncu cannot run inside the timed process",
+                         "peak_source": peak_src, "bytes_per_launch": path_bytes,
                          "ms_per_launch": fused_ms, "launches_per_step": 2 if plan.n_long else 1,
                          "timing": "CUDA events around %d back-to-back steps on the launching stream / %d" % (args.steps, args.steps),
                          "algorithmic_bytes": "4TC + 4T + 2KN + 528N + 8 + 8N per unit (SURVEY.md 8d)"},

@@ -5,6 +5,9 @@ Host-side mirror of the reference interfaces for that path only:
     masks.create_masks / project_lengths_softmax                   (reference src/mucon/masks.py)
     temporal.WaveNetBlock + model.* forward helpers                (reference src/core/modules/temporal.py,
                                                                     src/mucon/models.py:360-374,567-582,746-773)
+    train.forward_train_packed / TrainStep, loss.mucon_loss*       (trainers.py:125-131, models.py:398-525)
+    shead.SHead, inference.infer_and_align                         (models.py:585-745; evaluators.py:128-180)
+    evaluate.align_videos, metrics.*                               (evaluators.py:147-243)
 All compute lives in libmucon_b200.so (C ABI: include/mucon_b200.h).  No CPU fallback.
 """
 from . import _lib  # noqa: F401

@@ -9,8 +9,9 @@ src/mucon/models.py:160-191,276-278) and its three forward helpers (models.py:36
 
 Internally activations are time-major ([rows, channels], videos concatenated) and every op is a
 call into libmucon_b200.so (include/mucon_b200.h); `BackbonePlan` holds the per-resolution row
-offsets of a batch of variable-length videos.  Forward only: training-mode dropout and autograd are
-not implemented here (the reference trains with its own PyTorch layers).
+offsets of a batch of variable-length videos.  This module is the inference forward; the training step (forward with
+kept activations, dropout, backward on tcgen05) is mucon_b200/train.py, the s-head mucon_b200/shead.py, the whole
+test-time pipeline mucon_b200/inference.py.
 """
 import ctypes as C
 import os
