@@ -753,28 +753,46 @@ tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats
     // GroupNorm + ReLU of the tile into shared memory (and to z_out).  A warp instruction covers 16 rows x 2 channel
     // quads: every row is read as one full 32-byte sector, and the four transposed stores of a lane hit banks
     // (quad*16 + e*4 + row) mod 32: all different across the warp.
-    for (int i = threadIdx.x; i < kTailRows * (kTailH / 4); i += blockDim.x) {
-      const int rsub = i & 15, cq = (i >> 4) & 1, rest = i >> 5;
-      const int r = (rest & 7) * 16 + rsub, c4 = ((rest >> 3) * 2 + cq) * 4;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nrow) {
-        const float4 xv = *reinterpret_cast<const float4*>(x + (rbase + r) * kTailH + c4);
-        const float4 mu = *reinterpret_cast<const float4*>(&gn_s[0][c4]), rs = *reinterpret_cast<const float4*>(&gn_s[1][c4]);
-        const float4 ga = *reinterpret_cast<const float4*>(&gn_s[2][c4]), be = *reinterpret_cast<const float4*>(&gn_s[3][c4]);
-        o.x = (xv.x - mu.x) * rs.x * ga.x + be.x;
-        o.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
-        o.z = (xv.z - mu.z) * rs.z * ga.z + be.z;
-        o.w = (xv.w - mu.w) * rs.w * ga.w + be.w;
-        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (z_out) *reinterpret_cast<float4*>(z_out + (rbase + r) * kTailH + c4) = o;
+    // (the 16 items of a thread in two batches of eight loads issued before any is used: ncu showed 65 % of the
+    // kernel's stalls waiting on these loads when each iteration loaded, computed and stored in turn)
+    constexpr int kItems = kTailRows * (kTailH / 4) / kTailThreads;   // 16
+    constexpr int kBatch = 8;
+#pragma unroll
+    for (int i0 = 0; i0 < kItems; i0 += kBatch) {
+      float4 xv[kBatch];
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        const int i = threadIdx.x + (i0 + q) * kTailThreads;
+        const int rsub = i & 15, cq = (i >> 4) & 1, rest = i >> 5;
+        const int r = (rest & 7) * 16 + rsub, c4 = ((rest >> 3) * 2 + cq) * 4;
+        xv[q] = r < nrow ? *reinterpret_cast<const float4*>(x + (rbase + r) * kTailH + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      Xs[(c4 + 0) * kTailLd + r] = o.x;
-      Xs[(c4 + 1) * kTailLd + r] = o.y;
-      Xs[(c4 + 2) * kTailLd + r] = o.z;
-      Xs[(c4 + 3) * kTailLd + r] = o.w;
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        const int i = threadIdx.x + (i0 + q) * kTailThreads;
+        const int rsub = i & 15, cq = (i >> 4) & 1, rest = i >> 5;
+        const int r = (rest & 7) * 16 + rsub, c4 = ((rest >> 3) * 2 + cq) * 4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrow) {
+          const float4 mu = *reinterpret_cast<const float4*>(&gn_s[0][c4]), rs = *reinterpret_cast<const float4*>(&gn_s[1][c4]);
+          const float4 ga = *reinterpret_cast<const float4*>(&gn_s[2][c4]), be = *reinterpret_cast<const float4*>(&gn_s[3][c4]);
+          o.x = (xv[q].x - mu.x) * rs.x * ga.x + be.x;
+          o.y = (xv[q].y - mu.y) * rs.y * ga.y + be.y;
+          o.z = (xv[q].z - mu.z) * rs.z * ga.z + be.z;
+          o.w = (xv[q].w - mu.w) * rs.w * ga.w + be.w;
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (z_out) *reinterpret_cast<float4*>(z_out + (rbase + r) * kTailH + c4) = o;
+        }
+        Xs[(c4 + 0) * kTailLd + r] = o.x;
+        Xs[(c4 + 1) * kTailLd + r] = o.y;
+        Xs[(c4 + 2) * kTailLd + r] = o.z;
+        Xs[(c4 + 3) * kTailLd + r] = o.w;
+      }
     }
     __syncthreads();
-    // classifier: one accumulator per (row, class), k ascending, bias last (the order of conv1d_kernel)
+    // classifier: one accumulator per (row, class), k ascending, bias last (the order of conv1d_kernel).  For an even CG
+    // two classes share one packed instruction (fma.rn.f32x2: two independent IEEE fp32 FMAs, same results as two
+    // scalar FMAs, half the issue slots -- the kernel is issue-bound)
     float acc[4][CG];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -782,26 +800,46 @@ tail_cls_lsm_kernel(const float* __restrict__ x, const float* __restrict__ stats
       for (int j = 0; j < CG; ++j) acc[i][j] = 0.f;
     const float* xr = Xs + rg * 4;
     const float* wr = Ws + cg * CG;
+    if constexpr (CG % 2 == 0) {
+      unsigned long long acc2[4][CG / 2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < CG / 2; ++j) acc2[i][j] = 0ull;   // (+0.f, +0.f)
 #pragma unroll 8
-    for (int k = 0; k < kTailH; ++k) {
-      const float4 x4 = *reinterpret_cast<const float4*>(xr + k * kTailLd);
-      const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-      float wv[CG];
-      if constexpr (CG % 2 == 0) {
+      for (int k = 0; k < kTailH; ++k) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xr + k * kTailLd);
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        unsigned long long w2[CG / 2];
 #pragma unroll
-        for (int j = 0; j < CG; j += 2) {
-          const float2 w2 = *reinterpret_cast<const float2*>(wr + k * NCP + j);
-          wv[j] = w2.x;
-          wv[j + 1] = w2.y;
+        for (int j = 0; j < CG / 2; ++j) w2[j] = *reinterpret_cast<const unsigned long long*>(wr + k * NCP + 2 * j);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          unsigned long long xx;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xv[i]));
+#pragma unroll
+          for (int j = 0; j < CG / 2; ++j)
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(xx), "l"(w2[j]));
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < CG; ++j) wv[j] = wr[k * NCP + j];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < CG; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+        for (int j = 0; j < CG / 2; ++j)
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2 * j]), "=f"(acc[i][2 * j + 1]) : "l"(acc2[i][j]));
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < kTailH; ++k) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xr + k * kTailLd);
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        float wv[CG];
+#pragma unroll
+        for (int j = 0; j < CG; ++j) wv[j] = wr[k * NCP + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < CG; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+      }
     }
     // + bias, log-softmax over the row's classes (8 lanes x CG classes)
 #pragma unroll

@@ -182,3 +182,20 @@ def test_fused_tail_equals_separate_kernels(cuda_device, ncls):
     assert torch.allclose(z, z2, rtol=1e-5, atol=1e-5), (z - z2).abs().max().item()
     assert torch.allclose(table, table2, rtol=1e-5, atol=2e-5), (table - table2).abs().max().item()
     assert torch.allclose(torch.logsumexp(table, 1), torch.zeros_like(table[:, 0]), atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_pipelined_inference_is_bit_identical(cuda_device):
+    """infer_pooled_pipelined (projection and layer kernels of consecutive video chunks side by side on disjoint SMs,
+    mucon_set_sm_limit) returns exactly infer_pooled_packed's table"""
+    import numpy as np
+    from mucon_b200.temporal import MuConBackbone
+    torch.manual_seed(5)
+    m = MuConBackbone(input_feature_size=256).eval().to(cuda_device)
+    T = np.array([700, 333, 64, 1999, 16, 128, 129, 1024, 17, 300, 2500, 900])
+    plan = m.plan(T, cuda_device)
+    feats = torch.randn(int(T.sum()), 256, device=cuda_device).abs() * 0.5
+    want, off = m.infer_pooled_packed(feats, plan)
+    got, off2 = m.infer_pooled_pipelined(feats, T, n_chunks=3, proj_sms=80)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(off, off2)
