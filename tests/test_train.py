@@ -359,3 +359,63 @@ def test_fused_tail_backward_equals_torch_ops(cuda_device):
                      m.conv_classifier.weight.grad.clone(), m.conv_classifier.bias.grad.clone()))
     for a, b in zip(*outs):
         assert torch.allclose(a, b, rtol=2e-3, atol=2e-3 * b.abs().max().item()), (a - b).abs().max().item()
+
+
+@pytest.mark.gpu
+def test_training_step_with_dropout_masks(cuda_device):
+    """dropout (temporal.py:51) in the training kernels: with the SAME inverted-dropout masks injected into the
+    tcgen05 path and into an fp32 torch restatement of the layer (y = mask * conv_1x1(relu(dilated(x))) + x), output and
+    every parameter gradient agree at the TF32 level"""
+    from mucon_b200 import train
+    from mucon_b200.temporal import MuConBackbone
+    torch.manual_seed(11)
+    Ts = [640, 1030, 77, 300]
+    m = MuConBackbone(input_feature_size=256).to(cuda_device).train()
+    ft = m.ft
+    plan = m.plan(Ts, cuda_device)
+    feats = torch.randn(int(sum(Ts)), 256, device=cuda_device).abs() * 0.5
+    p = 0.25
+    masks, level = [], 0
+    for i in range(ft.num_stages):
+        masks.append((torch.rand(plan.rows[level], 128, device=cuda_device) >= p).float() / (1 - p))
+        if i in ft.pooling_layers:
+            level += 1
+    out = train._WaveNetBlockFn.apply(ft, plan, feats, masks, *train._param_list(ft))
+    R = torch.randn_like(out)
+    (out * R).sum().backward()
+    got = {k: v.grad.detach().clone() for k, v in ft.named_parameters()}
+    got_out = out.detach().clone()
+    # fp32 restatement with the same masks, video by video
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for q in ft.parameters():
+            q.grad = None
+        outs = []
+        offs = [np.concatenate([[0], np.cumsum(t)]) for t in plan.T]
+        for v, T in enumerate(Ts):
+            x = F.relu(F.conv1d(feats[offs[0][v]:offs[0][v + 1]].t()[None], ft.first_conv.weight, ft.first_conv.bias))
+            level = 0
+            for i, l in enumerate(ft.layers):
+                d = ft.stages[i]
+                y = F.relu(F.conv1d(x, l.dilated_conv.weight, l.dilated_conv.bias, dilation=d, padding=d))
+                y = F.conv1d(y, l.conv_1x1.weight, l.conv_1x1.bias)
+                mk = masks[i][offs[level][v]:offs[level][v + 1]].t()[None]
+                x = y * mk + x
+                if i in ft.pooling_layers:
+                    x = F.max_pool1d(x, 2)
+                    level += 1
+            outs.append(F.conv1d(F.relu(x), ft.last_conv.weight, ft.last_conv.bias)[0].t())
+        want = torch.cat(outs)
+        (want * R).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    rms = want.pow(2).mean().sqrt().item()
+    assert (got_out - want).abs().max().item() <= 2e-2 * rms
+    for k, q in ft.named_parameters():
+        w_ = q.grad.double()
+        if w_.abs().max().item() == 0.0:
+            assert got[k].abs().max().item() == 0.0, k
+            continue
+        rel = ((got[k].double() - w_).norm() / w_.norm()).item()
+        assert rel <= 6e-2, (k, rel)
