@@ -1,0 +1,62 @@
+"""Host-side logic that needs no GPU: array-form candidate sets, the c3 sharding used by bench.py, the train plan's
+nearest-neighbour index table, the batched loss's index bookkeeping."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_flat_candidates_equal_nested_lists():
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan, FlatCandidates
+    rng = np.random.default_rng(0)
+    T = rng.integers(300, 4000, 23)
+    cands = [[rng.integers(0, 48, int(rng.integers(2, 9))).tolist() for _ in range(int(rng.integers(1, 6)))] for _ in T]
+    means = rng.uniform(30, 400, (len(T), 48))
+    a = AlignPlan(T, cands, 48, device="cpu", len_params=poisson_params(means), labels="best")
+    b = AlignPlan(T, FlatCandidates.from_lists(cands), 48, device="cpu", len_params=poisson_params(means), labels="best")
+    for name in ("tr", "tr_off", "cand_off", "unit_vid", "warp_unit", "order_v", "bp_off", "lab_off"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert a.U == b.U and a.max_N == b.max_N and a.n_cta == b.n_cta and a.n_lane_warps == b.n_lane_warps
+    with pytest.raises(ValueError):
+        AlignPlan(T, FlatCandidates([1] * len(T), [3] * (len(T) - 1), [0] * 3 * (len(T) - 1)), 48, device="cpu",
+                  len_params=poisson_params(means))
+
+
+def test_c3_sharding_keeps_all_candidates_of_a_video_together():
+    import bench
+    from mucon_b200 import dist as mdist
+    T, trs, _ = bench.make_split(0)
+    for world in (2, 4, 8):
+        shards = mdist.shard_videos(T, [64] * len(T), world)
+        allv = np.sort(np.concatenate(shards))
+        assert np.array_equal(allv, np.arange(len(T)))
+        load = np.array([T[s].sum() for s in shards], dtype=np.float64)
+        assert load.max() / load.mean() < 1.01      # greedy longest-first: within 1 % of perfect balance
+
+
+def test_train_plan_expand_index_is_torch_nearest():
+    """the frame -> pooled-row table of the training tail equals F.interpolate(mode='nearest')"""
+    import torch.nn.functional as F
+    from mucon_b200.temporal import BackbonePlan
+    from mucon_b200.train import _plan_train_tables
+    Ts = [700, 333, 17, 2048, 1999]
+    plan = BackbonePlan(Ts, 4, "cpu")
+    vid, idx, counts = _plan_train_tables(plan, "cpu")
+    pos = 0
+    for v, T in enumerate(Ts):
+        Tz = int(plan.T[-1][v])
+        want = F.interpolate(torch.arange(Tz, dtype=torch.float32)[None, None], T)[0, 0].long() + int(plan.off_host[-1][v])
+        assert torch.equal(idx[pos:pos + T], want), v
+        pos += T
+    assert counts.tolist() == [float(t) for t in plan.T[-1]]
+
+
+def test_smoothing_loss_packed_matches_reference_statements():
+    import torch.nn.functional as F
+    from mucon_b200.loss import smoothing_loss_packed
+    g = torch.Generator().manual_seed(0)
+    Ts = [40, 7, 130]
+    segs = [torch.randn(t, 12, generator=g) * 3 for t in Ts]
+    want = sum(torch.clamp(F.mse_loss(F.log_softmax(s, 1)[1:], F.log_softmax(s, 1)[:-1]), min=0.0, max=16.0) for s in segs) / 3
+    got = smoothing_loss_packed(torch.cat(segs), Ts)
+    assert abs(got.item() - want.item()) <= 1e-6 * max(1.0, abs(want.item()))
