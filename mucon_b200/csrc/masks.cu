@@ -383,18 +383,47 @@ flint_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off,
 // four class columns and every (32 / (C/4))-th frame of its part.  The partial sums of a row go to a workspace; the
 // warp that finishes a row's last part (a counter per row) adds the parts in order p = 0..7, so the result does not
 // depend on the order in which the warps ran.
+// Per-row constants of the evidence kernels, computed once per call by a thread per row (flint_rows_pre_kernel): the
+// items of flint_fwd_warp_kernel then start from ONE 64-byte record instead of a chain of dependent loads (row -> video
+// -> lengths) and ~200 instructions of geometry per lane.
+struct __align__(16) RowPre {
+  RowGeom g;        // 16 B
+  Regions r;        // 16 B
+  long long seg;    // first frame of the row's video in the packed logits (frames)
+  int T, pad0;
+  int pad1[4];
+};
+static_assert(sizeof(RowPre) == 64, "RowPre is one 64-byte record");
+
+__global__ void __launch_bounds__(128)
+flint_rows_pre_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                      const int64_t* __restrict__ seg_off, const int32_t* __restrict__ row_vid, int V, int n_rows,
+                      float overlap, int tmpl, int align, RowPre* __restrict__ pre) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int v = row_vid ? row_vid[row] : find_video(n_off, V, row);
+  const int T = Tv[v];
+  const int r0 = n_off[v], i = row - r0;
+  RowPre p;
+  p.g = row_geom(L, r0, i, T, overlap);
+  p.r = make_regions(make_screen(p.g, T, align), T, tmpl == 0);
+  p.seg = seg_off[v];
+  p.T = T;
+  p.pad0 = 0;
+  p.pad1[0] = p.pad1[1] = p.pad1[2] = p.pad1[3] = 0;
+  pre[row] = p;
+}
+
 constexpr int kFlintPartsMax = 8;
 constexpr int kFlintBatch = 8;
 template <int kFlintParts>
 __global__ void __launch_bounds__(256)
-flint_fwd_warp_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
-                      const int64_t* __restrict__ seg_off, const int32_t* __restrict__ row_vid, int V, int n_rows, int C,
-                      float overlap, int tmpl, int align, const float* __restrict__ seg, float* __restrict__ part_ws,
-                      unsigned int* __restrict__ counters, float* __restrict__ E) {
+flint_fwd_warp_kernel(const RowPre* __restrict__ pre, int n_rows, int C, int tmpl, int align,
+                      const float* __restrict__ seg, float* __restrict__ part_ws, unsigned int* __restrict__ counters,
+                      float* __restrict__ E) {
   __shared__ float tp[kWP];
   load_template(tp, tmpl);
   __syncthreads();
-  const bool box = tmpl == 0;
   const int C4 = C >> 2;
   const int FP = 32 / C4;                       // frames per warp iteration
   const int lane = threadIdx.x & 31;
@@ -405,15 +434,14 @@ flint_fwd_warp_kernel(const float* __restrict__ L, const int32_t* __restrict__ n
   const int n_items = n_rows * kFlintParts;
   for (int item = warp_g; item < n_items; item += n_warps) {
     const int row = item / kFlintParts, p = item - row * kFlintParts;
-    const int v = row_vid ? row_vid[row] : find_video(n_off, V, row);
-    const int T = Tv[v];
-    const int r0 = n_off[v], i = row - r0;
-    const RowGeom g = row_geom(L, r0, i, T, overlap);          // every lane, redundantly: no shuffle, no barrier
-    const Regions r = make_regions(make_screen(g, T, align), T, box);
+    const RowPre rp = pre[row];                                 // one 64-byte record, the same for every lane
+    const RowGeom g = rp.g;
+    const Regions r = rp.r;
+    const int T = rp.T;
     const int len = r.b1 - r.a0;
     const int t_lo = r.a0 + static_cast<int>(static_cast<long long>(len) * p / kFlintParts);
     const int t_hi = r.a0 + static_cast<int>(static_cast<long long>(len) * (p + 1) / kFlintParts);
-    const float4* sv = reinterpret_cast<const float4*>(seg + seg_off[v] * C);
+    const float4* sv = reinterpret_cast<const float4*>(seg + rp.seg * C);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
       // batches of kFlintBatch independent 16-byte loads issued before any of them is used (the mask evaluation has
@@ -654,7 +682,9 @@ extern "C" int mucon_flint_fwd(const float* L, const int32_t* n_off, const int32
 
 extern "C" int64_t mucon_flint_fwd_ws_words(int n_rows, int C) {
   if (n_rows < 0 || C < 1) return 0;
-  return static_cast<int64_t>(n_rows) * kFlintPartsMax * C + n_rows;   // float partials + one counter per row
+  // float partials + one counter per row (+ padding to 16 bytes) + one 64-byte RowPre per row
+  return static_cast<int64_t>(n_rows) * kFlintPartsMax * C + (static_cast<int64_t>(n_rows) + 3) / 4 * 4 +
+         static_cast<int64_t>(n_rows) * 16;
 }
 
 // ws: mucon_flint_fwd_ws_words(n_rows, C) 4-byte words, 16-byte aligned; its counters (the last n_rows words) must be
@@ -677,16 +707,20 @@ extern "C" int mucon_flint_fwd_ws(const float* L, const int32_t* n_off, const in
   long long grid = (items + 7) / 8;
   if (grid > 8LL * sms) grid = 8LL * sms;
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws + static_cast<int64_t>(n_rows) * kFlintPartsMax * C);
+  RowPre* pre = reinterpret_cast<RowPre*>(counters + (static_cast<int64_t>(n_rows) + 3) / 4 * 4);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  flint_rows_pre_kernel<<<(n_rows + 127) / 128, 128, 0, st>>>(L, n_off, T, seg_off, row_vid, V, n_rows, overlap, template_id,
+                                                              align_corners, pre);
+  MUCON_CUDA_CHECK(cudaGetLastError());
   if (parts == 8)
-    flint_fwd_warp_kernel<8><<<static_cast<int>(grid), 256, 0, st>>>(
-        L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, ws, counters, E);
+    flint_fwd_warp_kernel<8><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws,
+                                                                      counters, E);
   else if (parts == 2)
-    flint_fwd_warp_kernel<2><<<static_cast<int>(grid), 256, 0, st>>>(
-        L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, ws, counters, E);
+    flint_fwd_warp_kernel<2><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws,
+                                                                      counters, E);
   else
-    flint_fwd_warp_kernel<4><<<static_cast<int>(grid), 256, 0, st>>>(
-        L, n_off, T, seg_off, row_vid, V, n_rows, C, overlap, template_id, align_corners, seg, ws, counters, E);
+    flint_fwd_warp_kernel<4><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws,
+                                                                      counters, E);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
