@@ -267,6 +267,12 @@ int mucon_logfact_h(int fs, int max_len, double* out_h);
 int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
                     const int32_t* row_vid, int V, int n_rows /* n_off[V] */, int max_T /* max over T[] */,
                     float overlap, int template_id, int align_corners, float* L_scaled, float* out, void* stream);
+/* mucon_masks_fwd in two launches: a thread per row computes the row's geometry (prefix sum of the lengths, window,
+ * certified constant ranges) into ws (64 bytes per row, 16-byte aligned), then 64-thread groups write the rows from
+ * those records without any dependent metadata loads or barriers.  Same results as mucon_masks_fwd. */
+int mucon_masks_fwd_ws(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
+                       const int32_t* row_vid, int V, int n_rows, int max_T, float overlap, int template_id,
+                       int align_corners, float* L_scaled, float* out, void* ws, void* stream);
 /* grad_L[i] = d(sum(grad_out * masks))/dL[i], through pi (cumsum) and the scale.
  * grad_out has the layout of `out`; ws is scratch of 2*n_rows floats. */
 int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,

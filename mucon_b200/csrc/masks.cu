@@ -414,6 +414,59 @@ flint_rows_pre_kernel(const float* __restrict__ L, const int32_t* __restrict__ n
   pre[row] = p;
 }
 
+// create_masks with the rows' geometry precomputed the same way: a 64-thread group starts a row from its 64-byte record --
+// no dependent metadata loads, no serial prefix sum by the group's first thread, no barriers, no redundant region search.
+__global__ void __launch_bounds__(128)
+masks_rows_pre_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off, const int32_t* __restrict__ Tv,
+                      const int64_t* __restrict__ out_off, const int32_t* __restrict__ row_vid, int V, int n_rows,
+                      float overlap, int tmpl, int align, RowPre* __restrict__ pre, float* __restrict__ L_scaled) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int v = row_vid ? row_vid[row] : find_video(n_off, V, row);
+  const int T = Tv[v];
+  const int r0 = n_off[v], i = row - r0;
+  RowPre p;
+  p.g = row_geom(L, r0, i, T, overlap);
+  p.r = make_regions(make_screen(p.g, T, align), T, tmpl == 0);
+  p.seg = out_off[v] + static_cast<long long>(i) * T;
+  p.T = T;
+  p.pad0 = 0;
+  p.pad1[0] = p.pad1[1] = p.pad1[2] = p.pad1[3] = 0;
+  pre[row] = p;
+  if (L_scaled) L_scaled[row] = p.g.Ls;
+}
+
+__global__ void __launch_bounds__(kGroup * kGroupsPerCta)
+masks_fwd_pre_kernel(const RowPre* __restrict__ pre, int n_rows, int tmpl, int align, float* __restrict__ out) {
+  __shared__ float tp[kWP];
+  const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup;
+  load_template(tp, tmpl);
+  __syncthreads();
+  for (int row = blockIdx.x * kGroupsPerCta + grp; row < n_rows; row += gridDim.x * kGroupsPerCta) {
+    const RowPre p = pre[row];
+    const RowGeom g = p.g;
+    const Regions r = p.r;
+    const int T = p.T;
+    float* o = out + p.seg;
+    const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(o) >> 2) & 3);
+    const int head = min(T, (4 - mis) & 3);
+    if (gt < head) o[gt] = mask_value(tp, g, r, gt, T, align);
+    const int nvec = (T - head) >> 2;
+    float4* o4 = reinterpret_cast<float4*>(o + head);
+    for (int q = gt; q < nvec; q += kGroup) {
+      const int t = head + 4 * q;
+      float4 val;
+      if (t >= r.a1 && t + 3 < r.b0) val = make_float4(1.f, 1.f, 1.f, 1.f);
+      else if (t + 3 < r.a0 || t >= r.b1) val = make_float4(0.f, 0.f, 0.f, 0.f);
+      else val = make_float4(mask_value(tp, g, r, t, T, align), mask_value(tp, g, r, t + 1, T, align),
+                             mask_value(tp, g, r, t + 2, T, align), mask_value(tp, g, r, t + 3, T, align));
+      o4[q] = val;
+    }
+    const int t_tail = head + 4 * nvec + gt;
+    if (t_tail < T) o[t_tail] = mask_value(tp, g, r, t_tail, T, align);
+  }
+}
+
 constexpr int kFlintPartsMax = 8;
 constexpr int kFlintBatch = 8;
 template <int kFlintParts>
@@ -633,6 +686,26 @@ extern "C" int mucon_masks_fwd(const float* L, const int32_t* n_off, const int32
   if (rc != MUCON_OK) return rc;
   masks_fwd_kernel<<<mask_grid(n_rows), kGroup * kGroupsPerCta, 0, static_cast<cudaStream_t>(stream)>>>(L, n_off, T, out_off, row_vid, V, n_rows, overlap, template_id,
                                                                          align_corners, L_scaled, out);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+// ws: 64 bytes per mask row (16-byte aligned), overwritten
+extern "C" int mucon_masks_fwd_ws(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* out_off,
+                                  const int32_t* row_vid, int V, int n_rows, int max_T, float overlap, int template_id,
+                                  int align_corners, float* L_scaled, float* out, void* ws, void* stream) {
+  if (!L || !n_off || !T || !out_off || !out || !ws || V < 0 || n_rows < 0 || max_T < 0) return MUCON_EINVAL;
+  if (template_id < 0 || template_id > 2) return MUCON_EINVAL;
+  if (reinterpret_cast<uintptr_t>(ws) & 15) return MUCON_EALIGN;
+  if (V == 0 || n_rows == 0 || max_T == 0) return MUCON_OK;
+  int rc = ensure_templates();
+  if (rc != MUCON_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RowPre* pre = static_cast<RowPre*>(ws);
+  masks_rows_pre_kernel<<<(n_rows + 127) / 128, 128, 0, st>>>(L, n_off, T, out_off, row_vid, V, n_rows, overlap, template_id,
+                                                              align_corners, pre, L_scaled);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  masks_fwd_pre_kernel<<<mask_grid(n_rows), kGroup * kGroupsPerCta, 0, st>>>(pre, n_rows, template_id, align_corners, out);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

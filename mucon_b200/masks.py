@@ -27,8 +27,25 @@ def project_lengths_softmax(T, L):
     return T * torch.softmax(L, dim=0)
 
 
+_WS = {}
+
+
 def _launch_fwd(L, n_off, Ts, out_off, row_vid, V, n_rows, max_T, overlap, tid, align, L_scaled, out):
     st = torch.cuda.current_stream(L.device)
+    if n_rows >= 64:
+        # batches: the rows' geometry is computed by a first launch (a thread per row) into a workspace that is kept
+        # per (device, size) -- at reference sizes (one video, a handful of rows) the single launch below is faster
+        key = (str(L.device), int(n_rows))
+        ws = _WS.get(key)
+        if ws is None:
+            if len(_WS) > 64:
+                _WS.clear()
+            ws = _WS[key] = torch.empty(16 * n_rows + 4, dtype=torch.float32, device=L.device)
+        _lib.check(_lib.lib().mucon_masks_fwd_ws(
+            _lib.ptr(L), _lib.ptr(n_off), _lib.ptr(Ts), _lib.ptr(out_off), _lib.ptr(row_vid), C.c_int(V), C.c_int(n_rows),
+            C.c_int(max_T), C.c_float(overlap), C.c_int(tid), C.c_int(align), _lib.ptr(L_scaled), _lib.ptr(out),
+            _lib.ptr(ws), C.c_void_p(st.cuda_stream)), "mucon_masks_fwd_ws")
+        return
     _lib.check(_lib.lib().mucon_masks_fwd(
         _lib.ptr(L), _lib.ptr(n_off), _lib.ptr(Ts), _lib.ptr(out_off), _lib.ptr(row_vid), C.c_int(V), C.c_int(n_rows),
         C.c_int(max_T),
