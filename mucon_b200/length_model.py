@@ -71,13 +71,56 @@ class PoissonModel(LengthModel):
         self.mean_lengths = np.loadtxt(model) if isinstance(model, str) else model
         self.num_classes = self.mean_lengths.shape[0]
         self.max_len = max_length
+        self.renormalize = renormalize
         self.params = poisson_params(self.mean_lengths, renormalize)
         self.norms = self.params[:, 2]
         self._table = None
+        # The parameter triple (ln m, m, norms) reproduces the reference's table bit for bit when the mean lengths
+        # are float64 (what the evaluator passes, evaluators.py:155-165).  For any other dtype the reference's
+        # arithmetic runs partly in that dtype (length_model.py:54-71: the norms and l * log(m) - m in the input
+        # dtype, the rest promoted by NumPy's rules): then `exact_params` is False and the decoders take explicit
+        # rows from `rows_for`, which executes the reference's expressions with the reference's dtypes.
+        self.exact_params = np.asarray(self.mean_lengths).dtype == np.float64
+
+    def _low_precision_terms(self):
+        """(ln m, m, norms) as the reference computes them for non-float64 means (length_model.py:54-63)."""
+        m = np.asarray(self.mean_lengths)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            norms = np.zeros(m.shape)
+            if self.renormalize:
+                norms = np.round(m) * np.log(np.round(m)) - np.round(m)             # input dtype
+                tail = _log_tail(int(max(int(np.max(m, initial=1)), 1)))
+                mi = np.maximum(m.astype(np.int64), 0)
+                for c in range(len(m)):                                               # norms[c] = norms[c] - logFak
+                    norms[c] = norms[c] - np.float64(tail[mi[c]])
+            return np.log(m), m, norms
+
+    def rows_for(self, transcript, fs, J):
+        """[N, J] float64 rows[n, j-1] = table[j * fs, transcript[n]] with the reference's own operations and dtypes
+        (length_model.py:65-71: l * np.log(m) - m - logFak - norms, logFak an np.float64 scalar)."""
+        lnm, m, norms = self._low_precision_terms()
+        lf = log_factorial_prefix(self.max_len - 1)
+        tr = np.asarray(transcript, dtype=np.int64)
+        rows = np.full((tr.shape[0], J), -np.inf, dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for j in range(1, J + 1):
+                l = j * fs
+                if l < self.max_len:
+                    rows[:, j - 1] = (l * lnm - m - np.float64(lf[l]) - norms)[tr]
+        return rows
 
     @property
     def poisson(self):
         """The reference's full [max_len, C] table, built on demand (vectorised)."""
+        if self._table is None and not self.exact_params:
+            lnm, m, norms = self._low_precision_terms()
+            lf = log_factorial_prefix(self.max_len - 1)
+            t = np.zeros((self.max_len, self.num_classes))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                for l in range(1, self.max_len):
+                    t[l, :] = l * lnm - m - np.float64(lf[l]) - norms
+            t[0, :] = -np.inf
+            self._table = t
         if self._table is None:
             lf = log_factorial_prefix(self.max_len - 1)
             L = np.arange(self.max_len, dtype=np.float64)[:, None]
@@ -94,6 +137,8 @@ class PoissonModel(LengthModel):
     def score(self, length, label):
         if length >= self.max_len or length <= 0:
             return -np.inf
+        if not self.exact_params:
+            return self.poisson[length, label]
         lm, m, nrm = self.params[label]
         return ((length * lm - m) - log_factorial_prefix(self.max_len - 1)[length]) - nrm
 

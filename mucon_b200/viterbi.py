@@ -616,12 +616,14 @@ class Viterbi(object):
         max_len = int(max_len)
         J = max_len // fs
         kw = {}
-        if isinstance(lm, PoissonModel):
+        if isinstance(lm, PoissonModel) and lm.exact_params:
             kw["len_params"] = lm.params[None]
+        elif isinstance(lm, PoissonModel):
+            kw["len_rows"] = [lm.rows_for(tr, fs, J) for tr in cands]   # non-float64 means: the reference's dtypes
         else:
             kw["len_rows"] = [_length_rows(lm, tr, fs, J) for tr in cands]
         eng = self._eng()
-        if self.fast_single and len(cands) == 1 and isinstance(lm, PoissonModel) and J <= MAX_J_REGISTER \
+        if self.fast_single and len(cands) == 1 and isinstance(lm, PoissonModel) and lm.exact_params and J <= MAX_J_REGISTER \
                 and Cn % 4 == 0 and Cn <= 128:
             fast = self._decode_single(eng, logp, cands[0], lm, fs, max_len)
             if fast is not None:

@@ -87,3 +87,23 @@ def test_infeasible_inputs_raise():
         hyp_viterbi.decode(logp, [[0, 1]], tab)
     with pytest.raises(dense_viterbi.Infeasible):  # T < fs
         dense_viterbi.decode(logp[:20], [0, 1], rows)
+
+
+def test_poisson_model_float32_means_follow_the_reference_dtypes():
+    """PoissonModel built from float32 mean lengths: the reference's norms and l*log(m) - m run in float32
+    (length_model.py:54-71); the table and the decoder rows must equal the frozen reference table bit for bit
+    (tests/golden/poisson_f32.npz; minted under the NumPy version recorded in the file)."""
+    import os
+    import numpy as np
+    import pytest
+    from mucon_b200.length_model import PoissonModel
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "poisson_f32.npz"))
+    if str(g["numpy_version"]).split(".")[0] != np.__version__.split(".")[0]:
+        pytest.skip("minted under another NumPy major version (different promotion rules)")
+    lm = PoissonModel(g["means"])
+    assert not lm.exact_params
+    assert np.array_equal(lm.poisson[:40], g["table_head"], equal_nan=True)
+    assert np.array_equal(lm.poisson[np.arange(1, 67) * 30], g["table_rows"], equal_nan=True)
+    rows = lm.rows_for(g["transcript"], 30, 66)
+    assert np.array_equal(rows, g["table_rows"][:, g["transcript"]].T, equal_nan=True)
+    assert PoissonModel(g["means"].astype(np.float64)).exact_params

@@ -519,3 +519,19 @@ def test_peer_exchange_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
                         os.path.join(root, "scripts", "peer_exchange_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and '"peer_exchange_ok": true' in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_drop_in_decode_with_float32_mean_lengths(eng):
+    """a PoissonModel built from float32 means (rows in the reference's dtypes, not the float64 parameter triple):
+    score / labels / segments equal the reference's frozen decode"""
+    from mucon_b200 import PoissonModel, SingleTranscriptGrammar
+    from mucon_b200.viterbi import Viterbi
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "poisson_f32.npz"))
+    if str(g["numpy_version"]).split(".")[0] != np.__version__.split(".")[0]:
+        pytest.skip("minted under another NumPy major version")
+    dec = Viterbi(SingleTranscriptGrammar(g["transcript"].tolist(), 48), PoissonModel(g["means"]), frame_sampling=30,
+                  device=eng.device)
+    score, labels, segs = dec.decode(g["logp"])
+    assert same_score(score, g["score"])
+    assert labels == g["labels"].tolist()
+    assert [(s.label, s.length) for s in segs] == [tuple(x) for x in g["segs"].tolist()]
