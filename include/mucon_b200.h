@@ -138,6 +138,9 @@ typedef struct mucon_shead_weights {
   const float *hid_w, *hid_b, *cn_w, *cn_b, *l2_w, *l2_b, *att_v, *emb, *comb_w, *comb_b, *wih, *whh, *bih, *bhh,
       *t1_w, *t1_b, *t2_w, *t2_b, *n1_w, *n1_b, *n2_w, *n2_b;
 } mucon_shead_weights;
+/* out[m, n] = bias[n] + sum_k A[m, k] * B[k, n] in exact fp32 (CUDA cores): the s-head's input / attention projections.
+ * A [M, K], B [K, N] row-major, N % 128 == 0, K % 8 == 0, bias may be NULL. */
+int mucon_sgemm_bias(const float* A, const float* B, const float* bias, float* out, int64_t M, int K, int N, void* stream);
 int mucon_lstm_encoder(const float* xproj_f, const float* xproj_b, const float* whh_f, const float* whh_b,
                        const int64_t* row_off, const int32_t* order, int V, int H, float* enc_out, float* hn, float* cn,
                        void* stream);

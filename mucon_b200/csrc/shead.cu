@@ -401,6 +401,92 @@ seq_decoder_kernel(const mucon_shead_weights w, const float* __restrict__ enc /*
 }  // namespace
 }  // namespace mucon
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 GEMM with bias for the s-head's three projections (W_ih x_t of both directions, enc @ W1):
+//   out[m, n] = bias[n] + sum_k A[m, k] * B[k, n]      A [M, K] row-major, B [K, N] row-major, N % 128 == 0, K % 8 == 0
+// Exact fp32 on the CUDA cores (the s-head feeds discrete decisions; no TF32): 128 x 128 CTA tile, 256 threads, 8 x 8
+// outputs per thread (two LDS.128 of A and two of B per 64 FMAs), k ascending per output.
+namespace mucon {
+namespace {
+constexpr int kSgBM = 128, kSgBN = 128, kSgBK = 8;
+__global__ void __launch_bounds__(256)
+sgemm_bias_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ bias,
+                  float* __restrict__ out, int64_t M, int K, int N) {
+  __shared__ __align__(16) float As[2][kSgBK][kSgBM + 4];
+  __shared__ __align__(16) float Bs[2][kSgBK][kSgBN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * kSgBM;
+  const int n0 = blockIdx.y * kSgBN;
+  // loader roles: A tile [128 x 8]: thread -> (row tid / 2, k half tid % 2); B tile [8 x 128]: (k tid / 32, col quad tid % 32)
+  const int ar = tid >> 1, ak = (tid & 1) * 4;
+  const int bk = tid >> 5, bc = (tid & 31) * 4;
+  const bool a_ok = m0 + ar < M;
+  const float* ap = A + (m0 + ar) * K + ak;
+  const float* bp = B + static_cast<int64_t>(bk) * N + n0 + bc;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 av = a_ok ? *reinterpret_cast<const float4*>(ap) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bv = *reinterpret_cast<const float4*>(bp);
+  const int nk = K / kSgBK;
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    As[buf][ak + 0][ar] = av.x; As[buf][ak + 1][ar] = av.y; As[buf][ak + 2][ar] = av.z; As[buf][ak + 3][ar] = av.w;
+    *reinterpret_cast<float4*>(&Bs[buf][bk][bc]) = bv;
+    __syncthreads();
+    if (kb + 1 < nk) {   // the next k-block's loads are in flight while this one is multiplied
+      av = a_ok ? *reinterpret_cast<const float4*>(ap + (kb + 1) * kSgBK) : make_float4(0.f, 0.f, 0.f, 0.f);
+      bv = *reinterpret_cast<const float4*>(bp + static_cast<int64_t>(kb + 1) * kSgBK * N);
+    }
+#pragma unroll
+    for (int k = 0; k < kSgBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    // (double-buffered shared tiles: the stores of block kb + 1 go to the other buffer, one barrier per k-block)
+  }
+  float bz[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bz[j] = bias ? bias[n0 + tx * 8 + j] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m < M) {
+      float* o = out + m * N + n0 + tx * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[i][0] + bz[0], acc[i][1] + bz[1], acc[i][2] + bz[2], acc[i][3] + bz[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[i][4] + bz[4], acc[i][5] + bz[5], acc[i][6] + bz[6], acc[i][7] + bz[7]);
+    }
+  }
+}
+}  // namespace
+}  // namespace mucon
+
+extern "C" int mucon_sgemm_bias(const float* A, const float* B, const float* bias, float* out, int64_t M, int K, int N,
+                                void* stream) {
+  using namespace mucon;
+  if (!A || !B || !out || M < 0 || K < 1 || N < 1) return MUCON_EINVAL;
+  if (N % kSgBN != 0 || K % kSgBK != 0) return MUCON_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return MUCON_EALIGN;
+  if (M == 0) return MUCON_OK;
+  const int64_t gx = (M + kSgBM - 1) / kSgBM;
+  if (gx > 0x7fffffff) return MUCON_EUNSUPPORTED;
+  sgemm_bias_kernel<<<dim3(static_cast<unsigned>(gx), N / kSgBN), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, B, bias, out,
+                                                                                                                 M, K, N);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
 extern "C" int mucon_lstm_encoder(const float* xproj_f, const float* xproj_b, const float* whh_f, const float* whh_b,
                                   const int64_t* row_off, const int32_t* order, int V, int H, float* enc_out, float* hn,
                                   float* cn, void* stream) {

@@ -91,8 +91,13 @@ class SHead(nn.Module):
                         n_steps=e(0, dt=torch.int32), encoder_out=e(0, 2 * H))
         if z.shape[0] == 0:
             z = torch.zeros((1, H), dtype=torch.float32, device=dev)   # no pooled rows at all: keep the launches valid
-        xp_f = conv1d_rows(z, w["wih_f"], w["b_f"], row_off, V, max_Tz)            # [rows, 512]
-        xp_b = conv1d_rows(z, w["wih_b"], w["b_b"], row_off, V, max_Tz)
+        def sgemm(A, B, bias):   # exact fp32 (mucon_sgemm_bias): A [M, K] . B [K, N] + bias
+            out = torch.empty((A.shape[0], B.shape[1]), dtype=torch.float32, device=dev)
+            _lib.check(lib.mucon_sgemm_bias(_lib.ptr(A), _lib.ptr(B), _lib.ptr(bias), _lib.ptr(out), C.c_int64(A.shape[0]),
+                                            C.c_int(A.shape[1]), C.c_int(B.shape[1]), _stream(dev)), "mucon_sgemm_bias")
+            return out
+        xp_f = sgemm(z, w["wih_f"][0], w["b_f"])                                    # [rows, 512]
+        xp_b = sgemm(z, w["wih_b"][0], w["b_b"])
         enc = torch.empty((z.shape[0], 2 * H), dtype=torch.float32, device=dev)
         hn = torch.empty((V, 2, H), dtype=torch.float32, device=dev)
         cn = torch.empty((V, 2, H), dtype=torch.float32, device=dev)
@@ -100,7 +105,7 @@ class SHead(nn.Module):
         _lib.check(lib.mucon_lstm_encoder(_lib.ptr(xp_f), _lib.ptr(xp_b), _lib.ptr(w["whh_f"]), _lib.ptr(w["whh_b"]),
                                           _lib.ptr(row_off), _lib.ptr(order), C.c_int(V), C.c_int(H), _lib.ptr(enc),
                                           _lib.ptr(hn), _lib.ptr(cn), _stream(dev)), "mucon_lstm_encoder")
-        enc_ready = conv1d_rows(enc, w["w1"], w["zero_h"], row_off, V, max_Tz)      # [rows, 128] (models.py:627-629)
+        enc_ready = sgemm(enc, w["w1"][0], None)                                     # [rows, 128] (models.py:627-629)
         if teacher_forcing:
             if transcripts_tf_input is None:
                 raise ValueError("teacher forcing needs transcripts_tf_input")
