@@ -12,9 +12,9 @@
 //                           launched beforehand (mucon_conv1d).  W_hh (512 x 128 fp32 = 256 KB) lives half in registers
 //                           (64 per thread, thread j owns gate row j) and half in shared memory; every weight fetched
 //                           feeds the four recurrences; a step is 4 x 128 FMAs per thread and two barriers.
-//   seq_decoder_kernel      one CTA per four videos (in lockstep over the decoding steps, finished ones masked): all
-//                           decoding steps; every mat-vec is a warp per output row with the lanes across the input
-//                           (coalesced weight reads from L2, each weight used for the four videos), fp32 throughout.
+//   seq_decoder_kernel      one CTA per kDecB videos (= 1; more run in lockstep with finished ones masked): all decoding
+//                           steps; every mat-vec is a warp per EIGHT output rows with the lanes across the input
+//                           (coalesced weight reads from L2, eight independent rows in flight), fp32 throughout.
 // Arithmetic is fp32 with expf / tanhf / logf (no fast-math); sums run in a different order than torch's LSTM /
 // Linear kernels, so outputs agree with the reference to ~1e-5, not bit for bit (tests/test_shead.py).
 #include <math.h>
@@ -151,7 +151,8 @@ namespace {
 
 constexpr int kDecThreads = 256;
 constexpr int kMaxWords = 128;   // C + 1 <= 128
-constexpr int kDecB = 4;         // videos per CTA: a weight row read from L2 feeds four decoders
+constexpr int kDecB = 1;         // videos per CTA decoded in lockstep (c2: 1 -> 2.7 ms, 2 -> 3.0 ms, 4 -> 4.3 ms: the decoder is
+                                 // bound by the latency of its chain of small phases, not by weight traffic, so more CTAs win)
 constexpr int kDecVec = 3 * kH + 3 * kH + (kH + kMaxWords) + 2 * kG + kH;   // floats of per-video vectors
 
 // out[b][r] = act(bias[r] + sum_k W[r, k] * x[b][k]) for r < rows, b < kDecB: a warp takes kDecR rows at a time with the
