@@ -241,6 +241,25 @@ def main_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # N > 1: run this rank on the CPUs next to its GPU (NVML's ideal CPU set) BEFORE the pinned host buffers are
+    # allocated and first touched, so that the e2e leg's H2D copies read NUMA-local memory
+    numa = {"bound": False}
+    if world > 1 and not args.no_numa:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank), (ncpu + 63) // 64)
+            ideal = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1}
+            allowed = ideal & set(os.sched_getaffinity(0))
+            if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+                os.sched_setaffinity(0, allowed)
+                numa = {"bound": True, "cpus": len(allowed)}
+            else:
+                numa = {"bound": False, "why": "the GPU's ideal CPU set does not narrow this process's cpuset",
+                        "ideal": len(ideal), "allowed": len(os.sched_getaffinity(0))}
+        except Exception as e_:
+            numa = {"bound": False, "why": str(e_)[:80]}
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -662,7 +681,7 @@ def main_ours(args, rank, world, local_rank):
                     "breakdown_rank0_ms": {"plan_build": plan_ms, "h2d": h2d_ms, "kernel": kern_ms, "d2h": d2h_ms,
                                            "note": "timed one at a time; in the step the plan build overlaps the H2D copy"},
                     "h2d_gbs_rank0": h2d / (h2d_ms * 1e-3) / 1e9,
-                    "per_rank_ms": per_rank_e2e,
+                    "per_rank_ms": per_rank_e2e, "numa_rank0": numa,
                     "limiter": "host-to-device copy of the log-probabilities (740 MB per rank per step over PCIe); with "
                                "N ranks copying at once the host side is shared, so e2e scales worse than the kernels"},
             "per_rank_ms_per_step": per_rank_ms,
@@ -728,6 +747,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-backbone", action="store_true", help="skip the backbone + alignment leg")
     ap.add_argument("--no-legs", action="store_true", help="skip the c1 / c3 / c4 / training-step legs")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind ranks to the CPUs next to their GPU")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: result exchange by peer stores from the kernels (default) or an NCCL all_gather per step")
     args = ap.parse_args()
