@@ -576,20 +576,22 @@ class MuConBackbone(nn.Module):
         s_proj.wait_event(start)
         s_lay.wait_event(start)
         tables = []
-        for k, pl in enumerate(plans):
-            with torch.cuda.stream(s_proj):
-                lib.mucon_set_sm_limit(C.c_int(proj_sms))
-                x0 = self.ft.project_packed(feats[int(rows[k]):int(rows[k + 1])], precision)
-                ev = torch.cuda.Event()
-                ev.record(s_proj)
-            x0.record_stream(s_lay)
-            with torch.cuda.stream(s_lay):
-                s_lay.wait_event(ev)
-                lib.mucon_set_sm_limit(C.c_int(max(sms - proj_sms, 8)))
-                tb, _ = self.infer_pooled_packed(None, pl, precision=precision, x0=x0)
-                tb.record_stream(main)
-            tables.append(tb)
-        lib.mucon_set_sm_limit(C.c_int(0))
+        try:
+            for k, pl in enumerate(plans):
+                with torch.cuda.stream(s_proj):
+                    lib.mucon_set_sm_limit(C.c_int(proj_sms))
+                    x0 = self.ft.project_packed(feats[int(rows[k]):int(rows[k + 1])], precision)
+                    ev = torch.cuda.Event()
+                    ev.record(s_proj)
+                x0.record_stream(s_lay)
+                with torch.cuda.stream(s_lay):
+                    s_lay.wait_event(ev)
+                    lib.mucon_set_sm_limit(C.c_int(max(sms - proj_sms, 8)))
+                    tb, _ = self.infer_pooled_packed(None, pl, precision=precision, x0=x0)
+                    tb.record_stream(main)
+                tables.append(tb)
+        finally:
+            lib.mucon_set_sm_limit(C.c_int(0))   # never leave the cap behind: every later launch of this thread would obey it
         done = torch.cuda.Event()
         done.record(s_lay)
         main.wait_event(done)
