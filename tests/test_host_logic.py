@@ -60,3 +60,38 @@ def test_smoothing_loss_packed_matches_reference_statements():
     want = sum(torch.clamp(F.mse_loss(F.log_softmax(s, 1)[1:], F.log_softmax(s, 1)[:-1]), min=0.0, max=16.0) for s in segs) / 3
     got = smoothing_loss_packed(torch.cat(segs), Ts)
     assert abs(got.item() - want.item()) <= 1e-6 * max(1.0, abs(want.item()))
+
+
+def test_both_bench_arms_see_the_same_arrays():
+    """the reference arm's sample is a prefix of the arrays the GPU arm aligns"""
+    import bench
+    T, trs, _ = bench.make_split(0)
+    jobs = bench.cpu_sample_jobs(3, seed=0)
+    ours = bench.make_host_logp(T[:3], trs[:3], 0)
+    pos = 0
+    for v in range(3):
+        assert np.array_equal(ours[pos:pos + int(T[v])], jobs[v][0])
+        assert np.array_equal(jobs[v][1], trs[v])
+        pos += int(T[v])
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` prints one JSON line with the keys the driver reads (CPU only, bounded sample)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == bench_metric() and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def bench_metric():
+    import bench
+    return bench.METRIC
