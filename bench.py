@@ -67,6 +67,20 @@ def device_logp(T, trs, seed, device):
     return torch.log_softmax(x, dim=1).contiguous()
 
 
+def bench_config(world, collective):
+    """The `config` object of the JSON line -- the same for both arms (the driver compares them)."""
+    T, _, _ = make_split(0)
+    Tsum = int(T.sum())
+    return {"workload": WORKLOAD, "videos_per_gpu": V_PER_GPU, "frames_per_gpu": Tsum,
+            "l2": "inputs (%.0f MB log-probs per GPU) are larger than the 126 MB L2" % (4 * Tsum * C / 1e6),
+            "collective": ("none in the step: scores + segment lengths are stored into every rank's receive "
+                           "buffer by the kernels (NVLink peer stores); one barrier ends the timed region"
+                           if collective == "peer" else
+                           "all_gather(scores, segment lengths), overlapped with the next step") if world > 1 else "none",
+            "inputs": "host-generated (numpy, seed rank+3000): the same arrays the reference arm samples from; "
+                      "every rank has the seed-0 split's lengths / transcripts and its own log-probabilities"}
+
+
 def make_host_logp(T, trs, seed):
     """The rank's log-probabilities generated on the HOST with the recipe and generator state the reference arm's
     sample uses (cpu_sample_jobs): both arms see identical arrays (the reference arm the first n videos of them)."""
@@ -221,7 +235,7 @@ def main_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sampled": sample},
+        "config": bench_config(args.gpus, args.collective), "sampled": sample,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -666,14 +680,7 @@ def main_ours(args, rank, world, local_rank):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "videos_per_gpu": V_PER_GPU, "frames_per_gpu": Tsum,
-                       "l2": "inputs (%.0f MB log-probs per GPU) are larger than the 126 MB L2" % (scan_bytes / 1e6),
-                       "collective": ("none in the step: scores + segment lengths are stored into every rank's receive "
-                                      "buffer by the kernels (NVLink peer stores); one barrier ends the timed region"
-                                      if args.collective == "peer" else
-                                      "all_gather(scores, segment lengths), overlapped with the next step") if world > 1 else "none",
-                       "inputs": "host-generated (numpy, seed rank+3000): the same arrays the reference arm samples from; "
-                                 "every rank has the seed-0 split's lengths / transcripts and its own log-probabilities"},
+            "config": bench_config(world, args.collective),
             "clocks": sampler.summary(),
             "e2e": {"value": frames_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,

@@ -95,3 +95,10 @@ def test_reference_arm_json_contract():
 def bench_metric():
     import bench
     return bench.METRIC
+
+
+def test_both_arms_print_the_same_config():
+    import bench
+    assert bench.bench_config(1, "peer") == bench.bench_config(1, "peer")
+    c = bench.bench_config(8, "peer")
+    assert c["workload"] == bench.WORKLOAD and c["videos_per_gpu"] == 1712 and "larger than the 126 MB L2" in c["l2"]
