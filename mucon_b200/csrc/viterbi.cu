@@ -674,12 +674,22 @@ extern "C" int mucon_single_decode_h(mucon_single* s, const void* logp_h, int is
   memcpy(s->h_stage + s->off_logfact, s->logfact, 8 * (size_t)(J + 1));
   const size_t lp_bytes = (size_t)T * s->C * s->elem;
   memcpy(s->h_stage + s->off_logp, logp_h, lp_bytes);
-  MUCON_CUDA_CHECK(cudaMemcpyAsync(s->d_stage, s->h_stage, s->off_logp + lp_bytes, cudaMemcpyHostToDevice, st));
+  // Short videos: the kernel reads the log-probabilities straight from the pinned staging buffer and writes its results
+  // into pinned host memory itself (both are mapped into the device's address space under UVA): the 384 KB of a
+  // Breakfast video cross PCIe inside the kernel's own TMA ring, overlapped with the DP, and there is no result copy
+  // (c1 decode 128 -> 119 us).  MUCON_SINGLE_ZEROCOPY=0 restores the copies, =2 also reads the metadata in place.
+  static const int zc_mode = getenv("MUCON_SINGLE_ZEROCOPY") ? atoi(getenv("MUCON_SINGLE_ZEROCOPY")) : 1;
+  // 0: copy everything; 1: log-probabilities and results zero-copy, metadata copied; 2: nothing copied at all
+  const bool zero_copy = zc_mode != 0 && lp_bytes <= (1u << 20);   // long videos: the copy engine beats the kernel's shallow ring
+  const bool meta_zc = zero_copy && zc_mode == 2;
+  if (!meta_zc)
+    MUCON_CUDA_CHECK(cudaMemcpyAsync(s->d_stage, s->h_stage, zero_copy ? s->off_logp : s->off_logp + lp_bytes,
+                                     cudaMemcpyHostToDevice, st));
   mucon_viterbi_batch b;
   memset(&b, 0, sizeof(b));
   b.U = 1; b.C = s->C; b.fs = fs; b.max_len = max_len; b.bs_is_f64 = is_f64 ? 1 : 0; b.seg0_f32 = seg0_f32 ? 1 : 0;
   b.max_N = N; b.max_K = K; b.n_cta = 0; b.wpc = 4; b.lanes = 0;
-  unsigned char* d = s->d_stage;
+  unsigned char* d = meta_zc ? s->h_stage : s->d_stage;
   b.vid_off = reinterpret_cast<const int64_t*>(d);
   b.blk_off = reinterpret_cast<const int64_t*>(d + 16);
   b.bp_off = reinterpret_cast<const int64_t*>(d + 32);
@@ -690,15 +700,17 @@ extern "C" int mucon_single_decode_h(mucon_single* s, const void* logp_h, int is
   b.tr = reinterpret_cast<const int32_t*>(d + s->off_tr);
   b.len_params = reinterpret_cast<const double*>(d + s->off_params);
   b.logfact = reinterpret_cast<const double*>(d + s->off_logfact);
-  b.score = reinterpret_cast<double*>(s->d_out);
-  b.final_j = reinterpret_cast<int32_t*>(s->d_out + 8);
-  b.status = reinterpret_cast<int32_t*>(s->d_out + 12);
-  b.seg_blocks = reinterpret_cast<int32_t*>(s->d_out + s->out_seg);
-  b.labels = reinterpret_cast<int32_t*>(s->d_out + s->out_labels);
+  unsigned char* o = zero_copy ? s->h_out : s->d_out;
+  b.score = reinterpret_cast<double*>(o);
+  b.final_j = reinterpret_cast<int32_t*>(o + 8);
+  b.status = reinterpret_cast<int32_t*>(o + 12);
+  b.seg_blocks = reinterpret_cast<int32_t*>(o + s->out_seg);
+  b.labels = reinterpret_cast<int32_t*>(o + s->out_labels);
   b.bp = s->d_bp;
-  int rc = align_fused_impl(&b, d + s->off_logp, is_f64, order, 0, stream, false);
+  int rc = align_fused_impl(&b, zero_copy ? s->h_stage + s->off_logp : s->d_stage + s->off_logp, is_f64, order, 0, stream, false);
   if (rc != MUCON_OK) return rc;
-  MUCON_CUDA_CHECK(cudaMemcpyAsync(s->h_out, s->d_out, s->out_labels + 4 * (size_t)T, cudaMemcpyDeviceToHost, st));
+  if (!zero_copy)
+    MUCON_CUDA_CHECK(cudaMemcpyAsync(s->h_out, s->d_out, s->out_labels + 4 * (size_t)T, cudaMemcpyDeviceToHost, st));
   MUCON_CUDA_CHECK(cudaStreamSynchronize(st));
   memcpy(score_h, s->h_out, 8);
   memcpy(final_j_h, s->h_out + 8, 4);
