@@ -283,9 +283,9 @@ int mucon_masks_bwd(const float* L, const int32_t* n_off, const int32_t* T, cons
                     const float* grad_out, float* ws, float* grad_L, void* stream);
 /* mucon_flint_fwd with a warp per (mask row, eighth of its window) instead of a CTA per row: no block barriers, the
  * long windows no longer set the tail.  ws: mucon_flint_fwd_ws_words(n_rows, C) 4-byte words (16-byte aligned):
- * [partial sums | one counter per row | one 64-byte geometry record per row]; zero it once -- the counters are left at
- * zero on return, the rest is overwritten.  A first launch computes the rows' geometry (a thread per row); the partial
- * sums of a row are added in a fixed order by the warp that finishes last, so E does not depend on scheduling. */
+ * [partial sums | reserved | one 64-byte geometry record per row], overwritten.  Three launches: the rows' geometry (a
+ * thread per row), the partial sums (a warp per item), and their addition in a fixed order (a thread per (row, four
+ * classes)), so E does not depend on scheduling. */
 int64_t mucon_flint_fwd_ws_words(int n_rows, int C);
 int mucon_flint_fwd_ws(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
                        const int32_t* row_vid, int V, int n_rows, int C, float overlap, int template_id,

@@ -380,9 +380,10 @@ flint_fwd_kernel(const float* __restrict__ L, const int32_t* __restrict__ n_off,
 // The same evidence with a WARP per (mask row, part): a row's window is cut into kFlintParts equal parts, item
 // row * kFlintParts + p is taken by one warp, grid-stride -- no block-level barrier anywhere, 64 warps per SM each
 // with several 16-byte loads in flight, and a 5000-frame window is eight items instead of one CTA's tail.  A lane owns
-// four class columns and every (32 / (C/4))-th frame of its part.  The partial sums of a row go to a workspace; the
-// warp that finishes a row's last part (a counter per row) adds the parts in order p = 0..7, so the result does not
-// depend on the order in which the warps ran.
+// four class columns and every (32 / (C/4))-th frame of its part.  The partial sums of a row go to a workspace and a
+// small second kernel adds them in the fixed order p = 0 .. parts-1, so the result does not depend on the order in which
+// the warps ran (a first version let the warp that finished a row last do the sum: the fence and the counter round trip
+// per item cost more than the extra launch, 0.209 vs 0.196 ms on the c2 split).
 // Per-row constants of the evidence kernels, computed once per call by a thread per row (flint_rows_pre_kernel): the
 // items of flint_fwd_warp_kernel then start from ONE 64-byte record instead of a chain of dependent loads (row -> video
 // -> lengths) and ~200 instructions of geometry per lane.
@@ -472,8 +473,7 @@ constexpr int kFlintBatch = 8;
 template <int kFlintParts>
 __global__ void __launch_bounds__(256)
 flint_fwd_warp_kernel(const RowPre* __restrict__ pre, int n_rows, int C, int tmpl, int align,
-                      const float* __restrict__ seg, float* __restrict__ part_ws, unsigned int* __restrict__ counters,
-                      float* __restrict__ E) {
+                      const float* __restrict__ seg, float* __restrict__ part_ws) {
   __shared__ float tp[kWP];
   load_template(tp, tmpl);
   __syncthreads();
@@ -526,25 +526,26 @@ flint_fwd_warp_kernel(const RowPre* __restrict__ pre, int n_rows, int C, int tmp
     }
     float4* pw = reinterpret_cast<float4*>(part_ws + (static_cast<long long>(row) * kFlintParts + p) * C);
     if (fq == 0 && c4 < C4) pw[c4] = acc;
-    __threadfence();
-    __syncwarp();
-    unsigned int old = 0;
-    if (lane == 0) old = atomicAdd(counters + row, 1u);
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old == kFlintParts - 1) {   // this warp completed the row: ordered sum of its parts
-      __threadfence();
-      if (lane < C4) {
-        const float4* pr = reinterpret_cast<const float4*>(part_ws + static_cast<long long>(row) * kFlintParts * C);
-        float4 sum = __ldcg(pr + lane);
-        for (int q = 1; q < kFlintParts; ++q) {
-          const float4 a = __ldcg(pr + q * C4 + lane);
-          sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
-        }
-        reinterpret_cast<float4*>(E + static_cast<long long>(row) * C)[lane] = sum;
-      }
-      if (lane == 0) counters[row] = 0;   // ready for the next call
-    }
   }
+}
+
+// E[row, :] = the row's partial sums added in the fixed order p = 0 .. parts-1 (a thread per (row, four classes)): the
+// result does not depend on the order in which the warps of flint_fwd_warp_kernel ran, and those warps neither fence nor
+// touch a counter.
+__global__ void __launch_bounds__(256)
+flint_fwd_combine_kernel(const float* __restrict__ part_ws, int n_rows, int C, int parts, float* __restrict__ E) {
+  const int C4 = C >> 2;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n_rows) * C4) return;
+  const long long row = i / C4;
+  const int c4 = static_cast<int>(i - row * C4);
+  const float4* pr = reinterpret_cast<const float4*>(part_ws + row * parts * C);
+  float4 sum = pr[c4];
+  for (int q = 1; q < parts; ++q) {
+    const float4 a = pr[q * C4 + c4];
+    sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
+  }
+  reinterpret_cast<float4*>(E + row * C)[c4] = sum;
 }
 
 // d seg[t, :] = sum_r mask_r[t] * gE[r, :] over the rows of the frame's video.  One CTA per chunk of
@@ -760,8 +761,7 @@ extern "C" int64_t mucon_flint_fwd_ws_words(int n_rows, int C) {
          static_cast<int64_t>(n_rows) * 16;
 }
 
-// ws: mucon_flint_fwd_ws_words(n_rows, C) 4-byte words, 16-byte aligned; its counters (the last n_rows words) must be
-// zero on entry -- they are left zero on return, so a workspace zeroed once can be reused call after call.
+// ws: mucon_flint_fwd_ws_words(n_rows, C) 4-byte words, 16-byte aligned: [partial sums | (unused) | row records]; overwritten.
 extern "C" int mucon_flint_fwd_ws(const float* L, const int32_t* n_off, const int32_t* T, const int64_t* seg_off,
                                   const int32_t* row_vid, int V, int n_rows, int C, float overlap, int template_id,
                                   int align_corners, const float* seg, float* ws, float* E, void* stream) {
@@ -785,15 +785,16 @@ extern "C" int mucon_flint_fwd_ws(const float* L, const int32_t* n_off, const in
   flint_rows_pre_kernel<<<(n_rows + 127) / 128, 128, 0, st>>>(L, n_off, T, seg_off, row_vid, V, n_rows, overlap, template_id,
                                                               align_corners, pre);
   MUCON_CUDA_CHECK(cudaGetLastError());
-  if (parts == 8)
-    flint_fwd_warp_kernel<8><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws,
-                                                                      counters, E);
-  else if (parts == 2)
-    flint_fwd_warp_kernel<2><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws,
-                                                                      counters, E);
+  const int np = parts == 8 ? 8 : (parts == 2 ? 2 : 4);
+  if (np == 8)
+    flint_fwd_warp_kernel<8><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws);
+  else if (np == 2)
+    flint_fwd_warp_kernel<2><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws);
   else
-    flint_fwd_warp_kernel<4><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws,
-                                                                      counters, E);
+    flint_fwd_warp_kernel<4><<<static_cast<int>(grid), 256, 0, st>>>(pre, n_rows, C, template_id, align_corners, seg, ws);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  const long long n_out = static_cast<long long>(n_rows) * (C >> 2);
+  flint_fwd_combine_kernel<<<static_cast<int>((n_out + 255) / 256), 256, 0, st>>>(ws, n_rows, C, np, E);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }
