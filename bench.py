@@ -417,7 +417,7 @@ def main_ours(args, rank, world, local_rank):
                 barrier()
                 return a.elapsed_time(b_) / n
 
-            nfull = 5
+            nfull = 10
             full_ms = timed(full_step, nfull)
             bb_ms = timed(backbone_step, nfull)
             enc_ms = timed(lambda: net.encode_packed(feats, bplan), nfull)
