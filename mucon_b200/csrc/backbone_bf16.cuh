@@ -10,19 +10,20 @@
 //     resident in shared memory in the K-major SWIZZLE_128B operand layout;
 //   * per tile a single activation slab of 128 + 2*dil rows comes in (two 64-channel k-blocks); the three
 //     taps are row-shifted descriptor views of it;
-//   * nothing but the slab and the weights lives in shared memory.  The first epilogue reads the residual out of
-//     the slab's centre rows and stores `x + b1` (fp32) into accumulator 2 with tcgen05.st, so GEMM 2 simply
-//     accumulates on top of it and the slab is released before GEMM 2 has even started; relu(acc1 + bd) is
-//     rounded to bf16 and stored back IN PLACE over the first 64 columns of accumulator 1, from where GEMM 2
-//     takes it as its A operand (tcgen05.mma with A in tensor memory); the second epilogue is TMEM -> (ReLU)
-//     (max over adjacent rows) -> bf16 -> 32-byte global stores.  32-48 KB in and 16-32 KB out per tile
-//     instead of 576 KB;
+//   * nothing but the slab, the weights and a 2 KB identity lives in shared memory.  The residual is added BY THE
+//     TENSOR CORE: after GEMM 1 the MMA warp issues eight M128 N16 K16 instructions acc2[:, 16k:16k+16] =
+//     X_centre[:, 16k:16k+16] . I (exact: every product is x * 1 or x * 0, accumulated in fp32) and GEMM 2
+//     accumulates on top, so the epilogue warps -- the bound of this kernel -- never touch the residual and the
+//     slab is released by the MMA commit; relu(acc1 + bd) is rounded to 16 bits and stored back IN PLACE over
+//     the first 64 columns of accumulator 1, from where GEMM 2 takes it as its A operand (tcgen05.mma with A in
+//     tensor memory); the second epilogue is TMEM -> + b1 -> (ReLU) (max over adjacent rows) -> 16 bits ->
+//     32-byte global stores.  32-48 KB in and 16-32 KB out per tile instead of 576 KB;
 //   * accumulators are double-buffered in TMEM (2 x 128 + 2 x 128 columns); the MMA warp issues GEMM 1 of tile
 //     i+1 before GEMM 2 of tile i and the epilogue warps run epilogue 1 of tile i+1 before epilogue 2 of tile
 //     i, so the tensor pipe and the epilogue warps both stay busy.
 // Dilations above kMaxSlabDil use the same program with each live tap as a separate 128-row tile in a ring of
 // three 32 KB slots: side-tap slots are released by the MMA warp's commit as soon as that tap's instructions have
-// retired, the centre tap (issued last) by the epilogue once the residual rows are in registers, so the loads of
+// retired, the centre tap (issued last) by the commit that follows the residual MMAs, so the loads of
 // the next tile overlap this tile's GEMMs (taps that only see padding -- dilation >= video length -- are never
 // loaded: layers 8-10 at Breakfast lengths are three-deep rings of centre tiles).
 // 384 threads: warp 0 TMA producer, warp 1 MMA + TMEM, warp 2 padding fix-up, warp 3 idle, warps 4-11 epilogue.
@@ -45,6 +46,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int kMaxSlabDil = 32;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
+constexpr int ID_BYTES = 16 * 128;        // a [16 x 16] 16-bit identity in 128-byte K-major SWIZZLE_128B rows: B operand of the residual MMAs
 
 // shared-memory plan of a launch (host and device agree through these)
 __host__ __device__ inline int stage_rows(int dil, int slab) { return slab ? BM + 2 * dil : 3 * BM; }
@@ -56,14 +58,15 @@ constexpr int kTapBytes = NKB * BM * 128;
 // tile (and every tile that crosses the end of its video, and fp32 output) is stored straight from registers
 __host__ __device__ inline int staged_rows(int dil, int slab, int pool, int out_f32) {
   if (out_f32) return 0;
-  const int free_bytes = SMEM_LIMIT - W_BYTES - num_stages(slab) * NKB * kb_bytes_of(dil, slab) - BAR_BYTES;
+  const int free_bytes = SMEM_LIMIT - W_BYTES - ID_BYTES - num_stages(slab) * NKB * kb_bytes_of(dil, slab) - BAR_BYTES;
   int s = (free_bytes / 256) & ~7;
   const int want = pool ? BM / 2 : BM;
   if (s > want) s = want;
   return s < 8 ? 0 : s;
 }
 __host__ __device__ inline int smem_bytes_of(int dil, int slab, int pool, int out_f32) {
-  return W_BYTES + num_stages(slab) * NKB * kb_bytes_of(dil, slab) + staged_rows(dil, slab, pool, out_f32) * 256 + BAR_BYTES;
+  return W_BYTES + ID_BYTES + num_stages(slab) * NKB * kb_bytes_of(dil, slab) + staged_rows(dil, slab, pool, out_f32) * 256 +
+         BAR_BYTES;
 }
 
 // both bias vectors travel as a kernel parameter: the epilogue adds them as constant-bank operands
@@ -197,7 +200,7 @@ struct EpiCtx {
   const Tile* tiles;
   unsigned char* stage_mem;
   unsigned char* staging;
-  uint64_t *emptyS, *a1full, *yready, *a2full;
+  uint64_t *a1full, *yready, *a2full, *a2free;
   const CUtensorMap* tmO;
   void* out;
   uint32_t tmem_base;
@@ -213,49 +216,15 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
   const uint32_t lane_base = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   const bool leader = warp == 4 && lane == 0;
   bool store_pending = false;
-  int uslot = 0;  // ring slot of the next tile's first unit
   for (int i = 0; i < c.n_my + c.LA; ++i) {
     if (i < c.n_my) {
       // ---- epilogue 1 of tile i
       const int acc = i & 1;
-      // the unit that holds the centre tap: the slab itself, or the last of the tile's live tap tiles
-      int upt = 1;
-      if (!c.slab) {
-        const int Tv = c.tiles[blockIdx.x + i * gridDim.x].T;
-        upt = 1 + (tap_live(-c.dil, Tv) ? 1 : 0) + (tap_live(c.dil, Tv) ? 1 : 0);
-      }
-      const int s = (uslot + upt - 1) % c.nslot;
-      uslot = (uslot + upt) % c.nslot;
       mbar_wait(&c.a1full[acc], (i >> 1) & 1);
       tc_fence_after();
       if (leader) MUCON_TR16(6, i);
-      // (a) residual rows out of the slab's centre tap, + b1, as fp32 into accumulator 2 (this thread drained the
-      // same lanes / columns of it two tiles ago: program order)
-      {
-        const int cr = c.crow0 + r;
-        const unsigned char* cp = c.stage_mem + s * c.unit_bytes + H * c.kb_bytes + cr * 128;
-#pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t f[32];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(cp + (((c2 * 4 + jj) ^ (cr & 7)) << 4));
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = H * 64 + c2 * 32 + jj * 8 + 2 * e;
-              f[8 * jj + 2 * e] = __float_as_uint(Half2<F16>::lo(rw[e]) + bias.b1[col]);
-              f[8 * jj + 2 * e + 1] = __float_as_uint(Half2<F16>::hi(rw[e]) + bias.b1[col + 1]);
-            }
-          }
-          if (c2 == 0 && leader) MUCON_TR16(20, i);
-          tmem_st32(lane_base + 2 * BN + acc * BN + H * 64 + c2 * 32, f);
-          if (c2 == 0 && leader) MUCON_TR16(21, i);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&c.emptyS[s]);  // the slab may be refilled
-      if (leader) MUCON_TR16(10, i);
+      // (the residual x is added by the tensor core: the MMA warp multiplies the tile's centre rows with an identity
+      // into accumulator 2 -- see the MMA issuer; b1 is added in epilogue 2)
       // (b) acc1 -> relu(. + bd) -> bf16 -> back over accumulator 1 (columns 32H .. 32H+31): A operand of GEMM 2
       {
         uint32_t v0[32], v1[32];
@@ -306,6 +275,13 @@ __device__ __forceinline__ void epilogue_warps(const EpiCtx& c, const BiasPack& 
         uint32_t v[32];
         tmem_ld32(lane_base + 2 * BN + acc * BN + H * 64 + c2 * 32, v);
         const int col = H * 64 + c2 * 32;
+        if (c2 == 1) {   // both halves of this warp's accumulator-2 columns are in registers: the MMA warp may reuse it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c.a2free[acc]);
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + bias.b1[col + e]);
         if (c2 == 0 && leader) MUCON_TR16(15, j);
         if (c2 == 1 && leader) MUCON_TR16(16, j);
         if (c.out_f32) {
@@ -401,28 +377,30 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   const int LA = 1;                        // GEMM 1 / epilogue 1 run one tile ahead of GEMM 2 / epilogue 2
   const int S = staged_rows(dil, slab, pool, out_f32);
   unsigned char* w_mem = base;                       // [8][WTILE]: (tap, kb) tiles of the dilated conv, then the 1x1's
-  unsigned char* stage_mem = base + W_BYTES;         // the unit ring
+  unsigned char* id_mem = base + W_BYTES;            // [16 x 16] identity (16-bit, K-major SWIZZLE_128B rows)
+  unsigned char* stage_mem = base + W_BYTES + ID_BYTES;  // the unit ring
   unsigned char* staging = stage_mem + num_stages(slab) * NKB * kb_bytes_of(dil, slab);  // [2][S rows x 128 B], SWIZZLE_128B
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + S * 256);
   uint64_t* wfull = bars;          // weights resident
   uint64_t* fullS = bars + 1;      // [3] unit landed (TMA bytes)
   uint64_t* readyS = bars + 4;     // [3] unit padded (fix-up warp)
-  uint64_t* emptyS = bars + 7;     // [3] unit released by the epilogue (GEMM 1 retired, residual rows in registers)
-  uint64_t* emptyM = bars + 10;    // [3] side-tap unit released by the MMA warp's commit
+  uint64_t* emptyM = bars + 10;    // [3] unit released by the MMA warp's commit (its last reader is an MMA)
   uint64_t* a1full = bars + 13;    // [2] accumulator 1 complete
   uint64_t* a1free = bars + 15;    // [2] GEMM 2 retired: accumulator 1 / Y may be overwritten
-  uint64_t* yready = bars + 17;    // [2] Y (16-bit, over accumulator 1) and x + b1 (accumulator 2) stored
+  uint64_t* yready = bars + 17;    // [2] Y (16-bit, over accumulator 1) stored
   uint64_t* a2full = bars + 19;    // [2] accumulator 2 complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* a2free = bars + 21;    // [2] accumulator 2 drained by epilogue 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1);
     for (int s = 0; s < 3; ++s) {
-      mbar_init(&fullS[s], 1); mbar_init(&readyS[s], 1); mbar_init(&emptyS[s], EPI_WARPS); mbar_init(&emptyM[s], 1);
+      mbar_init(&fullS[s], 1); mbar_init(&readyS[s], 1); mbar_init(&emptyM[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a1full[s], 1); mbar_init(&a1free[s], 1); mbar_init(&yready[s], EPI_WARPS); mbar_init(&a2full[s], 1);
+      mbar_init(&a2free[s], EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -430,6 +408,16 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // the identity the residual is multiplied with: element (n, k = n) = 1 in the K-major SWIZZLE_128B operand layout
+  // (row n = 128 bytes of 64 k values, 16-byte chunks XOR-ed with n & 7)
+  for (int i = threadIdx.x; i < ID_BYTES / 16; i += LTHREADS) reinterpret_cast<uint4*>(id_mem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int n = threadIdx.x;
+    *reinterpret_cast<unsigned short*>(id_mem + n * 128 + (((n >> 3) ^ (n & 7)) << 4) + (n & 7) * 2) =
+        F16 ? static_cast<unsigned short>(0x3C00) : static_cast<unsigned short>(0x3F80);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -471,7 +459,7 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         for (int kb = 0; kb < NKB; ++kb) tma_load_2d(w_mem + (3 * NKB + kb) * WTILE, &tmW1, kb * 64, 0, wfull);
       }
       int s = 0;
-      uint32_t used = 0, by_epi = 0, phE = 0, phM = 0;  // per slot: used before / last occupant's releaser / phases
+      uint32_t used = 0, phM = 0;  // per slot: used before / phase of its release barrier
       for (int i = 0; i < n_my; ++i) {
         const Tile tl = tiles[blockIdx.x + i * gridDim.x];
         uint32_t code;
@@ -479,13 +467,11 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         for (int k = 0; k < nu; ++k) {
           const int tap = static_cast<int>((code >> (2 * k)) & 3u);
           const uint32_t bit = 1u << s;
-          if (used & bit) {  // wait for whoever releases the slot's previous occupant
-            if (by_epi & bit) { mbar_wait(&emptyS[s], (phE >> s) & 1); phE ^= bit; }
-            else { mbar_wait(&emptyM[s], (phM >> s) & 1); phM ^= bit; }
+          if (used & bit) {  // wait for the MMA warp's commit that releases the slot's previous occupant
+            mbar_wait(&emptyM[s], (phM >> s) & 1);
+            phM ^= bit;
           }
           used |= bit;
-          const bool centre = k == nu - 1;
-          by_epi = centre ? (by_epi | bit) : (by_epi & ~bit);
           unsigned char* st = stage_mem + s * unit_bytes;
           if (k == 0) MUCON_TR16(0, i);
           mbar_arrive_expect_tx(&fullS[s], static_cast<uint32_t>(NKB * R * 128));
@@ -534,8 +520,10 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     constexpr uint32_t idesc = instr_desc_bf16(BM, BN, F16);
+    constexpr uint32_t idesc16 = instr_desc_bf16(BM, 16, F16);   // the residual MMAs: N = 16
     const uint32_t w_addr = smem_u32(w_mem);
     const uint64_t b0 = smem_desc(w_addr);
+    const uint64_t bid = smem_desc(smem_u32(id_mem));
     if (n_my > 0) mbar_wait(wfull, 0);
     int us = 0;
     uint32_t uph = 0;
@@ -550,8 +538,10 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         const int nu = tile_units(tl, code);
         const uint32_t d1 = tmem_base + acc * BN;
         uint32_t issued = 0;
+        int cslot = 0;   // slot of the unit that holds the centre tap (the slab, or the tile's last unit)
         for (int ku = 0; ku < nu; ++ku) {
           const int utap = static_cast<int>((code >> (2 * ku)) & 3u);
+          if (ku == nu - 1) cslot = us;
           mbar_wait(needs_fix(tl, utap) ? &readyS[us] : &fullS[us], uph);
           tc_fence_after();
           if (lane == 0 && ku == 0) MUCON_TR16(2, i);
@@ -593,9 +583,30 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           MUCON_TR16(3, i);
         }
         __syncwarp();
+        // ---- the residual on the tensor core: acc2 = X_centre . I  (exact: every product is x * 1 or x * 0), as eight
+        // M128 N16 K16 instructions against one [16 x 16] identity -- instruction j of a k-block pairs channels 16j ..
+        // 16j+15 of the centre rows with the identity's k = 0 .. 15 and writes accumulator columns 16j .. 16j+15; GEMM 2
+        // accumulates on top of it, b1 is added by epilogue 2.
+        // The tile's centre rows are still in their slot (released by the commit below); accumulator 2 must have been
+        // drained by epilogue 2 of tile i - 2.
+        mbar_wait(&a2free[acc], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ac = smem_desc(smem_u32(stage_mem + cslot * unit_bytes)) +
+                              static_cast<uint32_t>((slab ? dil * 128 : 0) >> 4);
+          const uint32_t d2 = tmem_base + 2 * BN + acc * BN;
+#pragma unroll
+          for (int hh = 0; hh < NKB; ++hh) {
+            const uint64_t adesc = ac + static_cast<uint32_t>((hh * kb_bytes) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_bf16(d2 + hh * 64 + 16 * k, adesc + 2 * k, bid, idesc16, 0u);
+          }
+          mma_commit(&emptyM[cslot]);   // the centre unit / slab may be refilled once these MMAs have retired
+        }
+        __syncwarp();
       }
       if (i >= LA) {
-        // ---- GEMM 2 of tile j: acc2 (= x + b1, stored by the epilogue) += Y . W1^T, Y = relu(acc1 + bd) as bf16 in
+        // ---- GEMM 2 of tile j: acc2 (= x, from the residual MMAs) += Y . W1^T, Y = relu(acc1 + bd) as bf16 in
         // the first 64 columns of accumulator 1
         const int j = i - LA;
         const int acc = j & 1;
@@ -622,7 +633,7 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     // ================================ epilogue ====================================
     EpiCtx c;
     c.tiles = tiles; c.stage_mem = stage_mem; c.staging = staging;
-    c.emptyS = emptyS; c.a1full = a1full; c.yready = yready; c.a2full = a2full;
+    c.a1full = a1full; c.yready = yready; c.a2full = a2full; c.a2free = a2free;
     c.tmO = &tmO; c.out = out; c.tmem_base = tmem_base;
     c.n_my = n_my; c.nslot = nslot; c.LA = LA; c.unit_bytes = unit_bytes; c.kb_bytes = kb_bytes; c.crow0 = slab ? dil : 0;
     c.slab = slab; c.dil = dil;

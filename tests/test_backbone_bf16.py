@@ -95,11 +95,13 @@ def test_reference_golden_end_to_end_precisions(cuda_device, i, precision):
     print(f"\n[{precision}] case {i} T={T} D={D}: z max|err|/RMS={err.max() / rms(want_z):.4f} rms(err)/RMS="
           f"{rms(err) / rms(want_z):.5f}; logp max|err|/RMS={errl.max() / rms(want):.4f} rms(err)/RMS="
           f"{rms(errl) / rms(want):.5f} argmax agree={np.mean(np.argmax(got, 1) == np.argmax(want, 1)):.4f}")
-    # stated bars (max |err| and RMS error, both relative to the RMS of the reference tensor): fp16 and tf32:
-    # max <= 2e-2 (measured <= 1.6e-2 / 1.1e-2), RMS error <= 2e-3; bf16: rounding the residual stream to an 8-bit
+    # stated bars (max |err| and RMS error, both relative to the RMS of the reference tensor): tf32: max <= 2e-2
+    # (measured <= 1.1e-2); fp16: max <= 3e-2 = SURVEY.md 8c's bar (measured <= 2.2e-2; the maximum is one element
+    # of a small-variance GroupNorm group and moves between 1.5e-2 and 2.2e-2 with the order in which the layer
+    # kernel adds the bias, while the RMS error stays at 1.1e-3 to 1.3e-3); RMS error <= 2e-3 for both; bf16: rounding the residual stream to an 8-bit
     # mantissa at every layer gives a 1e-2 RMS error and single elements (small-variance GroupNorm groups) up
     # to 0.1 * RMS -- outside SURVEY.md 8c's 3e-2, which is why fp16 is the default 16-bit type
-    max_bar, rms_bar, agree = {"fp16": (2e-2, 2e-3, 0.995), "tf32": (2e-2, 2e-3, 0.995), "bf16": (1.5e-1, 1.5e-2, 0.97)}[precision]
+    max_bar, rms_bar, agree = {"fp16": (3e-2, 2e-3, 0.995), "tf32": (2e-2, 2e-3, 0.995), "bf16": (1.5e-1, 1.5e-2, 0.97)}[precision]
     assert rms(err) <= rms_bar * rms(want_z) and rms(errl) <= rms_bar * rms(want)
     assert err.max() <= max_bar * rms(want_z)
     assert errl.max() <= max_bar * rms(want)
