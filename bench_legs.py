@@ -117,7 +117,9 @@ def leg_c3(device, rank, world, make_split, device_logp, steps=5):
         dist.all_reduce(need, op=dist.ReduceOp.MAX)
     cap = int(need.item())
     from mucon_b200.viterbi import FlatCandidates
-    flat = FlatCandidates.from_lists(cands)   # candidate sets as arrays (how a beam search would hand them over)
+    t0 = time.perf_counter()
+    flat = FlatCandidates.from_lists(cands)   # candidate sets as arrays (how a beam search would hand them over) + the
+    flat_s = time.perf_counter() - t0         # reference's tie order between candidates (grammar.tie_ranks, Python sets)
     AlignPlan(Tm[:8], FlatCandidates.from_lists(cands[:8]), 48, device=device, len_params=params[:8], labels="best")
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -161,6 +163,7 @@ def leg_c3(device, rank, world, make_split, device_logp, steps=5):
                     "(strong scaling): scan + DP of every unit + per-video arg-max + winner labels",
             "n_gpus": world, "scaling": "strong", "mode": eng.last_mode, "units_this_rank": int(plan.U),
             "ms_per_step": ms, "aligned_frames_per_s": frames / (ms * 1e-3), "plan_build_s_max_over_ranks": prep_s,
+            "lists_to_arrays_and_tie_ranks_s_rank0": flat_s,
             "exchange": ("peer stores from the kernel epilogue, equal to an NCCL all_gather: %s" % ok) if world > 1 else "none"}
 
 

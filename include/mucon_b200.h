@@ -243,6 +243,16 @@ int mucon_viterbi_align_fused_pooled(const mucon_viterbi_batch* batch_h, const v
 int mucon_viterbi_select(const double* score, const int32_t* status, const int32_t* cand_off,
                          int V, int32_t* best, void* stream);
 
+/* The same arg-max with the reference's order between candidates whose scores tie EXACTLY: its hypothesis dict is
+ * insertion-ordered and finalize_decoding (viterbi.py:125-138) takes `score >= best`, so the final hypothesis latest
+ * in the dict wins.  That order is structural: larger tie_rank[2u] (place of the transcript's first label in the
+ * grammar's successor iteration), then larger final_j[u] + transcript length, then larger tie_rank[2u + 1] (dense
+ * rank of the rest of the transcript's successor places, a proper prefix first); mucon_b200/grammar.py:tie_ranks
+ * builds both from the grammar's own successor sets.  Remaining ties (duplicate transcripts): lowest index. */
+int mucon_viterbi_select_ranked(const double* score, const int32_t* status, const int32_t* cand_off, int V,
+                                const int32_t* final_j, const int32_t* tr_off, const int32_t* tie_rank,
+                                int32_t* best, void* stream);
+
 /* Labels for selected units from their seg_blocks: sel[i] is a unit index (or <0 to skip) whose
  * labels are written at labels + out_off[i]. */
 int mucon_viterbi_labels(const int32_t* sel, int n_sel, const int64_t* out_off,

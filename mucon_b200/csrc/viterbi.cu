@@ -178,6 +178,55 @@ __global__ void select_kernel(const double* __restrict__ score, const int32_t* _
   if (lane == 0) best[v] = bi;
 }
 
+// The same arg-max with the reference's tie order between candidates.  Its hypothesis table is an insertion-ordered
+// dict and finalize_decoding (viterbi.py:125-138) takes `score >= best`, so of several final hypotheses with EXACTLY the
+// same score the one latest in the dict wins.  The dict order is structural (decode_frame, viterbi.py:93-123: for every
+// old key first "stay", then the successors in the grammar's iteration order; an existing key keeps its place): a
+// final key (transcript p of d labels, last segment of l blocks) sits at the position of the choice sequence
+// [p[0]; stay x (K - l - d + 1); p[1], .., p[d-1]; stay x (l - 1)], compared lexicographically with stay < any
+// successor.  Hence: later = larger rank of p[0], then larger l + d, then larger rank sequence of p[1:] (a proper
+// prefix is earlier).  tie_rank[2u] = rank of p[0], tie_rank[2u + 1] = dense rank of p[1:] among the video's
+// candidates, both built on the host from the grammar's own successor sets (grammar.tie_ranks).
+struct SelKey {
+  double v;
+  int r0, ld, r1, i;
+};
+__device__ __forceinline__ bool sel_later(const SelKey& a, const SelKey& b) {   // a beats b
+  if (b.i < 0) return a.i >= 0;
+  if (a.i < 0) return false;
+  if (a.v != b.v) return a.v > b.v;
+  if (a.r0 != b.r0) return a.r0 > b.r0;
+  if (a.ld != b.ld) return a.ld > b.ld;
+  if (a.r1 != b.r1) return a.r1 > b.r1;
+  return a.i < b.i;
+}
+__global__ void select_ranked_kernel(const double* __restrict__ score, const int32_t* __restrict__ status,
+                                     const int32_t* __restrict__ cand_off, int V, const int32_t* __restrict__ final_j,
+                                     const int32_t* __restrict__ tr_off, const int32_t* __restrict__ tie_rank,
+                                     int32_t* __restrict__ best) {
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= V) return;
+  const int lane = threadIdx.x & 31;
+  const int a = cand_off[v], e = cand_off[v + 1];
+  SelKey b{0.0, 0, 0, 0, -1};
+  for (int i = a + lane; i < e; i += 32) {
+    if (status[i] == MUCON_UNIT_INFEASIBLE) continue;
+    const SelKey x{score[i], tie_rank[2 * i], final_j[i] + (tr_off[i + 1] - tr_off[i]), tie_rank[2 * i + 1], i};
+    if (sel_later(x, b)) b = x;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    SelKey o;
+    o.v = __shfl_xor_sync(0xffffffffu, b.v, off);
+    o.r0 = __shfl_xor_sync(0xffffffffu, b.r0, off);
+    o.ld = __shfl_xor_sync(0xffffffffu, b.ld, off);
+    o.r1 = __shfl_xor_sync(0xffffffffu, b.r1, off);
+    o.i = __shfl_xor_sync(0xffffffffu, b.i, off);
+    if (sel_later(o, b)) b = o;
+  }
+  if (lane == 0) best[v] = b.i;
+}
+
 constexpr int kLabelsMaxN = 128;
 __global__ void __launch_bounds__(256) labels_kernel(const int32_t* __restrict__ sel, const int64_t* __restrict__ out_off,
                                                      const int64_t* __restrict__ vid_off,
@@ -817,6 +866,18 @@ extern "C" int mucon_viterbi_select(const double* score, const int32_t* status, 
   const int wpb = 4;
   select_kernel<<<(V + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(score, status, cand_off, V,
                                                                                           best);
+  MUCON_CUDA_CHECK(cudaGetLastError());
+  return MUCON_OK;
+}
+
+extern "C" int mucon_viterbi_select_ranked(const double* score, const int32_t* status, const int32_t* cand_off, int V,
+                                           const int32_t* final_j, const int32_t* tr_off, const int32_t* tie_rank,
+                                           int32_t* best, void* stream) {
+  if (!score || !status || !cand_off || !final_j || !tr_off || !tie_rank || !best || V < 0) return MUCON_EINVAL;
+  if (V == 0) return MUCON_OK;
+  const int wpb = 4;
+  select_ranked_kernel<<<(V + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      score, status, cand_off, V, final_j, tr_off, tie_rank, best);
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

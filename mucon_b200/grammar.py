@@ -40,7 +40,10 @@ class _TranscriptSetGrammar(Grammar):
                 self.candidates.append(tr)
             path = tr + [self.end_symbol()]
             for i, nxt in enumerate(path):
-                self.successors.setdefault((self.start_symbol(),) + tuple(path[:i]), set()).add(nxt)
+                # built exactly like grammar.py:150-154 ({x}.union(old)): the ITERATION order of these sets decides
+                # which of two candidates with equal scores the reference returns (tie_ranks below)
+                ctx = (self.start_symbol(),) + tuple(path[:i])
+                self.successors[ctx] = {nxt}.union(self.successors.get(ctx, set()))
 
     def n_classes(self):
         return self.num_classes
@@ -99,3 +102,46 @@ def lower_grammar(grammar):
     if not out:
         raise ValueError("grammar admits no transcript")
     return out
+
+
+def tie_ranks(successors, candidates, start=-1):
+    """[len(candidates), 2] int32 for mucon_viterbi_select_ranked: the place of each candidate's final hypothesis in
+    the reference's insertion-ordered hypothesis dict, as far as the grammar decides it (viterbi.py:93-138: successors
+    are visited in the iteration order of the grammar's sets, `>=` lets the later hypothesis win an exact tie).
+    Column 0: place of the first label among the start context's successors; column 1: dense rank of the places of the
+    remaining labels, compared as sequences (a proper prefix is earlier).  The data-dependent middle key -- last
+    segment length + transcript length -- is added on the device."""
+    place = {}
+
+    def places(ctx):
+        got = place.get(ctx)
+        if got is None:
+            got = place[ctx] = {int(x): i for i, x in enumerate(successors.get(ctx, ()))}
+        return got
+
+    seqs = []
+    for tr in candidates:
+        ctx = (start,)
+        r = []
+        for x in tr:
+            x = int(x)
+            r.append(places(ctx)[x])
+            ctx = ctx + (x,)
+        seqs.append(tuple(r))
+    rest = {t: i for i, t in enumerate(sorted({q[1:] for q in seqs}))}
+    out = np.zeros((len(seqs), 2), dtype=np.int32)
+    for i, q in enumerate(seqs):
+        out[i, 0] = q[0] if q else 0
+        out[i, 1] = rest[q[1:]]
+    return out
+
+
+def tie_ranks_for_lists(candidates, start=-1, end=-2):
+    """tie_ranks for a plain list of transcripts = what ModifiedPathGrammar(candidates) (grammar.py:178-191) implies."""
+    succ = {}
+    for tr in candidates:
+        path = [int(x) for x in tr] + [end]
+        for i, nxt in enumerate(path):
+            ctx = (start,) + tuple(path[:i])
+            succ[ctx] = set([nxt]).union(succ.get(ctx, set()))
+    return tie_ranks(succ, candidates, start)

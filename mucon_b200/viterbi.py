@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .grammar import lower_grammar
+from .grammar import lower_grammar, tie_ranks, tie_ranks_for_lists
 from .length_model import PoissonModel, log_factorial_prefix
 
 __all__ = ["Viterbi", "ViterbiEngine", "AlignPlan", "Segment", "default_seg0_f32"]
@@ -73,16 +73,20 @@ class _Blob:
 
 class FlatCandidates:
     """Candidate transcripts of a batch as three arrays: n_cands [V] (candidates per video), lengths [U]
-    (labels per candidate, videos in order) and labels [sum lengths] (all transcripts concatenated)."""
+    (labels per candidate, videos in order) and labels [sum lengths] (all transcripts concatenated).
+    tie_rank [U, 2] (optional, grammar.tie_ranks): which candidate wins an EXACT score tie the way the reference's
+    hypothesis dict decides it; without it the lowest candidate index wins."""
 
-    def __init__(self, n_cands, lengths, labels):
-        self.n_cands, self.lengths, self.labels = n_cands, lengths, labels
+    def __init__(self, n_cands, lengths, labels, tie_rank=None):
+        self.n_cands, self.lengths, self.labels, self.tie_rank = n_cands, lengths, labels, tie_rank
 
     @classmethod
     def from_lists(cls, candidates):
         lengths = np.fromiter((len(t) for cl in candidates for t in cl), dtype=np.int64)
         labels = np.fromiter((x for cl in candidates for t in cl for x in t), dtype=np.int32, count=int(lengths.sum()))
-        return cls(np.fromiter((len(cl) for cl in candidates), dtype=np.int64, count=len(candidates)), lengths, labels)
+        ties = np.concatenate([tie_ranks_for_lists(cl) for cl in candidates]) if len(candidates) else None
+        return cls(np.fromiter((len(cl) for cl in candidates), dtype=np.int64, count=len(candidates)), lengths, labels,
+                   ties)
 
 
 MAX_J_REGISTER = 128  # kDpMaxJ in csrc/viterbi_dp.cuh
@@ -103,7 +107,7 @@ class AlignPlan:
 
     def __init__(self, T, candidates, n_classes, fs=30, max_len=2000, len_params=None, len_rows=None,
                  device=None, want_bp=True, labels="best", groups=None, long_K=None, payload_capacity=None,
-                 force_generic=False, len_params_dev=None):
+                 force_generic=False, len_params_dev=None, tie_rank=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.fs, self.max_len, self.C = int(fs), int(max_len), int(n_classes)
         self.J = self.max_len // self.fs
@@ -142,6 +146,18 @@ class AlignPlan:
         self.max_N = int(nlen.max()) if U else 1
         self.single = bool(U == V)
         self.labels_mode = labels
+        # which candidate wins an EXACT score tie: the reference's dict order (mucon_viterbi_select_ranked).  Lists of
+        # transcripts get the ranks ModifiedPathGrammar would imply; FlatCandidates carry their own (`tie_rank`
+        # attribute) or fall back to "lowest index" (mucon_viterbi_select).
+        if tie_rank is None and isinstance(candidates, FlatCandidates):
+            tie_rank = getattr(candidates, "tie_rank", None)
+        elif tie_rank is None and not self.single and labels == "best":
+            tie_rank = np.concatenate([tie_ranks_for_lists(cl) for cl in candidates]) if U else None
+        if tie_rank is not None:
+            tie_rank = np.ascontiguousarray(tie_rank, dtype=np.int32)
+            if tie_rank.shape != (U, 2):
+                raise ValueError("tie_rank must be [n_units, 2]")
+        self.tie_rank = tie_rank
         uT = T[self.unit_vid]
         uK = K[self.unit_vid]
         # labels: per-unit ("all") or per-video, written for the best candidate ("best")
@@ -231,6 +247,8 @@ class AlignPlan:
         blob.add("tr", self.tr)
         blob.add("tr_off", self.tr_off)
         blob.add("cand_off", self.cand_off)
+        if self.tie_rank is not None:
+            blob.add("tie_rank", self.tie_rank.reshape(-1))
         blob.add("lab_off", self.lab_off)
         blob.add("bp_off", self.bp_off[:-1] if U else self.bp_off)
         blob.add("order_v", self.order_v)
@@ -469,9 +487,15 @@ class ViterbiEngine:
     def _finish(self, plan, sp):
         lib, p = self.lib, plan.p
         if plan.labels_mode == "best" and not plan.single:
-            _lib.check(lib.mucon_viterbi_select(
-                _lib.ptr(plan.score), _lib.ptr(plan.status), C.c_void_p(p["cand_off"]), C.c_int(plan.V),
-                _lib.ptr(plan.best), sp), "mucon_viterbi_select")
+            if plan.tie_rank is not None:
+                _lib.check(lib.mucon_viterbi_select_ranked(
+                    _lib.ptr(plan.score), _lib.ptr(plan.status), C.c_void_p(p["cand_off"]), C.c_int(plan.V),
+                    _lib.ptr(plan.final_j), C.c_void_p(p["tr_off"]), C.c_void_p(p["tie_rank"]),
+                    _lib.ptr(plan.best), sp), "mucon_viterbi_select_ranked")
+            else:
+                _lib.check(lib.mucon_viterbi_select(
+                    _lib.ptr(plan.score), _lib.ptr(plan.status), C.c_void_p(p["cand_off"]), C.c_int(plan.V),
+                    _lib.ptr(plan.best), sp), "mucon_viterbi_select")
             _lib.check(lib.mucon_viterbi_labels(
                 _lib.ptr(plan.best), C.c_int(plan.V), C.c_void_p(p["vid_lab_off"]), C.c_void_p(p["vid_off"]),
                 C.c_void_p(p["unit_vid"]), C.c_void_p(p["tr"]), C.c_void_p(p["tr_off"]),
@@ -628,6 +652,8 @@ class Viterbi(object):
             fast = self._decode_single(eng, logp, cands[0], lm, fs, max_len)
             if fast is not None:
                 return fast
+        if len(cands) > 1 and isinstance(getattr(self.grammar, "successors", None), dict):
+            kw["tie_rank"] = tie_ranks(self.grammar.successors, cands, self.grammar.start_symbol())
         plan = AlignPlan([T], [cands], Cn, fs=fs, max_len=max_len, device=eng.device, labels="best", **kw)
         dev_logp = torch.from_numpy(np.ascontiguousarray(logp)).to(eng.device)
         if self.np_mode is None:

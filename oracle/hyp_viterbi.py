@@ -28,12 +28,15 @@ START, END = -1, -2  # grammar.py:19-24
 
 
 def build_successors(candidates):
-    """Prefix tree: history tuple -> set of admissible next labels (grammar.py:201-207)."""
+    """Prefix tree: history tuple -> set of admissible next labels (grammar.py:201-207).  Built with the reference's
+    own statement ({x}.union(old)): the ITERATION order of these sets fixes the order of the hypothesis table and
+    with it which of several equally-scored final hypotheses wins (tests/golden/ties.npz)."""
     succ = {}
     for tr in candidates:
-        path = list(tr) + [END]
+        path = [int(x) for x in tr] + [END]
         for i, nxt in enumerate(path):
-            succ.setdefault((START,) + tuple(path[:i]), set()).add(nxt)
+            hist = (START,) + tuple(path[:i])
+            succ[hist] = {nxt}.union(succ.get(hist, set()))
     return succ
 
 
