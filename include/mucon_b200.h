@@ -418,6 +418,14 @@ int mucon_wavenet_layer_tf32_pair(const float* x, float* out, const float* Wd_kc
 int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd_kco, const float* bd_h, const void* W1_kco,
                              const float* b1_h, const void* tiles, int num_tiles, int64_t rows, int64_t rows_out,
                              int dilation, int pool, int relu_final, int out_f32, int fp16, void* stream);
+/* The same launch with the skip connection optional: residual == 0 gives out = conv_1x1(relu(conv_k3(x) + bd)) + b1.
+ * With an identity centre tap, bd = 0 and a dilation no video reaches (side taps then see only padding and are never
+ * loaded) that is a plain 1x1 convolution of non-negative 16-bit rows on the resident-weight pipeline: how the fast
+ * path runs `last_conv` (temporal.py:144-145, its input has just been through the ReLU of :144). */
+int mucon_wavenet_layer_bf16_ex(const void* x, void* out, const void* Wd_kco, const float* bd_h, const void* W1_kco,
+                                const float* b1_h, const void* tiles, int num_tiles, int64_t rows, int64_t rows_out,
+                                int dilation, int pool, int relu_final, int out_f32, int fp16, int residual,
+                                void* stream);
 /* k = 1 or k = 3 dilated Conv1d with padding = dilation (temporal.py:21-31,48-52), fp32:
  *   out[t, co] = bias[co] + sum_tap sum_ci W_tco[tap][ci][co] * f(in[t + (tap - taps/2)*dilation, ci])
  * f = ReLU when relu_in; ReLU on the result when relu_out; `residual` ([rows, Cout] or NULL) is

@@ -17,7 +17,7 @@ SYMBOLS = [
     "mucon_viterbi_blockscores", "mucon_viterbi_decode", "mucon_viterbi_decode_generic", "mucon_viterbi_pack_lanes_h", "mucon_viterbi_decode_lanes", "mucon_viterbi_pack_h", "mucon_viterbi_align_fused", "mucon_viterbi_align_fused_tail", "mucon_viterbi_align_fused_pooled", "mucon_viterbi_select", "mucon_viterbi_select_ranked", "mucon_viterbi_labels",
     "mucon_poisson_params_h", "mucon_logfact_h", "mucon_sgemm_bias", "mucon_lstm_encoder", "mucon_seq_decoder", "mucon_class_mean_params", "mucon_single_create", "mucon_single_destroy", "mucon_single_decode_h", "mucon_peer_alloc", "mucon_peer_open", "mucon_peer_close", "mucon_peer_free",
     "mucon_masks_fwd", "mucon_masks_fwd_ws", "mucon_masks_bwd", "mucon_flint_fwd", "mucon_flint_fwd_ws", "mucon_flint_fwd_ws_words", "mucon_flint_bwd", "mucon_mask_template_h",
-    "mucon_gemm_tf32_bias_act", "mucon_gemm_tf32_bias_act_bf16", "mucon_wavenet_layer_bf16", "mucon_conv_gemm_tf32", "mucon_conv_gemm_tf32_shifts", "mucon_conv_gemm_tf32_ex", "mucon_wgrad_tf32", "mucon_maxpool2_bwd", "mucon_groupnorm_relu_bwd", "mucon_expand_rows_bwd", "mucon_wavenet_layer_tf32", "mucon_wavenet_layer_tf32_pair", "mucon_conv1d", "mucon_maxpool2", "mucon_pool2", "mucon_groupnorm_relu", "mucon_logsoftmax_expand", "mucon_logsoftmax_rows", "mucon_tail_logprobs", "mucon_expand_rows",
+    "mucon_gemm_tf32_bias_act", "mucon_gemm_tf32_bias_act_bf16", "mucon_wavenet_layer_bf16", "mucon_wavenet_layer_bf16_ex", "mucon_conv_gemm_tf32", "mucon_conv_gemm_tf32_shifts", "mucon_conv_gemm_tf32_ex", "mucon_wgrad_tf32", "mucon_maxpool2_bwd", "mucon_groupnorm_relu_bwd", "mucon_expand_rows_bwd", "mucon_wavenet_layer_tf32", "mucon_wavenet_layer_tf32_pair", "mucon_conv1d", "mucon_maxpool2", "mucon_pool2", "mucon_groupnorm_relu", "mucon_logsoftmax_expand", "mucon_logsoftmax_rows", "mucon_tail_logprobs", "mucon_expand_rows",
     "mucon_vit_mof", "mucon_vit_segment_metrics", "mucon_vit_segment_metrics_ws_words",
 ]
 

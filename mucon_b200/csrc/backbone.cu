@@ -565,10 +565,22 @@ extern "C" int mucon_wavenet_layer_tf32_pair(const float* x, float* out, const f
   return launch_layer(x, out, Wd_kco, bd, W1_kco, b1, tiles, num_tiles, rows, dilation, pool, relu_final, true, stream);
 }
 
+extern "C" int mucon_wavenet_layer_bf16_ex(const void* x, void* out, const void* Wd_kco, const float* bd_h,
+                                           const void* W1_kco, const float* b1_h, const void* tiles, int num_tiles,
+                                           int64_t rows, int64_t rows_out, int dilation, int pool, int relu_final,
+                                           int out_f32, int fp16, int residual, void* stream);
 extern "C" int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd_kco, const float* bd_h,
                                         const void* W1_kco, const float* b1_h, const void* tiles, int num_tiles,
                                         int64_t rows, int64_t rows_out, int dilation, int pool, int relu_final,
                                         int out_f32, int fp16, void* stream) {
+  return mucon_wavenet_layer_bf16_ex(x, out, Wd_kco, bd_h, W1_kco, b1_h, tiles, num_tiles, rows, rows_out, dilation, pool,
+                                     relu_final, out_f32, fp16, 1, stream);
+}
+
+extern "C" int mucon_wavenet_layer_bf16_ex(const void* x, void* out, const void* Wd_kco, const float* bd_h,
+                                           const void* W1_kco, const float* b1_h, const void* tiles, int num_tiles,
+                                           int64_t rows, int64_t rows_out, int dilation, int pool, int relu_final,
+                                           int out_f32, int fp16, int residual, void* stream) {
   if (num_tiles == 0 || rows == 0 || rows_out == 0) return MUCON_OK;  // nothing to produce
   if (!x || !out || !Wd_kco || !bd_h || !W1_kco || !b1_h || !tiles || num_tiles < 0 || rows < 0 || rows_out < 0 ||
       dilation < 1)
@@ -605,7 +617,7 @@ extern "C" int mucon_wavenet_layer_bf16(const void* x, void* out, const void* Wd
   MUCON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, layer16::SMEM_LIMIT));
   kern<<<grid, layer16::LTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       tx, twd, tw1, to, bp, static_cast<const layer16::Tile*>(tiles), num_tiles, dilation, slab, out, pool, relu_final,
-      out_f32 ? 1 : 0);
+      (out_f32 ? 1 : 0) | (residual ? 0 : 2));
   MUCON_CUDA_CHECK(cudaGetLastError());
   return MUCON_OK;
 }

@@ -375,6 +375,10 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   const int unit_bytes = NKB * kb_bytes;
   const int nslot = slab ? 2 : kRingSlots;
   const int LA = 1;                        // GEMM 1 / epilogue 1 run one tile ahead of GEMM 2 / epilogue 2
+  // out_f32 carries two flags: bit 0 = fp32 output, bit 1 = NO residual (out = conv_1x1(relu(conv(x) + bd)) + b1: with
+  // an identity centre tap and dead side taps this is a plain 1x1 conv of non-negative 16-bit rows -- last_conv)
+  const bool no_res = (out_f32 & 2) != 0;
+  out_f32 &= 1;
   const int S = staged_rows(dil, slab, pool, out_f32);
   unsigned char* w_mem = base;                       // [8][WTILE]: (tap, kb) tiles of the dilated conv, then the 1x1's
   unsigned char* id_mem = base + W_BYTES;            // [16 x 16] identity (16-bit, K-major SWIZZLE_128B rows)
@@ -595,11 +599,13 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           const uint64_t ac = smem_desc(smem_u32(stage_mem + cslot * unit_bytes)) +
                               static_cast<uint32_t>((slab ? dil * 128 : 0) >> 4);
           const uint32_t d2 = tmem_base + 2 * BN + acc * BN;
+          if (!no_res) {
 #pragma unroll
-          for (int hh = 0; hh < NKB; ++hh) {
-            const uint64_t adesc = ac + static_cast<uint32_t>((hh * kb_bytes) >> 4);
+            for (int hh = 0; hh < NKB; ++hh) {
+              const uint64_t adesc = ac + static_cast<uint32_t>((hh * kb_bytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma_bf16(d2 + hh * 64 + 16 * k, adesc + 2 * k, bid, idesc16, 0u);
+              for (int k = 0; k < 4; ++k) mma_bf16(d2 + hh * 64 + 16 * k, adesc + 2 * k, bid, idesc16, 0u);
+            }
           }
           mma_commit(&emptyM[cslot]);   // the centre unit / slab may be refilled once these MMAs have retired
         }
@@ -620,7 +626,7 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // 8 x K16: 8 columns of packed bf16 pairs each
             const uint64_t bdesc = b0 + static_cast<uint32_t>(((3 * NKB + (k >> 2)) * WTILE) >> 4) + 2 * (k & 3);
-            mma_bf16_ts(d2, ya + 8 * k, bdesc, idesc, 1u);
+            mma_bf16_ts(d2, ya + 8 * k, bdesc, idesc, (no_res && k == 0) ? 0u : 1u);
           }
           mma_commit(&a2full[acc]);
           mma_commit(&a1free[acc]);

@@ -151,6 +151,9 @@ def wavenet_layer_rows(x, Wd_kco, bd, W1_kco, b1, plan, level, dilation, pool, r
 DEFAULT_PRECISION = os.environ.get("MUCON_BACKBONE_PRECISION", "fp16")
 
 
+_ZERO_BIAS = np.zeros(128, dtype=np.float32)
+
+
 def _host_f32(t):
     """contiguous float32 host copy of a (small) tensor, as a ctypes pointer keeps it alive through the call"""
     a = np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32) if isinstance(t, torch.Tensor) else \
@@ -158,21 +161,37 @@ def _host_f32(t):
     return a
 
 
-def wavenet_layer_bf16_rows(x, Wd_kco16, bd, W1_kco16, b1, plan, level, dilation, pool, relu_final, out_f32=False):
+def wavenet_layer_bf16_rows(x, Wd_kco16, bd, W1_kco16, b1, plan, level, dilation, pool, relu_final, out_f32=False,
+                            residual=True):
     """One WaveNet layer (+ optional max-pool) in a single tcgen05 launch, 16-bit operands.  x [rows(level), 128]
     bfloat16 or float16 (the weights must have the same type).
-    bd / b1: biases, as host float32 arrays (numpy) or tensors (copied to the host: pass numpy in hot loops)."""
+    bd / b1: biases, as host float32 arrays (numpy) or tensors (copied to the host: pass numpy in hot loops).
+    residual=False drops the skip connection (out = conv_1x1(relu(conv(x) + bd)) + b1)."""
     tiles, n_tiles = plan.ltiles[(level, "pool" if pool else "same")]
     assert x.dtype in (torch.bfloat16, torch.float16) and Wd_kco16.dtype == x.dtype and W1_kco16.dtype == x.dtype
     out = torch.empty((plan.rows[level + 1] if pool else x.shape[0], 128),
                       dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
     bd_h, b1_h = _host_f32(bd), _host_f32(b1)
-    _lib.check(_lib.lib().mucon_wavenet_layer_bf16(
+    _lib.check(_lib.lib().mucon_wavenet_layer_bf16_ex(
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(Wd_kco16), bd_h.ctypes.data_as(C.c_void_p), _lib.ptr(W1_kco16),
         b1_h.ctypes.data_as(C.c_void_p), _lib.ptr(tiles), C.c_int(n_tiles), C.c_int64(x.shape[0]),
         C.c_int64(out.shape[0]), C.c_int(dilation), C.c_int(int(pool)), C.c_int(int(relu_final)),
-        C.c_int(int(out_f32)), C.c_int(int(x.dtype == torch.float16)), _stream(x.device)), "mucon_wavenet_layer_bf16")
+        C.c_int(int(out_f32)), C.c_int(int(x.dtype == torch.float16)), C.c_int(int(residual)), _stream(x.device)),
+        "mucon_wavenet_layer_bf16_ex")
     return out
+
+
+LAST_CONV_16 = os.environ.get("MUCON_LAST_CONV_16", "1") != "0"
+DEAD_DILATION = 1 << 20   # no video is that long: both side taps only see padding and are never loaded
+
+
+def conv1x1_bf16_rows(x, ident_k16, W_k16, bias_h, plan, level):
+    """Plain 1x1 conv of NON-NEGATIVE 16-bit rows -> fp32 on the resident-weight layer pipeline: GEMM 1 multiplies with
+    an identity centre tap (exact; relu(x) = x), GEMM 2 with W, no skip connection.  This is how the fast path runs
+    last_conv (temporal.py:144-145; its input has just been through the ReLU of :144): 55 us instead of the 190 us the
+    one-tap TF32 conv_gemm_kernel needs for the 2720 partly filled tiles of the c2 batch at T/16."""
+    return wavenet_layer_bf16_rows(x, ident_k16, _ZERO_BIAS, W_k16, bias_h, plan, level, DEAD_DILATION, False, False,
+                                   out_f32=True, residual=False)
 
 
 def maxpool2_rows(x, plan, level, mode=0):
@@ -267,6 +286,12 @@ class WaveNetBlock(nn.Module):
                 w["layers_kh16"] = [(a.to(torch.float16).contiguous(), b.to(torch.float16).contiguous())
                                     for a, b in w["layers_k"]]
                 w["layers_bias_h"] = [(_host_f32(l.dilated_conv.bias), _host_f32(l.conv_1x1.bias)) for l in self.layers]
+                # last_conv on the 16-bit layer pipeline (conv1x1_bf16_rows): an identity centre tap + its own weights
+                ident = torch.zeros(3 * 128, 128, device=w["last_k"].device)
+                ident[128:256] = torch.eye(128, device=ident.device)
+                w["last_k16"] = {dt: (ident.to(dt).contiguous(), w["last_k"].to(dt).contiguous())
+                                 for dt in (torch.float16, torch.bfloat16)}
+                w["last_b_h"] = _host_f32(self.last_conv.bias)
             self._cache = (key, w)
         return self._cache[1]
 
@@ -317,11 +342,16 @@ class WaveNetBlock(nn.Module):
                 pooled = self.pooling and i in self.pooling_layers
                 wdk, w1k = w["layers_kh16" if precision == "fp16" else "layers_k16"][i]
                 bd, b1 = w["layers_bias_h"][i]
-                # the last layer hands fp32 to last_conv (with the ReLU of temporal.py:144 folded into its store)
+                # the ReLU of temporal.py:144 is folded into the last layer's store; without LAST_CONV_16 that layer
+                # hands fp32 to the TF32 last_conv
                 x = wavenet_layer_bf16_rows(x, wdk, bd, w1k, b1, plan, level, self.stages[i], pooled,
-                                            relu_final=(i == last), out_f32=(i == last and not pooled))
+                                            relu_final=(i == last),
+                                            out_f32=(i == last and not pooled and not LAST_CONV_16))
                 if pooled:
                     level += 1
+            if LAST_CONV_16 and x.dtype == dt:
+                ident, wl = w["last_k16"][dt]
+                return conv1x1_bf16_rows(x, ident, wl, w["last_b_h"], plan, level)                  # temporal.py:144-145
             if x.dtype != torch.float32:
                 x = x.float()
             return conv_gemm_rows(x, w["last_k"], w["last_b"], plan, level)                          # temporal.py:144-145

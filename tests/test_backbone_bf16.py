@@ -70,6 +70,32 @@ def test_bf16_layer_kernel(cuda_device, dil, dt):
                                    bad.nonzero()[:4].tolist())
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_last_conv_on_the_layer_pipeline(cuda_device, dt):
+    """conv1x1_bf16_rows (the layer kernel without its skip connection, identity centre tap, dead side taps): a plain
+    1x1 conv of non-negative 16-bit rows -> fp32, against torch fp32 on the same rounded operands.  The identity GEMM
+    and the 16-bit round trip of relu(x) are exact, so only the accumulation order differs: 1e-4 relative to the row
+    scale.  With the skip connection (residual=True) the same call adds x back."""
+    from mucon_b200.temporal import DEAD_DILATION, BackbonePlan, conv1x1_bf16_rows, wavenet_layer_bf16_rows
+    g = torch.Generator().manual_seed(5)
+    Ts = [700, 333, 64, 1999, 16, 128, 129, 127, 1, 2, 3, 140, 19]
+    plan = BackbonePlan(Ts, 1, cuda_device)
+    x16 = torch.randn(sum(Ts), 128, generator=g).relu().to(dt)
+    w16 = (torch.randn(128, 128, generator=g) / 11).to(dt)          # [Cout, Cin]
+    b = torch.randn(128, generator=g)
+    ident = torch.zeros(3 * 128, 128)
+    ident[128:256] = torch.eye(128)
+    dev = cuda_device
+    got = conv1x1_bf16_rows(x16.to(dev), ident.to(dt).to(dev), w16.to(dev), b.numpy(), plan, 0)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.float32 and got.shape == (sum(Ts), 128)
+    want = x16.double() @ w16.double().t() + b.double()
+    assert (got.cpu().double() - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+    skip = wavenet_layer_bf16_rows(x16.to(dev), ident.to(dt).to(dev), np.zeros(128, np.float32), w16.to(dev), b.numpy(),
+                                   plan, 0, DEAD_DILATION, False, False, out_f32=True, residual=True)
+    assert (skip.cpu().double() - (want + x16.double())).abs().max().item() <= 1e-4 * want.abs().max().item()
+
+
 @pytest.mark.parametrize("precision", ["fp16", "bf16", "tf32"])
 @pytest.mark.parametrize("i", range(len(CASES)))
 def test_reference_golden_end_to_end_precisions(cuda_device, i, precision):
