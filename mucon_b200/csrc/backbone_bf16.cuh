@@ -504,16 +504,8 @@ wavenet_layer_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           const int first = slab ? -dil : (tap - 1) * dil;
           const int lo = -(tl.t0 + first);          // rows below lo are before the video
           const int hi = tl.T - (tl.t0 + first);    // rows from hi on are after it
-          for (int r = lane; r < R; r += 32) {
-            if (r < lo || r >= hi) {
 #pragma unroll
-              for (int kb = 0; kb < NKB; ++kb) {
-                uint4* p = reinterpret_cast<uint4*>(st + kb * kb_bytes + r * 128);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) p[c] = make_uint4(0u, 0u, 0u, 0u);
-              }
-            }
-          }
+          for (int kb = 0; kb < NKB; ++kb) zero_pad_rows(st + kb * kb_bytes, lo, hi, R, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncwarp();

@@ -94,6 +94,19 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Conv1d zero padding inside an operand tile whose rows are 128-byte lines (the swizzle only permutes the 16-byte
+// chunks INSIDE a line): rows [0, lo) and [hi, rows) of the tile lie outside the video and are cleared.  Consecutive
+// lanes take consecutive 16-byte chunks (a warp store covers four whole rows, 512 contiguous bytes: no bank
+// conflicts) -- a lane per row would put all 32 lanes on the same four banks, 32-way serialised, which made the
+// fix-up warp the longest link of the per-tile chain wherever most tiles are partly filled (the T/8 and T/16 levels).
+__device__ __forceinline__ void zero_pad_rows(unsigned char* tile, int lo, int hi, int rows, int lane) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const int e0 = (lo < rows ? (lo > 0 ? lo : 0) : rows) * 128;
+  for (int o = lane * 16; o < e0; o += 512) *reinterpret_cast<uint4*>(tile + o) = z;
+  const int b1 = (hi > 0 ? hi : 0) * 128, e1 = rows * 128;
+  for (int o = b1 + lane * 16; o < e1; o += 512) *reinterpret_cast<uint4*>(tile + o) = z;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -382,14 +395,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int kc = 0; kc < KB_PER_TAP; ++kc) {
           mbar_wait(&full[s], ph);
           if (fix) {
-            // a tile row is one 128-byte line (the swizzle permutes 16-byte chunks inside it)
-            float4* a4 = reinterpret_cast<float4*>(stage_mem + s * STAGE_BYTES);
-            for (int r = lane; r < BM; r += 32) {
-              if (r < lo || r >= hi) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a4[r * 8 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
+            zero_pad_rows(stage_mem + s * STAGE_BYTES, lo, hi, BM, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           }
           __syncwarp();
@@ -664,13 +670,7 @@ wavenet_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int kc = 0; kc < KB_PER_TAP; ++kc) {
           mbar_wait(&full[s], ph);
           if (fix) {
-            float4* a4 = reinterpret_cast<float4*>(stage_mem + s * STAGE_BYTES);
-            for (int r = lane; r < BM; r += 32) {
-              if (r < lo || r >= hi) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a4[r * 8 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
+            zero_pad_rows(stage_mem + s * STAGE_BYTES, lo, hi, BM, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           }
           __syncwarp();
@@ -976,13 +976,7 @@ wavenet_layer_slab_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       for (int kc = 0; kc < KB_PER_TAP; ++kc) {
         mbar_wait(&fullS[ss], phs);
         if (fix) {
-          float4* a4 = reinterpret_cast<float4*>(slab_mem + ss * SLAB_BYTES);
-          for (int r = lane; r < rows; r += 32) {
-            if (r < lo || r >= hi) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) a4[r * 8 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
+          zero_pad_rows(slab_mem + ss * SLAB_BYTES, lo, hi, rows, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncwarp();
