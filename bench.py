@@ -672,11 +672,15 @@ def main_ours(args, rank, world, local_rank):
         path_bytes = scan_bytes + dp_bytes
         fused_gbs = path_bytes / (fused_ms * 1e-3) / 1e9
         scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("align_fused_kernel_dram_bytes")
-        except Exception:
-            pass
+        traffic, traffic_src = (None, None) if (args.no_traffic or world > 1) else measure_traffic()
+        if traffic is None:
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("align_fused_kernel_dram_bytes")
+                traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of both launches from the ncu --set full capture "
+                               "profiles/r1d_align_fused_pair_c2.md (profiles/traffic.json); not re-measured in this run" +
+                               (" (N > 1 or --no-traffic)" if (args.no_traffic or world > 1) else " (ncu did not run: %s)" % traffic_src))
+            except Exception:
+                pass
         out = {
             "metric": METRIC, "value": frames_all / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -700,9 +704,7 @@ def main_ours(args, rank, world, local_rank):
                              "with 8 lanes per segment" % (2, plan.n_long) if plan.n_long else ", one launch"),
                          "achieved": fused_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fused_gbs / hbm_peak,
                          "traffic": traffic,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of both launches from the ncu --set "
-                                           "full capture profiles/r1d_align_fused_pair_c2.md (profiles/traffic.json); not "
-                                           "re-measured in this run -- ncu cannot run inside the timed process",
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "bytes_per_launch": path_bytes,
                          "ms_per_launch": fused_ms, "launches_per_step": 2 if plan.n_long else 1,
                          "timing": "CUDA events around %d back-to-back steps on the launching stream / %d" % (args.steps, args.steps),
@@ -747,6 +749,41 @@ def main_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def measure_traffic(timeout=240):
+    """DRAM bytes of one step's alignment launches, measured NOW on this GPU: ncu (two DRAM counters only) around a child
+    process that runs the same plan on the same split (scripts/prof_fused.py), after this process has finished timing.
+    Returns (bytes, source) or (None, reason)."""
+    import shutil
+    import subprocess
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "no ncu"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:align_fused", "-s", "4", "-c", "2", "--csv", sys.executable, os.path.join(ROOT, "scripts", "prof_fused.py")]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    except Exception as e:
+        return None, type(e).__name__
+    import csv
+    import io
+    rows = [x for x in csv.reader(io.StringIO(r.stdout)) if len(x) > 5]
+    hdr = next((x for x in rows if "Metric Value" in x and "Metric Unit" in x), None)
+    if hdr is None:
+        return None, "no ncu table (rc %d)" % r.returncode
+    vi, ui, ki = hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Kernel Name")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, kernels = 0.0, set()
+    for x in rows:
+        if x is hdr or x[ui] not in scale:
+            continue
+        total += float(x[vi].replace(",", "")) * scale[x[ui]]
+        kernels.add(x[ki][:40])
+    if not total:
+        return None, "empty ncu table"
+    return int(total), ("measured in this run: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum around "
+                        "scripts/prof_fused.py (same split and plan), both launches of one step: %s" % sorted(kernels))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -756,6 +793,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-backbone", action="store_true", help="skip the backbone + alignment leg")
     ap.add_argument("--no-legs", action="store_true", help="skip the c1 / c3 / c4 / training-step legs")
+    ap.add_argument("--no-traffic", action="store_true", help="do not re-measure roofline.traffic with ncu (N = 1 only)")
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind ranks to the CPUs next to their GPU")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: result exchange by peer stores from the kernels (default) or an NCCL all_gather per step")

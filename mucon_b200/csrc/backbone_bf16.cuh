@@ -58,6 +58,9 @@ constexpr int kTapBytes = NKB * BM * 128;
 // tile (and every tile that crosses the end of its video, and fp32 output) is stored straight from registers
 __host__ __device__ inline int staged_rows(int dil, int slab, int pool, int out_f32) {
   if (out_f32) return 0;
+#ifdef MUCON_L16_NOSTAGE
+  return 0;   // experiment: every tile stored straight from registers (scripts/ab_layers.py)
+#endif
   const int free_bytes = SMEM_LIMIT - W_BYTES - ID_BYTES - num_stages(slab) * NKB * kb_bytes_of(dil, slab) - BAR_BYTES;
   int s = (free_bytes / 256) & ~7;
   const int want = pool ? BM / 2 : BM;

@@ -32,3 +32,18 @@ for dil, pool in ((1, False), (2, False), (4, True), (32, False), (64, False), (
         ts.append(a.elapsed_time(b))
     ts = sorted(ts[2:])
     print(f"level 0 dil {dil:4d} pool {int(pool)}: {ts[len(ts) // 2] * 1e3:8.1f} us")
+
+# cost of the residual MMAs: the same launches without the skip connection
+for dil, pool in ((1, False), (4, True), (64, False)):
+    for res in (True, False):
+        ts = []
+        for r in range(8):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            temporal.wavenet_layer_bf16_rows(x, wdk, bd, w1k, b1, plan, 0, dil, pool, False, residual=res)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts = sorted(ts[2:])
+        print(f"level 0 dil {dil:4d} pool {int(pool)} residual {int(res)}: {ts[len(ts) // 2] * 1e3:8.1f} us")
