@@ -321,6 +321,25 @@ struct TapShifts {
   int s[kMaxTaps];
 };
 
+// Epilogue phase A of conv_gemm_kernel: TMEM (lane = row) -> + bias -> activation -> padded shared tile.  The bias sits
+// in shared memory (zeros when the launch has none) and is read four values at a time.
+template <int MODE>
+__device__ __forceinline__ void epi_phase_a(uint32_t taddr, const float* bias_s, float* et, int lane) {
+#pragma unroll
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+      float4 v = make_float4(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y,
+                             __uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w);
+      if (MODE != 0) { v.x = act_mode(v.x, MODE); v.y = act_mode(v.y, MODE); v.z = act_mode(v.z, MODE); v.w = act_mode(v.w, MODE); }
+      *reinterpret_cast<float4*>(et + lane * EPI_LD + c * 32 + j) = v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(CTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const Tile* __restrict__ tiles, int num_tiles, const TapShifts ts, const float* __restrict__ bias,
@@ -340,7 +359,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  __shared__ __align__(16) float bias_s[C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < C) bias_s[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;   // published by the __syncthreads below
   if (threadIdx.x == 0) {
     for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
@@ -451,22 +472,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_after();
       // phase A: TMEM -> registers (lane = row) -> + bias (ReLU) -> padded shared tile
       float* et = epi_mem + (warp - 3) * (EPI_BYTES / 4);
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[e] = __uint_as_float(r[j + e]);
-            if (bias) v[e] += __ldg(bias + c * 32 + j + e);
-            v[e] = act_mode(v[e], relu_mid);
-          }
-          *reinterpret_cast<float4*>(et + lane * EPI_LD + c * 32 + j) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      // one uniform branch per tile, the activation compiled into each variant (not a test per element)
+      if (relu_mid == 0) epi_phase_a<0>(taddr, bias_s, et, lane);
+      else if (relu_mid == 1) epi_phase_a<1>(taddr, bias_s, et, lane);
+      else epi_phase_a<2>(taddr, bias_s, et, lane);
       // the accumulator is drained: hand it back before the (slower) global phase
       tc_fence_before();
       __syncwarp();

@@ -1,7 +1,9 @@
-"""GPU scratch tool: last_conv (conv_gemm_kernel, one tap) on the c2 split's deepest level, timed alone."""
+"""GPU scratch tool: the one-tap TF32 conv_gemm_kernel (last_conv of the TF32 path) per level of the c2 split and on
+synthetic plans of full / partly filled tiles, timed alone with the L2 flushed: microseconds per 128-row tile."""
 import os
 import sys
 
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,27 +13,31 @@ from mucon_b200 import temporal  # noqa: E402
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 m = temporal.MuConBackbone().eval().to(dev)
+w = m.ft._weights()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def run(plan, lvl, name):
+    rows = plan.rows[lvl]
+    x = torch.randn(rows, 128, device=dev)
+    ts = []
+    for r in range(7):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        temporal.conv_gemm_rows(x, w["last_k"], w["last_b"], plan, lvl)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    t = sorted(ts[2:])[2]
+    nt = plan.n_tiles[lvl]
+    print(f"{name:34s} rows {rows:8d} tiles {nt:6d}: {t:8.1f} us = {t / max(1, -(-nt // 148)):6.2f} us per tile and CTA")
+
+
 T, trs, _ = bench.make_split(0)
 plan = m.plan(T)
-w = m.ft._weights()
-level = max(k for k in range(8) if k < len(plan.rows))
-for lvl in sorted({level, len(plan.rows) - 1}):
-    rows = plan.rows[lvl]
-    for kind in ("randn", "relu(randn)", "zeros"):
-        x = torch.randn(rows, 128, device=dev)
-        if kind == "relu(randn)":
-            x = x.relu()
-        if kind == "zeros":
-            x.zero_()
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        ts = []
-        for r in range(8):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            y = temporal.conv_gemm_rows(x, w["last_k"], w["last_b"], plan, lvl)
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b) * 1e3)
-        ts = sorted(ts[2:])
-        print(f"level {lvl} rows {rows} input {kind:12s}: {ts[len(ts) // 2]:7.1f} us  (min {ts[0]:.1f})")
+for lvl in range(len(plan.rows)):
+    run(plan, lvl, f"c2 level {lvl}")
+for Tv, V in ((128, 2720), (140, 1712), (256, 1360), (64, 2720), (1280, 272), (12800, 27)):
+    p = temporal.BackbonePlan(np.full(V, Tv), 0, dev)
+    run(p, 0, f"{V} videos of {Tv} rows")
