@@ -181,6 +181,7 @@ def wavenet_layer_bf16_rows(x, Wd_kco16, bd, W1_kco16, b1, plan, level, dilation
     return out
 
 
+PADDED_WIDTHS = (32, 64)   # hidden sizes served by a zero-padded 128-channel twin (WaveNetBlock._padded_twin)
 LAST_CONV_16 = os.environ.get("MUCON_LAST_CONV_16", "1") != "0"
 DEAD_DILATION = 1 << 20   # no video is that long: both side taps only see padding and are never loaded
 
@@ -270,6 +271,30 @@ class WaveNetBlock(nn.Module):
     def n_pools(self):
         return sum(1 for i in range(self.num_stages) if self.pooling and i in self.pooling_layers)
 
+    def _padded_twin(self):
+        """WaveNetBlock(out_dims=128) holding this block's parameters zero-padded to 128 channels (cached by parameter
+        versions; not a registered submodule, so state_dict() is unchanged)."""
+        key = tuple(p._version for p in self.parameters()) + (str(self.first_conv.weight.device),)
+        got = self.__dict__.get("_twin")
+        if got is not None and got[0] == key:
+            return got[1]
+        h = self.out_dims
+        twin = WaveNetBlock(self.in_channels, stages=self.stages, out_dims=128, kernel_size=self.kernel_size,
+                            pooling=self.pooling, pooling_layers=self.pooling_layers, pooling_type=self.pooling_type,
+                            dropout_rate=self.dropout_rate, leaky=self.leaky).to(self.first_conv.weight.device).eval()
+        with torch.no_grad():
+            for p in twin.parameters():
+                p.zero_()
+            twin.first_conv.weight[:h].copy_(self.first_conv.weight)
+            twin.first_conv.bias[:h].copy_(self.first_conv.bias)
+            for mine, theirs in zip(self.layers + [self], twin.layers + [twin]):
+                convs = [("last_conv",)] if mine is self else [("dilated_conv",), ("conv_1x1",)]
+                for (name,) in convs:
+                    getattr(theirs, name).weight[:h, :h].copy_(getattr(mine, name).weight)
+                    getattr(theirs, name).bias[:h].copy_(getattr(mine, name).bias)
+        self.__dict__["_twin"] = (key, twin)
+        return twin
+
     def _weights(self):
         key = tuple(p._version for p in self.parameters()) + (str(self.first_conv.weight.device),)
         if self._cache is None or self._cache[0] != key:
@@ -319,6 +344,13 @@ class WaveNetBlock(nn.Module):
             raise ValueError(f"precision {precision!r}")
         if precision == "fp32":
             tensor_cores = False
+        if tensor_cores and self.out_dims in PADDED_WIDTHS and self.in_channels % 32 == 0:
+            # model.ft.hidden_size = 32 / 64 on the 128-channel tensor-core kernels: a 128-channel twin whose extra
+            # channels have zero weights and biases computes exact zeros there (relu(0) = 0, 0 + 0 = 0, max(0, 0) = 0)
+            # and never feeds them into the real ones
+            z = self._padded_twin().forward_packed(feats, plan, tensor_cores=True, fused_layers=fused_layers,
+                                                   precision=precision, x0=x0)
+            return z[:, :self.out_dims].contiguous()
         act = 2 if self.leaky else 1                       # activation mode of the kernels' relu flags
         pool_mode = 0 if self.pooling_type == "max" else 1
         if act != 1 or pool_mode != 0:
