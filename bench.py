@@ -591,7 +591,33 @@ def main_ours(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         p_last = e2e_step()
     barrier()
+    e2e_serial_s = (time.perf_counter() - t0) / e2e_steps
+    # The same steps through the streaming API (viterbi.HostAlignPipeline): every step still copies its 740 MB of
+    # log-probabilities host -> device and its labels / scores / segment lengths device -> host, but step i's kernels and
+    # device -> host copy run under step i + 1's host -> device copy (three streams, two device input buffers).
+    from mucon_b200.viterbi import HostAlignPipeline
+    pipe = HostAlignPipeline(eng)
+
+    def mk_plan():
+        return AlignPlan(T, cands, C, fs=FS, max_len=MAX_LEN, device=device, len_params=poisson_params(means), labels="best")
+
+    def e2e_stream(n):
+        prev, last = None, None
+        for _ in range(n):
+            tk = pipe.submit(host_logp, mk_plan, seg0_f32=True)
+            if prev is not None:
+                last = pipe.result(prev)
+            prev = tk
+        return pipe.result(prev)
+
+    e2e_stream(3)
+    barrier()
+    t0 = time.perf_counter()
+    res_last = e2e_stream(e2e_steps)
+    barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_same = bool(torch.equal(res_last[1], host_labels) and torch.equal(res_last[2], host_small) and
+                    torch.equal(res_last[3], host_seg))   # the streamed results equal the serial step's
     # where an e2e step goes: the parts timed one at a time (in the step itself the plan build overlaps the H2D copy)
     def wall(fn, n=3):
         torch.cuda.synchronize()
@@ -690,7 +716,9 @@ def main_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": frames_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                    "what": "AlignPlan build + pinned H2D of log-probs + fused kernel + D2H of labels/scores/segments",
+                    "what": "viterbi.HostAlignPipeline: per step AlignPlan build + pinned H2D of the log-probs + fused kernel + D2H "
+                            "of labels/scores/segments; step i's kernels and D2H run under step i+1's H2D (three streams)",
+                    "serial_ms_per_step": e2e_serial_s * 1e3, "streamed_equals_serial": e2e_same,
                     "breakdown_rank0_ms": {"plan_build": plan_ms, "h2d": h2d_ms, "kernel": kern_ms, "d2h": d2h_ms,
                                            "note": "timed one at a time; in the step the plan build overlaps the H2D copy"},
                     "h2d_gbs_rank0": h2d / (h2d_ms * 1e-3) / 1e9,

@@ -517,6 +517,85 @@ class ViterbiEngine:
         return out
 
 
+class HostAlignPipeline:
+    """Alignment of a STREAM of host batches (pinned log-probabilities in, pinned labels / scores / segment lengths out)
+    with the three legs of a step on three streams: the host->device copy of batch i + 1 runs while the kernels of
+    batch i run and while the results of batch i go back (PCIe is full duplex), so a steady stream costs the
+    host->device copy alone.  `depth` device input buffers; a slot is reused only after its results were collected.
+
+        pipe = HostAlignPipeline(engine)
+        t = pipe.submit(host_logp, lambda: AlignPlan(T, candidates, C, device=engine.device, len_params=...))
+        plan, labels, score, seg_blocks = pipe.result(t)      # pinned host tensors, valid until the slot is reused
+    """
+
+    def __init__(self, engine, depth=2):
+        self.eng, self.depth = engine, int(depth)
+        dev = engine.device
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.slots = [dict(busy=False) for _ in range(self.depth)]
+        self.n = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    @staticmethod
+    def _fit(slot, name, numel, dtype, **kw):
+        t = slot.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = slot[name] = torch.empty(max(int(numel), 1), dtype=dtype, **kw)
+        return t[:numel]
+
+    def submit(self, host_logp, make_plan, seg0_f32=None):
+        """host_logp: pinned CPU tensor [sum T, C] (float32 / float64); make_plan(): the batch's AlignPlan -- called here,
+        on the host, while the copy is in flight.  Returns a ticket for result()."""
+        if host_logp.is_cuda or not host_logp.is_contiguous():
+            raise TypeError("host_logp must be a contiguous CPU tensor (pinned for an asynchronous copy)")
+        ticket = self.n
+        slot = self.slots[ticket % self.depth]
+        if slot["busy"]:
+            raise _lib.MuconError("HostAlignPipeline: collect result(%d) before submitting again" % slot["ticket"])
+        dev = self.eng.device
+        dev_in = slot.get("dev_in")
+        if dev_in is None or dev_in.shape != host_logp.shape or dev_in.dtype != host_logp.dtype:
+            dev_in = slot["dev_in"] = torch.empty(host_logp.shape, dtype=host_logp.dtype, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self.s_in.wait_stream(cur)            # whatever produced host_logp / freed the buffers on the caller's stream
+        if slot.get("ran") is not None:
+            self.s_in.wait_event(slot["ran"])  # the previous kernels of this slot have read dev_in
+        with torch.cuda.stream(self.s_in):
+            dev_in.copy_(host_logp, non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            plan = make_plan()                 # host work + the plan's metadata upload, under the copy
+            self.s_run.wait_event(ev_in)
+            self.eng.run(plan, dev_in, seg0_f32=seg0_f32, write_bs=False, stream=self.s_run)
+            ran = torch.cuda.Event()
+            ran.record(self.s_run)
+        self.s_out.wait_event(ran)
+        with torch.cuda.stream(self.s_out):
+            labels = self._fit(slot, "labels", plan.labels.numel(), torch.int32, pin_memory=True)
+            score = self._fit(slot, "score", plan.score.numel(), torch.float64, pin_memory=True)
+            seg = self._fit(slot, "seg", plan.seg_blocks.numel(), torch.int32, pin_memory=True)
+            labels.copy_(plan.labels, non_blocking=True)
+            score.copy_(plan.score, non_blocking=True)
+            seg.copy_(plan.seg_blocks, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.s_out)
+        slot.update(busy=True, ticket=ticket, plan=plan, ran=ran, done=done, out=(labels, score, seg))
+        self.h2d_bytes = host_logp.numel() * host_logp.element_size() + getattr(plan, "h2d_meta_bytes", 0)
+        self.d2h_bytes = labels.numel() * 4 + score.numel() * 8 + seg.numel() * 4
+        self.n += 1
+        return ticket
+
+    def result(self, ticket):
+        """Blocks until batch `ticket` is back on the host: (plan, labels, score, seg_blocks)."""
+        slot = self.slots[ticket % self.depth]
+        if not slot["busy"] or slot["ticket"] != ticket:
+            raise _lib.MuconError("HostAlignPipeline: no pending batch %d" % ticket)
+        slot["done"].synchronize()
+        slot["busy"] = False
+        return (slot["plan"],) + slot["out"]
+
+
 def _length_rows(length_model, transcript, fs, J):
     """Generic lowering of any LengthModel: rows[n, j-1] = score(j*fs, label_n)."""
     tab = getattr(length_model, "poisson", None)

@@ -551,3 +551,54 @@ def test_drop_in_decode_with_float32_mean_lengths(eng):
     assert same_score(score, g["score"])
     assert labels == g["labels"].tolist()
     assert [(s.label, s.length) for s in segs] == [tuple(x) for x in g["segs"].tolist()]
+
+
+def test_host_align_pipeline_equals_serial_runs(eng):
+    """viterbi.HostAlignPipeline (H2D of batch i+1 under the kernels and the D2H of batch i, three streams, two input
+    buffers): every batch's labels / scores / segment lengths equal a serial run of the same batch, also when the batch
+    shape changes from one submit to the next and when more batches than slots are in flight over time."""
+    from mucon_b200 import _lib
+    from mucon_b200.length_model import poisson_params
+    from mucon_b200.viterbi import AlignPlan, HostAlignPipeline
+    rng = np.random.default_rng(23)
+    C = 48
+    batches = []
+    for b in range(5):
+        V = 40 if b != 3 else 17
+        T = rng.integers(300, 4000, V)
+        trs = [rng.integers(0, C, int(rng.integers(2, 9))).tolist() for _ in range(V)]
+        means = np.stack([synth.class_means(rng.dirichlet(np.ones(len(tr))).astype(np.float32), tr, C, int(t))
+                          for tr, t in zip(trs, T)])
+        logp = torch.log_softmax(torch.randn(int(T.sum()), C, generator=torch.Generator().manual_seed(b)), 1).contiguous()
+        batches.append((T, trs, means, logp.pin_memory()))
+
+    def mk(T, trs, means):
+        return lambda: AlignPlan(T, [[tr] for tr in trs], C, device=eng.device, len_params=poisson_params(means))
+
+    want = []
+    for T, trs, means, logp in batches:
+        plan = mk(T, trs, means)()
+        eng.run(plan, logp.to(eng.device), seg0_f32=True)
+        out = eng.fetch(plan)
+        want.append((out["labels"].copy(), out["score"].copy(), out["seg_blocks"].copy()))
+    pipe = HostAlignPipeline(eng)
+    prev = None
+    got = {}
+    for b, (T, trs, means, logp) in enumerate(batches):
+        tk = pipe.submit(logp, mk(T, trs, means), seg0_f32=True)
+        if prev is not None:
+            _, la, sc, sg = pipe.result(prev)
+            got[prev] = (la.numpy().copy(), sc.numpy().copy(), sg.numpy().copy())
+        prev = tk
+    _, la, sc, sg = pipe.result(prev)
+    got[prev] = (la.numpy().copy(), sc.numpy().copy(), sg.numpy().copy())
+    for b in range(len(batches)):
+        for a, w in zip(got[b], want[b]):
+            assert np.array_equal(a, w), b
+    # a slot cannot be reused before its results were collected
+    t0 = pipe.submit(batches[0][3], mk(*batches[0][:3]), seg0_f32=True)
+    t1 = pipe.submit(batches[1][3], mk(*batches[1][:3]), seg0_f32=True)
+    with pytest.raises(_lib.MuconError):
+        pipe.submit(batches[2][3], mk(*batches[2][:3]), seg0_f32=True)
+    pipe.result(t0)
+    pipe.result(t1)
