@@ -615,7 +615,11 @@ def main_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     res_last = e2e_stream(e2e_steps)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_stream_s = (time.perf_counter() - t0) / e2e_steps
+    # both are user-facing calls of the package; the line reports the faster one and both times (with several ranks on
+    # one host the streamed form's concurrent H2D + D2H + plan builds contend on the host side and the serial step wins)
+    e2e_s = min(e2e_stream_s, e2e_serial_s)
+    e2e_mode = "streamed (viterbi.HostAlignPipeline)" if e2e_stream_s <= e2e_serial_s else "serial (AlignPlan + ViterbiEngine.run per step)"
     e2e_same = bool(torch.equal(res_last[1], host_labels) and torch.equal(res_last[2], host_small) and
                     torch.equal(res_last[3], host_seg))   # the streamed results equal the serial step's
     # where an e2e step goes: the parts timed one at a time (in the step itself the plan build overlaps the H2D copy)
@@ -667,13 +671,20 @@ def main_ours(args, rank, world, local_rank):
     per_rank_ms = [total_ms / args.steps]
     per_rank_e2e = [e2e_s * 1e3]
     if world > 1:
-        mine = torch.tensor([total_ms / args.steps, e2e_s * 1e3], dtype=torch.float64, device=device)
-        allr = torch.empty(2 * world, dtype=torch.float64, device=device)
+        mine = torch.tensor([total_ms / args.steps, e2e_serial_s * 1e3, e2e_stream_s * 1e3], dtype=torch.float64, device=device)
+        allr = torch.empty(3 * world, dtype=torch.float64, device=device)
         dist.all_gather_into_tensor(allr, mine)
-        per_rank_ms, per_rank_e2e = allr.view(world, 2)[:, 0].tolist(), allr.view(world, 2)[:, 1].tolist()
-        t = torch.tensor([total_ms, scan_ms, dp_ms, e2e_s, fused_ms], dtype=torch.float64, device=device)
+        allr = allr.view(world, 3)
+        per_rank_ms = allr[:, 0].tolist()
+        # one mode for the whole job: the one whose slowest rank is faster
+        e2e_serial_s, e2e_stream_s = float(allr[:, 1].max()) * 1e-3, float(allr[:, 2].max()) * 1e-3
+        streamed = e2e_stream_s <= e2e_serial_s
+        e2e_s = min(e2e_stream_s, e2e_serial_s)
+        e2e_mode = "streamed (viterbi.HostAlignPipeline)" if streamed else "serial (AlignPlan + ViterbiEngine.run per step)"
+        per_rank_e2e = allr[:, 2 if streamed else 1].tolist()
+        t = torch.tensor([total_ms, scan_ms, dp_ms, fused_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, scan_ms, dp_ms, e2e_s, fused_ms = t.tolist()
+        total_ms, scan_ms, dp_ms, fused_ms = t.tolist()
         fr = torch.tensor([plan.aligned_frames], dtype=torch.float64, device=device)
         dist.all_reduce(fr, op=dist.ReduceOp.SUM)
         frames_all = float(fr.item())
@@ -716,9 +727,11 @@ def main_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": frames_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                    "what": "viterbi.HostAlignPipeline: per step AlignPlan build + pinned H2D of the log-probs + fused kernel + D2H "
-                            "of labels/scores/segments; step i's kernels and D2H run under step i+1's H2D (three streams)",
-                    "serial_ms_per_step": e2e_serial_s * 1e3, "streamed_equals_serial": e2e_same,
+                    "what": "per step AlignPlan build + pinned H2D of the log-probs + fused kernel + D2H of labels/scores/segments; "
+                            "streamed = viterbi.HostAlignPipeline (step i's kernels and D2H under step i+1's H2D, three "
+                            "streams), serial = one step at a time; the faster of the two is the value",
+                    "mode": e2e_mode, "serial_ms_per_step": e2e_serial_s * 1e3, "streamed_ms_per_step": e2e_stream_s * 1e3,
+                    "streamed_equals_serial": e2e_same,
                     "breakdown_rank0_ms": {"plan_build": plan_ms, "h2d": h2d_ms, "kernel": kern_ms, "d2h": d2h_ms,
                                            "note": "timed one at a time; in the step the plan build overlaps the H2D copy"},
                     "h2d_gbs_rank0": h2d / (h2d_ms * 1e-3) / 1e9,
