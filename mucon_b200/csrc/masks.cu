@@ -471,7 +471,7 @@ masks_fwd_pre_kernel(const RowPre* __restrict__ pre, int n_rows, int tmpl, int a
 constexpr int kFlintPartsMax = 8;
 constexpr int kFlintBatch = 8;
 template <int kFlintParts>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 flint_fwd_warp_kernel(const RowPre* __restrict__ pre, int n_rows, int C, int tmpl, int align,
                       const float* __restrict__ seg, float* __restrict__ part_ws) {
   __shared__ float tp[kWP];
@@ -777,9 +777,10 @@ extern "C" int mucon_flint_fwd_ws(const float* L, const int32_t* n_off, const in
   const int sms = mucon_device_sm_count();
   static const int parts = getenv("MUCON_FLINT_PARTS") ? atoi(getenv("MUCON_FLINT_PARTS")) : 8;
   const long long items = static_cast<long long>(n_rows) * parts;
-  static const int bps = getenv("MUCON_FLINT_BPS") ? atoi(getenv("MUCON_FLINT_BPS")) : 24;  // CTAs per SM in the grid
-  // (measured on c2, 11839 rows: parts 4 / 8 CTAs per SM 0.196 ms, parts 8 / 24 per SM 0.174 ms -- finer items balance the
-  // ragged windows and shorten the last wave)
+  static const int bps = getenv("MUCON_FLINT_BPS") ? atoi(getenv("MUCON_FLINT_BPS")) : 48;  // CTAs per SM in the grid
+  // (measured on c2, 11839 rows: parts 4 / 8 CTAs per SM 0.196 ms; parts 8 / 24 per SM 0.174 ms -- finer items balance the
+  // ragged windows and shorten the last wave; with the kernel held to 64 registers (four resident CTAs instead of three,
+  // __launch_bounds__(256, 4)) and 48 per SM 0.160 ms; 48 registers spill and lose: 0.194 ms)
   long long grid = (items + 7) / 8;
   if (grid > static_cast<long long>(bps) * sms) grid = static_cast<long long>(bps) * sms;
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws + static_cast<int64_t>(n_rows) * kFlintPartsMax * C);
