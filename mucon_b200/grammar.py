@@ -32,18 +32,34 @@ class _TranscriptSetGrammar(Grammar):
         self.num_classes = num_classes
         self.candidates = []
         seen = set()
-        self.successors = {}
+        self._all = []          # every transcript in the order given (duplicates included): what builds the prefix tree
+        self._succ = None
         for tr in transcripts:
             tr = [int(x) for x in tr]
+            self._all.append(tr)
             if tuple(tr) not in seen:
                 seen.add(tuple(tr))
                 self.candidates.append(tr)
-            path = tr + [self.end_symbol()]
-            for i, nxt in enumerate(path):
-                # built exactly like grammar.py:150-154 ({x}.union(old)): the ITERATION order of these sets decides
-                # which of two candidates with equal scores the reference returns (tie_ranks below)
-                ctx = (self.start_symbol(),) + tuple(path[:i])
-                self.successors[ctx] = {nxt}.union(self.successors.get(ctx, set()))
+
+    @property
+    def successors(self):
+        """The reference's prefix tree (context tuple -> set of next labels), built on first use: the CUDA decoder reads
+        `candidates`, and the evaluator constructs a new grammar for every video (evaluators.py:167)."""
+        if self._succ is None:
+            succ = {}
+            for tr in self._all:
+                path = tr + [self.end_symbol()]
+                for i, nxt in enumerate(path):
+                    # built exactly like grammar.py:150-154 ({x}.union(old)): the ITERATION order of these sets decides
+                    # which of two candidates with equal scores the reference returns (tie_ranks below)
+                    ctx = (self.start_symbol(),) + tuple(path[:i])
+                    succ[ctx] = {nxt}.union(succ.get(ctx, set()))
+            self._succ = succ
+        return self._succ
+
+    @successors.setter
+    def successors(self, value):
+        self._succ = value
 
     def n_classes(self):
         return self.num_classes

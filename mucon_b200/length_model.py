@@ -39,6 +39,21 @@ def poisson_params(mean_lengths, renormalize=True):
     """[C, 3] float64: ln m, m, norms (length_model.py:54-63)."""
     m = np.asarray(mean_lengths, dtype=np.float64)
     out = np.empty(m.shape + (3,), dtype=np.float64)
+    if renormalize and m.ndim == 1 and m.size and m.min() > 0.5:
+        # every mean rounds to >= 1: no log(0) / 0 * inf to silence -- the same operations in the same order as below,
+        # without the error-state context, the clamp and the wrappers (this runs once per video in the evaluator's
+        # call pattern: 17 -> 9 us)
+        np.log(m, out=out[:, 0])
+        out[:, 1] = m
+        r = np.rint(m)
+        mi = m.astype(np.int64)
+        tail = _log_tail(int(mi.max()))
+        t = np.log(r)
+        t *= r
+        t -= r
+        t -= tail[mi]
+        out[:, 2] = t
+        return out
     with np.errstate(divide="ignore", invalid="ignore"):
         out[..., 0] = np.log(m)
         out[..., 1] = m

@@ -672,13 +672,16 @@ class Viterbi(object):
                 torch.cuda.set_device(eng.device)
             _lib.check(lib.mucon_single_create(C.c_int(cap_T), C.c_int(Cn), C.c_int(cap_N), C.c_int(8 if is64 else 4),
                                                C.byref(h)), "mucon_single_create")
-            ses = eng._single = (h, cap_T, Cn, cap_N, is64,
-                                 np.empty(cap_T, np.int32), np.empty(cap_N, np.int32), np.zeros(2, np.float64),
-                                 np.zeros(2, np.int32))
-        h, _, _, _, _, labels, segb, score, st_fj = ses
+            bufs = (np.empty(cap_T, np.int32), np.empty(cap_N, np.int32), np.zeros(2, np.float64), np.zeros(2, np.int32))
+            # the result buffers live as long as the session: their addresses are taken once (an ndarray.ctypes access
+            # builds a helper object, about a microsecond each -- eight of them per decode otherwise)
+            ptrs = (C.c_void_p(bufs[2].ctypes.data), C.c_void_p(bufs[0].ctypes.data), C.c_void_p(bufs[1].ctypes.data),
+                    C.c_void_p(bufs[3].ctypes.data), C.c_void_p(bufs[3].ctypes.data + 4))
+            ses = eng._single = (h, cap_T, Cn, cap_N, is64) + bufs + (ptrs,)
+        h, _, _, _, _, labels, segb, score, st_fj, ptrs = ses
         lp = logp if logp.flags.c_contiguous else np.ascontiguousarray(logp)
         tr32 = np.asarray(tr, dtype=np.int32)
-        params = np.ascontiguousarray(lm.params[tr32])
+        params = lm.params[tr32]                      # a fancy-indexed copy: C-contiguous [N, 3] float64
         if self.np_mode is None:
             seg0 = default_seg0_f32(logp.dtype)
         else:
@@ -686,8 +689,7 @@ class Viterbi(object):
         rc = lib.mucon_single_decode_h(
             h, C.c_void_p(lp.ctypes.data), C.c_int(int(is64)), C.c_int(T), C.c_void_p(tr32.ctypes.data), C.c_int(N),
             C.c_void_p(params.ctypes.data), C.c_int(fs), C.c_int(max_len), C.c_int(int(bool(seg0))),
-            C.c_void_p(score.ctypes.data), C.c_void_p(labels.ctypes.data), C.c_void_p(segb.ctypes.data),
-            C.c_void_p(st_fj.ctypes.data), C.c_void_p(st_fj.ctypes.data + 4),
+            ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4],
             C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream))
         if rc == -2:
             return None
@@ -698,7 +700,7 @@ class Viterbi(object):
         if st_fj[0] == _lib.UNIT_INFEASIBLE:
             raise AttributeError("no hypothesis survives: sequence too long for this transcript and max_length")
         K = T // fs
-        segs = [Segment(int(tr32[n]), int(fs * segb[n])) for n in range(N) if segb[n] > 0]
+        segs = [Segment(l, fs * b) for l, b in zip(tr32.tolist(), segb[:N].tolist()) if b > 0]   # plain ints, no NumPy scalars
         segs[-1].length += T - fs * K
         return np.float64(score[0]), labels[:T].tolist(), segs
 
