@@ -12,6 +12,7 @@ transcript) units in two kernel launches; that is what bench.py and the multi-GP
 All compute happens in libmucon_b200.so (CUDA, sm_100a); there is no CPU fallback.
 """
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -24,10 +25,22 @@ from .length_model import PoissonModel, log_factorial_prefix
 __all__ = ["Viterbi", "ViterbiEngine", "AlignPlan", "Segment", "default_seg0_f32"]
 
 
+_NUMPY2 = int(np.__version__.split(".")[0]) >= 2
+
+
 def default_seg0_f32(dtype):
     """The float mix the installed NumPy gives the reference decoder:
     with float32 log-probs NumPy >= 2 keeps segment 0 in float32, NumPy 1.x promotes to float64."""
-    return np.dtype(dtype) == np.float32 and int(np.__version__.split(".")[0]) >= 2
+    return _NUMPY2 and np.dtype(dtype) == np.float32
+
+
+def _raw_stream(device):
+    """cudaStream_t of torch's current stream on `device` as an int (the private fast path triton also uses; the
+    public objects cost two extra microseconds per call, which the one-video-per-call pattern notices)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream(device).cuda_stream
 
 
 class Segment(object):
@@ -690,7 +703,7 @@ class Viterbi(object):
             h, C.c_void_p(lp.ctypes.data), C.c_int(int(is64)), C.c_int(T), C.c_void_p(tr32.ctypes.data), C.c_int(N),
             C.c_void_p(params.ctypes.data), C.c_int(fs), C.c_int(max_len), C.c_int(int(bool(seg0))),
             ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4],
-            C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream))
+            C.c_void_p(_raw_stream(eng.device)))
         if rc == -2:
             return None
         _lib.check(rc, "mucon_single_decode_h")
@@ -718,10 +731,16 @@ class Viterbi(object):
         cands = lower_grammar(self.grammar)
         lm = self.length_model
         max_len = lm.max_length()
-        if not np.isfinite(max_len):
+        if not math.isfinite(max_len):
             raise TypeError("length model without a finite max_length() is not supported")
         max_len = int(max_len)
         J = max_len // fs
+        eng = self._eng()
+        if self.fast_single and len(cands) == 1 and isinstance(lm, PoissonModel) and lm.exact_params and J <= MAX_J_REGISTER \
+                and Cn % 4 == 0 and Cn <= 128:
+            fast = self._decode_single(eng, logp, cands[0], lm, fs, max_len)
+            if fast is not None:
+                return fast
         kw = {}
         if isinstance(lm, PoissonModel) and lm.exact_params:
             kw["len_params"] = lm.params[None]
@@ -729,12 +748,6 @@ class Viterbi(object):
             kw["len_rows"] = [lm.rows_for(tr, fs, J) for tr in cands]   # non-float64 means: the reference's dtypes
         else:
             kw["len_rows"] = [_length_rows(lm, tr, fs, J) for tr in cands]
-        eng = self._eng()
-        if self.fast_single and len(cands) == 1 and isinstance(lm, PoissonModel) and lm.exact_params and J <= MAX_J_REGISTER \
-                and Cn % 4 == 0 and Cn <= 128:
-            fast = self._decode_single(eng, logp, cands[0], lm, fs, max_len)
-            if fast is not None:
-                return fast
         if len(cands) > 1 and isinstance(getattr(self.grammar, "successors", None), dict):
             kw["tie_rank"] = tie_ranks(self.grammar.successors, cands, self.grammar.start_symbol())
         plan = AlignPlan([T], [cands], Cn, fs=fs, max_len=max_len, device=eng.device, labels="best", **kw)
