@@ -128,20 +128,17 @@ def tie_ranks(successors, candidates, start=-1):
     remaining labels, compared as sequences (a proper prefix is earlier).  The data-dependent middle key -- last
     segment length + transcript length -- is added on the device."""
     place = {}
-
-    def places(ctx):
-        got = place.get(ctx)
-        if got is None:
-            got = place[ctx] = {int(x): i for i, x in enumerate(successors.get(ctx, ()))}
-        return got
-
+    get = place.get
     seqs = []
     for tr in candidates:
         ctx = (start,)
         r = []
         for x in tr:
             x = int(x)
-            r.append(places(ctx)[x])
+            pl = get(ctx)
+            if pl is None:
+                pl = place[ctx] = {int(y): i for i, y in enumerate(successors.get(ctx, ()))}
+            r.append(pl[x])
             ctx = ctx + (x,)
         seqs.append(tuple(r))
     rest = {t: i for i, t in enumerate(sorted({q[1:] for q in seqs}))}
@@ -155,9 +152,13 @@ def tie_ranks(successors, candidates, start=-1):
 def tie_ranks_for_lists(candidates, start=-1, end=-2):
     """tie_ranks for a plain list of transcripts = what ModifiedPathGrammar(candidates) (grammar.py:178-191) implies."""
     succ = {}
+    empty = frozenset()
+    get = succ.get
     for tr in candidates:
-        path = [int(x) for x in tr] + [end]
-        for i, nxt in enumerate(path):
-            ctx = (start,) + tuple(path[:i])
-            succ[ctx] = set([nxt]).union(succ.get(ctx, set()))
+        ctx = (start,)
+        for nxt in tr:
+            nxt = int(nxt)
+            succ[ctx] = {nxt}.union(get(ctx, empty))     # the reference's statement (grammar.py:185-189): order matters
+            ctx = ctx + (nxt,)
+        succ[ctx] = {end}.union(get(ctx, empty))
     return tie_ranks(succ, candidates, start)
