@@ -102,3 +102,34 @@ def test_both_arms_print_the_same_config():
     assert bench.bench_config(1, "peer") == bench.bench_config(1, "peer")
     c = bench.bench_config(8, "peer")
     assert c["workload"] == bench.WORKLOAD and c["videos_per_gpu"] == 1712 and "larger than the 126 MB L2" in c["l2"]
+
+
+def test_grammar_prefix_tree_is_lazy_and_iterates_like_the_reference():
+    """The grammars build `successors` on first use (the evaluator constructs one per video and the CUDA path reads
+    `candidates` only); when built, the sets are the reference's ({x}.union(old), grammar.py:150-154,185-189,203-207) --
+    same members AND same iteration order, which decides exact ties between candidates (tests/test_ties.py)."""
+    import os
+    import random
+    import sys
+    from mucon_b200.grammar import ModifiedPathGrammar, SingleTranscriptGrammar
+    g = SingleTranscriptGrammar([3, 7, 3], 10)
+    assert g._succ is None and g.candidates == [[3, 7, 3]]
+    assert g.possible_successors((-1, 3)) == {7} and g.score((-1,), 3) == 0.0 and g.score((-1,), 4) == -np.inf
+    assert g._succ is not None
+    g.successors = {(-1,): {1}}          # the attribute stays assignable, as on the reference's objects
+    assert g.possible_successors((-1,)) == {1}
+    if not os.path.isdir("/root/reference/src"):
+        return
+    sys.path.insert(0, "/root/reference/src")
+    try:
+        from core.viterbi.grammar import ModifiedPathGrammar as RefGrammar
+    finally:
+        sys.path.pop(0)
+    rng = random.Random(5)
+    for _ in range(300):
+        C = rng.choice([5, 12, 48, 300])
+        trs = [[rng.randrange(C) for _ in range(rng.randrange(1, 6))] for _ in range(rng.randrange(1, 10))]
+        ours, ref = ModifiedPathGrammar(trs, C), RefGrammar([list(t) for t in trs], C)
+        assert set(ours.successors) == set(ref.successors)
+        for ctx, nxt in ref.successors.items():
+            assert list(ours.successors[ctx]) == list(nxt), (trs, ctx)
